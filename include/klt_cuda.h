@@ -1,0 +1,153 @@
+/* include/klt_cuda.h -- thin C-ABI between the plain-C KLT host library and
+ * the hand-written sm_100a CUDA kernels (csrc/klt_dev.cu).
+ *
+ * extern "C", POD arguments only, every entry point returns 0 on success or a
+ * non-zero code with a message retrievable through klt_dev_error(); the C side
+ * (csrc/klt_track.c, csrc/klt_select.c) funnels failures into KLTError(), the
+ * reference's error convention (reference src/V1/error.c:23-33).
+ *
+ * Each entry point names the reference interface it replaces.  A binding from
+ * another host language (cgo, JNI, ctypes ...) needs exactly these symbols;
+ * see INTEGRATION.md.
+ *
+ * Data layout on the device: every float image is row-major with a row pitch
+ * rounded up to 32 floats (128 B); one "pyramid set" holds, for each level l,
+ * the smoothed image L_l and its gradients gx_l, gy_l.  A context owns two
+ * sets (slots 0 and 1): the previous frame and the frame being built.
+ */
+#ifndef KLT_CUDA_H
+#define KLT_CUDA_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KLT_DEV_MAX_TAPS   71   /* reference src/V1/convolve.c:16 MAX_KERNEL_WIDTH */
+#define KLT_DEV_MAX_LEVELS 12
+
+typedef struct klt_dev klt_dev;   /* opaque device context: stream, buffers */
+
+/* One separable kernel pair for a given sigma, generated on the host exactly
+ * as reference src/V1/convolve.c:60-114 (_computeKernels) does. */
+typedef struct {
+  int   gauss_width;                 /* odd */
+  int   deriv_width;                 /* odd */
+  float gauss[KLT_DEV_MAX_TAPS];     /* normalised Gaussian            */
+  float deriv[KLT_DEV_MAX_TAPS];     /* normalised derivative of Gauss */
+} klt_dev_taps;
+
+/* What to build from one u8 frame.
+ * replaces: _KLTToFloatImage + _KLTComputeSmoothedImage + _KLTComputePyramid +
+ * per-level _KLTComputeGradients as sequenced in reference
+ * src/V1/trackFeatures.c:1309-1321 (and selectGoodFeatures.c:354-363 when
+ * nlevels_built == 1). */
+typedef struct {
+  int ncols, nrows;            /* frame size                                    */
+  int nlevels;                 /* pyramid levels of the context geometry        */
+  int subsampling;             /* 2,4,8,16,32                                   */
+  int nlevels_built;           /* 1 for selection, nlevels for tracking         */
+  int smooth;                  /* 0: level 0 = (float) pixels, no pre-smoothing */
+  int exact;                   /* 1: reference-order, non-fused mul/add (bit-exact
+                                  against the CPU reference); 0: FMA (default)  */
+  klt_dev_taps smooth_taps;    /* sigma = smooth_sigma_fact * max(window)       */
+  klt_dev_taps pyramid_taps;   /* sigma = subsampling * pyramid_sigma_fact      */
+  klt_dev_taps grad_taps;      /* sigma = grad_sigma                            */
+} klt_dev_build_desc;
+
+/* replaces the scalar arguments of _trackFeature / KLTTrackFeatures
+ * (reference src/V1/trackFeatures.c:381-399, :1364-1376, :1396). */
+typedef struct {
+  int   window_width, window_height;
+  float step_factor;
+  int   max_iterations;
+  float min_determinant;
+  float min_displacement;
+  float max_residue;
+  int   borderx, bordery;
+  int   exact;
+} klt_dev_track_params;
+
+/* replaces the scalar arguments of _KLTSelectGoodFeatures /
+ * _enforceMinimumDistance (reference src/V1/selectGoodFeatures.c:297-453). */
+typedef struct {
+  int window_width, window_height;
+  int borderx, bordery;
+  int nSkippedPixels;
+  int mindist;
+  int min_eigenvalue;
+  int overwrite_all;           /* 1 = SELECTING_ALL, 0 = REPLACING_SOME */
+} klt_dev_select_params;
+
+/* ---- lifetime ---------------------------------------------------------- */
+int  klt_dev_count(void);                                /* visible CUDA devices, 0 if none */
+int  klt_dev_create(int device, klt_dev **out);          /* device < 0: current device      */
+void klt_dev_destroy(klt_dev *d);
+const char *klt_dev_error(const klt_dev *d);             /* text of the last failure        */
+const char *klt_dev_create_error(void);                  /* text when klt_dev_create failed */
+int  klt_dev_device(const klt_dev *d);
+void *klt_dev_stream(const klt_dev *d);                  /* the cudaStream_t all work runs on */
+
+/* ---- pyramids ---------------------------------------------------------- */
+/* Build slot's pyramids from a frame.  img_is_device == 0: img is a host
+ * pointer (pageable or pinned), copied H2D on the context stream;
+ * != 0: img is a device pointer with row pitch img_pitch bytes.
+ * Asynchronous with respect to the host unless img is pageable. */
+int klt_dev_build(klt_dev *d, int slot, const unsigned char *img,
+                  int img_is_device, size_t img_pitch,
+                  const klt_dev_build_desc *desc);
+int klt_dev_slot_valid(const klt_dev *d, int slot);      /* 1 if slot holds a full pyramid set */
+void klt_dev_invalidate(klt_dev *d, int slot);           /* slot < 0: both */
+int klt_dev_geometry(const klt_dev *d, int *ncols, int *nrows, int *nlevels, int *subsampling);
+
+/* ---- tracking ---------------------------------------------------------- */
+/* replaces the feature loop of KLTTrackFeatures (reference
+ * src/V1/trackFeatures.c:1343-1437): x,y,val are host arrays of n features,
+ * updated in place; features with val < 0 are left untouched.  Synchronous. */
+int klt_dev_track(klt_dev *d, int slot_prev, int slot_cur,
+                  const klt_dev_track_params *p, int n,
+                  float *x, float *y, int *val);
+
+/* Device-resident variant for pipelined drivers: the feature arrays stay in
+ * HBM between calls; nothing is copied and the host is not synchronised. */
+int klt_dev_features_upload(klt_dev *d, int n, const float *x, const float *y, const int *val);
+int klt_dev_track_resident(klt_dev *d, int slot_prev, int slot_cur,
+                           const klt_dev_track_params *p);
+int klt_dev_features_download(klt_dev *d, int n, float *x, float *y, int *val);   /* synchronises */
+
+/* ---- selection --------------------------------------------------------- */
+/* replaces the eigenvalue loop, _sortPointList and _enforceMinimumDistance of
+ * _KLTSelectGoodFeatures (reference src/V1/selectGoodFeatures.c:373-446) on
+ * the level-0 gradients of `slot`.  Ties in the ranking are resolved in raster
+ * order (== the reference built with -DKLT_USE_QSORT on glibc).  Synchronous. */
+int klt_dev_select(klt_dev *d, int slot, const klt_dev_select_params *p,
+                   int n, float *x, float *y, int *val);
+
+/* ---- introspection (parity tests, debugging) --------------------------- */
+/* which: 0 image, 1 gradx, 2 grady.  out: dense ncols*nrows floats of that level. */
+int klt_dev_read_level(klt_dev *d, int slot, int which, int level, float *out);
+int klt_dev_level_dims(const klt_dev *d, int level, int *ncols, int *nrows);
+/* int min-eigenvalue of every candidate pixel in raster order (the pointlist
+ * `val` column of reference selectGoodFeatures.c:396-423); returns the count
+ * through *npoints; out may be NULL to query the count only. */
+int klt_dev_eigen_map(klt_dev *d, int slot, const klt_dev_select_params *p,
+                      int *out, int *npoints);
+int klt_dev_sync(klt_dev *d);
+/* number of kernels this context has launched so far */
+unsigned long long klt_dev_launch_count(const klt_dev *d);
+/* 1 if the last klt_dev_build used the fused tiled kernels, 0 if it took the
+ * generic (any radius / any subsampling) kernels */
+int klt_dev_last_build_path(const klt_dev *d);
+/* force the generic kernels (cross-check of the tiled ones); default 0 */
+void klt_dev_force_generic(klt_dev *d, int on);
+/* device time between the two calls, measured with CUDA events recorded on the
+ * context's own stream (the stream the kernels run on) */
+int klt_dev_timer_start(klt_dev *d);
+int klt_dev_timer_stop(klt_dev *d, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -194,9 +194,6 @@ class KLTLibrary:
 
     def read_pgm(self, fname: str) -> np.ndarray:
         nc, nr = C.c_int(0), C.c_int(0)
-        # read the header through the library to learn the size, then the pixels
-        with open(fname, "rb") as fh:
-            pass
         hdr = self.lib.pgmReadFile(fname.encode(), None, C.byref(nc), C.byref(nr))
         buf = (C.c_ubyte * (nc.value * nr.value)).from_address(hdr)
         out = np.frombuffer(buf, dtype=np.uint8).reshape(nr.value, nc.value).copy()

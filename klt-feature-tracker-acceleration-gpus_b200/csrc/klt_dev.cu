@@ -1,0 +1,1361 @@
+// klt_dev.cu -- hand-written sm_100a CUDA kernels + the C-ABI of include/klt_cuda.h.
+//
+// Replaces (reference file:line):
+//   _KLTToFloatImage / _convolveImageHoriz / _convolveImageVert / _convolveSeparate /
+//   _KLTComputeSmoothedImage / _KLTComputeGradients      src/V1/convolve.c:37-314
+//   _KLTComputePyramid                                    src/V1/pyramid.c:87-131
+//   eigenvalue loop, _sortPointList, _enforceMinimumDistance
+//                                                         src/V1/selectGoodFeatures.c:102-239,373-446
+//   _interpolate ... _trackFeature, feature loop          src/V1/trackFeatures.c:31-486,1343-1437
+//
+// Numerics.  Every kernel exists in two arithmetic modes selected by a template
+// flag:  EXACT = reference order of operations with separately rounded multiply
+// and add (bit-identical to the CPU reference built without FMA);  !EXACT = the
+// same order with fused multiply-add and shuffle-tree reductions (production,
+// within 1e-4 relative of the reference).
+//
+// Border semantics of the separable passes (convolve.c:164-178, :216-237): the
+// horizontal pass writes 0 for x < R or x >= W-R, the vertical pass consumes that
+// result and writes 0 for y < R or y >= H-R.  Interior outputs only ever touch
+// in-range inputs, so tiles may zero-fill reads outside the image.
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "klt_cuda.h"
+
+#define KLT_TRACKED         0
+#define KLT_NOT_FOUND      -1
+#define KLT_SMALL_DET      -2
+#define KLT_MAX_ITERATIONS -3
+#define KLT_OOB            -4
+#define KLT_LARGE_RESIDUE  -5
+
+// ---------------------------------------------------------------------------
+// arithmetic helpers
+// ---------------------------------------------------------------------------
+template <bool EXACT>
+__device__ __forceinline__ float mac(float acc, float a, float b) {
+  if (EXACT) return __fadd_rn(acc, __fmul_rn(a, b));
+  return fmaf(a, b, acc);
+}
+template <bool EXACT>
+__device__ __forceinline__ float mul(float a, float b) {
+  if (EXACT) return __fmul_rn(a, b);
+  return a * b;
+}
+
+// taps in application order: k[m] multiplies in[x - R + m]  (the reference walks
+// its array backwards, convolve.c:169-173, so k[m] = ref[w-1-m]).
+struct TapsR {
+  int   w;
+  float k[KLT_DEV_MAX_TAPS];
+};
+
+static constexpr int NT = 256;   // threads per CTA of every tile kernel
+
+// ---------------------------------------------------------------------------
+// generic kernels: any radius, any subsampling.  One thread per output sample.
+// Used for parameter combinations the tiled kernels are not instantiated for,
+// and as an independent cross-check of the tiled kernels.
+// ---------------------------------------------------------------------------
+template <typename SrcT, bool EXACT>
+__global__ void conv_h_generic(const SrcT* __restrict__ src, int spitch, int W, int H,
+                               TapsR taps, int stride, int off,
+                               float* __restrict__ out, int opitch, int Wout) {
+  const int xo = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (xo >= Wout || y >= H) return;
+  const int R = taps.w / 2;
+  const int xs = stride * xo + off;
+  float acc = 0.0f;
+  if (xs >= R && xs < W - R) {
+    const SrcT* p = src + (size_t)y * spitch + (xs - R);
+    for (int m = 0; m < taps.w; ++m) acc = mac<EXACT>(acc, (float)p[m], taps.k[m]);
+  }
+  out[(size_t)y * opitch + xo] = acc;
+}
+
+template <bool EXACT>
+__global__ void conv_v_generic(const float* __restrict__ src, int spitch, int Wout, int Hsrc,
+                               TapsR taps, int stride, int off,
+                               float* __restrict__ out, int opitch, int Hout) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int yo = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= Wout || yo >= Hout) return;
+  const int R = taps.w / 2;
+  const int ys = stride * yo + off;
+  float acc = 0.0f;
+  if (ys >= R && ys < Hsrc - R) {
+    const float* p = src + (size_t)(ys - R) * spitch + x;
+    for (int m = 0; m < taps.w; ++m) acc = mac<EXACT>(acc, p[(size_t)m * spitch], taps.k[m]);
+  }
+  out[(size_t)yo * opitch + x] = acc;
+}
+
+// _KLTToFloatImage (convolve.c:37-53) for smoothBeforeSelecting == FALSE
+__global__ void u8_to_f32_kernel(const unsigned char* __restrict__ src, int spitch, int W, int H,
+                                 float* __restrict__ out, int opitch) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x < W && y < H) out[(size_t)y * opitch + x] = (float)src[(size_t)y * spitch + x];
+}
+
+// ---------------------------------------------------------------------------
+// tiled kernels.  A CTA owns one output tile; the source region (tile + halo)
+// is staged once in shared memory, the horizontal pass runs from shared memory
+// into shared memory with a register-blocked sliding window (float4 loads, PX
+// outputs per thread), the vertical pass runs from shared memory to global with
+// a register sliding window (PY outputs per thread, lanes along x => coalesced
+// 128 B stores).  The horizontal result never goes to HBM.
+// ---------------------------------------------------------------------------
+template <typename SrcT>
+__device__ __forceinline__ void stage_region(float* s, int sp, const SrcT* __restrict__ src,
+                                             int spitch, int W, int H, int gx0, int gy0,
+                                             int cols, int rows) {
+  for (int i = threadIdx.x; i < rows * cols; i += NT) {
+    const int r = i / cols, c = i - r * cols;
+    const int gx = gx0 + c, gy = gy0 + r;
+    float v = 0.0f;
+    if (gx >= 0 && gx < W && gy >= 0 && gy < H) v = (float)__ldg(src + (size_t)gy * spitch + gx);
+    s[r * sp + c] = v;
+  }
+}
+
+// geometry of a tile kernel, all compile time.
+//   SS  : subsampling between source and output (1 for plain convolution)
+//   RM  : halo radius staged around the tile (max radius of the taps used)
+template <int SS, int RM, int TXO, int TYO, int PX>
+struct TileGeo {
+  static constexpr int IW   = SS * (TXO - 1) + 2 * RM + 1;           // staged columns
+  static constexpr int IH   = SS * (TYO - 1) + 2 * RM + 1;           // staged rows
+  static constexpr int NWIN = SS * (PX - 1) + 2 * RM + 1;            // window of one thread
+  static constexpr int NV4  = (NWIN + 3) / 4;
+  static constexpr int SP0  = SS * (TXO - PX) + 4 * NV4;
+  static constexpr int SP   = (SP0 > IW ? SP0 : IW) + ((4 - ((SP0 > IW ? SP0 : IW) & 3)) & 3);
+  static constexpr int IN_FLOATS = IH * SP;
+};
+
+// ---- level 0: u8 frame -> smoothed float image -----------------------------
+// replaces _KLTToFloatImage + _KLTComputeSmoothedImage (convolve.c:37-53,300-314)
+template <int R, bool EXACT>
+__global__ void __launch_bounds__(NT)
+smooth_u8_tile(const unsigned char* __restrict__ src, int spitch, int W, int H, TapsR taps,
+               float* __restrict__ out, int opitch) {
+  constexpr int TX = 64, TY = 32, PX = 4, PY = 8;
+  using G = TileGeo<1, R, TX, TY, PX>;
+  extern __shared__ __align__(16) float smem[];
+  float* sIn = smem;
+  float* sH = smem + G::IN_FLOATS;            // [IH][TX]
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+
+  stage_region(sIn, G::SP, src, spitch, W, H, x0 - R, y0 - R, G::IW, G::IH);
+  __syncthreads();
+
+  for (int item = threadIdx.x; item < G::IH * (TX / PX); item += NT) {
+    const int r = item / (TX / PX), g = item - r * (TX / PX);
+    float win[4 * G::NV4];
+    const float4* p = reinterpret_cast<const float4*>(sIn + r * G::SP + g * PX);
+#pragma unroll
+    for (int v = 0; v < G::NV4; ++v) {
+      const float4 t = p[v];
+      win[4 * v] = t.x; win[4 * v + 1] = t.y; win[4 * v + 2] = t.z; win[4 * v + 3] = t.w;
+    }
+    float o[PX];
+#pragma unroll
+    for (int q = 0; q < PX; ++q) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int m = 0; m < 2 * R + 1; ++m) acc = mac<EXACT>(acc, win[q + m], taps.k[m]);
+      const int xg = x0 + g * PX + q;
+      o[q] = (xg < R || xg >= W - R) ? 0.0f : acc;
+    }
+    *reinterpret_cast<float4*>(sH + r * TX + g * PX) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  __syncthreads();
+
+  for (int item = threadIdx.x; item < TX * (TY / PY); item += NT) {
+    const int gy = item / TX, c = item - gy * TX;
+    float win[PY + 2 * R];
+#pragma unroll
+    for (int i = 0; i < PY + 2 * R; ++i) win[i] = sH[(gy * PY + i) * TX + c];
+    const int xg = x0 + c;
+#pragma unroll
+    for (int q = 0; q < PY; ++q) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int m = 0; m < 2 * R + 1; ++m) acc = mac<EXACT>(acc, win[q + m], taps.k[m]);
+      const int yg = y0 + gy * PY + q;
+      if (yg < R || yg >= H - R) acc = 0.0f;
+      if (xg < W && yg < H) out[(size_t)yg * opitch + xg] = acc;
+    }
+  }
+}
+
+// ---- gradients of one level ------------------------------------------------
+// replaces _KLTComputeGradients (convolve.c:273-293): gradx = V_g(H_d(img)),
+// grady = V_d(H_g(img)); both horizontal passes share one staged window.
+template <int RG, int RD, bool EXACT>
+__global__ void __launch_bounds__(NT)
+grad_tile(const float* __restrict__ src, int spitch, int W, int H, TapsR tg, TapsR td,
+          float* __restrict__ outx, float* __restrict__ outy, int opitch) {
+  constexpr int RM = RG > RD ? RG : RD;
+  constexpr int TX = 64, TY = 32, PX = 4, PY = 8;
+  using G = TileGeo<1, RM, TX, TY, PX>;
+  extern __shared__ __align__(16) float smem[];
+  float* sIn = smem;
+  float* sHd = smem + G::IN_FLOATS;           // [IH][TX]  horizontal derivative
+  float* sHg = sHd + G::IH * TX;              // [IH][TX]  horizontal gaussian
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+
+  stage_region(sIn, G::SP, src, spitch, W, H, x0 - RM, y0 - RM, G::IW, G::IH);
+  __syncthreads();
+
+  for (int item = threadIdx.x; item < G::IH * (TX / PX); item += NT) {
+    const int r = item / (TX / PX), g = item - r * (TX / PX);
+    float win[4 * G::NV4];
+    const float4* p = reinterpret_cast<const float4*>(sIn + r * G::SP + g * PX);
+#pragma unroll
+    for (int v = 0; v < G::NV4; ++v) {
+      const float4 t = p[v];
+      win[4 * v] = t.x; win[4 * v + 1] = t.y; win[4 * v + 2] = t.z; win[4 * v + 3] = t.w;
+    }
+    float od[PX], og[PX];
+#pragma unroll
+    for (int q = 0; q < PX; ++q) {
+      float a = 0.0f, b = 0.0f;
+#pragma unroll
+      for (int m = 0; m < 2 * RD + 1; ++m) a = mac<EXACT>(a, win[q + (RM - RD) + m], td.k[m]);
+#pragma unroll
+      for (int m = 0; m < 2 * RG + 1; ++m) b = mac<EXACT>(b, win[q + (RM - RG) + m], tg.k[m]);
+      const int xg = x0 + g * PX + q;
+      od[q] = (xg < RD || xg >= W - RD) ? 0.0f : a;
+      og[q] = (xg < RG || xg >= W - RG) ? 0.0f : b;
+    }
+    *reinterpret_cast<float4*>(sHd + r * TX + g * PX) = make_float4(od[0], od[1], od[2], od[3]);
+    *reinterpret_cast<float4*>(sHg + r * TX + g * PX) = make_float4(og[0], og[1], og[2], og[3]);
+  }
+  __syncthreads();
+
+  for (int item = threadIdx.x; item < TX * (TY / PY); item += NT) {
+    const int gy = item / TX, c = item - gy * TX;
+    float wd[PY + 2 * RM], wg[PY + 2 * RM];
+#pragma unroll
+    for (int i = 0; i < PY + 2 * RM; ++i) {
+      wd[i] = sHd[(gy * PY + i) * TX + c];
+      wg[i] = sHg[(gy * PY + i) * TX + c];
+    }
+    const int xg = x0 + c;
+#pragma unroll
+    for (int q = 0; q < PY; ++q) {
+      float a = 0.0f, b = 0.0f;
+#pragma unroll
+      for (int m = 0; m < 2 * RG + 1; ++m) a = mac<EXACT>(a, wd[q + (RM - RG) + m], tg.k[m]);
+#pragma unroll
+      for (int m = 0; m < 2 * RD + 1; ++m) b = mac<EXACT>(b, wg[q + (RM - RD) + m], td.k[m]);
+      const int yg = y0 + gy * PY + q;
+      if (yg < RG || yg >= H - RG) a = 0.0f;
+      if (yg < RD || yg >= H - RD) b = 0.0f;
+      if (xg < W && yg < H) {
+        outx[(size_t)yg * opitch + xg] = a;
+        outy[(size_t)yg * opitch + xg] = b;
+      }
+    }
+  }
+}
+
+// ---- one pyramid step --------------------------------------------------------
+// replaces the smooth + subsample step of _KLTComputePyramid (pyramid.c:112-124):
+// the Gaussian is evaluated only at the kept samples (SS*x + SS/2, SS*y + SS/2).
+template <int SS, int R, int TXO, int TYO, int PY, bool EXACT>
+__global__ void __launch_bounds__(NT)
+pyrdown_tile(const float* __restrict__ src, int spitch, int W, int H, TapsR taps,
+             float* __restrict__ out, int opitch, int Wout, int Hout) {
+  constexpr int PX = 4;
+  using G = TileGeo<SS, R, TXO, TYO, PX>;
+  extern __shared__ __align__(16) float smem[];
+  float* sIn = smem;
+  float* sH = smem + G::IN_FLOATS;            // [IH][TXO]
+  const int x0 = blockIdx.x * TXO, y0 = blockIdx.y * TYO;
+  const int xs0 = SS * x0 + SS / 2 - R, ys0 = SS * y0 + SS / 2 - R;
+
+  stage_region(sIn, G::SP, src, spitch, W, H, xs0, ys0, G::IW, G::IH);
+  __syncthreads();
+
+  for (int item = threadIdx.x; item < G::IH * (TXO / PX); item += NT) {
+    const int r = item / (TXO / PX), g = item - r * (TXO / PX);
+    float win[4 * G::NV4];
+    const float4* p = reinterpret_cast<const float4*>(sIn + r * G::SP + SS * g * PX);
+#pragma unroll
+    for (int v = 0; v < G::NV4; ++v) {
+      const float4 t = p[v];
+      win[4 * v] = t.x; win[4 * v + 1] = t.y; win[4 * v + 2] = t.z; win[4 * v + 3] = t.w;
+    }
+    float o[PX];
+#pragma unroll
+    for (int q = 0; q < PX; ++q) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int m = 0; m < 2 * R + 1; ++m) acc = mac<EXACT>(acc, win[SS * q + m], taps.k[m]);
+      const int xs = SS * (x0 + g * PX + q) + SS / 2;
+      o[q] = (xs < R || xs >= W - R) ? 0.0f : acc;
+    }
+    *reinterpret_cast<float4*>(sH + r * TXO + g * PX) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  __syncthreads();
+
+  for (int item = threadIdx.x; item < TXO * (TYO / PY); item += NT) {
+    const int gy = item / TXO, c = item - gy * TXO;
+    constexpr int NW = SS * (PY - 1) + 2 * R + 1;
+    float win[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) win[i] = sH[(SS * gy * PY + i) * TXO + c];
+    const int xo = x0 + c;
+#pragma unroll
+    for (int q = 0; q < PY; ++q) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int m = 0; m < 2 * R + 1; ++m) acc = mac<EXACT>(acc, win[SS * q + m], taps.k[m]);
+      const int yo = y0 + gy * PY + q;
+      const int ys = SS * yo + SS / 2;
+      if (ys < R || ys >= H - R) acc = 0.0f;
+      if (xo < Wout && yo < Hout) out[(size_t)yo * opitch + xo] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// selection kernels
+// ---------------------------------------------------------------------------
+// Eigenvalue map (selectGoodFeatures.c:396-423, :289-292).  One thread per
+// candidate pixel; the 3 window sums run in raster order with separately
+// rounded multiply/add, the eigenvalue formula in double exactly as the
+// reference, then truncation to int.  Always exact: the result is an integer
+// ranking key, so 1-ulp differences would reorder candidates.
+__global__ void mineig_kernel(const float* __restrict__ gx, const float* __restrict__ gy, int pitch,
+                              int bx, int by, int step, int nxc, int nyc, int hw, int hh,
+                              int* __restrict__ vals, unsigned* __restrict__ idx) {
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x;
+  const int iy = blockIdx.y * blockDim.y + threadIdx.y;
+  if (ix >= nxc || iy >= nyc) return;
+  const int x = bx + ix * step, y = by + iy * step;
+  float gxx = 0.0f, gxy = 0.0f, gyy = 0.0f;
+  for (int yy = y - hh; yy <= y + hh; ++yy) {
+    const float* px = gx + (size_t)yy * pitch + (x - hw);
+    const float* py = gy + (size_t)yy * pitch + (x - hw);
+    for (int i = 0; i <= 2 * hw; ++i) {
+      const float a = __ldg(px + i), b = __ldg(py + i);
+      gxx = __fadd_rn(gxx, __fmul_rn(a, a));
+      gxy = __fadd_rn(gxy, __fmul_rn(a, b));
+      gyy = __fadd_rn(gyy, __fmul_rn(b, b));
+    }
+  }
+  const float dif = __fsub_rn(gxx, gyy);
+  const float rad = __fadd_rn(__fmul_rn(dif, dif), __fmul_rn(__fmul_rn(4.0f, gxy), gxy));
+  const double ev = __ddiv_rn(__dsub_rn((double)__fadd_rn(gxx, gyy), sqrt((double)rad)), 2.0);
+  const float v = (float)ev;
+  const int n = iy * nxc + ix;
+  vals[n] = (int)v;          // truncation toward zero, as the C cast
+  idx[n] = (unsigned)n;
+}
+
+// featuremap pre-stamp of the surviving features in REPLACING_SOME mode
+// (selectGoodFeatures.c:160-166): one CTA per feature.
+__global__ void stamp_existing_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                      const int* __restrict__ val, unsigned char* fmap,
+                                      int d, int W, int H) {
+  const int f = blockIdx.x;
+  if (val[f] < 0 || d < 0) return;
+  const int cx = (int)x[f], cy = (int)y[f];
+  const int side = 2 * d + 1;
+  for (int i = threadIdx.x; i < side * side; i += blockDim.x) {
+    const int ix = cx - d + i % side, iy = cy - d + i / side;
+    if (ix >= 0 && ix < W && iy >= 0 && iy < H) fmap[(size_t)iy * W + ix] = 1;
+  }
+}
+
+// Greedy minimum-distance pass (selectGoodFeatures.c:168-235) on the sorted
+// candidate list, made deterministic AND parallel: one CTA walks the list in
+// batches of 1024 consecutive ranks.  Threads test the featuremap in parallel,
+// survivors are compacted in rank order, and warp 0 resolves them sequentially
+// in rank order against the candidates already accepted in this batch (the
+// only ones not yet stamped).  This reproduces the sequential result exactly
+// for any batch size.
+static constexpr int GB = 1024;
+
+// exclusive block-wide position of each thread's flag among the set flags, in
+// thread order; returns the total through *total_out (valid for all threads).
+// Contains two __syncthreads; s_wcount is scratch of GB/32 ints.
+__device__ __forceinline__ int block_rank(bool flag, int* s_wcount, int* s_total_tmp, int* total_out) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned bal = __ballot_sync(0xffffffffu, flag);
+  if (lane == 0) s_wcount[wid] = __popc(bal);
+  __syncthreads();
+  if (wid == 0) {
+    const int c = s_wcount[lane];
+    int inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    s_wcount[lane] = inc - c;                    // exclusive prefix over warps
+    if (lane == 31) *s_total_tmp = inc;
+  }
+  __syncthreads();
+  *total_out = *s_total_tmp;
+  return s_wcount[wid] + __popc(bal & ((1u << lane) - 1u));
+}
+
+__global__ void __launch_bounds__(GB)
+enforce_mindist_kernel(const int* __restrict__ sval, const unsigned* __restrict__ sidx, int npoints,
+                       int nxc, int bx, int by, int step, int W, int H,
+                       unsigned char* fmap, int d, int min_eig, int overwrite_all,
+                       int n, float* x, float* y, int* val, int* open_slots) {
+  __shared__ int s_x[GB], s_y[GB], s_v[GB];      // survivors of the batch, rank order
+  __shared__ int s_ax[GB], s_ay[GB];             // accepted in this batch
+  __shared__ int s_wcount[GB / 32];
+  __shared__ int s_tmp, s_nacc, s_total, s_done;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+  // open slots in ascending index (selectGoodFeatures.c:207-210)
+  int nopen = 0;
+  for (int b0 = 0; b0 < n; b0 += GB) {
+    const int i = b0 + tid;
+    const bool open = (i < n) && (overwrite_all || val[i] < 0);
+    int cnt;
+    const int pos = block_rank(open, s_wcount, &s_tmp, &cnt);
+    if (open) open_slots[nopen + pos] = i;
+    nopen += cnt;
+    __syncthreads();                             // s_wcount / s_tmp reuse
+  }
+  if (tid == 0) { s_total = 0; s_done = (nopen == 0); s_nacc = 0; }
+  __syncthreads();
+  volatile unsigned char* vmap = fmap;
+  bool done = (nopen == 0);
+
+  for (int base = 0; base < npoints && !done; base += GB) {
+    const int i = base + tid;
+    int cx = 0, cy = 0, cv = 0;
+    bool alive = false;
+    if (i < npoints) {
+      cv = sval[i];
+      const unsigned id = sidx[i];
+      cx = bx + (int)(id % (unsigned)nxc) * step;
+      cy = by + (int)(id / (unsigned)nxc) * step;
+      alive = (cv >= min_eig) && (vmap[(size_t)cy * W + cx] == 0);
+    }
+    int nsurv;
+    const int pos = block_rank(alive, s_wcount, &s_tmp, &nsurv);     // 2 barriers
+    if (alive) { s_x[pos] = cx; s_y[pos] = cy; s_v[pos] = cv; }
+    // the list is sorted descending: once the first candidate of a batch is
+    // below the threshold nothing at or after it can be accepted
+    if (tid == 0 && cv < min_eig) s_done = 1;
+    __syncthreads();
+    if (wid == 0) {
+      int nacc = 0, total = s_total;
+      for (int s = 0; s < nsurv && total < nopen; ++s) {
+        const int px = s_x[s], py = s_y[s];
+        bool hit = false;
+        for (int a = lane; a < nacc; a += 32) {
+          const int dx = px - s_ax[a], dy = py - s_ay[a];
+          if (dx <= d && dx >= -d && dy <= d && dy >= -d) hit = true;
+        }
+        if (!__any_sync(0xffffffffu, hit)) {
+          if (lane == 0) {
+            s_ax[nacc] = px; s_ay[nacc] = py;
+            const int slot = open_slots[total];
+            x[slot] = (float)px; y[slot] = (float)py; val[slot] = s_v[s];
+          }
+          ++nacc; ++total;
+          __syncwarp();
+        }
+      }
+      if (lane == 0) { s_nacc = nacc; s_total = total; if (total >= nopen) s_done = 1; }
+    }
+    __syncthreads();
+    {
+      const int nacc = s_nacc, side = 2 * d + 1;
+      if (d >= 0) {
+        const int cells = side * side;
+        for (int w = tid; w < nacc * cells; w += GB) {
+          const int a = w / cells, cidx = w - a * cells;
+          const int ix = s_ax[a] - d + cidx % side, iy = s_ay[a] - d + cidx / side;
+          if (ix >= 0 && ix < W && iy >= 0 && iy < H) fmap[(size_t)iy * W + ix] = 1;
+        }
+      }
+      done = (s_done != 0);
+    }
+    __syncthreads();      // stamps visible to the next batch; s_done stable while read
+  }
+  // out of candidates: the still-open slots become NOT_FOUND (:175-195)
+  const int total = s_total;
+  for (int k = total + tid; k < nopen; k += GB) {
+    const int slot = open_slots[k];
+    x[slot] = -1.0f; y[slot] = -1.0f; val[slot] = KLT_NOT_FOUND;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// tracker: one warp per feature, coarse to fine, all levels in one launch
+// ---------------------------------------------------------------------------
+struct PyrView {
+  const float* img[KLT_DEV_MAX_LEVELS];
+  const float* gx[KLT_DEV_MAX_LEVELS];
+  const float* gy[KLT_DEV_MAX_LEVELS];
+  int ncols[KLT_DEV_MAX_LEVELS], nrows[KLT_DEV_MAX_LEVELS], pitch[KLT_DEV_MAX_LEVELS];
+};
+
+struct TrackArgs {
+  int   nlevels;
+  float ss;
+  int   ww, wh;
+  float step_factor;
+  int   max_iterations;
+  float min_determinant, min_displacement, max_residue;
+  int   borderx, bordery;
+  int   ncols, nrows;
+};
+
+// bilinear weights of _interpolate (trackFeatures.c:31-57): the four products
+// (1-ax)(1-ay), ax(1-ay), (1-ax)ay, ax*ay are rounded first, then multiplied by
+// the pixels and summed left to right.
+struct Bilin {
+  int   off;                 // yt * pitch + xt
+  float w00, w01, w10, w11;
+};
+template <bool EXACT>
+__device__ __forceinline__ Bilin bilin_setup(float x, float y, int pitch) {
+  const int xt = (int)x, yt = (int)y;
+  const float ax = __fsub_rn(x, (float)xt), ay = __fsub_rn(y, (float)yt);
+  const float omx = __fsub_rn(1.0f, ax), omy = __fsub_rn(1.0f, ay);
+  Bilin b;
+  b.off = yt * pitch + xt;
+  b.w00 = __fmul_rn(omx, omy);
+  b.w01 = __fmul_rn(ax, omy);
+  b.w10 = __fmul_rn(omx, ay);
+  b.w11 = __fmul_rn(ax, ay);
+  return b;
+}
+template <bool EXACT>
+__device__ __forceinline__ float bilin_fetch(const float* __restrict__ img, int pitch, const Bilin& b) {
+  const float* p = img + b.off;
+  const float p00 = __ldg(p), p01 = __ldg(p + 1), p10 = __ldg(p + pitch), p11 = __ldg(p + pitch + 1);
+  if (EXACT) {
+    float s = __fmul_rn(b.w00, p00);
+    s = __fadd_rn(s, __fmul_rn(b.w01, p01));
+    s = __fadd_rn(s, __fmul_rn(b.w10, p10));
+    s = __fadd_rn(s, __fmul_rn(b.w11, p11));
+    return s;
+  }
+  return fmaf(b.w11, p11, fmaf(b.w10, p10, fmaf(b.w01, p01, b.w00 * p00)));
+}
+
+__device__ __forceinline__ bool window_oob(float x, float y, int hw, int hh, int nc, int nr) {
+  // trackFeatures.c:418-425, one_plus_eps = 1.001f
+  return (__fsub_rn(x, (float)hw) < 0.0f || __fsub_rn((float)nc, __fadd_rn(x, (float)hw)) < 1.001f ||
+          __fsub_rn(y, (float)hh) < 0.0f || __fsub_rn((float)nr, __fadd_rn(y, (float)hh)) < 1.001f);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// PPL = window pixels per lane (ceil(ww*wh / 32)); the frame-1 samples of the
+// window are constant while a level iterates, so they are sampled once per
+// level and kept in registers.
+template <bool EXACT, int PPL>
+__global__ void __launch_bounds__(128)
+track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n,
+             float* __restrict__ fx, float* __restrict__ fy, int* __restrict__ fval) {
+  extern __shared__ float s_win[];     // EXACT only: [warps][3][npix]
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int f = blockIdx.x * (blockDim.x >> 5) + wib;
+  if (f >= n) return;
+  if (fval[f] < 0) return;             // only features that are not lost (:1346)
+
+  const int ww = a.ww, wh = a.wh, hw = ww / 2, hh = wh / 2, npix = ww * wh;
+  float* swx = s_win + (size_t)wib * 3 * npix;
+  float* swy = swx + npix;
+  float* swd = swy + npix;
+
+  float xloc = fx[f], yloc = fy[f];
+  for (int r = a.nlevels - 1; r >= 0; --r) { xloc = __fdiv_rn(xloc, a.ss); yloc = __fdiv_rn(yloc, a.ss); }
+  float xout = xloc, yout = yloc;
+  int status = KLT_TRACKED;
+
+  // per-lane window offsets (raster order: pixel p -> (i,j) = (p % ww - hw, p / ww - hh))
+  float offi[PPL], offj[PPL];
+#pragma unroll
+  for (int k = 0; k < PPL; ++k) {
+    const int p = lane + 32 * k;
+    const int pp = p < npix ? p : 0;
+    offi[k] = (float)(pp % ww - hw);
+    offj[k] = (float)(pp / ww - hh);
+  }
+
+  for (int r = a.nlevels - 1; r >= 0; --r) {
+    xloc = __fmul_rn(xloc, a.ss); yloc = __fmul_rn(yloc, a.ss);
+    xout = __fmul_rn(xout, a.ss); yout = __fmul_rn(yout, a.ss);
+    const int nc = p1.ncols[r], nr = p1.nrows[r], pitch = p1.pitch[r];
+    const float* __restrict__ i1 = p1.img[r];
+    const float* __restrict__ gx1 = p1.gx[r];
+    const float* __restrict__ gy1 = p1.gy[r];
+    const float* __restrict__ i2 = p2.img[r];
+    const float* __restrict__ gx2 = p2.gx[r];
+    const float* __restrict__ gy2 = p2.gy[r];
+
+    // ---- _trackFeature (trackFeatures.c:381-486) at this level -------------
+    const float x1 = xloc, y1 = yloc;
+    float x2 = xout, y2 = yout;
+    int iteration = 0;
+    float dx = 0.0f, dy = 0.0f;
+    float t_i[PPL], t_gx[PPL], t_gy[PPL];
+    bool have_template = false;
+    const bool oob1 = window_oob(x1, y1, hw, hh, nc, nr);
+
+    do {
+      if (oob1 || window_oob(x2, y2, hw, hh, nc, nr)) { status = KLT_OOB; break; }
+      if (!have_template) {
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+          if (lane + 32 * k < npix) {
+            const Bilin b = bilin_setup<EXACT>(__fadd_rn(x1, offi[k]), __fadd_rn(y1, offj[k]), pitch);
+            t_i[k] = bilin_fetch<EXACT>(i1, pitch, b);
+            t_gx[k] = bilin_fetch<EXACT>(gx1, pitch, b);
+            t_gy[k] = bilin_fetch<EXACT>(gy1, pitch, b);
+          } else { t_i[k] = 0.0f; t_gx[k] = 0.0f; t_gy[k] = 0.0f; }
+        }
+        have_template = true;
+      }
+      float gxx = 0.0f, gxy = 0.0f, gyy = 0.0f, ex = 0.0f, ey = 0.0f;
+      if (EXACT) {
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+          const int p = lane + 32 * k;
+          if (p < npix) {
+            const Bilin b = bilin_setup<EXACT>(__fadd_rn(x2, offi[k]), __fadd_rn(y2, offj[k]), pitch);
+            swd[p] = __fsub_rn(t_i[k], bilin_fetch<EXACT>(i2, pitch, b));
+            swx[p] = __fadd_rn(t_gx[k], bilin_fetch<EXACT>(gx2, pitch, b));
+            swy[p] = __fadd_rn(t_gy[k], bilin_fetch<EXACT>(gy2, pitch, b));
+          }
+        }
+        __syncwarp();
+        // five sequential raster-order sums, one per lane (:227-279)
+        float acc = 0.0f;
+        if (lane < 5) {
+          const float* A = (lane <= 1) ? swx : (lane == 2 ? swy : swd);
+          const float* B = (lane == 0 || lane == 3) ? swx : swy;
+          for (int p = 0; p < npix; ++p) acc = __fadd_rn(acc, __fmul_rn(A[p], B[p]));
+        }
+        gxx = __shfl_sync(0xffffffffu, acc, 0);
+        gxy = __shfl_sync(0xffffffffu, acc, 1);
+        gyy = __shfl_sync(0xffffffffu, acc, 2);
+        ex = __shfl_sync(0xffffffffu, acc, 3);
+        ey = __shfl_sync(0xffffffffu, acc, 4);
+        __syncwarp();
+      } else {
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+          if (lane + 32 * k < npix) {
+            const Bilin b = bilin_setup<EXACT>(x2 + offi[k], y2 + offj[k], pitch);
+            const float df = t_i[k] - bilin_fetch<EXACT>(i2, pitch, b);
+            const float sx = t_gx[k] + bilin_fetch<EXACT>(gx2, pitch, b);
+            const float sy = t_gy[k] + bilin_fetch<EXACT>(gy2, pitch, b);
+            gxx = fmaf(sx, sx, gxx); gxy = fmaf(sx, sy, gxy); gyy = fmaf(sy, sy, gyy);
+            ex = fmaf(df, sx, ex); ey = fmaf(df, sy, ey);
+          }
+        }
+        gxx = warp_sum(gxx); gxy = warp_sum(gxy); gyy = warp_sum(gyy);
+        ex = warp_sum(ex); ey = warp_sum(ey);
+      }
+      ex = __fmul_rn(ex, a.step_factor);
+      ey = __fmul_rn(ey, a.step_factor);
+      // _solveEquation (:293-307)
+      const float det = __fsub_rn(__fmul_rn(gxx, gyy), __fmul_rn(gxy, gxy));
+      if (det < a.min_determinant) { status = KLT_SMALL_DET; break; }
+      dx = __fdiv_rn(__fsub_rn(__fmul_rn(gyy, ex), __fmul_rn(gxy, ey)), det);
+      dy = __fdiv_rn(__fsub_rn(__fmul_rn(gxx, ey), __fmul_rn(gxy, ex)), det);
+      status = KLT_TRACKED;
+      x2 = __fadd_rn(x2, dx);
+      y2 = __fadd_rn(y2, dy);
+      ++iteration;
+    } while ((fabsf(dx) >= a.min_displacement || fabsf(dy) >= a.min_displacement) &&
+             iteration < a.max_iterations);
+
+    // :459-462
+    if (window_oob(x2, y2, hw, hh, nc, nr)) status = KLT_OOB;
+
+    // :464-474 residue of the final alignment
+    if (status == KLT_TRACKED) {
+      float sum = 0.0f;
+      if (EXACT) {
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+          const int p = lane + 32 * k;
+          if (p < npix) {
+            const Bilin b = bilin_setup<EXACT>(__fadd_rn(x2, offi[k]), __fadd_rn(y2, offj[k]), pitch);
+            swd[p] = fabsf(__fsub_rn(t_i[k], bilin_fetch<EXACT>(i2, pitch, b)));
+          }
+        }
+        __syncwarp();
+        if (lane == 0)
+          for (int p = 0; p < npix; ++p) sum = __fadd_rn(sum, swd[p]);
+        sum = __shfl_sync(0xffffffffu, sum, 0);
+        __syncwarp();
+      } else {
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+          if (lane + 32 * k < npix) {
+            const Bilin b = bilin_setup<EXACT>(x2 + offi[k], y2 + offj[k], pitch);
+            sum += fabsf(t_i[k] - bilin_fetch<EXACT>(i2, pitch, b));
+          }
+        }
+        sum = warp_sum(sum);
+      }
+      if (__fdiv_rn(sum, (float)npix) > a.max_residue) status = KLT_LARGE_RESIDUE;
+    }
+
+    // :479-484 return value of _trackFeature
+    int v;
+    if (status == KLT_SMALL_DET) v = KLT_SMALL_DET;
+    else if (status == KLT_OOB) v = KLT_OOB;
+    else if (status == KLT_LARGE_RESIDUE) v = KLT_LARGE_RESIDUE;
+    else if (iteration >= a.max_iterations) v = KLT_MAX_ITERATIONS;
+    else v = KLT_TRACKED;
+    status = v;
+    xout = x2; yout = y2;
+    if (v == KLT_SMALL_DET || v == KLT_OOB) break;      // :1378
+  }
+
+  // record (:1383-1437)
+  if (lane == 0) {
+    const bool outside = (xout < (float)a.borderx || xout > (float)(a.ncols - 1 - a.borderx) ||
+                          yout < (float)a.bordery || yout > (float)(a.nrows - 1 - a.bordery));
+    if (status == KLT_OOB || outside) {
+      fx[f] = -1.0f; fy[f] = -1.0f; fval[f] = KLT_OOB;
+    } else if (status != KLT_TRACKED) {
+      fx[f] = -1.0f; fy[f] = -1.0f; fval[f] = status;
+    } else {
+      fx[f] = xout; fy[f] = yout; fval[f] = KLT_TRACKED;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side of the C-ABI
+// ---------------------------------------------------------------------------
+struct Level {
+  int w, h, pitch;           // pitch in floats
+  float *img, *gx, *gy;
+};
+struct PyrSet {
+  Level lv[KLT_DEV_MAX_LEVELS];
+  int built_levels;          // 0 = nothing valid
+};
+
+struct klt_dev {
+  int device;
+  cudaStream_t stream;
+  char err[512];
+  unsigned long long launches;
+  int last_path, force_generic;
+  // geometry
+  int W, H, L, ss;
+  PyrSet set[2];
+  float* arena;
+  float* tmp;                // generic path: horizontal-pass result, W*H floats
+  unsigned char* frame;      // dense u8 staging of the frame being built
+  size_t frame_cap;
+  // features
+  float *d_x, *d_y; int* d_val; int feat_cap; int feat_n;
+  float *h_x, *h_y; int* h_val;   // pinned staging
+  // selection
+  int *c_val[2]; unsigned* c_idx[2]; size_t cand_cap;
+  void* cub_tmp; size_t cub_bytes;
+  unsigned char* fmap; size_t fmap_cap;
+  int* open_slots; int open_cap;
+  // timing
+  cudaEvent_t ev_a, ev_b; int ev_made;
+};
+
+static char g_create_err[512] = "";
+
+static int fail(klt_dev* d, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(d ? d->err : g_create_err, 512, fmt, ap);
+  va_end(ap);
+  return 1;
+}
+#define CU(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess)                                                             \
+      return fail(d, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+static TapsR reversed(const float* k, int w) {
+  TapsR t;
+  memset(&t, 0, sizeof(t));
+  t.w = w;
+  for (int m = 0; m < w; ++m) t.k[m] = k[w - 1 - m];
+  return t;
+}
+
+extern "C" int klt_dev_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+extern "C" const char* klt_dev_create_error(void) { return g_create_err; }
+extern "C" const char* klt_dev_error(const klt_dev* d) { return d ? d->err : g_create_err; }
+extern "C" int klt_dev_device(const klt_dev* d) { return d->device; }
+extern "C" void* klt_dev_stream(const klt_dev* d) { return (void*)d->stream; }
+extern "C" unsigned long long klt_dev_launch_count(const klt_dev* d) { return d->launches; }
+extern "C" int klt_dev_last_build_path(const klt_dev* d) { return d->last_path; }
+extern "C" void klt_dev_force_generic(klt_dev* d, int on) { d->force_generic = on; }
+
+extern "C" int klt_dev_create(int device, klt_dev** out) {
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, "no CUDA device available (%s); this library has no CPU path",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+  if (device >= n) return fail(nullptr, "device %d requested but only %d present", device, n);
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+  klt_dev* c = (klt_dev*)calloc(1, sizeof(klt_dev));
+  if (!c) return fail(nullptr, "out of host memory");
+  c->device = device;
+  e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { free(c); return fail(nullptr, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+  *out = c;
+  return 0;
+}
+
+static void free_geometry(klt_dev* d) {
+  cudaFree(d->arena); d->arena = nullptr;
+  cudaFree(d->tmp); d->tmp = nullptr;
+  memset(d->set, 0, sizeof(d->set));
+  d->W = d->H = d->L = d->ss = 0;
+}
+
+extern "C" void klt_dev_destroy(klt_dev* d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  cudaStreamSynchronize(d->stream);
+  free_geometry(d);
+  cudaFree(d->frame);
+  cudaFree(d->d_x); cudaFree(d->d_y); cudaFree(d->d_val);
+  cudaFreeHost(d->h_x); cudaFreeHost(d->h_y); cudaFreeHost(d->h_val);
+  for (int i = 0; i < 2; ++i) { cudaFree(d->c_val[i]); cudaFree(d->c_idx[i]); }
+  cudaFree(d->cub_tmp); cudaFree(d->fmap); cudaFree(d->open_slots);
+  if (d->ev_made) { cudaEventDestroy(d->ev_a); cudaEventDestroy(d->ev_b); }
+  cudaStreamDestroy(d->stream);
+  free(d);
+}
+
+static int ensure_geometry(klt_dev* d, int W, int H, int L, int ss) {
+  if (d->arena && d->W == W && d->H == H && d->L == L && d->ss == ss) return 0;
+  if (W <= 0 || H <= 0) return fail(d, "bad image size %d x %d", W, H);
+  if (L < 1 || L > KLT_DEV_MAX_LEVELS) return fail(d, "nPyramidLevels %d not in 1..%d", L, KLT_DEV_MAX_LEVELS);
+  if (L > 1 && ss != 2 && ss != 4 && ss != 8 && ss != 16 && ss != 32)
+    return fail(d, "Pyramid's subsampling must be either 2, 4, 8, 16, or 32");
+  CU(cudaStreamSynchronize(d->stream));
+  free_geometry(d);
+  size_t per_set = 0;
+  int w = W, h = H;
+  int ws[KLT_DEV_MAX_LEVELS], hs[KLT_DEV_MAX_LEVELS], ps[KLT_DEV_MAX_LEVELS];
+  for (int l = 0; l < L; ++l) {
+    ws[l] = w; hs[l] = h; ps[l] = (w + 31) / 32 * 32;
+    if (w < 1 || h < 1) return fail(d, "pyramid level %d is empty (%d x %d)", l, w, h);
+    per_set += 3 * (size_t)ps[l] * h;
+    if (L > 1) { w /= ss; h /= ss; }
+  }
+  CU(cudaMalloc(&d->arena, 2 * per_set * sizeof(float)));
+  CU(cudaMalloc(&d->tmp, (size_t)ps[0] * H * sizeof(float)));
+  float* p = d->arena;
+  for (int s = 0; s < 2; ++s)
+    for (int l = 0; l < L; ++l) {
+      Level& lv = d->set[s].lv[l];
+      lv.w = ws[l]; lv.h = hs[l]; lv.pitch = ps[l];
+      const size_t n = (size_t)ps[l] * hs[l];
+      lv.img = p; p += n; lv.gx = p; p += n; lv.gy = p; p += n;
+    }
+  d->W = W; d->H = H; d->L = L; d->ss = ss;
+  return 0;
+}
+
+extern "C" int klt_dev_geometry(const klt_dev* d, int* W, int* H, int* L, int* ss) {
+  if (W) *W = d->W; if (H) *H = d->H; if (L) *L = d->L; if (ss) *ss = d->ss;
+  return d->arena != nullptr;
+}
+extern "C" int klt_dev_slot_valid(const klt_dev* d, int slot) {
+  return d->arena && slot >= 0 && slot < 2 && d->set[slot].built_levels == d->L;
+}
+extern "C" void klt_dev_invalidate(klt_dev* d, int slot) {
+  for (int s = 0; s < 2; ++s) if (slot < 0 || slot == s) d->set[s].built_levels = 0;
+}
+extern "C" int klt_dev_level_dims(const klt_dev* d, int level, int* w, int* h) {
+  if (!d->arena || level < 0 || level >= d->L) return 1;
+  *w = d->set[0].lv[level].w; *h = d->set[0].lv[level].h;
+  return 0;
+}
+extern "C" int klt_dev_sync(klt_dev* d) {
+  CU(cudaSetDevice(d->device));
+  CU(cudaStreamSynchronize(d->stream));
+  return 0;
+}
+
+// ---- kernel dispatch ----------------------------------------------------------
+template <typename K>
+static int set_smem(klt_dev* d, K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+template <int R, bool EXACT>
+static int launch_smooth_u8(klt_dev* d, const unsigned char* src, int spitch, int W, int H,
+                            const TapsR& t, float* out, int opitch) {
+  using G = TileGeo<1, R, 64, 32, 4>;
+  const size_t smem = (G::IN_FLOATS + G::IH * 64) * sizeof(float);
+  if (set_smem(d, smooth_u8_tile<R, EXACT>, smem)) return 1;
+  dim3 grid((W + 63) / 64, (H + 31) / 32);
+  smooth_u8_tile<R, EXACT><<<grid, NT, smem, d->stream>>>(src, spitch, W, H, t, out, opitch);
+  d->launches++;
+  return 0;
+}
+template <bool EXACT>
+static int smooth_u8_dispatch(klt_dev* d, const unsigned char* src, int spitch, int W, int H,
+                              const TapsR& t, float* out, int opitch, bool* done) {
+  *done = true;
+  switch (t.w / 2) {
+    case 1: return launch_smooth_u8<1, EXACT>(d, src, spitch, W, H, t, out, opitch);
+    case 2: return launch_smooth_u8<2, EXACT>(d, src, spitch, W, H, t, out, opitch);
+    case 3: return launch_smooth_u8<3, EXACT>(d, src, spitch, W, H, t, out, opitch);
+    case 4: return launch_smooth_u8<4, EXACT>(d, src, spitch, W, H, t, out, opitch);
+    case 5: return launch_smooth_u8<5, EXACT>(d, src, spitch, W, H, t, out, opitch);
+    case 6: return launch_smooth_u8<6, EXACT>(d, src, spitch, W, H, t, out, opitch);
+    default: *done = false; return 0;
+  }
+}
+
+template <int RG, int RD, bool EXACT>
+static int launch_grad(klt_dev* d, const float* src, int spitch, int W, int H, const TapsR& tg,
+                       const TapsR& td, float* ox, float* oy, int opitch) {
+  constexpr int RM = RG > RD ? RG : RD;
+  using G = TileGeo<1, RM, 64, 32, 4>;
+  const size_t smem = (G::IN_FLOATS + 2 * G::IH * 64) * sizeof(float);
+  if (set_smem(d, grad_tile<RG, RD, EXACT>, smem)) return 1;
+  dim3 grid((W + 63) / 64, (H + 31) / 32);
+  grad_tile<RG, RD, EXACT><<<grid, NT, smem, d->stream>>>(src, spitch, W, H, tg, td, ox, oy, opitch);
+  d->launches++;
+  return 0;
+}
+template <bool EXACT>
+static int grad_dispatch(klt_dev* d, const float* src, int spitch, int W, int H, const TapsR& tg,
+                         const TapsR& td, float* ox, float* oy, int opitch, bool* done) {
+  *done = true;
+  const int rg = tg.w / 2, rd = td.w / 2;
+  if (rg == 3 && rd == 3) return launch_grad<3, 3, EXACT>(d, src, spitch, W, H, tg, td, ox, oy, opitch);
+  if (rg == 2 && rd == 2) return launch_grad<2, 2, EXACT>(d, src, spitch, W, H, tg, td, ox, oy, opitch);
+  if (rg == 4 && rd == 4) return launch_grad<4, 4, EXACT>(d, src, spitch, W, H, tg, td, ox, oy, opitch);
+  if (rg == 4 && rd == 5) return launch_grad<4, 5, EXACT>(d, src, spitch, W, H, tg, td, ox, oy, opitch);
+  if (rg == 5 && rd == 6) return launch_grad<5, 6, EXACT>(d, src, spitch, W, H, tg, td, ox, oy, opitch);
+  *done = false;
+  return 0;
+}
+
+template <int SS, int R, int TXO, int TYO, int PY, bool EXACT>
+static int launch_pyrdown(klt_dev* d, const float* src, int spitch, int W, int H, const TapsR& t,
+                          float* out, int opitch, int Wout, int Hout) {
+  using G = TileGeo<SS, R, TXO, TYO, 4>;
+  const size_t smem = (G::IN_FLOATS + G::IH * TXO) * sizeof(float);
+  if (set_smem(d, pyrdown_tile<SS, R, TXO, TYO, PY, EXACT>, smem)) return 1;
+  dim3 grid((Wout + TXO - 1) / TXO, (Hout + TYO - 1) / TYO);
+  pyrdown_tile<SS, R, TXO, TYO, PY, EXACT><<<grid, NT, smem, d->stream>>>(src, spitch, W, H, t, out,
+                                                                         opitch, Wout, Hout);
+  d->launches++;
+  return 0;
+}
+template <bool EXACT>
+static int pyrdown_dispatch(klt_dev* d, int ss, const float* src, int spitch, int W, int H,
+                            const TapsR& t, float* out, int opitch, int Wout, int Hout, bool* done) {
+  *done = true;
+  const int r = t.w / 2;
+  if (ss == 2 && r == 5) return launch_pyrdown<2, 5, 32, 32, 4, EXACT>(d, src, spitch, W, H, t, out, opitch, Wout, Hout);
+  if (ss == 4 && r == 10) return launch_pyrdown<4, 10, 32, 16, 2, EXACT>(d, src, spitch, W, H, t, out, opitch, Wout, Hout);
+  *done = false;
+  return 0;
+}
+
+// generic two-kernel separable pass through d->tmp
+template <typename SrcT, bool EXACT>
+static int generic_separable(klt_dev* d, const SrcT* src, int spitch, int W, int H, const TapsR& kh,
+                             const TapsR& kv, int stride, float* out, int opitch, int Wout, int Hout) {
+  const int off = stride / 2;
+  const int tp = d->set[0].lv[0].pitch;
+  dim3 b(32, 8);
+  dim3 g1((Wout + 31) / 32, (H + 7) / 8);
+  conv_h_generic<SrcT, EXACT><<<g1, b, 0, d->stream>>>(src, spitch, W, H, kh, stride, off, d->tmp, tp, Wout);
+  dim3 g2((Wout + 31) / 32, (Hout + 7) / 8);
+  conv_v_generic<EXACT><<<g2, b, 0, d->stream>>>(d->tmp, tp, Wout, H, kv, stride, off, out, opitch, Hout);
+  d->launches += 2;
+  return 0;
+}
+
+template <bool EXACT>
+static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitch,
+                      const klt_dev_build_desc* q) {
+  const int W = q->ncols, H = q->nrows;
+  bool tiled_all = true, done = false;
+  // level 0
+  if (q->smooth) {
+    const TapsR ts = reversed(q->smooth_taps.gauss, q->smooth_taps.gauss_width);
+    done = false;
+    if (!d->force_generic)
+      if (smooth_u8_dispatch<EXACT>(d, src, spitch, W, H, ts, S.lv[0].img, S.lv[0].pitch, &done)) return 1;
+    if (!done) {
+      tiled_all = false;
+      if (generic_separable<unsigned char, EXACT>(d, src, spitch, W, H, ts, ts, 1, S.lv[0].img,
+                                                  S.lv[0].pitch, W, H)) return 1;
+    }
+  } else {
+    dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
+    u8_to_f32_kernel<<<g, b, 0, d->stream>>>(src, spitch, W, H, S.lv[0].img, S.lv[0].pitch);
+    d->launches++;
+  }
+  // coarser levels
+  if (q->nlevels_built > 1) {
+    const TapsR tp = reversed(q->pyramid_taps.gauss, q->pyramid_taps.gauss_width);
+    for (int l = 1; l < q->nlevels_built; ++l) {
+      const Level& a = S.lv[l - 1];
+      const Level& b = S.lv[l];
+      done = false;
+      if (!d->force_generic)
+        if (pyrdown_dispatch<EXACT>(d, q->subsampling, a.img, a.pitch, a.w, a.h, tp, b.img, b.pitch,
+                                    b.w, b.h, &done)) return 1;
+      if (!done) {
+        tiled_all = false;
+        if (generic_separable<float, EXACT>(d, a.img, a.pitch, a.w, a.h, tp, tp, q->subsampling,
+                                            b.img, b.pitch, b.w, b.h)) return 1;
+      }
+    }
+  }
+  // gradients
+  {
+    const TapsR tg = reversed(q->grad_taps.gauss, q->grad_taps.gauss_width);
+    const TapsR td = reversed(q->grad_taps.deriv, q->grad_taps.deriv_width);
+    for (int l = 0; l < q->nlevels_built; ++l) {
+      const Level& a = S.lv[l];
+      done = false;
+      if (!d->force_generic)
+        if (grad_dispatch<EXACT>(d, a.img, a.pitch, a.w, a.h, tg, td, a.gx, a.gy, a.pitch, &done)) return 1;
+      if (!done) {
+        tiled_all = false;
+        if (generic_separable<float, EXACT>(d, a.img, a.pitch, a.w, a.h, td, tg, 1, a.gx, a.pitch, a.w, a.h)) return 1;
+        if (generic_separable<float, EXACT>(d, a.img, a.pitch, a.w, a.h, tg, td, 1, a.gy, a.pitch, a.w, a.h)) return 1;
+      }
+    }
+  }
+  d->last_path = tiled_all ? 1 : 0;
+  return 0;
+}
+
+static int check_taps(klt_dev* d, const klt_dev_taps& t, const char* what) {
+  if (t.gauss_width < 1 || t.gauss_width > KLT_DEV_MAX_TAPS || !(t.gauss_width & 1) ||
+      t.deriv_width < 1 || t.deriv_width > KLT_DEV_MAX_TAPS || !(t.deriv_width & 1))
+    return fail(d, "%s taps have invalid widths %d/%d", what, t.gauss_width, t.deriv_width);
+  return 0;
+}
+
+extern "C" int klt_dev_build(klt_dev* d, int slot, const unsigned char* img, int img_is_device,
+                             size_t img_pitch, const klt_dev_build_desc* q) {
+  if (!d || !q || !img) return fail(d, "klt_dev_build: null argument");
+  if (slot < 0 || slot > 1) return fail(d, "klt_dev_build: slot %d", slot);
+  CU(cudaSetDevice(d->device));
+  if (q->nlevels_built < 1 || q->nlevels_built > q->nlevels) return fail(d, "nlevels_built %d of %d", q->nlevels_built, q->nlevels);
+  if (check_taps(d, q->grad_taps, "gradient")) return 1;
+  if (q->smooth && check_taps(d, q->smooth_taps, "smoothing")) return 1;
+  if (q->nlevels_built > 1 && check_taps(d, q->pyramid_taps, "pyramid")) return 1;
+  if (ensure_geometry(d, q->ncols, q->nrows, q->nlevels, q->subsampling)) return 1;
+  const int W = q->ncols, H = q->nrows;
+  const unsigned char* src = img;
+  int spitch = (int)img_pitch;
+  if (!img_is_device) {
+    const size_t bytes = (size_t)W * H;
+    if (d->frame_cap < bytes) {
+      CU(cudaStreamSynchronize(d->stream));
+      cudaFree(d->frame); d->frame = nullptr; d->frame_cap = 0;
+      CU(cudaMalloc(&d->frame, bytes));
+      d->frame_cap = bytes;
+    }
+    CU(cudaMemcpyAsync(d->frame, img, bytes, cudaMemcpyHostToDevice, d->stream));
+    src = d->frame;
+    spitch = W;
+  } else if (spitch < W) {
+    return fail(d, "device frame pitch %d < width %d", spitch, W);
+  }
+  PyrSet& S = d->set[slot];
+  S.built_levels = 0;
+  const int rc = q->exact ? build_impl<true>(d, S, src, spitch, q) : build_impl<false>(d, S, src, spitch, q);
+  if (rc) return rc;
+  CU(cudaGetLastError());
+  S.built_levels = q->nlevels_built;
+  return 0;
+}
+
+extern "C" int klt_dev_read_level(klt_dev* d, int slot, int which, int level, float* out) {
+  if (!d->arena || slot < 0 || slot > 1 || level < 0 || level >= d->L) return fail(d, "read_level: bad slot/level");
+  CU(cudaSetDevice(d->device));
+  const Level& lv = d->set[slot].lv[level];
+  const float* src = which == 0 ? lv.img : which == 1 ? lv.gx : lv.gy;
+  CU(cudaMemcpy2DAsync(out, (size_t)lv.w * sizeof(float), src, (size_t)lv.pitch * sizeof(float),
+                       (size_t)lv.w * sizeof(float), lv.h, cudaMemcpyDeviceToHost, d->stream));
+  CU(cudaStreamSynchronize(d->stream));
+  return 0;
+}
+
+// ---- features --------------------------------------------------------------------
+static int ensure_features(klt_dev* d, int n) {
+  if (n <= d->feat_cap) return 0;
+  CU(cudaStreamSynchronize(d->stream));
+  cudaFree(d->d_x); cudaFree(d->d_y); cudaFree(d->d_val);
+  cudaFreeHost(d->h_x); cudaFreeHost(d->h_y); cudaFreeHost(d->h_val);
+  d->d_x = d->d_y = nullptr; d->d_val = nullptr; d->h_x = d->h_y = nullptr; d->h_val = nullptr;
+  d->feat_cap = 0;
+  const int cap = (n + 1023) / 1024 * 1024;
+  CU(cudaMalloc(&d->d_x, cap * sizeof(float)));
+  CU(cudaMalloc(&d->d_y, cap * sizeof(float)));
+  CU(cudaMalloc(&d->d_val, cap * sizeof(int)));
+  CU(cudaMallocHost(&d->h_x, cap * sizeof(float)));
+  CU(cudaMallocHost(&d->h_y, cap * sizeof(float)));
+  CU(cudaMallocHost(&d->h_val, cap * sizeof(int)));
+  d->feat_cap = cap;
+  return 0;
+}
+
+extern "C" int klt_dev_features_upload(klt_dev* d, int n, const float* x, const float* y, const int* val) {
+  CU(cudaSetDevice(d->device));
+  if (n < 0) return fail(d, "negative feature count");
+  if (ensure_features(d, n > 0 ? n : 1)) return 1;
+  // the pinned staging buffers may still be in flight from a previous call
+  CU(cudaStreamSynchronize(d->stream));
+  memcpy(d->h_x, x, n * sizeof(float));
+  memcpy(d->h_y, y, n * sizeof(float));
+  memcpy(d->h_val, val, n * sizeof(int));
+  CU(cudaMemcpyAsync(d->d_x, d->h_x, n * sizeof(float), cudaMemcpyHostToDevice, d->stream));
+  CU(cudaMemcpyAsync(d->d_y, d->h_y, n * sizeof(float), cudaMemcpyHostToDevice, d->stream));
+  CU(cudaMemcpyAsync(d->d_val, d->h_val, n * sizeof(int), cudaMemcpyHostToDevice, d->stream));
+  d->feat_n = n;
+  return 0;
+}
+
+extern "C" int klt_dev_features_download(klt_dev* d, int n, float* x, float* y, int* val) {
+  CU(cudaSetDevice(d->device));
+  if (n > d->feat_n) return fail(d, "download of %d features but %d resident", n, d->feat_n);
+  CU(cudaMemcpyAsync(d->h_x, d->d_x, n * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
+  CU(cudaMemcpyAsync(d->h_y, d->d_y, n * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
+  CU(cudaMemcpyAsync(d->h_val, d->d_val, n * sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+  CU(cudaStreamSynchronize(d->stream));
+  memcpy(x, d->h_x, n * sizeof(float));
+  memcpy(y, d->h_y, n * sizeof(float));
+  memcpy(val, d->h_val, n * sizeof(int));
+  return 0;
+}
+
+static void make_view(const PyrSet& S, int L, PyrView* v) {
+  memset(v, 0, sizeof(*v));
+  for (int l = 0; l < L; ++l) {
+    v->img[l] = S.lv[l].img; v->gx[l] = S.lv[l].gx; v->gy[l] = S.lv[l].gy;
+    v->ncols[l] = S.lv[l].w; v->nrows[l] = S.lv[l].h; v->pitch[l] = S.lv[l].pitch;
+  }
+}
+
+template <bool EXACT, int PPL>
+static int launch_track(klt_dev* d, const PyrView& v1, const PyrView& v2, const TrackArgs& a, int n) {
+  const int warps = 4;
+  const size_t smem = EXACT ? (size_t)warps * 3 * a.ww * a.wh * sizeof(float) : 0;
+  if (set_smem(d, track_kernel<EXACT, PPL>, smem)) return 1;
+  track_kernel<EXACT, PPL><<<(n + warps - 1) / warps, warps * 32, smem, d->stream>>>(
+      v1, v2, a, n, d->d_x, d->d_y, d->d_val);
+  d->launches++;
+  return 0;
+}
+
+extern "C" int klt_dev_track_resident(klt_dev* d, int slot_prev, int slot_cur,
+                                      const klt_dev_track_params* p) {
+  CU(cudaSetDevice(d->device));
+  if (!klt_dev_slot_valid(d, slot_prev) || !klt_dev_slot_valid(d, slot_cur))
+    return fail(d, "klt_dev_track: pyramid slot %d or %d not built", slot_prev, slot_cur);
+  if (p->window_width < 3 || p->window_height < 3 || !(p->window_width & 1) || !(p->window_height & 1))
+    return fail(d, "tracking window %d x %d must be odd and >= 3", p->window_width, p->window_height);
+  const int n = d->feat_n;
+  if (n == 0) return 0;
+  PyrView v1, v2;
+  make_view(d->set[slot_prev], d->L, &v1);
+  make_view(d->set[slot_cur], d->L, &v2);
+  TrackArgs a;
+  a.nlevels = d->L; a.ss = (float)d->ss; a.ww = p->window_width; a.wh = p->window_height;
+  a.step_factor = p->step_factor; a.max_iterations = p->max_iterations;
+  a.min_determinant = p->min_determinant; a.min_displacement = p->min_displacement;
+  a.max_residue = p->max_residue; a.borderx = p->borderx; a.bordery = p->bordery;
+  a.ncols = d->W; a.nrows = d->H;
+  const int npix = a.ww * a.wh;
+  const int ppl = (npix + 31) / 32;
+  int rc;
+  if (p->exact) {
+    if (ppl <= 2) rc = launch_track<true, 2>(d, v1, v2, a, n);
+    else if (ppl <= 4) rc = launch_track<true, 4>(d, v1, v2, a, n);
+    else if (ppl <= 8) rc = launch_track<true, 8>(d, v1, v2, a, n);
+    else if (ppl <= 16) rc = launch_track<true, 16>(d, v1, v2, a, n);
+    else return fail(d, "tracking window %d x %d too large (max 512 pixels)", a.ww, a.wh);
+  } else {
+    if (ppl <= 2) rc = launch_track<false, 2>(d, v1, v2, a, n);
+    else if (ppl <= 4) rc = launch_track<false, 4>(d, v1, v2, a, n);
+    else if (ppl <= 8) rc = launch_track<false, 8>(d, v1, v2, a, n);
+    else if (ppl <= 16) rc = launch_track<false, 16>(d, v1, v2, a, n);
+    else return fail(d, "tracking window %d x %d too large (max 512 pixels)", a.ww, a.wh);
+  }
+  if (rc) return rc;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int klt_dev_track(klt_dev* d, int slot_prev, int slot_cur, const klt_dev_track_params* p,
+                             int n, float* x, float* y, int* val) {
+  if (klt_dev_features_upload(d, n, x, y, val)) return 1;
+  if (klt_dev_track_resident(d, slot_prev, slot_cur, p)) return 1;
+  return klt_dev_features_download(d, n, x, y, val);
+}
+
+// ---- selection --------------------------------------------------------------------
+struct CandGeo { int bx, by, step, nxc, nyc; long npoints; };
+
+static CandGeo cand_geometry(const klt_dev* d, const klt_dev_select_params* p) {
+  CandGeo g;
+  g.bx = p->borderx; g.by = p->bordery;
+  if (g.bx < p->window_width / 2) g.bx = p->window_width / 2;
+  if (g.by < p->window_height / 2) g.by = p->window_height / 2;
+  g.step = p->nSkippedPixels + 1;
+  const int spanx = d->W - 2 * g.bx, spany = d->H - 2 * g.by;
+  g.nxc = spanx > 0 ? (spanx + g.step - 1) / g.step : 0;
+  g.nyc = spany > 0 ? (spany + g.step - 1) / g.step : 0;
+  g.npoints = (long)g.nxc * g.nyc;
+  return g;
+}
+
+static int ensure_candidates(klt_dev* d, size_t n) {
+  if (n <= d->cand_cap) return 0;
+  CU(cudaStreamSynchronize(d->stream));
+  for (int i = 0; i < 2; ++i) { cudaFree(d->c_val[i]); cudaFree(d->c_idx[i]); d->c_val[i] = nullptr; d->c_idx[i] = nullptr; }
+  cudaFree(d->cub_tmp); d->cub_tmp = nullptr; d->cand_cap = 0;
+  for (int i = 0; i < 2; ++i) {
+    CU(cudaMalloc(&d->c_val[i], n * sizeof(int)));
+    CU(cudaMalloc(&d->c_idx[i], n * sizeof(unsigned)));
+  }
+  size_t bytes = 0;
+  CU(cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, d->c_val[0], d->c_val[1], d->c_idx[0],
+                                               d->c_idx[1], (int)n, 0, 32, d->stream));
+  CU(cudaMalloc(&d->cub_tmp, bytes ? bytes : 16));
+  d->cub_bytes = bytes;
+  d->cand_cap = n;
+  return 0;
+}
+
+static int run_mineig(klt_dev* d, int slot, const klt_dev_select_params* p, const CandGeo& g) {
+  const Level& lv = d->set[slot].lv[0];
+  dim3 b(32, 8), grid((g.nxc + 31) / 32, (g.nyc + 7) / 8);
+  mineig_kernel<<<grid, b, 0, d->stream>>>(lv.gx, lv.gy, lv.pitch, g.bx, g.by, g.step, g.nxc, g.nyc,
+                                           p->window_width / 2, p->window_height / 2, d->c_val[0], d->c_idx[0]);
+  d->launches++;
+  return 0;
+}
+
+extern "C" int klt_dev_eigen_map(klt_dev* d, int slot, const klt_dev_select_params* p, int* out, int* npoints) {
+  CU(cudaSetDevice(d->device));
+  if (!d->arena || slot < 0 || slot > 1 || d->set[slot].built_levels < 1) return fail(d, "eigen_map: slot %d has no level 0", slot);
+  const CandGeo g = cand_geometry(d, p);
+  if (npoints) *npoints = (int)g.npoints;
+  if (!out || g.npoints == 0) return 0;
+  if (ensure_candidates(d, (size_t)g.npoints)) return 1;
+  if (run_mineig(d, slot, p, g)) return 1;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, d->c_val[0], g.npoints * sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+  CU(cudaStreamSynchronize(d->stream));
+  return 0;
+}
+
+extern "C" int klt_dev_select(klt_dev* d, int slot, const klt_dev_select_params* p, int n,
+                              float* x, float* y, int* val) {
+  CU(cudaSetDevice(d->device));
+  if (!d->arena || slot < 0 || slot > 1 || d->set[slot].built_levels < 1) return fail(d, "select: slot %d has no level 0", slot);
+  if (n <= 0) return 0;
+  const CandGeo g = cand_geometry(d, p);
+  int mindist = p->mindist < 0 ? 0 : p->mindist;
+  const int dist = mindist - 1;                    // the reference works with mindist-1 (:157)
+  const int min_eig = p->min_eigenvalue < 1 ? 1 : p->min_eigenvalue;   // (:148)
+  if (klt_dev_features_upload(d, n, x, y, val)) return 1;
+  const size_t npx = (size_t)d->W * d->H;
+  if (d->fmap_cap < npx) {
+    CU(cudaStreamSynchronize(d->stream));
+    cudaFree(d->fmap); d->fmap = nullptr; d->fmap_cap = 0;
+    CU(cudaMalloc(&d->fmap, npx));
+    d->fmap_cap = npx;
+  }
+  if (d->open_cap < n) {
+    CU(cudaStreamSynchronize(d->stream));
+    cudaFree(d->open_slots); d->open_slots = nullptr; d->open_cap = 0;
+    CU(cudaMalloc(&d->open_slots, (size_t)n * sizeof(int)));
+    d->open_cap = n;
+  }
+  CU(cudaMemsetAsync(d->fmap, 0, npx, d->stream));
+  const int* sval = nullptr; const unsigned* sidx = nullptr;
+  if (g.npoints > 0) {
+    if (ensure_candidates(d, (size_t)g.npoints)) return 1;
+    if (run_mineig(d, slot, p, g)) return 1;
+    size_t bytes = d->cub_bytes;
+    CU(cub::DeviceRadixSort::SortPairsDescending(d->cub_tmp, bytes, d->c_val[0], d->c_val[1], d->c_idx[0],
+                                                 d->c_idx[1], (int)g.npoints, 0, 32, d->stream));
+    d->launches += 4;   // cub: histogram + onesweep passes (counted conservatively)
+    sval = d->c_val[1]; sidx = d->c_idx[1];
+  }
+  if (!p->overwrite_all) {
+    stamp_existing_kernel<<<n, 128, 0, d->stream>>>(d->d_x, d->d_y, d->d_val, d->fmap, dist, d->W, d->H);
+    d->launches++;
+  }
+  enforce_mindist_kernel<<<1, GB, 0, d->stream>>>(sval, sidx, (int)g.npoints, g.nxc > 0 ? g.nxc : 1, g.bx, g.by,
+                                                 g.step, d->W, d->H, d->fmap, dist, min_eig,
+                                                 p->overwrite_all, n, d->d_x, d->d_y, d->d_val, d->open_slots);
+  d->launches++;
+  CU(cudaGetLastError());
+  return klt_dev_features_download(d, n, x, y, val);
+}
+
+// ---- device timing on the context stream (benches) ------------------------------
+// CUDA events recorded on the stream the kernels are launched on; torch's own
+// events would only see torch's current stream.
+extern "C" int klt_dev_timer_start(klt_dev* d) {
+  CU(cudaSetDevice(d->device));
+  if (!d->ev_made) { CU(cudaEventCreate(&d->ev_a)); CU(cudaEventCreate(&d->ev_b)); d->ev_made = 1; }
+  CU(cudaEventRecord(d->ev_a, d->stream));
+  return 0;
+}
+extern "C" int klt_dev_timer_stop(klt_dev* d, float* ms) {
+  CU(cudaSetDevice(d->device));
+  if (!d->ev_made) return fail(d, "timer_stop without timer_start");
+  CU(cudaEventRecord(d->ev_b, d->stream));
+  CU(cudaEventSynchronize(d->ev_b));
+  CU(cudaEventElapsedTime(ms, d->ev_a, d->ev_b));
+  return 0;
+}

@@ -1,0 +1,41 @@
+/* klt_internal.h -- private to the host C side of libklt_b200. */
+#ifndef KLT_INTERNAL_H
+#define KLT_INTERNAL_H
+
+#include "klt.h"
+#include "klt_b200.h"
+#include "klt_cuda.h"
+
+extern int KLT_verbose;
+
+/* per-tracking-context device state (csrc/klt_context.c) */
+typedef struct klt_tc_state {
+  KLT_TrackingContext tc;
+  klt_dev *dev;          /* created on first use of the hot path            */
+  int device;            /* CUDA device ordinal, -1 = KLT_B200_DEVICE / current */
+  int exact;             /* arithmetic mode for tracking pyramids            */
+  int last_slot;         /* slot holding the previous frame's pyramids       */
+  struct klt_tc_state *next;
+} klt_tc_state;
+
+klt_tc_state *klt_state_get(KLT_TrackingContext tc);          /* creates the record   */
+klt_tc_state *klt_state_find(KLT_TrackingContext tc);         /* NULL if none         */
+void klt_state_drop(KLT_TrackingContext tc);                  /* destroys the device  */
+klt_dev *klt_state_device(klt_tc_state *s);                   /* KLTError on failure  */
+
+/* taps with the reference's sigma cache (csrc/klt_taps.c) */
+void klt_taps_for(float sigma, klt_dev_taps *out);            /* cache rule applies   */
+void _KLTGetKernelWidths(float sigma, int *gauss_width, int *gaussderiv_width);
+
+/* shared parameter repair (window odd and >= 3) */
+void klt_fix_window(KLT_TrackingContext tc, const char *who, int style);
+
+/* build descriptor from a tracking context */
+void klt_fill_build_desc(KLT_TrackingContext tc, int ncols, int nrows,
+                         int nlevels_built, int smooth, int exact,
+                         klt_dev_build_desc *q);
+
+/* list <-> SoA staging */
+void klt_list_to_arrays(KLT_FeatureList fl, float *x, float *y, int *v);
+
+#endif

@@ -1,0 +1,209 @@
+/* klt_track.c -- KLTTrackFeatures on the GPU.
+ *
+ * Host orchestration of reference src/V1/trackFeatures.c:1234-1529
+ * (KLTTrackFeatures): window repair (:1258-1278), reuse of the previous frame's
+ * pyramids in sequentialMode (:1285-1294) or building them from img1
+ * (:1295-1308), building the pyramids of img2 (:1311-1321), the feature loop
+ * (:1343-1437, one warp per feature in csrc/klt_dev.cu), and the pyramid
+ * hand-over (:1503-1519).  The lighting-insensitive and affine-consistency
+ * variants (:125-220, :506-1224) are not on the accelerated path: asking for
+ * them is a KLTError rather than a silent CPU fallback.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "klt_internal.h"
+
+#define DEVCALL(s, call)                                                     \
+  do {                                                                       \
+    if ((call) != 0) KLTError("(KLT/B200) %s", klt_dev_error((s)->dev));      \
+  } while (0)
+
+static void fill_track_params(KLT_TrackingContext tc, int exact, klt_dev_track_params *p)
+{
+  p->window_width = tc->window_width;
+  p->window_height = tc->window_height;
+  p->step_factor = tc->step_factor;
+  p->max_iterations = tc->max_iterations;
+  p->min_determinant = tc->min_determinant;
+  p->min_displacement = tc->min_displacement;
+  p->max_residue = tc->max_residue;
+  p->borderx = tc->borderx;
+  p->bordery = tc->bordery;
+  p->exact = exact;
+}
+
+static void check_supported(KLT_TrackingContext tc)
+{
+  if (tc->lighting_insensitive)
+    KLTError("(KLTTrackFeatures) lighting_insensitive tracking is not implemented "
+             "on the GPU path (and there is no CPU path)");
+  if (tc->affineConsistencyCheck >= 0)
+    KLTError("(KLTTrackFeatures) affineConsistencyCheck >= 0 is not implemented "
+             "on the GPU path (and there is no CPU path)");
+}
+
+/* Returns the slot holding frame 1's pyramids, building them if necessary. */
+static int prepare_previous(KLT_TrackingContext tc, klt_tc_state *s, const KLT_PixelType *img1,
+                            int on_device, size_t pitch, int ncols, int nrows)
+{
+  klt_dev *dev = klt_state_device(s);
+  int gw = 0, gh = 0, gl = 0, gs = 0;
+
+  if (tc->sequentialMode && tc->pyramid_last != NULL && s->last_slot >= 0 &&
+      klt_dev_slot_valid(dev, s->last_slot)) {
+    klt_dev_geometry(dev, &gw, &gh, &gl, &gs);
+    if (gw != ncols || gh != nrows)
+      KLTError("(KLTTrackFeatures) Size of incoming image (%d by %d) "
+               "is different from size of previous image (%d by %d)\n",
+               ncols, nrows, gw, gh);
+    if (gl == tc->nPyramidLevels && (gl == 1 || gs == tc->subsampling))
+      return s->last_slot;
+    /* pyramid parameters changed between frames: fall through and rebuild */
+  }
+  if (img1 == NULL)
+    KLTError("(KLTTrackFeatures) no previous pyramid is held and img1 is NULL");
+  {
+    klt_dev_build_desc q;
+    klt_fill_build_desc(tc, ncols, nrows, tc->nPyramidLevels, 1, s->exact, &q);
+    DEVCALL(s, klt_dev_build(dev, 0, img1, on_device, pitch, &q));
+  }
+  return 0;
+}
+
+static void hand_over(KLT_TrackingContext tc, klt_tc_state *s, int slot_cur)
+{
+  if (tc->sequentialMode) {
+    s->last_slot = slot_cur;
+    tc->pyramid_last = tc->pyramid_last_gradx = tc->pyramid_last_grady = (void *)s;
+  } else {
+    s->last_slot = -1;
+    klt_dev_invalidate(s->dev, -1);
+    tc->pyramid_last = tc->pyramid_last_gradx = tc->pyramid_last_grady = NULL;
+  }
+}
+
+static void track_common(KLT_TrackingContext tc, const KLT_PixelType *img1,
+                         const KLT_PixelType *img2, int on_device, size_t pitch,
+                         int ncols, int nrows, KLT_FeatureList fl)
+{
+  klt_tc_state *s = klt_state_get(tc);
+  klt_dev *dev;
+  klt_dev_build_desc q;
+  klt_dev_track_params tp;
+  int slot_prev, slot_cur, n = fl->nFeatures, i;
+  float *x, *y;
+  int *v;
+
+  if (KLT_verbose >= 1) {
+    fprintf(stderr, "(KLT) Tracking %d features in a %d by %d image...  ",
+            KLTCountRemainingFeatures(fl), ncols, nrows);
+    fflush(stderr);
+  }
+  klt_fix_window(tc, "KLTTrackFeatures", 1);
+  check_supported(tc);
+  dev = klt_state_device(s);
+
+  slot_prev = prepare_previous(tc, s, img1, on_device, pitch, ncols, nrows);
+  slot_cur = 1 - slot_prev;
+  klt_fill_build_desc(tc, ncols, nrows, tc->nPyramidLevels, 1, s->exact, &q);
+  DEVCALL(s, klt_dev_build(dev, slot_cur, img2, on_device, pitch, &q));
+
+  x = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+  y = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+  v = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  if (!x || !y || !v) KLTError("(KLTTrackFeatures) Out of memory");
+  klt_list_to_arrays(fl, x, y, v);
+  fill_track_params(tc, s->exact, &tp);
+  DEVCALL(s, klt_dev_track(dev, slot_prev, slot_cur, &tp, n, x, y, v));
+  for (i = 0; i < n; i++) {
+    KLT_Feature f = fl->feature[i];
+    if (f->val < 0) continue;                 /* lost features are not touched (:1346) */
+    f->x = x[i];
+    f->y = y[i];
+    f->val = v[i];
+    if (v[i] < 0) {                           /* lost now: drop affine templates (:1387-1392) */
+      free(f->aff_img); free(f->aff_img_gradx); free(f->aff_img_grady);
+      f->aff_img = f->aff_img_gradx = f->aff_img_grady = NULL;
+    }
+  }
+  free(x); free(y); free(v);
+
+  hand_over(tc, s, slot_cur);
+
+  if (KLT_verbose >= 1) {
+    fprintf(stderr, "\n\t%d features successfully tracked.\n", KLTCountRemainingFeatures(fl));
+    fflush(stderr);
+  }
+}
+
+void KLTTrackFeatures(KLT_TrackingContext tc, KLT_PixelType *img1, KLT_PixelType *img2,
+                      int ncols, int nrows, KLT_FeatureList fl)
+{
+  track_common(tc, img1, img2, 0, (size_t)ncols, ncols, nrows, fl);
+}
+
+void KLTTrackFeaturesDevice(KLT_TrackingContext tc, const KLT_PixelType *d_img1,
+                            const KLT_PixelType *d_img2, size_t pitch,
+                            int ncols, int nrows, KLT_FeatureList fl)
+{
+  track_common(tc, d_img1, d_img2, 1, pitch, ncols, nrows, fl);
+}
+
+/* ---- resident-feature pipeline (no host sync per frame) ----------------------- */
+void KLTB200ResidentBegin(KLT_TrackingContext tc, const KLT_PixelType *img1, int on_device,
+                          size_t pitch, int ncols, int nrows, KLT_FeatureList fl)
+{
+  klt_tc_state *s = klt_state_get(tc);
+  const int n = fl->nFeatures;
+  float *x = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+  float *y = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+  int *v = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  int slot;
+  if (!x || !y || !v) KLTError("(KLTB200ResidentBegin) Out of memory");
+  klt_fix_window(tc, "KLTTrackFeatures", 1);
+  check_supported(tc);
+  if (!tc->sequentialMode)
+    KLTError("(KLTB200ResidentBegin) the resident pipeline needs tc->sequentialMode = TRUE");
+  slot = prepare_previous(tc, s, img1, on_device, pitch ? pitch : (size_t)ncols, ncols, nrows);
+  hand_over(tc, s, slot);
+  klt_list_to_arrays(fl, x, y, v);
+  DEVCALL(s, klt_dev_features_upload(s->dev, n, x, y, v));
+  free(x); free(y); free(v);
+}
+
+void KLTB200ResidentStep(KLT_TrackingContext tc, const KLT_PixelType *img2, int on_device,
+                         size_t pitch, int ncols, int nrows)
+{
+  klt_tc_state *s = klt_state_get(tc);
+  klt_dev_build_desc q;
+  klt_dev_track_params tp;
+  int slot_prev, slot_cur;
+  if (tc->pyramid_last == NULL || s->last_slot < 0)
+    KLTError("(KLTB200ResidentStep) call KLTB200ResidentBegin first");
+  slot_prev = s->last_slot;
+  slot_cur = 1 - slot_prev;
+  klt_fill_build_desc(tc, ncols, nrows, tc->nPyramidLevels, 1, s->exact, &q);
+  DEVCALL(s, klt_dev_build(s->dev, slot_cur, img2, on_device, pitch ? pitch : (size_t)ncols, &q));
+  fill_track_params(tc, s->exact, &tp);
+  DEVCALL(s, klt_dev_track_resident(s->dev, slot_prev, slot_cur, &tp));
+  hand_over(tc, s, slot_cur);
+}
+
+void KLTB200ResidentEnd(KLT_TrackingContext tc, KLT_FeatureList fl)
+{
+  klt_tc_state *s = klt_state_get(tc);
+  const int n = fl->nFeatures;
+  float *x = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+  float *y = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+  int *v = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  int i;
+  if (!x || !y || !v) KLTError("(KLTB200ResidentEnd) Out of memory");
+  DEVCALL(s, klt_dev_features_download(klt_state_device(s), n, x, y, v));
+  for (i = 0; i < n; i++) {
+    fl->feature[i]->x = x[i];
+    fl->feature[i]->y = y[i];
+    fl->feature[i]->val = v[i];
+  }
+  free(x); free(y); free(v);
+}

@@ -1,0 +1,145 @@
+"""Stage-level parity of the CUDA kernels against the oracle, through the C-ABI
+(klt_dev_build / klt_dev_read_level / klt_dev_eigen_map).
+
+exact mode  : bit-identical images (np.array_equal)
+fast mode   : |a-b| / max(|b|,1) <= 1e-4  (north_star tolerance)
+Both the tiled kernels and the generic (any radius) kernels are checked.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests.conftest import synth_image
+from tests.gpu_common import REL_TOL_IMAGES, device_pyramids, params_from_tc, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L(pkg):
+    from importlib import import_module
+    lib = import_module(pkg.__name__ + ".runtime").load()
+    lib.require_gpu()
+    lib.KLTSetVerbosity(0)
+    return lib
+
+
+def _check_build(L, oracle, img, tc, exact, generic, expect_tiled=None):
+    dev = L.KLTB200Device(tc)
+    L.klt_dev_force_generic(dev, 1 if generic else 0)
+    h, w = img.shape
+    q = L.build_desc(tc, w, h, exact=exact)
+    L.dev_build(dev, 0, img, q)
+    if expect_tiled is not None and not generic:
+        assert L.klt_dev_last_build_path(dev) == (1 if expect_tiled else 0)
+    nl = tc.contents.nPyramidLevels
+    got = device_pyramids(L, dev, 0, nl)
+    p = params_from_tc(oracle, tc)
+    want = oracle.build_pyramids(img, p)
+    names = ("img", "gradx", "grady")
+    for which in range(3):
+        for l in range(nl):
+            a, b = got[which][l], want.level(which, l)
+            assert a.shape == b.shape
+            if exact:
+                if not np.array_equal(a, b):
+                    bad = np.argwhere(a != b)
+                    raise AssertionError("%s level %d: %d of %d pixels differ, first at %s: %r vs %r"
+                                         % (names[which], l, len(bad), a.size, bad[0],
+                                            a[tuple(bad[0])], b[tuple(bad[0])]))
+            else:
+                e = rel_err(a, b).max()
+                assert e <= REL_TOL_IMAGES, "%s level %d: rel err %g" % (names[which], l, e)
+    L.klt_dev_force_generic(dev, 0)
+
+
+SHAPES = [(240, 320), (243, 321), (48, 64), (37, 1000), (600, 33), (130, 257)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("exact", [1, 0])
+@pytest.mark.parametrize("generic", [0, 1])
+def test_default_config_pyramids(L, oracle, shape, exact, generic):
+    h, w = shape
+    img = synth_image(w, h, seed=h * 1000 + w)
+    tc = L.KLTCreateTrackingContext()          # L=2, ss=4, window 7
+    _check_build(L, oracle, img, tc, exact, generic, expect_tiled=True)
+    L.KLTFreeTrackingContext(tc)
+
+
+@pytest.mark.parametrize("exact", [1, 0])
+@pytest.mark.parametrize("generic", [0, 1])
+def test_config4_shape_four_levels_ss2(L, oracle, exact, generic):
+    img = synth_image(700, 500, seed=4)
+    tc = L.KLTCreateTrackingContext()
+    tc.contents.nPyramidLevels, tc.contents.subsampling = 4, 2
+    L.KLTUpdateTCBorder(tc)
+    assert tc.contents.borderx == 64
+    _check_build(L, oracle, img, tc, exact, generic, expect_tiled=True)
+    L.KLTFreeTrackingContext(tc)
+
+
+@pytest.mark.parametrize("window,grad_sigma,ss,levels,psf", [
+    (3, 1.0, 2, 3, 0.9), (5, 0.7, 4, 2, 0.9), (9, 1.4, 2, 2, 0.9), (11, 1.8, 8, 2, 0.9),
+    (15, 1.0, 4, 3, 0.9), (7, 2.5, 16, 2, 0.3), (7, 1.0, 32, 2, 0.2)])
+def test_other_radii_and_subsamplings(L, oracle, window, grad_sigma, ss, levels, psf):
+    # (sigma = ss * pyramid_sigma_fact above ~11 needs more than 71 taps: a KLTError in
+    #  the reference and here, so the large subsamplings use a smaller factor)
+    img = synth_image(640, 480, seed=window)
+    for exact in (1, 0):
+        tc = L.KLTCreateTrackingContext()
+        t = tc.contents
+        t.window_width = t.window_height = window
+        t.grad_sigma = grad_sigma
+        t.pyramid_sigma_fact = psf
+        t.nPyramidLevels, t.subsampling = levels, ss
+        L.KLTUpdateTCBorder(tc)
+        _check_build(L, oracle, img, tc, exact, generic=0)
+        L.KLTFreeTrackingContext(tc)
+
+
+def test_real_frames_exact(L, oracle, provided):
+    tc = L.KLTCreateTrackingContext()
+    for img in provided[:3]:
+        _check_build(L, oracle, img, tc, exact=1, generic=0, expect_tiled=True)
+    L.KLTFreeTrackingContext(tc)
+
+
+def test_no_presmoothing_level0(L, oracle, provided):
+    """smoothBeforeSelecting == FALSE: level 0 is the raw float image."""
+    img = provided[0]
+    tc = L.KLTCreateTrackingContext()
+    dev = L.KLTB200Device(tc)
+    q = L.build_desc(tc, img.shape[1], img.shape[0], nlevels_built=1, smooth=0, exact=1)
+    L.dev_build(dev, 0, img, q)
+    assert np.array_equal(L.dev_level(dev, 0, 0, 0), img.astype(np.float32))
+    gx, gy = oracle.gradients(img.astype(np.float32), 1.0)
+    assert np.array_equal(L.dev_level(dev, 0, 1, 0), gx)
+    assert np.array_equal(L.dev_level(dev, 0, 2, 0), gy)
+    L.KLTFreeTrackingContext(tc)
+
+
+@pytest.mark.parametrize("shape,window,skip", [((240, 320), 7, 0), ((243, 321), 7, 0),
+                                               ((200, 300), 5, 0), ((200, 300), 9, 2)])
+def test_eigenvalue_map_is_integer_exact(L, oracle, provided, shape, window, skip):
+    h, w = shape
+    img = provided[0] if shape == (240, 320) else synth_image(w, h, seed=h + w)
+    tc = L.KLTCreateTrackingContext()
+    t = tc.contents
+    t.window_width = t.window_height = window
+    t.nSkippedPixels = skip
+    L.KLTUpdateTCBorder(tc)
+    dev = L.KLTB200Device(tc)
+    q = L.build_desc(tc, w, h, nlevels_built=1, exact=1)
+    L.dev_build(dev, 0, img, q)
+    got = L.dev_eigen_map(dev, 0, L.select_params(tc))
+    p = params_from_tc(oracle, tc)
+    f = oracle.smooth(oracle.to_float(img), p.smooth_sigma_fact * window)
+    gx, gy = oracle.gradients(f, 1.0)
+    pts = oracle.mineig_points(gx, gy, window, window, t.borderx, t.bordery, skip)
+    assert len(got) == len(pts)
+    assert np.array_equal(got, pts[:, 2])
+    if shape == (240, 320):
+        assert len(got) == 52224          # gprof call count of the golden run
+    L.KLTFreeTrackingContext(tc)
