@@ -145,6 +145,16 @@ void klt_dev_force_generic(klt_dev *d, int on);
  * context's own stream (the stream the kernels run on) */
 int klt_dev_timer_start(klt_dev *d);
 int klt_dev_timer_stop(klt_dev *d, float *ms);
+/* per-kernel device time: between begin and end every kernel launch of this
+ * context is bracketed by CUDA events on the context stream and accumulated by
+ * kernel class; klt_dev_profile_get returns the class name (NULL past the end) */
+int klt_dev_profile_begin(klt_dev *d);
+int klt_dev_profile_end(klt_dev *d);
+int klt_dev_profile_kernels(void);
+const char *klt_dev_profile_get(const klt_dev *d, int kid, unsigned long long *launches, double *total_ms);
+/* number of features that entered klt_dev_track* with val >= 0 since the last
+ * reset, counted on the device (the metric's numerator for resident pipelines) */
+int klt_dev_live_total(klt_dev *d, unsigned long long *out, int reset);
 
 #ifdef __cplusplus
 }

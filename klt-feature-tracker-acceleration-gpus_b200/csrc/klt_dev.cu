@@ -573,13 +573,15 @@ __device__ __forceinline__ float warp_sum(float v) {
 template <bool EXACT, int PPL>
 __global__ void __launch_bounds__(128)
 track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n,
-             float* __restrict__ fx, float* __restrict__ fy, int* __restrict__ fval) {
+             float* __restrict__ fx, float* __restrict__ fy, int* __restrict__ fval,
+             unsigned long long* __restrict__ live_total) {
   extern __shared__ float s_win[];     // EXACT only: [warps][3][npix]
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int f = blockIdx.x * (blockDim.x >> 5) + wib;
   if (f >= n) return;
   if (fval[f] < 0) return;             // only features that are not lost (:1346)
+  if (lane == 0) atomicAdd(live_total, 1ULL);
 
   const int ww = a.ww, wh = a.wh, hw = ww / 2, hh = wh / 2, npix = ww * wh;
   float* swx = s_win + (size_t)wib * 3 * npix;
@@ -752,6 +754,18 @@ track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n,
 // ---------------------------------------------------------------------------
 // host side of the C-ABI
 // ---------------------------------------------------------------------------
+// kernel classes, for launch accounting and per-kernel event timing
+enum KernelId {
+  KID_SMOOTH_U8 = 0, KID_GRAD, KID_PYRDOWN, KID_TRACK, KID_MINEIG, KID_SORT, KID_STAMP,
+  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_COUNT
+};
+static const char* const kKernelNames[KID_COUNT] = {
+  "smooth_u8_tile", "grad_tile", "pyrdown_tile", "track_kernel", "mineig_kernel",
+  "cub_radix_sort", "stamp_existing_kernel", "enforce_mindist_kernel",
+  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel"
+};
+static constexpr int PROF_POOL = 2048;     // event pairs in flight before folding
+
 struct Level {
   int w, h, pitch;           // pitch in floats
   float *img, *gx, *gy;
@@ -784,6 +798,42 @@ struct klt_dev {
   int* open_slots; int open_cap;
   // timing
   cudaEvent_t ev_a, ev_b; int ev_made;
+  // per-kernel profiling (klt_dev_profile_*)
+  int prof_on, prof_used;
+  cudaEvent_t* prof_ev;          // 2 * PROF_POOL events
+  int* prof_kid;
+  double prof_ms[KID_COUNT];
+  unsigned long long prof_n[KID_COUNT];
+  // features entering klt_dev_track* with val >= 0, accumulated on the device
+  unsigned long long* d_live;
+};
+
+// RAII around one kernel launch: counts it and, in profiling mode, brackets it
+// with CUDA events on the context stream.
+static void prof_fold(klt_dev* d) {
+  if (d->prof_used == 0) return;
+  cudaEventSynchronize(d->prof_ev[2 * (d->prof_used - 1) + 1]);
+  for (int i = 0; i < d->prof_used; ++i) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, d->prof_ev[2 * i], d->prof_ev[2 * i + 1]) == cudaSuccess) {
+      d->prof_ms[d->prof_kid[i]] += ms;
+      d->prof_n[d->prof_kid[i]] += 1;
+    }
+  }
+  d->prof_used = 0;
+}
+struct Launch {
+  klt_dev* d; int slot;
+  Launch(klt_dev* d_, int kid) : d(d_), slot(-1) {
+    d->launches++;
+    if (d->prof_on) {
+      if (d->prof_used == PROF_POOL) prof_fold(d);
+      slot = d->prof_used++;
+      d->prof_kid[slot] = kid;
+      cudaEventRecord(d->prof_ev[2 * slot], d->stream);
+    }
+  }
+  ~Launch() { if (slot >= 0) cudaEventRecord(d->prof_ev[2 * slot + 1], d->stream); }
 };
 
 static char g_create_err[512] = "";
@@ -839,6 +889,9 @@ extern "C" int klt_dev_create(int device, klt_dev** out) {
   c->device = device;
   e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { free(c); return fail(nullptr, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+  e = cudaMalloc(&c->d_live, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemsetAsync(c->d_live, 0, sizeof(unsigned long long), c->stream);
+  if (e != cudaSuccess) { cudaStreamDestroy(c->stream); free(c); return fail(nullptr, "cudaMalloc: %s", cudaGetErrorString(e)); }
   *out = c;
   return 0;
 }
@@ -861,6 +914,8 @@ extern "C" void klt_dev_destroy(klt_dev* d) {
   for (int i = 0; i < 2; ++i) { cudaFree(d->c_val[i]); cudaFree(d->c_idx[i]); }
   cudaFree(d->cub_tmp); cudaFree(d->fmap); cudaFree(d->open_slots);
   if (d->ev_made) { cudaEventDestroy(d->ev_a); cudaEventDestroy(d->ev_b); }
+  if (d->prof_ev) { for (int i = 0; i < 2 * PROF_POOL; ++i) cudaEventDestroy(d->prof_ev[i]); free(d->prof_ev); free(d->prof_kid); }
+  cudaFree(d->d_live);
   cudaStreamDestroy(d->stream);
   free(d);
 }
@@ -931,8 +986,8 @@ static int launch_smooth_u8(klt_dev* d, const unsigned char* src, int spitch, in
   const size_t smem = (G::IN_FLOATS + G::IH * 64) * sizeof(float);
   if (set_smem(d, smooth_u8_tile<R, EXACT>, smem)) return 1;
   dim3 grid((W + 63) / 64, (H + 31) / 32);
-  smooth_u8_tile<R, EXACT><<<grid, NT, smem, d->stream>>>(src, spitch, W, H, t, out, opitch);
-  d->launches++;
+  { Launch l(d, KID_SMOOTH_U8);
+    smooth_u8_tile<R, EXACT><<<grid, NT, smem, d->stream>>>(src, spitch, W, H, t, out, opitch); }
   return 0;
 }
 template <bool EXACT>
@@ -958,8 +1013,8 @@ static int launch_grad(klt_dev* d, const float* src, int spitch, int W, int H, c
   const size_t smem = (G::IN_FLOATS + 2 * G::IH * 64) * sizeof(float);
   if (set_smem(d, grad_tile<RG, RD, EXACT>, smem)) return 1;
   dim3 grid((W + 63) / 64, (H + 31) / 32);
-  grad_tile<RG, RD, EXACT><<<grid, NT, smem, d->stream>>>(src, spitch, W, H, tg, td, ox, oy, opitch);
-  d->launches++;
+  { Launch l(d, KID_GRAD);
+    grad_tile<RG, RD, EXACT><<<grid, NT, smem, d->stream>>>(src, spitch, W, H, tg, td, ox, oy, opitch); }
   return 0;
 }
 template <bool EXACT>
@@ -983,9 +1038,9 @@ static int launch_pyrdown(klt_dev* d, const float* src, int spitch, int W, int H
   const size_t smem = (G::IN_FLOATS + G::IH * TXO) * sizeof(float);
   if (set_smem(d, pyrdown_tile<SS, R, TXO, TYO, PY, EXACT>, smem)) return 1;
   dim3 grid((Wout + TXO - 1) / TXO, (Hout + TYO - 1) / TYO);
-  pyrdown_tile<SS, R, TXO, TYO, PY, EXACT><<<grid, NT, smem, d->stream>>>(src, spitch, W, H, t, out,
-                                                                         opitch, Wout, Hout);
-  d->launches++;
+  { Launch l(d, KID_PYRDOWN);
+    pyrdown_tile<SS, R, TXO, TYO, PY, EXACT><<<grid, NT, smem, d->stream>>>(src, spitch, W, H, t, out,
+                                                                           opitch, Wout, Hout); }
   return 0;
 }
 template <bool EXACT>
@@ -1007,10 +1062,11 @@ static int generic_separable(klt_dev* d, const SrcT* src, int spitch, int W, int
   const int tp = d->set[0].lv[0].pitch;
   dim3 b(32, 8);
   dim3 g1((Wout + 31) / 32, (H + 7) / 8);
-  conv_h_generic<SrcT, EXACT><<<g1, b, 0, d->stream>>>(src, spitch, W, H, kh, stride, off, d->tmp, tp, Wout);
+  { Launch l(d, KID_GENERIC_H);
+    conv_h_generic<SrcT, EXACT><<<g1, b, 0, d->stream>>>(src, spitch, W, H, kh, stride, off, d->tmp, tp, Wout); }
   dim3 g2((Wout + 31) / 32, (Hout + 7) / 8);
-  conv_v_generic<EXACT><<<g2, b, 0, d->stream>>>(d->tmp, tp, Wout, H, kv, stride, off, out, opitch, Hout);
-  d->launches += 2;
+  { Launch l(d, KID_GENERIC_V);
+    conv_v_generic<EXACT><<<g2, b, 0, d->stream>>>(d->tmp, tp, Wout, H, kv, stride, off, out, opitch, Hout); }
   return 0;
 }
 
@@ -1032,8 +1088,8 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
     }
   } else {
     dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
+    Launch l(d, KID_U8_TO_F32);
     u8_to_f32_kernel<<<g, b, 0, d->stream>>>(src, spitch, W, H, S.lv[0].img, S.lv[0].pitch);
-    d->launches++;
   }
   // coarser levels
   if (q->nlevels_built > 1) {
@@ -1187,9 +1243,9 @@ static int launch_track(klt_dev* d, const PyrView& v1, const PyrView& v2, const 
   const int warps = 4;
   const size_t smem = EXACT ? (size_t)warps * 3 * a.ww * a.wh * sizeof(float) : 0;
   if (set_smem(d, track_kernel<EXACT, PPL>, smem)) return 1;
-  track_kernel<EXACT, PPL><<<(n + warps - 1) / warps, warps * 32, smem, d->stream>>>(
-      v1, v2, a, n, d->d_x, d->d_y, d->d_val);
-  d->launches++;
+  { Launch l(d, KID_TRACK);
+    track_kernel<EXACT, PPL><<<(n + warps - 1) / warps, warps * 32, smem, d->stream>>>(
+        v1, v2, a, n, d->d_x, d->d_y, d->d_val, d->d_live); }
   return 0;
 }
 
@@ -1276,9 +1332,9 @@ static int ensure_candidates(klt_dev* d, size_t n) {
 static int run_mineig(klt_dev* d, int slot, const klt_dev_select_params* p, const CandGeo& g) {
   const Level& lv = d->set[slot].lv[0];
   dim3 b(32, 8), grid((g.nxc + 31) / 32, (g.nyc + 7) / 8);
-  mineig_kernel<<<grid, b, 0, d->stream>>>(lv.gx, lv.gy, lv.pitch, g.bx, g.by, g.step, g.nxc, g.nyc,
-                                           p->window_width / 2, p->window_height / 2, d->c_val[0], d->c_idx[0]);
-  d->launches++;
+  { Launch l(d, KID_MINEIG);
+    mineig_kernel<<<grid, b, 0, d->stream>>>(lv.gx, lv.gy, lv.pitch, g.bx, g.by, g.step, g.nxc, g.nyc,
+                                             p->window_width / 2, p->window_height / 2, d->c_val[0], d->c_idx[0]); }
   return 0;
 }
 
@@ -1325,19 +1381,19 @@ extern "C" int klt_dev_select(klt_dev* d, int slot, const klt_dev_select_params*
     if (ensure_candidates(d, (size_t)g.npoints)) return 1;
     if (run_mineig(d, slot, p, g)) return 1;
     size_t bytes = d->cub_bytes;
-    CU(cub::DeviceRadixSort::SortPairsDescending(d->cub_tmp, bytes, d->c_val[0], d->c_val[1], d->c_idx[0],
-                                                 d->c_idx[1], (int)g.npoints, 0, 32, d->stream));
-    d->launches += 4;   // cub: histogram + onesweep passes (counted conservatively)
+    { Launch l(d, KID_SORT);   // several cub kernels, timed and counted as one
+      CU(cub::DeviceRadixSort::SortPairsDescending(d->cub_tmp, bytes, d->c_val[0], d->c_val[1], d->c_idx[0],
+                                                   d->c_idx[1], (int)g.npoints, 0, 32, d->stream)); }
     sval = d->c_val[1]; sidx = d->c_idx[1];
   }
   if (!p->overwrite_all) {
+    Launch l(d, KID_STAMP);
     stamp_existing_kernel<<<n, 128, 0, d->stream>>>(d->d_x, d->d_y, d->d_val, d->fmap, dist, d->W, d->H);
-    d->launches++;
   }
-  enforce_mindist_kernel<<<1, GB, 0, d->stream>>>(sval, sidx, (int)g.npoints, g.nxc > 0 ? g.nxc : 1, g.bx, g.by,
-                                                 g.step, d->W, d->H, d->fmap, dist, min_eig,
-                                                 p->overwrite_all, n, d->d_x, d->d_y, d->d_val, d->open_slots);
-  d->launches++;
+  { Launch l(d, KID_ENFORCE);
+    enforce_mindist_kernel<<<1, GB, 0, d->stream>>>(sval, sidx, (int)g.npoints, g.nxc > 0 ? g.nxc : 1, g.bx, g.by,
+                                                   g.step, d->W, d->H, d->fmap, dist, min_eig,
+                                                   p->overwrite_all, n, d->d_x, d->d_y, d->d_val, d->open_slots); }
   CU(cudaGetLastError());
   return klt_dev_features_download(d, n, x, y, val);
 }
@@ -1357,5 +1413,43 @@ extern "C" int klt_dev_timer_stop(klt_dev* d, float* ms) {
   CU(cudaEventRecord(d->ev_b, d->stream));
   CU(cudaEventSynchronize(d->ev_b));
   CU(cudaEventElapsedTime(ms, d->ev_a, d->ev_b));
+  return 0;
+}
+
+// ---- per-kernel profiling -----------------------------------------------------------
+extern "C" int klt_dev_profile_begin(klt_dev* d) {
+  CU(cudaSetDevice(d->device));
+  if (!d->prof_ev) {
+    d->prof_ev = (cudaEvent_t*)calloc(2 * PROF_POOL, sizeof(cudaEvent_t));
+    d->prof_kid = (int*)calloc(PROF_POOL, sizeof(int));
+    if (!d->prof_ev || !d->prof_kid) return fail(d, "out of host memory");
+    for (int i = 0; i < 2 * PROF_POOL; ++i) CU(cudaEventCreate(&d->prof_ev[i]));
+  }
+  CU(cudaStreamSynchronize(d->stream));
+  memset(d->prof_ms, 0, sizeof(d->prof_ms));
+  memset(d->prof_n, 0, sizeof(d->prof_n));
+  d->prof_used = 0;
+  d->prof_on = 1;
+  return 0;
+}
+extern "C" int klt_dev_profile_end(klt_dev* d) {
+  CU(cudaSetDevice(d->device));
+  CU(cudaStreamSynchronize(d->stream));
+  prof_fold(d);
+  d->prof_on = 0;
+  return 0;
+}
+extern "C" int klt_dev_profile_kernels(void) { return KID_COUNT; }
+extern "C" const char* klt_dev_profile_get(const klt_dev* d, int kid, unsigned long long* launches, double* total_ms) {
+  if (kid < 0 || kid >= KID_COUNT) return nullptr;
+  if (launches) *launches = d->prof_n[kid];
+  if (total_ms) *total_ms = d->prof_ms[kid];
+  return kKernelNames[kid];
+}
+extern "C" int klt_dev_live_total(klt_dev* d, unsigned long long* out, int reset) {
+  CU(cudaSetDevice(d->device));
+  CU(cudaMemcpyAsync(out, d->d_live, sizeof(*out), cudaMemcpyDeviceToHost, d->stream));
+  if (reset) CU(cudaMemsetAsync(d->d_live, 0, sizeof(*out), d->stream));
+  CU(cudaStreamSynchronize(d->stream));
   return 0;
 }

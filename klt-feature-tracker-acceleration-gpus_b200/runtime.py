@@ -76,6 +76,11 @@ DEV_API = {
     "klt_dev_force_generic": (None, [C.c_void_p, C.c_int]),
     "klt_dev_timer_start": (C.c_int, [C.c_void_p]),
     "klt_dev_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "klt_dev_profile_begin": (C.c_int, [C.c_void_p]),
+    "klt_dev_profile_end": (C.c_int, [C.c_void_p]),
+    "klt_dev_profile_kernels": (C.c_int, []),
+    "klt_dev_profile_get": (C.c_char_p, [C.c_void_p, C.c_int, C.POINTER(C.c_ulonglong), C.POINTER(C.c_double)]),
+    "klt_dev_live_total": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]),
     # include/klt_b200.h
     "KLTB200SetDevice": (None, [_TC, C.c_int]),
     "KLTB200SetExact": (None, [_TC, C.c_int]),
@@ -166,6 +171,17 @@ class B200Library(capi.KLTLibrary):
         if n.value:
             self.dev_check(dev, self.lib.klt_dev_eigen_map(dev, slot, C.byref(sp),
                                                            out.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return out
+
+
+    def profile(self, dev) -> dict:
+        """{kernel class: (launches, total ms)} accumulated since klt_dev_profile_begin"""
+        out = {}
+        for k in range(self.lib.klt_dev_profile_kernels()):
+            n, ms = C.c_ulonglong(0), C.c_double(0.0)
+            name = self.lib.klt_dev_profile_get(dev, k, C.byref(n), C.byref(ms))
+            if name and n.value:
+                out[name.decode()] = (int(n.value), float(ms.value))
         return out
 
 
