@@ -58,8 +58,12 @@ def algorithmic_bytes(ncols, nrows, nlevels, ss):
         "smooth_u8_tile": 5 * px[0],                                   # read u8, write L0
         "grad_tile": 12 * sum(px),                                     # read L_l, write gx_l, gy_l
         "pyrdown_tile": sum(4 * px[l - 1] + 4 * px[l] for l in range(1, nlevels)),
+        "l0_fused_kernel": 13 * px[0],                                 # read u8, write L0, gx0, gy0
+        "level_fused_kernel": sum(4 * px[l - 1] + 12 * px[l] for l in range(1, nlevels)),
         "frame_pipeline": ncols * nrows + 12 * sum(px),                # fully fused floor
     }
+    # when level 0 is fused, the stand-alone gradient kernel only sees the coarser levels
+    per_kernel["grad_tile_coarse"] = 12 * sum(px[1:])
     return per_kernel, px
 
 
@@ -267,11 +271,14 @@ def run_b200(args, rank, local_rank, world):
         for name, (n, tot) in prof.items():
             per_step = tot / K
             ent = {"launches_per_step": n / K, "ms_per_step": round(per_step, 5)}
-            if name in bytes_tab:
-                ent["algorithmic_bytes_per_step"] = bytes_tab[name]
-                ent["gbs"] = round(bytes_tab[name] / (per_step * 1e-3) / 1e9, 1)
+            key = name
+            if name == "grad_tile" and "l0_fused_kernel" in prof:
+                key = "grad_tile_coarse"
+            if key in bytes_tab:
+                ent["algorithmic_bytes_per_step"] = bytes_tab[key]
+                ent["gbs"] = round(bytes_tab[key] / (per_step * 1e-3) / 1e9, 1)
             kernels[name] = ent
-        pipe = ["smooth_u8_tile", "grad_tile", "pyrdown_tile", "frame_pipeline_fused"]
+        pipe = ["smooth_u8_tile", "grad_tile", "pyrdown_tile", "l0_fused_kernel", "level_fused_kernel"]
         hbm_kernels = {k: v for k, v in kernels.items() if "gbs" in v}
         dom = max(hbm_kernels, key=lambda k: hbm_kernels[k]["ms_per_step"]) if hbm_kernels else None
         traffic = None

@@ -141,6 +141,10 @@ unsigned long long klt_dev_launch_count(const klt_dev *d);
 int klt_dev_last_build_path(const klt_dev *d);
 /* force the generic kernels (cross-check of the tiled ones); default 0 */
 void klt_dev_force_generic(klt_dev *d, int on);
+/* keep the tiled kernels but not the fused TMA level-0 kernel (cross-check); default 0 */
+void klt_dev_disable_fused(klt_dev *d, int on);
+/* 1 if the last klt_dev_build ran the fused TMA level-0 kernel */
+int klt_dev_last_build_fused(const klt_dev *d);
 /* device time between the two calls, measured with CUDA events recorded on the
  * context's own stream (the stream the kernels run on) */
 int klt_dev_timer_start(klt_dev *d);

@@ -58,6 +58,8 @@ struct TapsR {
 
 static constexpr int NT = 256;   // threads per CTA of every tile kernel
 
+#include "klt_fused.cuh"
+
 // ---------------------------------------------------------------------------
 // generic kernels: any radius, any subsampling.  One thread per output sample.
 // Used for parameter combinations the tiled kernels are not instantiated for,
@@ -757,12 +759,12 @@ track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n,
 // kernel classes, for launch accounting and per-kernel event timing
 enum KernelId {
   KID_SMOOTH_U8 = 0, KID_GRAD, KID_PYRDOWN, KID_TRACK, KID_MINEIG, KID_SORT, KID_STAMP,
-  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_COUNT
+  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_L0_FUSED, KID_COUNT
 };
 static const char* const kKernelNames[KID_COUNT] = {
   "smooth_u8_tile", "grad_tile", "pyrdown_tile", "track_kernel", "mineig_kernel",
   "cub_radix_sort", "stamp_existing_kernel", "enforce_mindist_kernel",
-  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel"
+  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel", "l0_fused_kernel"
 };
 static constexpr int PROF_POOL = 2048;     // event pairs in flight before folding
 
@@ -780,14 +782,14 @@ struct klt_dev {
   cudaStream_t stream;
   char err[512];
   unsigned long long launches;
-  int last_path, force_generic;
+  int last_path, force_generic, no_fused, last_fused;
   // geometry
   int W, H, L, ss;
   PyrSet set[2];
   float* arena;
   float* tmp;                // generic path: horizontal-pass result, W*H floats
-  unsigned char* frame;      // dense u8 staging of the frame being built
-  size_t frame_cap;
+  unsigned char* frame;      // u8 staging of the frame being built, row pitch frame_pitch
+  size_t frame_cap; int frame_pitch;
   // features
   float *d_x, *d_y; int* d_val; int feat_cap; int feat_n;
   float *h_x, *h_y; int* h_val;   // pinned staging
@@ -872,6 +874,8 @@ extern "C" void* klt_dev_stream(const klt_dev* d) { return (void*)d->stream; }
 extern "C" unsigned long long klt_dev_launch_count(const klt_dev* d) { return d->launches; }
 extern "C" int klt_dev_last_build_path(const klt_dev* d) { return d->last_path; }
 extern "C" void klt_dev_force_generic(klt_dev* d, int on) { d->force_generic = on; }
+extern "C" void klt_dev_disable_fused(klt_dev* d, int on) { d->no_fused = on; }
+extern "C" int klt_dev_last_build_fused(const klt_dev* d) { return d->last_fused; }
 
 extern "C" int klt_dev_create(int device, klt_dev** out) {
   *out = nullptr;
@@ -1054,6 +1058,64 @@ static int pyrdown_dispatch(klt_dev* d, int ss, const float* src, int spitch, in
   return 0;
 }
 
+// ---- TMA tensor maps -----------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn tma_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    cudaGetLastError();
+  }
+  return fn;
+}
+// 2-D row-major tensor of `elem` bytes per element; zero fill outside [0,w) x [0,h)
+static bool make_tensor_map(CUtensorMap* m, const void* base, CUtensorMapDataType dt, int elem, int w, int h,
+                            size_t pitch_bytes, int box_w, int box_h) {
+  EncodeTiledFn enc = tma_encoder();
+  if (!enc) return false;
+  if (((uintptr_t)base & 15) || (pitch_bytes & 15) || ((box_w * elem) & 15) || box_w > 256 || box_h > 256)
+    return false;
+  cuuint64_t dims[2] = {(cuuint64_t)w, (cuuint64_t)h};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// fused level 0 (u8 -> L0, gx0, gy0); *done = false if this frame / these taps do not qualify
+template <bool EXACT>
+static int l0_fused_dispatch(klt_dev* d, const unsigned char* src, int spitch, int W, int H, const TapsR& ts,
+                             const TapsR& tg, const TapsR& td, const Level& lv, bool* done) {
+  *done = false;
+  if (ts.w != 2 * L0Geo::RS + 1 || tg.w != 2 * L0Geo::RG + 1 || td.w != 2 * L0Geo::RG + 1) return 0;
+  CUtensorMap map;
+  if (!make_tensor_map(&map, src, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, W, H, (size_t)spitch, L0Geo::U8_W,
+                       L0Geo::U8_H))
+    return 0;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[EXACT]) {
+    CU(cudaFuncSetAttribute(l0_fused_kernel<EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L0Geo::SMEM));
+    attr_set[EXACT] = true;
+  }
+  dim3 grid((W + L0Geo::TX - 1) / L0Geo::TX, (H + L0Geo::TY - 1) / L0Geo::TY);
+  { Launch l(d, KID_L0_FUSED);
+    l0_fused_kernel<EXACT><<<grid, 256, L0Geo::SMEM, d->stream>>>(map, W, H, ts, tg, td, lv.img, lv.gx, lv.gy,
+                                                                  lv.pitch); }
+  *done = true;
+  return 0;
+}
+
 // generic two-kernel separable pass through d->tmp
 template <typename SrcT, bool EXACT>
 static int generic_separable(klt_dev* d, const SrcT* src, int spitch, int W, int H, const TapsR& kh,
@@ -1075,8 +1137,19 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
                       const klt_dev_build_desc* q) {
   const int W = q->ncols, H = q->nrows;
   bool tiled_all = true, done = false;
-  // level 0
-  if (q->smooth) {
+  int grad_from = 0;                 // first level whose gradients are still to be computed
+  // level 0: fused TMA kernel (smooth + both gradients) when the frame and taps qualify
+  if (q->smooth && !d->force_generic && !d->no_fused) {
+    const TapsR ts = reversed(q->smooth_taps.gauss, q->smooth_taps.gauss_width);
+    const TapsR tg = reversed(q->grad_taps.gauss, q->grad_taps.gauss_width);
+    const TapsR td = reversed(q->grad_taps.deriv, q->grad_taps.deriv_width);
+    if (l0_fused_dispatch<EXACT>(d, src, spitch, W, H, ts, tg, td, S.lv[0], &done)) return 1;
+    if (done) grad_from = 1;
+  }
+  d->last_fused = grad_from;
+  if (grad_from == 1) {
+    // nothing left to do for level 0
+  } else if (q->smooth) {
     const TapsR ts = reversed(q->smooth_taps.gauss, q->smooth_taps.gauss_width);
     done = false;
     if (!d->force_generic)
@@ -1112,7 +1185,7 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
   {
     const TapsR tg = reversed(q->grad_taps.gauss, q->grad_taps.gauss_width);
     const TapsR td = reversed(q->grad_taps.deriv, q->grad_taps.deriv_width);
-    for (int l = 0; l < q->nlevels_built; ++l) {
+    for (int l = grad_from; l < q->nlevels_built; ++l) {
       const Level& a = S.lv[l];
       done = false;
       if (!d->force_generic)
@@ -1149,16 +1222,21 @@ extern "C" int klt_dev_build(klt_dev* d, int slot, const unsigned char* img, int
   const unsigned char* src = img;
   int spitch = (int)img_pitch;
   if (!img_is_device) {
-    const size_t bytes = (size_t)W * H;
+    const int fp = (W + 15) / 16 * 16;          // TMA needs a 16 B multiple row pitch
+    const size_t bytes = (size_t)fp * H;
     if (d->frame_cap < bytes) {
       CU(cudaStreamSynchronize(d->stream));
       cudaFree(d->frame); d->frame = nullptr; d->frame_cap = 0;
       CU(cudaMalloc(&d->frame, bytes));
       d->frame_cap = bytes;
     }
-    CU(cudaMemcpyAsync(d->frame, img, bytes, cudaMemcpyHostToDevice, d->stream));
+    if (fp == W)
+      CU(cudaMemcpyAsync(d->frame, img, bytes, cudaMemcpyHostToDevice, d->stream));
+    else
+      CU(cudaMemcpy2DAsync(d->frame, fp, img, W, W, H, cudaMemcpyHostToDevice, d->stream));
+    d->frame_pitch = fp;
     src = d->frame;
-    spitch = W;
+    spitch = fp;
   } else if (spitch < W) {
     return fail(d, "device frame pitch %d < width %d", spitch, W);
   }

@@ -74,6 +74,8 @@ DEV_API = {
     "klt_dev_launch_count": (C.c_ulonglong, [C.c_void_p]),
     "klt_dev_last_build_path": (C.c_int, [C.c_void_p]),
     "klt_dev_force_generic": (None, [C.c_void_p, C.c_int]),
+    "klt_dev_disable_fused": (None, [C.c_void_p, C.c_int]),
+    "klt_dev_last_build_fused": (C.c_int, [C.c_void_p]),
     "klt_dev_timer_start": (C.c_int, [C.c_void_p]),
     "klt_dev_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "klt_dev_profile_begin": (C.c_int, [C.c_void_p]),

@@ -25,14 +25,21 @@ def L(pkg):
     return lib
 
 
-def _check_build(L, oracle, img, tc, exact, generic, expect_tiled=None):
+def _check_build(L, oracle, img, tc, exact, generic, expect_tiled=None, expect_fused=None):
+    """generic: 0 = fastest path (fused TMA level 0 + tiled), 1 = generic kernels only,
+    2 = tiled kernels without the fused level-0 kernel"""
     dev = L.KLTB200Device(tc)
-    L.klt_dev_force_generic(dev, 1 if generic else 0)
+    L.klt_dev_force_generic(dev, 1 if generic == 1 else 0)
+    L.klt_dev_disable_fused(dev, 1 if generic == 2 else 0)
     h, w = img.shape
     q = L.build_desc(tc, w, h, exact=exact)
     L.dev_build(dev, 0, img, q)
-    if expect_tiled is not None and not generic:
+    if expect_tiled is not None and generic != 1:
         assert L.klt_dev_last_build_path(dev) == (1 if expect_tiled else 0)
+    if expect_fused is not None and generic == 0:
+        assert L.klt_dev_last_build_fused(dev) == (1 if expect_fused else 0)
+    if generic != 0:
+        assert L.klt_dev_last_build_fused(dev) == 0
     nl = tc.contents.nPyramidLevels
     got = device_pyramids(L, dev, 0, nl)
     p = params_from_tc(oracle, tc)
@@ -52,31 +59,59 @@ def _check_build(L, oracle, img, tc, exact, generic, expect_tiled=None):
                 e = rel_err(a, b).max()
                 assert e <= REL_TOL_IMAGES, "%s level %d: rel err %g" % (names[which], l, e)
     L.klt_dev_force_generic(dev, 0)
+    L.klt_dev_disable_fused(dev, 0)
 
 
-SHAPES = [(240, 320), (243, 321), (48, 64), (37, 1000), (600, 33), (130, 257)]
+SHAPES = [(240, 320), (243, 321), (48, 64), (37, 1000), (600, 33), (130, 257), (64, 64), (65, 129),
+          (200, 16), (40, 44)]
 
 
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("exact", [1, 0])
-@pytest.mark.parametrize("generic", [0, 1])
+@pytest.mark.parametrize("generic", [0, 1, 2])
 def test_default_config_pyramids(L, oracle, shape, exact, generic):
     h, w = shape
     img = synth_image(w, h, seed=h * 1000 + w)
     tc = L.KLTCreateTrackingContext()          # L=2, ss=4, window 7
-    _check_build(L, oracle, img, tc, exact, generic, expect_tiled=True)
+    _check_build(L, oracle, img, tc, exact, generic, expect_tiled=True, expect_fused=True)
     L.KLTFreeTrackingContext(tc)
 
 
 @pytest.mark.parametrize("exact", [1, 0])
-@pytest.mark.parametrize("generic", [0, 1])
+@pytest.mark.parametrize("generic", [0, 1, 2])
 def test_config4_shape_four_levels_ss2(L, oracle, exact, generic):
     img = synth_image(700, 500, seed=4)
     tc = L.KLTCreateTrackingContext()
     tc.contents.nPyramidLevels, tc.contents.subsampling = 4, 2
     L.KLTUpdateTCBorder(tc)
     assert tc.contents.borderx == 64
-    _check_build(L, oracle, img, tc, exact, generic, expect_tiled=True)
+    _check_build(L, oracle, img, tc, exact, generic, expect_tiled=True, expect_fused=True)
+    L.KLTFreeTrackingContext(tc)
+
+
+def test_fused_kernel_on_device_resident_pitched_frame(L, oracle):
+    """frame already in HBM with a row pitch larger than its width (torch tensor)"""
+    import torch
+    h, w, pitch = 300, 500, 512
+    img = synth_image(w, h, seed=77)
+    buf = torch.zeros((h, pitch), dtype=torch.uint8, device="cuda")
+    buf[:, :w] = torch.from_numpy(img).cuda()
+    torch.cuda.synchronize()
+    tc = L.KLTCreateTrackingContext()
+    dev = L.KLTB200Device(tc)
+    for exact in (1, 0):
+        q = L.build_desc(tc, w, h, exact=exact)
+        L.dev_build(dev, 1, None, q, device_ptr=buf.data_ptr(), pitch=pitch)
+        L.dev_check(dev, L.klt_dev_sync(dev))
+        assert L.klt_dev_last_build_fused(dev) == 1
+        want = oracle.build_pyramids(img, params_from_tc(oracle, tc))
+        for which in range(3):
+            for l in range(2):
+                a, b = L.dev_level(dev, 1, which, l), want.level(which, l)
+                if exact:
+                    assert np.array_equal(a, b), (which, l)
+                else:
+                    assert rel_err(a, b).max() <= REL_TOL_IMAGES
     L.KLTFreeTrackingContext(tc)
 
 
