@@ -143,7 +143,8 @@ int klt_dev_last_build_path(const klt_dev *d);
 void klt_dev_force_generic(klt_dev *d, int on);
 /* keep the tiled kernels but not the fused TMA level-0 kernel (cross-check); default 0 */
 void klt_dev_disable_fused(klt_dev *d, int on);
-/* 1 if the last klt_dev_build ran the fused TMA level-0 kernel */
+/* number of pyramid levels the last klt_dev_build produced with the fused TMA kernels
+ * (level 0: l0_fused_kernel, coarser levels: level_fused_kernel); 0 if none */
 int klt_dev_last_build_fused(const klt_dev *d);
 /* device time between the two calls, measured with CUDA events recorded on the
  * context's own stream (the stream the kernels run on) */

@@ -759,12 +759,12 @@ track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n,
 // kernel classes, for launch accounting and per-kernel event timing
 enum KernelId {
   KID_SMOOTH_U8 = 0, KID_GRAD, KID_PYRDOWN, KID_TRACK, KID_MINEIG, KID_SORT, KID_STAMP,
-  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_L0_FUSED, KID_COUNT
+  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_L0_FUSED, KID_LEVEL_FUSED, KID_COUNT
 };
 static const char* const kKernelNames[KID_COUNT] = {
   "smooth_u8_tile", "grad_tile", "pyrdown_tile", "track_kernel", "mineig_kernel",
   "cub_radix_sort", "stamp_existing_kernel", "enforce_mindist_kernel",
-  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel", "l0_fused_kernel"
+  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel", "l0_fused_kernel", "level_fused_kernel"
 };
 static constexpr int PROF_POOL = 2048;     // event pairs in flight before folding
 
@@ -778,7 +778,7 @@ struct PyrSet {
 };
 
 struct klt_dev {
-  int device;
+  int device, num_sms;
   cudaStream_t stream;
   char err[512];
   unsigned long long launches;
@@ -891,6 +891,8 @@ extern "C" int klt_dev_create(int device, klt_dev** out) {
   klt_dev* c = (klt_dev*)calloc(1, sizeof(klt_dev));
   if (!c) return fail(nullptr, "out of host memory");
   c->device = device;
+  cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
+  if (c->num_sms < 1) c->num_sms = 1;
   e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { free(c); return fail(nullptr, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
   e = cudaMalloc(&c->d_live, sizeof(unsigned long long));
@@ -1093,12 +1095,16 @@ static bool make_tensor_map(CUtensorMap* m, const void* base, CUtensorMapDataTyp
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static bool fused_grad_taps_ok(const TapsR& tg, const TapsR& td) {
+  return tg.w == 2 * FUSED_RG + 1 && td.w == 2 * FUSED_RG + 1 && td.k[FUSED_RG] == 0.0f;
+}
+
 // fused level 0 (u8 -> L0, gx0, gy0); *done = false if this frame / these taps do not qualify
 template <bool EXACT>
 static int l0_fused_dispatch(klt_dev* d, const unsigned char* src, int spitch, int W, int H, const TapsR& ts,
                              const TapsR& tg, const TapsR& td, const Level& lv, bool* done) {
   *done = false;
-  if (ts.w != 2 * L0Geo::RS + 1 || tg.w != 2 * L0Geo::RG + 1 || td.w != 2 * L0Geo::RG + 1) return 0;
+  if (ts.w != 2 * L0Geo::RS + 1 || !fused_grad_taps_ok(tg, td)) return 0;
   CUtensorMap map;
   if (!make_tensor_map(&map, src, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, W, H, (size_t)spitch, L0Geo::U8_W,
                        L0Geo::U8_H))
@@ -1108,11 +1114,48 @@ static int l0_fused_dispatch(klt_dev* d, const unsigned char* src, int spitch, i
     CU(cudaFuncSetAttribute(l0_fused_kernel<EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L0Geo::SMEM));
     attr_set[EXACT] = true;
   }
-  dim3 grid((W + L0Geo::TX - 1) / L0Geo::TX, (H + L0Geo::TY - 1) / L0Geo::TY);
+  const int tiles_x = (W + L0Geo::TX - 1) / L0Geo::TX, tiles_y = (H + L0Geo::TY - 1) / L0Geo::TY;
+  const int ntiles = tiles_x * tiles_y;
+  const int grid = ntiles < 3 * d->num_sms ? ntiles : 3 * d->num_sms;       // persistent, 3 CTAs / SM
   { Launch l(d, KID_L0_FUSED);
-    l0_fused_kernel<EXACT><<<grid, 256, L0Geo::SMEM, d->stream>>>(map, W, H, ts, tg, td, lv.img, lv.gx, lv.gy,
-                                                                  lv.pitch); }
+    l0_fused_kernel<EXACT><<<grid, 256, L0Geo::SMEM, d->stream>>>(map, W, H, tiles_x, ntiles, ts, tg, td,
+                                                                  lv.img, lv.gx, lv.gy, lv.pitch); }
   *done = true;
+  return 0;
+}
+
+// fused coarser level (L_{l-1} -> L_l, gx_l, gy_l)
+template <int SS, int R, int TX, int TY, bool EXACT>
+static int launch_level_fused(klt_dev* d, const Level& a, const Level& b, const TapsR& tp, const TapsR& tg,
+                              const TapsR& td, bool* done) {
+  using G = LvGeo<SS, R, TX, TY>;
+  *done = false;
+  CUtensorMap map;
+  if (!make_tensor_map(&map, a.img, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.w, a.h, (size_t)a.pitch * 4, G::SW, G::SH))
+    return 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(level_fused_kernel<SS, R, TX, TY, EXACT>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
+    attr_set = true;
+  }
+  const int tiles_x = (b.w + TX - 1) / TX, tiles_y = (b.h + TY - 1) / TY;
+  const int ntiles = tiles_x * tiles_y;
+  const int grid = ntiles < 2 * d->num_sms ? ntiles : 2 * d->num_sms;       // persistent, 2 CTAs / SM
+  { Launch l(d, KID_LEVEL_FUSED);
+    level_fused_kernel<SS, R, TX, TY, EXACT><<<grid, 256, G::SMEM, d->stream>>>(
+        map, a.w, a.h, b.w, b.h, tiles_x, ntiles, tp, tg, td, b.img, b.gx, b.gy, b.pitch); }
+  *done = true;
+  return 0;
+}
+template <bool EXACT>
+static int level_fused_dispatch(klt_dev* d, int ss, const Level& a, const Level& b, const TapsR& tp,
+                                const TapsR& tg, const TapsR& td, bool* done) {
+  *done = false;
+  if (!fused_grad_taps_ok(tg, td)) return 0;
+  const int r = tp.w / 2;
+  if (ss == 2 && r == 5) return launch_level_fused<2, 5, 64, 32, EXACT>(d, a, b, tp, tg, td, done);
+  if (ss == 4 && r == 10) return launch_level_fused<4, 10, 32, 16, EXACT>(d, a, b, tp, tg, td, done);
   return 0;
 }
 
@@ -1165,12 +1208,20 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
     u8_to_f32_kernel<<<g, b, 0, d->stream>>>(src, spitch, W, H, S.lv[0].img, S.lv[0].pitch);
   }
   // coarser levels
+  bool grads_done[KLT_DEV_MAX_LEVELS] = {false};
+  grads_done[0] = (grad_from == 1);
   if (q->nlevels_built > 1) {
     const TapsR tp = reversed(q->pyramid_taps.gauss, q->pyramid_taps.gauss_width);
+    const TapsR tg = reversed(q->grad_taps.gauss, q->grad_taps.gauss_width);
+    const TapsR td = reversed(q->grad_taps.deriv, q->grad_taps.deriv_width);
     for (int l = 1; l < q->nlevels_built; ++l) {
       const Level& a = S.lv[l - 1];
       const Level& b = S.lv[l];
       done = false;
+      if (!d->force_generic && !d->no_fused) {
+        if (level_fused_dispatch<EXACT>(d, q->subsampling, a, b, tp, tg, td, &done)) return 1;
+        if (done) { grads_done[l] = true; d->last_fused += 1; continue; }
+      }
       if (!d->force_generic)
         if (pyrdown_dispatch<EXACT>(d, q->subsampling, a.img, a.pitch, a.w, a.h, tp, b.img, b.pitch,
                                     b.w, b.h, &done)) return 1;
@@ -1185,7 +1236,8 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
   {
     const TapsR tg = reversed(q->grad_taps.gauss, q->grad_taps.gauss_width);
     const TapsR td = reversed(q->grad_taps.deriv, q->grad_taps.deriv_width);
-    for (int l = grad_from; l < q->nlevels_built; ++l) {
+    for (int l = 0; l < q->nlevels_built; ++l) {
+      if (grads_done[l]) continue;
       const Level& a = S.lv[l];
       done = false;
       if (!d->force_generic)

@@ -1,22 +1,30 @@
 // klt_fused.cuh -- TMA-staged, fused frame kernels (included by klt_dev.cu).
 //
-// l0_fused_kernel: one launch turns a u8 frame into level 0 of all three
-// pyramids.  Replaces _KLTToFloatImage + _KLTComputeSmoothedImage +
-// _KLTComputeGradients at level 0 (reference src/V1/convolve.c:37-53,273-314 as
-// called from trackFeatures.c:1311-1321) without the float image, the
-// horizontal-pass temporaries or the smoothed image ever being re-read from HBM:
-// algorithmic traffic = 1 B read + 12 B written per pixel.
+// l0_fused_kernel   : u8 frame          -> L0, gx0, gy0      (1 B read + 12 B written per pixel)
+// level_fused_kernel: L_{l-1} (float)   -> L_l, gx_l, gy_l   (one pyramid step + its gradients)
 //
-// Tile = 64x64 outputs, 256 threads, 4 stages in shared memory:
-//   TMA   u8 box 96x74 at (x0-16, y0-5)         (zero fill outside the image)
-//   A     horizontal Gaussian  -> Hs  [74][72]   (8 outputs / thread, one LDS.128 of 16 px)
-//   B     vertical   Gaussian  -> L0  [70][72]   (4 cols x 5 rows / thread) + float4 stores of L0
-//   C     horizontal DoG and G -> Hd,Hg [70][64] (8 outputs / thread)
-//   D     vertical   G and DoG -> gx, gy         (4 cols x 8 rows / thread, float4 stores)
-// Buffers have their column origin at x0-4 (16 B aligned) and row pitches chosen
-// so that the 128-bit shared accesses of a quarter warp fall in distinct banks.
-// The zero bands of the separable passes (convolve.c:164-178,216-237) are applied
-// only by tiles that touch the image border (BORDER template flag).
+// Replaces, per level, _KLTToFloatImage + _KLTComputeSmoothedImage (+ the smooth/subsample
+// step of _KLTComputePyramid) + _KLTComputeGradients (reference src/V1/convolve.c:37-53,
+// 273-314, src/V1/pyramid.c:112-124 as sequenced by trackFeatures.c:1311-1321) without any
+// float input image, horizontal-pass temporary or smoothed-before-subsample image touching HBM.
+//
+// Both kernels are persistent (grid = resident CTAs, static round-robin over tiles): the
+// TMA load of the next tile's source box is issued as soon as the current one has been
+// consumed, so its latency hides behind the remaining stages.  All stages of a tile run in
+// shared memory:
+//   L0   : TMA u8 box -> A: horizontal Gaussian -> B: vertical Gaussian (+ L0 stores)
+//   level: TMA f32 box -> P1: horizontal Gaussian at the kept columns -> P2: vertical Gaussian
+//          at the kept rows (+ L_l stores)
+//   both : C: horizontal DoG and Gaussian of the level tile -> D: vertical Gaussian / DoG,
+//          float4 stores of gx, gy
+// Every buffer has its column origin at x0-4 (16 B aligned) and a row pitch that is an odd
+// number of 16 B chunks, so that the quarter-warp lane mappings used below make every 128-bit
+// shared access conflict free.  128-bit shared loads are issued through inline PTX: left to
+// the compiler, windows with unused edge elements get narrowed into conflicting 32/64-bit loads.
+//
+// Zero bands of the separable passes (convolve.c:164-178, :216-237) are applied only by tiles
+// that touch the image border (BORDER flag, CTA uniform).  The derivative kernel's centre tap
+// is exactly 0 (convolve.c:79: -i * gauss with i = 0) and is skipped; the host checks that.
 #pragma once
 
 #include <cuda.h>          // CUtensorMap (types only; the encoder is fetched at run time)
@@ -45,13 +53,24 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phas
       "}" ::"r"(smem_u32(bar)), "r"(phase)
       : "memory");
 }
+// The innermost start coordinate must be a multiple of 16 bytes (measured on B200: a u8
+// box starting at x0-8 raises "illegal instruction"; x0-16 and negative / out-of-range
+// coordinates are fine and zero-filled).
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int cx, int cy,
                                             unsigned long long* bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<unsigned long long>(map)), "r"(cx), "r"(cy), "r"(smem_u32(bar))
       : "memory");
+}
+__device__ __forceinline__ float4 lds128(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(smem_u32(p)));
+  return v;
 }
 
 // u8 -> f32 without the conversion pipe: 0x4B0000bb is the float 2^23 + bb.
@@ -59,44 +78,86 @@ __device__ __forceinline__ float u8_to_float(unsigned word, unsigned byte_sel) {
   return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7440u + byte_sel)) - 8388608.0f;
 }
 
-struct L0Geo {
-  static constexpr int TX = 64, TY = 64;
-  static constexpr int RS = 2, RG = 3;                 // smoothing / gradient radii
-  static constexpr int U8_W = 96, U8_H = TY + 2 * (RS + RG);          // 96 x 74 bytes, cols <-> x0-16+c
-  static constexpr int HS_P = 76, HS_H = U8_H;                         // cols <-> x0-4+c
-  static constexpr int L0_P = 76, L0_H = TY + 2 * RG;                  // 70 rows <-> y0-3+r
-  static constexpr int HG_P = 68, HG_H = L0_H;                         // cols <-> x0+c
-  static constexpr int OFF_U8 = 0;
-  static constexpr int OFF_HS = U8_W * U8_H;                           // 7104, 16 B aligned
-  static constexpr int OFF_L0 = OFF_HS + HS_H * HS_P * 4;
-  static constexpr int OFF_HD = OFF_HS;                                // Hd reuses Hs
-  static constexpr int OFF_HG = OFF_L0 + L0_H * L0_P * 4;
-  static constexpr int OFF_BAR = OFF_HG + HG_H * HG_P * 4;
-  static constexpr int SMEM = OFF_BAR + 16;
-};
+__device__ __forceinline__ void fma4(float4& a, const float4& v, float k, bool exact) {
+  if (exact) {
+    a.x = __fadd_rn(a.x, __fmul_rn(v.x, k)); a.y = __fadd_rn(a.y, __fmul_rn(v.y, k));
+    a.z = __fadd_rn(a.z, __fmul_rn(v.z, k)); a.w = __fadd_rn(a.w, __fmul_rn(v.w, k));
+  } else {
+    a.x = fmaf(v.x, k, a.x); a.y = fmaf(v.y, k, a.y);
+    a.z = fmaf(v.z, k, a.z); a.w = fmaf(v.w, k, a.w);
+  }
+}
 
-// vertical 7-tap pass of 4 columns x 8 output rows from a shared [.][HG_P] buffer, scatter
-// form: every loaded row feeds the (up to 7) outputs it belongs to, taps in increasing order.
-template <bool EXACT, bool BORDER>
-__device__ __forceinline__ void l0_stage_d(const float* __restrict__ src, const TapsR& tk,
-                                           float* __restrict__ out, int opitch, int xg, int yg0,
-                                           int W, int H) {
-  constexpr int PY = 8, R = L0Geo::RG, P = L0Geo::HG_P;
+static constexpr int FUSED_RG = 3;       // gradient radius the fused kernels are built for
+
+// ---- stage C: horizontal DoG and Gaussian of a level tile ---------------------------------
+// sL [LH][LP]: tile col c <-> global x0-4+c.   sHd, sHg [LH][HP]: col c <-> global x0+c.
+// 8 outputs per thread from a 16-float window (4 x LDS.128); a warp covers 8 groups x 4 rows
+// (TX = 64) or 4 groups x 8 rows (TX = 32); a quarter warp is 4 groups x 2 rows, conflict free
+// because LP/4 and HP/4 are odd.
+template <bool EXACT, bool BORDER, int TX, int LH, int LP, int HP>
+__device__ __forceinline__ void stage_hgrad(const float* sL, float* sHd, float* sHg, const TapsR& tg,
+                                            const TapsR& td, int x0, int W) {
+  constexpr int RG = FUSED_RG;
+  constexpr int NGC = TX / 8;                       // groups per row: 8 or 4
+  constexpr int RPW = 32 / NGC;                     // rows per warp: 4 or 8
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & 3, rpar = (lane >> 2) & 1, rem = lane >> 3;
+  const int g = NGC == 8 ? 4 * (rem & 1) + sub : sub;
+  const int rl = NGC == 8 ? 2 * (rem >> 1) + rpar : 2 * rem + rpar;
+  for (int rb = warp * RPW; rb < LH; rb += 8 * RPW) {
+    const int r = rb + rl;
+    if (r < LH) {
+      float win[16];
+      const float* p = sL + r * LP + 8 * g;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const float4 t = lds128(p + 4 * v);
+        win[4 * v] = t.x; win[4 * v + 1] = t.y; win[4 * v + 2] = t.z; win[4 * v + 3] = t.w;
+      }
+      float od[8], og[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float a = 0.0f, b = 0.0f;
+#pragma unroll
+        for (int m = 0; m < 2 * RG + 1; ++m)
+          if (m != RG) a = mac<EXACT>(a, win[q + 1 + m], td.k[m]);        // centre tap is 0
+#pragma unroll
+        for (int m = 0; m < 2 * RG + 1; ++m) b = mac<EXACT>(b, win[q + 1 + m], tg.k[m]);
+        if (BORDER) {
+          const int xg = x0 + 8 * g + q;
+          if (xg < RG || xg >= W - RG) { a = 0.0f; b = 0.0f; }
+        }
+        od[q] = a; og[q] = b;
+      }
+      float4* dd = reinterpret_cast<float4*>(sHd + r * HP + 8 * g);
+      float4* dg = reinterpret_cast<float4*>(sHg + r * HP + 8 * g);
+      dd[0] = make_float4(od[0], od[1], od[2], od[3]);
+      dd[1] = make_float4(od[4], od[5], od[6], od[7]);
+      dg[0] = make_float4(og[0], og[1], og[2], og[3]);
+      dg[1] = make_float4(og[4], og[5], og[6], og[7]);
+    }
+  }
+}
+
+// ---- stage D: vertical 7-tap pass, 4 columns x PY rows per thread, straight to HBM ------------
+// scatter form: every loaded row feeds the outputs it belongs to, taps in increasing order
+// (== the reference's summation order for each output).
+template <bool EXACT, bool BORDER, int PY, int HP, bool SKIP_CENTRE>
+__device__ __forceinline__ void stage_vgrad(const float* __restrict__ src, const TapsR& tk,
+                                            float* __restrict__ out, int opitch, int xg, int yg0,
+                                            int W, int H) {
+  constexpr int R = FUSED_RG;
   float4 acc[PY];
 #pragma unroll
   for (int q = 0; q < PY; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int i = 0; i < PY + 2 * R; ++i) {
-    const float4 v = *reinterpret_cast<const float4*>(src + i * P);
+    const float4 v = lds128(src + i * HP);
 #pragma unroll
     for (int q = 0; q < PY; ++q) {
       const int m = i - q;
-      if (m >= 0 && m <= 2 * R) {
-        acc[q].x = mac<EXACT>(acc[q].x, v.x, tk.k[m]);
-        acc[q].y = mac<EXACT>(acc[q].y, v.y, tk.k[m]);
-        acc[q].z = mac<EXACT>(acc[q].z, v.z, tk.k[m]);
-        acc[q].w = mac<EXACT>(acc[q].w, v.w, tk.k[m]);
-      }
+      if (m >= 0 && m <= 2 * R && !(SKIP_CENTRE && m == R)) fma4(acc[q], v, tk.k[m], EXACT);
     }
   }
 #pragma unroll
@@ -111,125 +172,131 @@ __device__ __forceinline__ void l0_stage_d(const float* __restrict__ src, const 
   }
 }
 
+// gx = V_gauss(Hd), gy = V_deriv(Hg); first half of the CTA does gx, second half gy (warp uniform)
+template <bool EXACT, bool BORDER, int TX, int TY, int PY, int HP>
+__device__ __forceinline__ void stage_vgrad_both(const float* sHd, const float* sHg, const TapsR& tg,
+                                                 const TapsR& td, float* out_gx, float* out_gy,
+                                                 int opitch, int x0, int y0, int W, int H) {
+  constexpr int NCG = TX / 4, NRB = TY / PY, ITEMS = NCG * NRB;       // per output image
+  static_assert(ITEMS <= 128 && 128 % ITEMS == 0, "stage D mapping");
+  const int tid = threadIdx.x;
+  const int t = tid & 127;
+  if (t < ITEMS) {
+    const int blk = t / NCG, j = t - blk * NCG;
+    if (tid < 128)
+      stage_vgrad<EXACT, BORDER, PY, HP, false>(sHd + (blk * PY) * HP + 4 * j, tg, out_gx, opitch,
+                                                x0 + 4 * j, y0 + blk * PY, W, H);
+    else
+      stage_vgrad<EXACT, BORDER, PY, HP, true>(sHg + (blk * PY) * HP + 4 * j, td, out_gy, opitch,
+                                               x0 + 4 * j, y0 + blk * PY, W, H);
+  }
+}
+
+// ============================================================================================
+// level 0
+// ============================================================================================
+struct L0Geo {
+  static constexpr int TX = 64, TY = 64;
+  static constexpr int RS = 2, RG = FUSED_RG;                          // smoothing / gradient radii
+  static constexpr int U8_W = 96, U8_H = TY + 2 * (RS + RG);           // 96 x 74 bytes, col c <-> x0-16+c
+  static constexpr int HS_P = 76, HS_H = U8_H;                         // col c <-> x0-4+c, row r <-> y0-5+r
+  static constexpr int L0_P = 76, L0_H = TY + 2 * RG;                  // row r <-> y0-3+r
+  static constexpr int HG_P = 68, HG_H = L0_H;                         // col c <-> x0+c
+  static constexpr int OFF_U8 = 0;
+  static constexpr int OFF_HS = U8_W * U8_H;                           // 7104
+  static constexpr int OFF_L0 = OFF_HS + HS_H * HS_P * 4;
+  static constexpr int OFF_HD = OFF_HS;                                // Hd reuses Hs
+  static constexpr int OFF_HG = OFF_L0 + L0_H * L0_P * 4;
+  static constexpr int OFF_BAR = OFF_HG + HG_H * HG_P * 4;
+  static constexpr int SMEM = OFF_BAR + 16;
+};
+
+// stage A item: 8 outputs (Hs cols 8g..8g+7 <-> global x0-4+8g+q) of row r from 12 u8 pixels
 template <bool EXACT, bool BORDER>
-__device__ __forceinline__ void l0_fused_tile(unsigned char* smem, const CUtensorMap* map, int W, int H,
-                                              const TapsR& ts, const TapsR& tg, const TapsR& td,
-                                              float* __restrict__ out_img, float* __restrict__ out_gx,
-                                              float* __restrict__ out_gy, int opitch, int x0, int y0) {
+__device__ __forceinline__ void l0_stage_a_item(const unsigned char* sU8, float* sHs, const TapsR& ts,
+                                                int r, int g, int x0, int W) {
+  using G = L0Geo;
+  constexpr int RS = G::RS;
+  const uint2 wa = *reinterpret_cast<const uint2*>(sU8 + r * G::U8_W + 8 * g + 8);
+  const uint2 wb = *reinterpret_cast<const uint2*>(sU8 + r * G::U8_W + 8 * g + 16);
+  float px[12];                                         // global cols x0-6+8g .. x0+5+8g
+  px[0] = u8_to_float(wa.x, 2); px[1] = u8_to_float(wa.x, 3);
+  px[2] = u8_to_float(wa.y, 0); px[3] = u8_to_float(wa.y, 1);
+  px[4] = u8_to_float(wa.y, 2); px[5] = u8_to_float(wa.y, 3);
+  px[6] = u8_to_float(wb.x, 0); px[7] = u8_to_float(wb.x, 1);
+  px[8] = u8_to_float(wb.x, 2); px[9] = u8_to_float(wb.x, 3);
+  px[10] = u8_to_float(wb.y, 0); px[11] = u8_to_float(wb.y, 1);
+  float o[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int m = 0; m < 2 * RS + 1; ++m) acc = mac<EXACT>(acc, px[q + m], ts.k[m]);
+    if (BORDER) {
+      const int xg = x0 - 4 + 8 * g + q;
+      if (xg < RS || xg >= W - RS) acc = 0.0f;
+    }
+    o[q] = acc;
+  }
+  float4* dst = reinterpret_cast<float4*>(sHs + r * G::HS_P + 8 * g);
+  dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+  dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+}
+
+template <bool EXACT, bool BORDER>
+__device__ __forceinline__ void l0_fused_tile(unsigned char* smem, int W, const TapsR& ts, int x0) {
+  using G = L0Geo;
+  const unsigned char* sU8 = smem + G::OFF_U8;
+  float* sHs = reinterpret_cast<float*>(smem + G::OFF_HS);
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+
+  // ---- stage A: horizontal Gaussian, u8 -> Hs: 9 groups of 8 columns x 74 rows -------------
+  {
+    const int sub = lane & 3, rpar = (lane >> 2) & 1, half = (lane >> 3) & 1, rpair = lane >> 4;
+    for (int rb = warp * 4; rb < G::HS_H; rb += 32) {
+      const int r = rb + 2 * rpair + rpar;
+      if (r < G::HS_H) l0_stage_a_item<EXACT, BORDER>(sU8, sHs, ts, r, 4 * half + sub, x0, W);
+    }
+    if (tid < G::HS_H) l0_stage_a_item<EXACT, BORDER>(sU8, sHs, ts, tid, 8, x0, W);   // 9th group
+  }
+}
+
+template <bool EXACT, bool BORDER>
+__device__ __forceinline__ void l0_fused_tile_rest(unsigned char* smem, int W, int H, const TapsR& ts,
+                                                   const TapsR& tg, const TapsR& td,
+                                                   float* __restrict__ out_img,
+                                                   float* __restrict__ out_gx,
+                                                   float* __restrict__ out_gy, int opitch, int x0,
+                                                   int y0) {
   using G = L0Geo;
   constexpr int RS = G::RS, RG = G::RG;
-  unsigned char* sU8 = smem + G::OFF_U8;
   float* sHs = reinterpret_cast<float*>(smem + G::OFF_HS);
   float* sL0 = reinterpret_cast<float*>(smem + G::OFF_L0);
   float* sHd = reinterpret_cast<float*>(smem + G::OFF_HD);
   float* sHg = reinterpret_cast<float*>(smem + G::OFF_HG);
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + G::OFF_BAR);
   const int tid = threadIdx.x;
 
-  if (tid == 0) {
-    mbar_init(bar, 1);
-  }
-  __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(bar, G::U8_W * G::U8_H);
-    // the innermost TMA start coordinate must be a multiple of 16 bytes (measured on B200:
-    // x0-8 raises 'illegal instruction'), hence the 16-column left margin of the u8 tile
-    tma_load_2d(sU8, map, x0 - 16, y0 - (RS + RG), bar);
-  }
-  mbar_wait(bar, 0);
-
-  // lane -> (row, group) mapping shared by stages A and C: a quarter warp covers
-  // 4 groups x 2 rows, which with the odd (in 16 B chunks) pitches is conflict free.
-  const int lane = tid & 31, warp = tid >> 5;
-  const int sub = lane & 3, rpar = (lane >> 2) & 1, half = (lane >> 3) & 1, rpair = lane >> 4;
-
-  // ---- stage A: horizontal Gaussian, u8 -> Hs ------------------------------------------
-  // 9 groups of 8 columns per row (72 cols <-> x0-4 .. x0+67); a warp takes 4 rows x 8 groups,
-  // the 9th group of every row is handled by a tail loop.
-  for (int rb = warp * 4; rb < G::HS_H; rb += 32) {
-    const int r = rb + 2 * rpair + rpar;
-    const int g = 4 * half + sub;
-    if (r < G::HS_H) {
-      const uint2 wa = *reinterpret_cast<const uint2*>(sU8 + r * G::U8_W + 8 * g + 8);
-      const uint2 wb = *reinterpret_cast<const uint2*>(sU8 + r * G::U8_W + 8 * g + 16);
-      const uint4 w = make_uint4(wa.x, wa.y, wb.x, wb.y);   // global cols x0-8+8g .. x0+7+8g
-      float px[12];                                    // global cols x0-6+8g .. x0+5+8g
-      px[0] = u8_to_float(w.x, 2); px[1] = u8_to_float(w.x, 3);
-      px[2] = u8_to_float(w.y, 0); px[3] = u8_to_float(w.y, 1);
-      px[4] = u8_to_float(w.y, 2); px[5] = u8_to_float(w.y, 3);
-      px[6] = u8_to_float(w.z, 0); px[7] = u8_to_float(w.z, 1);
-      px[8] = u8_to_float(w.z, 2); px[9] = u8_to_float(w.z, 3);
-      px[10] = u8_to_float(w.w, 0); px[11] = u8_to_float(w.w, 1);
-      float o[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float acc = 0.0f;
-#pragma unroll
-        for (int m = 0; m < 2 * RS + 1; ++m) acc = mac<EXACT>(acc, px[q + m], ts.k[m]);
-        if (BORDER) {
-          const int xg = x0 - 4 + 8 * g + q;
-          if (xg < RS || xg >= W - RS) acc = 0.0f;
-        }
-        o[q] = acc;
-      }
-      float4* dst = reinterpret_cast<float4*>(sHs + r * G::HS_P + 8 * g);
-      dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-      dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-    }
-  }
-  // 9th group (cols 64..71): one item per row
-  if (tid < G::HS_H) {
-    const int r = tid, g = 8;
-    const uint2 wa = *reinterpret_cast<const uint2*>(sU8 + r * G::U8_W + 8 * g + 8);
-    const uint2 wb = *reinterpret_cast<const uint2*>(sU8 + r * G::U8_W + 8 * g + 16);
-    const uint4 w = make_uint4(wa.x, wa.y, wb.x, wb.y);
-    float px[12];
-    px[0] = u8_to_float(w.x, 2); px[1] = u8_to_float(w.x, 3);
-    px[2] = u8_to_float(w.y, 0); px[3] = u8_to_float(w.y, 1);
-    px[4] = u8_to_float(w.y, 2); px[5] = u8_to_float(w.y, 3);
-    px[6] = u8_to_float(w.z, 0); px[7] = u8_to_float(w.z, 1);
-    px[8] = u8_to_float(w.z, 2); px[9] = u8_to_float(w.z, 3);
-    px[10] = u8_to_float(w.w, 0); px[11] = u8_to_float(w.w, 1);
-    float o[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      float acc = 0.0f;
-#pragma unroll
-      for (int m = 0; m < 2 * RS + 1; ++m) acc = mac<EXACT>(acc, px[q + m], ts.k[m]);
-      if (BORDER) {
-        const int xg = x0 - 4 + 8 * g + q;
-        if (xg < RS || xg >= W - RS) acc = 0.0f;
-      }
-      o[q] = acc;
-    }
-    float4* dst = reinterpret_cast<float4*>(sHs + r * G::HS_P + 8 * g);
-    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-  }
-  __syncthreads();
-
-  // ---- stage B: vertical Gaussian, Hs -> L0 (shared + global) ------------------------------
-  // 18 column groups of 4 (cols <-> x0-4+4j) x 14 row blocks of 5 (L0 rows <-> y0-3+rr)
-  if (tid < 18 * 14) {
-    const int blk = tid / 18, j = tid - blk * 18;
+  // ---- stage B: vertical Gaussian, Hs -> L0 (shared + HBM) ------------------------------------
+  // 18 column groups of 4 (col c <-> x0-4+c) x 14 row blocks of 5.  Threads 0..223 take groups
+  // 0..15 (a quarter warp = 8 consecutive groups of one row block: contiguous 128 B), threads
+  // 224..251 the two halo groups.
+  if (tid < 252) {
     constexpr int PY = 5;
+    int blk, j;
+    if (tid < 224) { blk = tid >> 4; j = tid & 15; }
+    else { blk = (tid - 224) >> 1; j = 16 + ((tid - 224) & 1); }
     float4 acc[PY];
 #pragma unroll
     for (int q = 0; q < PY; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* src = sHs + (blk * PY) * G::HS_P + 4 * j;      // Hs row = L0 row + (RS) - RS ...
+    const float* src = sHs + (blk * PY) * G::HS_P + 4 * j;
 #pragma unroll
-    for (int i = 0; i < PY + 2 * RS; ++i) {
-      // L0 row rr (tile) <-> y0-3+rr needs Hs rows (y0-5+..): Hs row index = rr + m, m = 0..2RS
-      const float4 v = *reinterpret_cast<const float4*>(src + i * G::HS_P);
+    for (int i = 0; i < PY + 2 * RS; ++i) {            // L0 row rr needs Hs rows rr .. rr+2RS
+      const float4 v = lds128(src + i * G::HS_P);
 #pragma unroll
       for (int q = 0; q < PY; ++q) {
         const int m = i - q;
-        if (m >= 0 && m <= 2 * RS) {
-          acc[q].x = mac<EXACT>(acc[q].x, v.x, ts.k[m]);
-          acc[q].y = mac<EXACT>(acc[q].y, v.y, ts.k[m]);
-          acc[q].z = mac<EXACT>(acc[q].z, v.z, ts.k[m]);
-          acc[q].w = mac<EXACT>(acc[q].w, v.w, ts.k[m]);
-        }
+        if (m >= 0 && m <= 2 * RS) fma4(acc[q], v, ts.k[m], EXACT);
       }
     }
     const int xg = x0 - 4 + 4 * j;
@@ -249,68 +316,227 @@ __device__ __forceinline__ void l0_fused_tile(unsigned char* smem, const CUtenso
   }
   __syncthreads();
 
-  // ---- stage C: horizontal DoG and Gaussian, L0 -> Hd, Hg ----------------------------------
-  // 8 groups of 8 output columns (x0+8g ..) per L0 row; window = L0 tile cols 8g .. 8g+15
-  for (int rb = warp * 4; rb < G::L0_H; rb += 32) {
-    const int r = rb + 2 * rpair + rpar;
-    const int g = 4 * half + sub;
-    if (r < G::L0_H) {
-      float win[16];
-      const float4* p = reinterpret_cast<const float4*>(sL0 + r * G::L0_P + 8 * g);
-#pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        const float4 t = p[v];
-        win[4 * v] = t.x; win[4 * v + 1] = t.y; win[4 * v + 2] = t.z; win[4 * v + 3] = t.w;
-      }
-      float od[8], og[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float a = 0.0f, b = 0.0f;
-#pragma unroll
-        for (int m = 0; m < 2 * RG + 1; ++m) a = mac<EXACT>(a, win[q + 1 + m], td.k[m]);
-#pragma unroll
-        for (int m = 0; m < 2 * RG + 1; ++m) b = mac<EXACT>(b, win[q + 1 + m], tg.k[m]);
-        if (BORDER) {
-          const int xg = x0 + 8 * g + q;
-          if (xg < RG || xg >= W - RG) { a = 0.0f; b = 0.0f; }
-        }
-        od[q] = a; og[q] = b;
-      }
-      float4* dd = reinterpret_cast<float4*>(sHd + r * G::HG_P + 8 * g);
-      float4* dg = reinterpret_cast<float4*>(sHg + r * G::HG_P + 8 * g);
-      dd[0] = make_float4(od[0], od[1], od[2], od[3]);
-      dd[1] = make_float4(od[4], od[5], od[6], od[7]);
-      dg[0] = make_float4(og[0], og[1], og[2], og[3]);
-      dg[1] = make_float4(og[4], og[5], og[6], og[7]);
-    }
-  }
+  stage_hgrad<EXACT, BORDER, G::TX, G::L0_H, G::L0_P, G::HG_P>(sL0, sHd, sHg, tg, td, x0, W);
   __syncthreads();
-
-  // ---- stage D: vertical passes, Hd -> gx (Gaussian), Hg -> gy (DoG) -------------------------
-  // threads 0..127 produce gx, 128..255 gy (warp uniform); each 4 columns x 8 rows.
-  {
-    const int t = tid & 127;
-    const int blk = t >> 4, j = t & 15;             // 8 row blocks x 16 column groups
-    if (tid < 128)
-      l0_stage_d<EXACT, BORDER>(sHd + (blk * 8) * G::HG_P + 4 * j, tg, out_gx, opitch, x0 + 4 * j,
-                                y0 + blk * 8, W, H);
-    else
-      l0_stage_d<EXACT, BORDER>(sHg + (blk * 8) * G::HG_P + 4 * j, td, out_gy, opitch, x0 + 4 * j,
-                                y0 + blk * 8, W, H);
-  }
+  stage_vgrad_both<EXACT, BORDER, G::TX, G::TY, 8, G::HG_P>(sHd, sHg, tg, td, out_gx, out_gy, opitch,
+                                                            x0, y0, W, H);
 }
 
 template <bool EXACT>
 __global__ void __launch_bounds__(256, 3)
-l0_fused_kernel(const __grid_constant__ CUtensorMap map, int W, int H, TapsR ts, TapsR tg, TapsR td,
-                float* __restrict__ out_img, float* __restrict__ out_gx, float* __restrict__ out_gy,
-                int opitch) {
+l0_fused_kernel(const __grid_constant__ CUtensorMap map, int W, int H, int tiles_x, int ntiles,
+                TapsR ts, TapsR tg, TapsR td, float* __restrict__ out_img,
+                float* __restrict__ out_gx, float* __restrict__ out_gy, int opitch) {
+  using G = L0Geo;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int x0 = blockIdx.x * L0Geo::TX, y0 = blockIdx.y * L0Geo::TY;
-  // tiles whose 8-pixel margin stays inside the image never meet a zero band
-  const bool border = (x0 < 8) || (y0 < 8) || (x0 + L0Geo::TX + 8 > W) || (y0 + L0Geo::TY + 8 > H);
-  if (border)
-    l0_fused_tile<EXACT, true>(smem_raw, &map, W, H, ts, tg, td, out_img, out_gx, out_gy, opitch, x0, y0);
-  else
-    l0_fused_tile<EXACT, false>(smem_raw, &map, W, H, ts, tg, td, out_img, out_gx, out_gy, opitch, x0, y0);
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + G::OFF_BAR);
+  const int tid = threadIdx.x;
+  if (tid == 0) mbar_init(bar, 1);
+  __syncthreads();
+  int tile = blockIdx.x;
+  if (tid == 0 && tile < ntiles) {
+    mbar_expect_tx(bar, G::U8_W * G::U8_H);
+    tma_load_2d(smem_raw + G::OFF_U8, &map, (tile % tiles_x) * G::TX - 16,
+                (tile / tiles_x) * G::TY - (G::RS + G::RG), bar);
+  }
+  unsigned phase = 0;
+  for (; tile < ntiles; tile += gridDim.x) {
+    const int x0 = (tile % tiles_x) * G::TX, y0 = (tile / tiles_x) * G::TY;
+    // tiles whose 8-pixel margin stays inside the image never meet a zero band
+    const bool border = (x0 < 8) || (y0 < 8) || (x0 + G::TX + 8 > W) || (y0 + G::TY + 8 > H);
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    if (border) l0_fused_tile<EXACT, true>(smem_raw, W, ts, x0);
+    else l0_fused_tile<EXACT, false>(smem_raw, W, ts, x0);
+    __syncthreads();                 // u8 tile consumed (and the previous tile's stage D is done)
+    const int next = tile + gridDim.x;
+    if (tid == 0 && next < ntiles) {
+      mbar_expect_tx(bar, G::U8_W * G::U8_H);
+      tma_load_2d(smem_raw + G::OFF_U8, &map, (next % tiles_x) * G::TX - 16,
+                  (next / tiles_x) * G::TY - (G::RS + G::RG), bar);
+    }
+    if (border) l0_fused_tile_rest<EXACT, true>(smem_raw, W, H, ts, tg, td, out_img, out_gx, out_gy, opitch, x0, y0);
+    else l0_fused_tile_rest<EXACT, false>(smem_raw, W, H, ts, tg, td, out_img, out_gx, out_gy, opitch, x0, y0);
+    // stage D reads Hd (aliased on Hs) and Hg: the next tile's stage A must not start before
+    __syncthreads();
+  }
+}
+
+// ============================================================================================
+// levels >= 1: one pyramid step (Gaussian at the kept samples) + gradients
+// ============================================================================================
+template <int SS, int R, int TX, int TY>
+struct LvGeo {
+  static constexpr int RG = FUSED_RG;
+  static constexpr int LW = TX + 8, LH = TY + 2 * RG;                  // level tile, col c <-> x0-4+c
+  static constexpr int NGL = LW / 4;                                   // column groups of 4
+  static constexpr int LP = LW + 4;                                    // odd number of chunks
+  static constexpr int HP = TX + 4;
+  static constexpr int NW1 = 3 * SS + 2 * R + 1;                       // source window of 4 kept outputs
+  static constexpr int NV1 = (NW1 + 3) / 4;
+  static constexpr int SW0 = SS * 4 * (NGL - 1) + 4 * NV1;
+  static constexpr int SW = ((SW0 / 4) & 1) ? SW0 : SW0 + 4;           // source box width, odd chunks
+  static constexpr int SH = SS * (LH - 1) + 2 * R + 1;                 // source box height
+  static constexpr int XOFF = SS / 2 - R - 4 * SS;                     // source col of tile col 0, minus SS*x0
+  static constexpr int YOFF = SS / 2 - R - RG * SS;
+  static_assert(XOFF % 4 == 0, "source box must start on a 16 B boundary");
+  static_assert((LP / 4) % 2 == 1 && (HP / 4) % 2 == 1 && (SW / 4) % 2 == 1, "odd chunk pitches");
+  static constexpr int OFF_SRC = 0;
+  static constexpr int OFF_HP = SW * SH * 4;
+  static constexpr int OFF_L = OFF_HP + SH * LW * 4;
+  static constexpr int OFF_HD = OFF_L + LH * LP * 4;
+  static constexpr int OFF_HG = OFF_HD + LH * HP * 4;
+  static constexpr int OFF_BAR = OFF_HG + LH * HP * 4;
+  static constexpr int SMEM = OFF_BAR + 16;
+};
+
+// P1 item: 4 kept outputs (tile cols 4g..4g+3) of source row r
+template <bool EXACT, bool BORDER, int SS, int R, int TX, int TY>
+__device__ __forceinline__ void lv_p1_item(const float* sSrc, float* sHp, const TapsR& tp, int r, int g,
+                                           int x0, int Wsrc) {
+  using G = LvGeo<SS, R, TX, TY>;
+  float win[4 * G::NV1];
+  const float* p = sSrc + r * G::SW + SS * 4 * g;
+#pragma unroll
+  for (int v = 0; v < G::NV1; ++v) {
+    const float4 t = lds128(p + 4 * v);
+    win[4 * v] = t.x; win[4 * v + 1] = t.y; win[4 * v + 2] = t.z; win[4 * v + 3] = t.w;
+  }
+  float o[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int m = 0; m < 2 * R + 1; ++m) acc = mac<EXACT>(acc, win[SS * q + m], tp.k[m]);
+    if (BORDER) {
+      const int xs = SS * (x0 - 4 + 4 * g + q) + SS / 2;
+      if (xs < R || xs >= Wsrc - R) acc = 0.0f;
+    }
+    o[q] = acc;
+  }
+  *reinterpret_cast<float4*>(sHp + r * G::LW + 4 * g) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+template <bool EXACT, bool BORDER, int SS, int R, int TX, int TY>
+__device__ __forceinline__ void lv_stage_p1(const unsigned char* smem, const TapsR& tp, int x0, int Wsrc) {
+  using G = LvGeo<SS, R, TX, TY>;
+  const float* sSrc = reinterpret_cast<const float*>(smem + G::OFF_SRC);
+  float* sHp = const_cast<float*>(reinterpret_cast<const float*>(smem + G::OFF_HP));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // a warp covers 8 groups x 4 rows; quarter warp = (8/SS) groups x SS rows (conflict free, see top)
+  int g8, rl;
+  if (SS == 2) { g8 = 4 * ((lane >> 3) & 1) + (lane & 3); rl = 2 * (lane >> 4) + ((lane >> 2) & 1); }
+  else         { g8 = 2 * (lane >> 3) + (lane & 1);       rl = (lane >> 1) & 3; }
+  constexpr int NMAIN = (G::NGL / 8) * 8, NCH = NMAIN / 8, NRB = (G::SH + 3) / 4;
+  for (int u = warp; u < NRB * NCH; u += 8) {
+    const int rbk = u / NCH, ch = u - rbk * NCH;
+    const int r = 4 * rbk + rl;
+    if (r < G::SH) lv_p1_item<EXACT, BORDER, SS, R, TX, TY>(sSrc, sHp, tp, r, 8 * ch + g8, x0, Wsrc);
+  }
+  constexpr int NTAIL = G::NGL - NMAIN;
+  for (int it = tid; it < G::SH * NTAIL; it += 256) {
+    const int r = it / NTAIL, g = NMAIN + it - r * NTAIL;
+    lv_p1_item<EXACT, BORDER, SS, R, TX, TY>(sSrc, sHp, tp, r, g, x0, Wsrc);
+  }
+}
+
+template <bool EXACT, bool BORDER, int SS, int R, int TX, int TY>
+__device__ __forceinline__ void lv_stage_rest(unsigned char* smem, const TapsR& tp, const TapsR& tg,
+                                              const TapsR& td, int Hsrc, int W, int H,
+                                              float* __restrict__ out_img, float* __restrict__ out_gx,
+                                              float* __restrict__ out_gy, int opitch, int x0, int y0) {
+  using G = LvGeo<SS, R, TX, TY>;
+  constexpr int RG = G::RG;
+  const float* sHp = reinterpret_cast<const float*>(smem + G::OFF_HP);
+  float* sL = reinterpret_cast<float*>(smem + G::OFF_L);
+  float* sHd = reinterpret_cast<float*>(smem + G::OFF_HD);
+  float* sHg = reinterpret_cast<float*>(smem + G::OFF_HG);
+  const int tid = threadIdx.x;
+
+  // ---- P2: vertical Gaussian at the kept rows, Hp -> level tile (shared + HBM) -----------------
+  // item = 4 columns x 2 level rows; level row rr needs Hp rows SS*rr .. SS*rr+2R
+  {
+    constexpr int NMAIN = (G::NGL / 8) * 8, NPAIR = G::LH / 2, NTAIL = G::NGL - NMAIN;
+    static_assert(G::LH % 2 == 0, "level tile height must be even");
+    constexpr int NR2 = SS + 2 * R + 1;
+    for (int it = tid; it < NPAIR * G::NGL; it += 256) {
+      int pr, j;
+      if (it < NPAIR * NMAIN) { pr = it / NMAIN; j = it - pr * NMAIN; }
+      else { const int t2 = it - NPAIR * NMAIN; pr = t2 / NTAIL; j = NMAIN + t2 - pr * NTAIL; }
+      float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+      const float* src = sHp + (SS * 2 * pr) * G::LW + 4 * j;
+#pragma unroll
+      for (int i = 0; i < NR2; ++i) {
+        const float4 v = lds128(src + i * G::LW);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int m = i - SS * q;
+          if (m >= 0 && m <= 2 * R) fma4(acc[q], v, tp.k[m], EXACT);
+        }
+      }
+      const int xg = x0 - 4 + 4 * j;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int rr = 2 * pr + q;
+        const int yg = y0 - RG + rr;
+        if (BORDER) {
+          const int ys = SS * yg + SS / 2;
+          if (ys < R || ys >= Hsrc - R) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        *reinterpret_cast<float4*>(sL + rr * G::LP + 4 * j) = acc[q];
+        if (j >= 1 && j <= G::NGL - 2 && rr >= RG && rr < RG + TY) {
+          if (!BORDER || (xg < W && yg < H))
+            *reinterpret_cast<float4*>(out_img + (size_t)yg * opitch + xg) = acc[q];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  stage_hgrad<EXACT, BORDER, TX, G::LH, G::LP, G::HP>(sL, sHd, sHg, tg, td, x0, W);
+  __syncthreads();
+  constexpr int PY = (TX / 4) * (TY / 4) <= 128 ? 4 : 8;
+  stage_vgrad_both<EXACT, BORDER, TX, TY, PY, G::HP>(sHd, sHg, tg, td, out_gx, out_gy, opitch, x0, y0, W, H);
+}
+
+// W,H: size of the level being produced; Wsrc,Hsrc: size of the level it is made from
+template <int SS, int R, int TX, int TY, bool EXACT>
+__global__ void __launch_bounds__(256, 2)
+level_fused_kernel(const __grid_constant__ CUtensorMap map, int Wsrc, int Hsrc, int W, int H,
+                   int tiles_x, int ntiles, TapsR tp, TapsR tg, TapsR td,
+                   float* __restrict__ out_img, float* __restrict__ out_gx,
+                   float* __restrict__ out_gy, int opitch) {
+  using G = LvGeo<SS, R, TX, TY>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + G::OFF_BAR);
+  const int tid = threadIdx.x;
+  if (tid == 0) mbar_init(bar, 1);
+  __syncthreads();
+  int tile = blockIdx.x;
+  if (tid == 0 && tile < ntiles) {
+    mbar_expect_tx(bar, G::SW * G::SH * 4);
+    tma_load_2d(smem_raw + G::OFF_SRC, &map, SS * (tile % tiles_x) * TX + G::XOFF,
+                SS * (tile / tiles_x) * TY + G::YOFF, bar);
+  }
+  unsigned phase = 0;
+  for (; tile < ntiles; tile += gridDim.x) {
+    const int x0 = (tile % tiles_x) * TX, y0 = (tile / tiles_x) * TY;
+    // interior tiles (margins derived in DESIGN.md) never meet a zero band at either level
+    const bool border = (x0 < 8) || (y0 < 8) || (x0 + TX + 16 > W) || (y0 + TY + 16 > H);
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    if (border) lv_stage_p1<EXACT, true, SS, R, TX, TY>(smem_raw, tp, x0, Wsrc);
+    else lv_stage_p1<EXACT, false, SS, R, TX, TY>(smem_raw, tp, x0, Wsrc);
+    __syncthreads();                 // source box consumed
+    const int next = tile + gridDim.x;
+    if (tid == 0 && next < ntiles) {
+      mbar_expect_tx(bar, G::SW * G::SH * 4);
+      tma_load_2d(smem_raw + G::OFF_SRC, &map, SS * (next % tiles_x) * TX + G::XOFF,
+                  SS * (next / tiles_x) * TY + G::YOFF, bar);
+    }
+    if (border)
+      lv_stage_rest<EXACT, true, SS, R, TX, TY>(smem_raw, tp, tg, td, Hsrc, W, H, out_img, out_gx, out_gy, opitch, x0, y0);
+    else
+      lv_stage_rest<EXACT, false, SS, R, TX, TY>(smem_raw, tp, tg, td, Hsrc, W, H, out_img, out_gx, out_gy, opitch, x0, y0);
+    __syncthreads();                 // Hp / L / Hd / Hg free for the next tile
+  }
 }
