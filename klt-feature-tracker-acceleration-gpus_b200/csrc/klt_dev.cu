@@ -753,18 +753,20 @@ track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n,
   }
 }
 
+#include "klt_track_fast.cuh"
+
 // ---------------------------------------------------------------------------
 // host side of the C-ABI
 // ---------------------------------------------------------------------------
 // kernel classes, for launch accounting and per-kernel event timing
 enum KernelId {
   KID_SMOOTH_U8 = 0, KID_GRAD, KID_PYRDOWN, KID_TRACK, KID_MINEIG, KID_SORT, KID_STAMP,
-  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_L0_FUSED, KID_LEVEL_FUSED, KID_COUNT
+  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_L0_FUSED, KID_LEVEL_FUSED, KID_TRACK_FAST, KID_COUNT
 };
 static const char* const kKernelNames[KID_COUNT] = {
   "smooth_u8_tile", "grad_tile", "pyrdown_tile", "track_kernel", "mineig_kernel",
   "cub_radix_sort", "stamp_existing_kernel", "enforce_mindist_kernel",
-  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel", "l0_fused_kernel", "level_fused_kernel"
+  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel", "l0_fused_kernel", "level_fused_kernel", "track_fast_kernel"
 };
 static constexpr int PROF_POOL = 2048;     // event pairs in flight before folding
 
@@ -1379,6 +1381,26 @@ static int launch_track(klt_dev* d, const PyrView& v1, const PyrView& v2, const 
   return 0;
 }
 
+template <int WW, int RPL>
+static void launch_track_fast_t(klt_dev* d, const PyrView& v1, const PyrView& v2, const TrackArgs& a, int n) {
+  Launch l(d, KID_TRACK_FAST);
+  track_fast_kernel<WW, RPL><<<(8 * n + 127) / 128, 128, 0, d->stream>>>(v1, v2, a, n, d->d_x, d->d_y,
+                                                                        d->d_val, d->d_live);
+}
+// square odd windows up to 15x15; returns false if this window has no instantiation
+static bool launch_track_fast(klt_dev* d, const PyrView& v1, const PyrView& v2, const TrackArgs& a, int n) {
+  switch (a.ww) {
+    case 3: launch_track_fast_t<3, 1>(d, v1, v2, a, n); return true;
+    case 5: launch_track_fast_t<5, 1>(d, v1, v2, a, n); return true;
+    case 7: launch_track_fast_t<7, 1>(d, v1, v2, a, n); return true;
+    case 9: launch_track_fast_t<9, 2>(d, v1, v2, a, n); return true;
+    case 11: launch_track_fast_t<11, 2>(d, v1, v2, a, n); return true;
+    case 13: launch_track_fast_t<13, 2>(d, v1, v2, a, n); return true;
+    case 15: launch_track_fast_t<15, 2>(d, v1, v2, a, n); return true;
+    default: return false;
+  }
+}
+
 extern "C" int klt_dev_track_resident(klt_dev* d, int slot_prev, int slot_cur,
                                       const klt_dev_track_params* p) {
   CU(cudaSetDevice(d->device));
@@ -1406,6 +1428,8 @@ extern "C" int klt_dev_track_resident(klt_dev* d, int slot_prev, int slot_cur,
     else if (ppl <= 8) rc = launch_track<true, 8>(d, v1, v2, a, n);
     else if (ppl <= 16) rc = launch_track<true, 16>(d, v1, v2, a, n);
     else return fail(d, "tracking window %d x %d too large (max 512 pixels)", a.ww, a.wh);
+  } else if (!d->force_generic && a.ww == a.wh && a.ww <= 15 && launch_track_fast(d, v1, v2, a, n)) {
+    rc = 0;
   } else {
     if (ppl <= 2) rc = launch_track<false, 2>(d, v1, v2, a, n);
     else if (ppl <= 4) rc = launch_track<false, 4>(d, v1, v2, a, n);

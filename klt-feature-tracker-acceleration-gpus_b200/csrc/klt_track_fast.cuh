@@ -1,0 +1,221 @@
+// klt_track_fast.cuh -- production (FMA-mode) tracker kernel, included by klt_dev.cu.
+//
+// Same algorithm as track_kernel (reference src/V1/trackFeatures.c:381-486 per level and
+// :1343-1437 across levels) re-mapped for latency: the warp-per-feature kernel is bound by a
+// long dependent instruction chain (ncu: 2.6 k warp instructions per feature, 25 % issue
+// utilisation, every first touch of a level a DRAM miss).  Here
+//   * 8 lanes own one feature, 4 features share a warp: lane r of a group handles window row
+//     r - WH/2 (WW pixels, all independent => deep memory-level parallelism);
+//   * the bilinear weights are computed once per window position instead of once per pixel
+//     (the fractional offsets of x+i and x are equal up to float rounding);
+//   * the five window sums are reduced with 3 xor-shuffles over the 8 lanes, every lane ends
+//     up with the totals and solves the 2x2 system redundantly (no broadcast);
+//   * the footprint of the next finer level is prefetched into L2 while the current level
+//     iterates.
+// Windows up to 15 x 8*RPL rows are supported through the WW / RPL template parameters; the
+// bit-exact mode and larger windows stay on track_kernel.
+#pragma once
+
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+__device__ __forceinline__ float group_sum8(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+
+// one window row of bilinear samples: out[i] = interp(img, xt+i+ax, yrow+ay), i = 0..WW-1
+template <int WW>
+__device__ __forceinline__ void sample_row(const float* __restrict__ img, int pitch, int xt, int yrow,
+                                           float ax, float ay, float* out) {
+  const float* p0 = img + (size_t)yrow * pitch + xt;
+  const float* p1 = p0 + pitch;
+  float a[WW + 1], b[WW + 1];
+#pragma unroll
+  for (int i = 0; i <= WW; ++i) { a[i] = __ldg(p0 + i); b[i] = __ldg(p1 + i); }
+  const float w00 = (1.0f - ax) * (1.0f - ay), w01 = ax * (1.0f - ay), w10 = (1.0f - ax) * ay, w11 = ax * ay;
+#pragma unroll
+  for (int i = 0; i < WW; ++i)
+    out[i] = fmaf(w11, b[i + 1], fmaf(w10, b[i], fmaf(w01, a[i + 1], w00 * a[i])));
+}
+
+// WW: window width (odd, <= 15); RPL: window rows per lane (window height <= 8 * RPL)
+template <int WW, int RPL>
+__global__ void __launch_bounds__(128)
+track_fast_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, float* __restrict__ fx,
+                  float* __restrict__ fy, int* __restrict__ fval,
+                  unsigned long long* __restrict__ live_total) {
+  const int lane = threadIdx.x & 31;
+  const int r8 = lane & 7;                                   // lane within the feature group
+  const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;   // feature of this group
+  const int wh = a.wh, hw = WW / 2, hh = wh / 2;
+  const float inv_npix = 0.0f;                               // (unused; residue uses division below)
+  (void)inv_npix;
+
+  bool alive = false;                                        // feature still being tracked
+  float xloc = 0.0f, yloc = 0.0f;
+  if (f < n) {
+    const int v0 = fval[f];
+    alive = v0 >= 0;                                         // only features that are not lost (:1346)
+    if (alive) { xloc = fx[f]; yloc = fy[f]; }
+  }
+  {
+    const unsigned bal = __ballot_sync(0xffffffffu, alive && r8 == 0);
+    if (lane == 0 && bal) atomicAdd(live_total, (unsigned long long)__popc(bal));
+  }
+  if (!__any_sync(0xffffffffu, alive)) return;
+
+  for (int r = a.nlevels - 1; r >= 0; --r) { xloc = xloc / a.ss; yloc = yloc / a.ss; }
+  float xout = xloc, yout = yloc;
+  int status = KLT_TRACKED;
+  bool running = alive;                                      // false once a level returned SMALL_DET / OOB
+
+  // rows of the window this lane owns: j = r8 + 8*k - hh  (valid if r8 + 8*k < wh)
+  for (int r = a.nlevels - 1; r >= 0; --r) {
+    if (running) { xloc *= a.ss; yloc *= a.ss; xout *= a.ss; yout *= a.ss; }
+    const int nc = p1.ncols[r], nr = p1.nrows[r], pitch = p1.pitch[r];
+    const float* __restrict__ i1 = p1.img[r];
+    const float* __restrict__ gx1 = p1.gx[r];
+    const float* __restrict__ gy1 = p1.gy[r];
+    const float* __restrict__ i2 = p2.img[r];
+    const float* __restrict__ gx2 = p2.gx[r];
+    const float* __restrict__ gy2 = p2.gy[r];
+
+    // prefetch the footprint of the next finer level around the predicted positions
+    if (running && r > 0) {
+      const int pn = p1.pitch[r - 1], ncn = p1.ncols[r - 1], nrn = p1.nrows[r - 1];
+      const int px1 = (int)(xloc * a.ss) - hw, py1 = (int)(yloc * a.ss) - hh + r8;
+      const int px2 = (int)(xout * a.ss) - hw, py2 = (int)(yout * a.ss) - hh + r8;
+      if (px1 >= 0 && py1 >= 0 && px1 + WW < ncn && py1 < nrn) {
+        const size_t o = (size_t)py1 * pn + px1;
+        prefetch_l2(p1.img[r - 1] + o); prefetch_l2(p1.img[r - 1] + o + WW);
+        prefetch_l2(p1.gx[r - 1] + o);  prefetch_l2(p1.gx[r - 1] + o + WW);
+        prefetch_l2(p1.gy[r - 1] + o);  prefetch_l2(p1.gy[r - 1] + o + WW);
+      }
+      if (px2 >= 0 && py2 >= 0 && px2 + WW < ncn && py2 < nrn) {
+        const size_t o = (size_t)py2 * pn + px2;
+        prefetch_l2(p2.img[r - 1] + o); prefetch_l2(p2.img[r - 1] + o + WW);
+        prefetch_l2(p2.gx[r - 1] + o);  prefetch_l2(p2.gx[r - 1] + o + WW);
+        prefetch_l2(p2.gy[r - 1] + o);  prefetch_l2(p2.gy[r - 1] + o + WW);
+      }
+    }
+
+    // ---- _trackFeature at this level ----------------------------------------------------
+    const float x1 = xloc, y1 = yloc;
+    float x2 = xout, y2 = yout;
+    int iteration = 0;
+    float dx = 0.0f, dy = 0.0f;
+    float t_i[RPL][WW], t_gx[RPL][WW], t_gy[RPL][WW];
+    bool iterating = running;                                // this group still inside the do-while
+    int lvl_status = KLT_TRACKED;
+
+    if (iterating && window_oob(x1, y1, hw, hh, nc, nr)) { lvl_status = KLT_OOB; iterating = false; }
+    if (iterating && window_oob(x2, y2, hw, hh, nc, nr)) { lvl_status = KLT_OOB; iterating = false; }
+    if (iterating) {
+      const int xt = (int)x1, yt = (int)y1;
+      const float ax = x1 - (float)xt, ay = y1 - (float)yt;
+#pragma unroll
+      for (int k = 0; k < RPL; ++k) {
+        const int row = r8 + 8 * k;
+        if (row < wh) {
+          sample_row<WW>(i1, pitch, xt - hw, yt - hh + row, ax, ay, t_i[k]);
+          sample_row<WW>(gx1, pitch, xt - hw, yt - hh + row, ax, ay, t_gx[k]);
+          sample_row<WW>(gy1, pitch, xt - hw, yt - hh + row, ax, ay, t_gy[k]);
+        }
+      }
+    }
+
+    while (__any_sync(0xffffffffu, iterating)) {
+      float gxx = 0.0f, gxy = 0.0f, gyy = 0.0f, ex = 0.0f, ey = 0.0f;
+      if (iterating) {
+        const int xt = (int)x2, yt = (int)y2;
+        const float ax = x2 - (float)xt, ay = y2 - (float)yt;
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) {
+          const int row = r8 + 8 * k;
+          if (row < wh) {
+            float s_i[WW], s_gx[WW], s_gy[WW];
+            sample_row<WW>(i2, pitch, xt - hw, yt - hh + row, ax, ay, s_i);
+            sample_row<WW>(gx2, pitch, xt - hw, yt - hh + row, ax, ay, s_gx);
+            sample_row<WW>(gy2, pitch, xt - hw, yt - hh + row, ax, ay, s_gy);
+#pragma unroll
+            for (int i = 0; i < WW; ++i) {
+              const float df = t_i[k][i] - s_i[i];
+              const float sx = t_gx[k][i] + s_gx[i];
+              const float sy = t_gy[k][i] + s_gy[i];
+              gxx = fmaf(sx, sx, gxx); gxy = fmaf(sx, sy, gxy); gyy = fmaf(sy, sy, gyy);
+              ex = fmaf(df, sx, ex); ey = fmaf(df, sy, ey);
+            }
+          }
+        }
+      }
+      gxx = group_sum8(gxx); gxy = group_sum8(gxy); gyy = group_sum8(gyy);
+      ex = group_sum8(ex); ey = group_sum8(ey);
+      if (iterating) {
+        ex *= a.step_factor; ey *= a.step_factor;
+        const float det = gxx * gyy - gxy * gxy;
+        if (det < a.min_determinant) {
+          lvl_status = KLT_SMALL_DET; iterating = false;
+        } else {
+          dx = (gyy * ex - gxy * ey) / det;
+          dy = (gxx * ey - gxy * ex) / det;
+          x2 += dx; y2 += dy;
+          ++iteration;
+          const bool again = (fabsf(dx) >= a.min_displacement || fabsf(dy) >= a.min_displacement) &&
+                             iteration < a.max_iterations;
+          if (!again) iterating = false;
+          else if (window_oob(x2, y2, hw, hh, nc, nr)) { lvl_status = KLT_OOB; iterating = false; }
+        }
+      }
+    }
+
+    // after the loop (:459-474): bounds of the final position, then the residue
+    bool need_res = false;
+    if (running) {
+      if (window_oob(x2, y2, hw, hh, nc, nr)) lvl_status = KLT_OOB;
+      need_res = (lvl_status == KLT_TRACKED);
+    }
+    if (__any_sync(0xffffffffu, need_res)) {
+      float sum = 0.0f;
+      if (need_res) {
+        const int xt = (int)x2, yt = (int)y2;
+        const float ax = x2 - (float)xt, ay = y2 - (float)yt;
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) {
+          const int row = r8 + 8 * k;
+          if (row < wh) {
+            float s_i[WW];
+            sample_row<WW>(i2, pitch, xt - hw, yt - hh + row, ax, ay, s_i);
+#pragma unroll
+            for (int i = 0; i < WW; ++i) sum += fabsf(t_i[k][i] - s_i[i]);
+          }
+        }
+      }
+      sum = group_sum8(sum);
+      if (need_res && sum / (float)(WW * wh) > a.max_residue) lvl_status = KLT_LARGE_RESIDUE;
+    }
+    if (running) {
+      int v;                                               // return value of _trackFeature (:479-484)
+      if (lvl_status == KLT_SMALL_DET) v = KLT_SMALL_DET;
+      else if (lvl_status == KLT_OOB) v = KLT_OOB;
+      else if (lvl_status == KLT_LARGE_RESIDUE) v = KLT_LARGE_RESIDUE;
+      else if (iteration >= a.max_iterations) v = KLT_MAX_ITERATIONS;
+      else v = KLT_TRACKED;
+      status = v;
+      xout = x2; yout = y2;
+      if (v == KLT_SMALL_DET || v == KLT_OOB) running = false;       // :1378
+    }
+    if (!__any_sync(0xffffffffu, running)) break;
+  }
+
+  if (alive && r8 == 0) {                                   // record (:1383-1437)
+    const bool outside = (xout < (float)a.borderx || xout > (float)(a.ncols - 1 - a.borderx) ||
+                          yout < (float)a.bordery || yout > (float)(a.nrows - 1 - a.bordery));
+    if (status == KLT_OOB || outside) { fx[f] = -1.0f; fy[f] = -1.0f; fval[f] = KLT_OOB; }
+    else if (status != KLT_TRACKED) { fx[f] = -1.0f; fy[f] = -1.0f; fval[f] = status; }
+    else { fx[f] = xout; fy[f] = yout; fval[f] = KLT_TRACKED; }
+  }
+}

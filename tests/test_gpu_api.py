@@ -206,3 +206,18 @@ def test_lost_features_are_left_alone_and_nonsequential_mode(L, capi, oracle, or
     assert (v[::5] == -3).all()
     L.KLTFreeFeatureList(fl)
     L.KLTFreeTrackingContext(tc)
+
+
+@pytest.mark.parametrize("window", [(3, 3), (5, 5), (9, 9), (11, 11), (15, 15), (7, 5), (5, 9), (17, 17)])
+@pytest.mark.parametrize("exact", [1, 0])
+def test_track_other_window_sizes(L, capi, oracle, oracle_mod, window, exact):
+    """square windows up to 15 use the 8-lanes-per-feature kernel in fma mode, everything
+    else (and the exact mode) the warp-per-feature kernel"""
+    imgs = [synth_image(500, 400, seed=31, shift=(1.9 * t, 1.1 * t)) for t in range(3)]
+
+    def setup(tc):
+        tc.contents.window_width, tc.contents.window_height = window
+        L.KLTChangeTCPyramid(tc, 12)
+        L.KLTUpdateTCBorder(tc)
+    rep = _teacher_forced(L, capi, oracle, oracle_mod, imgs, 200, exact, setup)
+    assert rep[-1][3] > 60
