@@ -761,12 +761,12 @@ track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n,
 // kernel classes, for launch accounting and per-kernel event timing
 enum KernelId {
   KID_SMOOTH_U8 = 0, KID_GRAD, KID_PYRDOWN, KID_TRACK, KID_MINEIG, KID_SORT, KID_STAMP,
-  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_L0_FUSED, KID_LEVEL_FUSED, KID_TRACK_FAST, KID_COUNT
+  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_L0_FUSED, KID_LEVEL_FUSED, KID_TRACK_FAST, KID_TRACK7, KID_COUNT
 };
 static const char* const kKernelNames[KID_COUNT] = {
   "smooth_u8_tile", "grad_tile", "pyrdown_tile", "track_kernel", "mineig_kernel",
   "cub_radix_sort", "stamp_existing_kernel", "enforce_mindist_kernel",
-  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel", "l0_fused_kernel", "level_fused_kernel", "track_fast_kernel"
+  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel", "l0_fused_kernel", "level_fused_kernel", "track_fast_kernel", "track7_kernel"
 };
 static constexpr int PROF_POOL = 2048;     // event pairs in flight before folding
 
@@ -784,7 +784,7 @@ struct klt_dev {
   cudaStream_t stream;
   char err[512];
   unsigned long long launches;
-  int last_path, force_generic, no_fused, last_fused;
+  int last_path, force_generic, no_fused, last_fused, track7_off;
   // geometry
   int W, H, L, ss;
   PyrSet set[2];
@@ -876,7 +876,7 @@ extern "C" void* klt_dev_stream(const klt_dev* d) { return (void*)d->stream; }
 extern "C" unsigned long long klt_dev_launch_count(const klt_dev* d) { return d->launches; }
 extern "C" int klt_dev_last_build_path(const klt_dev* d) { return d->last_path; }
 extern "C" void klt_dev_force_generic(klt_dev* d, int on) { d->force_generic = on; }
-extern "C" void klt_dev_disable_fused(klt_dev* d, int on) { d->no_fused = on; }
+extern "C" void klt_dev_disable_fused(klt_dev* d, int on) { d->no_fused = on; d->track7_off = on; }
 extern "C" int klt_dev_last_build_fused(const klt_dev* d) { return d->last_fused; }
 
 extern "C" int klt_dev_create(int device, klt_dev** out) {
@@ -945,7 +945,7 @@ static int ensure_geometry(klt_dev* d, int W, int H, int L, int ss) {
     per_set += 3 * (size_t)ps[l] * h;
     if (L > 1) { w /= ss; h /= ss; }
   }
-  CU(cudaMalloc(&d->arena, 2 * per_set * sizeof(float)));
+  CU(cudaMalloc(&d->arena, 2 * per_set * sizeof(float) + 256));   // + slack for aligned over-reads
   CU(cudaMalloc(&d->tmp, (size_t)ps[0] * H * sizeof(float)));
   float* p = d->arena;
   for (int s = 0; s < 2; ++s)
@@ -1392,7 +1392,11 @@ static bool launch_track_fast(klt_dev* d, const PyrView& v1, const PyrView& v2, 
   switch (a.ww) {
     case 3: launch_track_fast_t<3, 1>(d, v1, v2, a, n); return true;
     case 5: launch_track_fast_t<5, 1>(d, v1, v2, a, n); return true;
-    case 7: launch_track_fast_t<7, 1>(d, v1, v2, a, n); return true;
+    case 7:
+      if (d->track7_off) { launch_track_fast_t<7, 1>(d, v1, v2, a, n); return true; }
+      { Launch l(d, KID_TRACK7);
+        track7_kernel<<<(8 * n + 127) / 128, 128, 0, d->stream>>>(v1, v2, a, n, d->d_x, d->d_y, d->d_val, d->d_live); }
+      return true;
     case 9: launch_track_fast_t<9, 2>(d, v1, v2, a, n); return true;
     case 11: launch_track_fast_t<11, 2>(d, v1, v2, a, n); return true;
     case 13: launch_track_fast_t<13, 2>(d, v1, v2, a, n); return true;

@@ -219,3 +219,209 @@ track_fast_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, float* __restrict_
     else { fx[f] = xout; fy[f] = yout; fval[f] = KLT_TRACKED; }
   }
 }
+
+// ---------------------------------------------------------------------------------------------
+// 7x7 window (the default and the window of every BASELINE config): vectorised footprint loads.
+//
+// ncu on track_fast_kernel: 14.2 M L1 sectors for 0.52 M load requests -- each scalar load of a
+// warp touches 32 different image rows, so the kernel is bound by L1TEX wavefronts, not by DRAM
+// or arithmetic.  A 7x7 window at a fractional position reads an 8x8 pixel footprint: 8 rows
+// for the 8 lanes of a feature group.  Lane r loads footprint row r as three aligned float4
+// (the 8 pixels straddle at most three 16 B chunks), realigns them in registers with two levels
+// of selects (offset 0..3), interpolates horizontally, and obtains the row below from lane r+1
+// with a shuffle for the vertical interpolation.  Loads per lane and image: 3 x LDG.128 instead
+// of 16 x LDG.32.
+// ---------------------------------------------------------------------------------------------
+struct Foot7 {
+  int off;        // element offset of the first aligned chunk of this lane's row
+  int o;          // 0..3: position of footprint column 0 inside the first chunk
+  float ax, ay;
+};
+__device__ __forceinline__ Foot7 foot7_setup(float x, float y, int pitch, int r8) {
+  const int xt = (int)x, yt = (int)y;
+  Foot7 f;
+  const int xs = xt - 3;                         // >= 0 (bounds were checked)
+  f.o = xs & 3;
+  f.off = (yt - 3 + r8) * pitch + (xs & ~3);
+  f.ax = x - (float)xt;
+  f.ay = y - (float)yt;
+  return f;
+}
+// window row r8 of the bilinear samples of one image (valid for r8 < 7)
+// gmask: the 8 lanes of this feature group (whole groups call this together)
+__device__ __forceinline__ void foot7_sample(const float* __restrict__ img, const Foot7& f, unsigned gmask,
+                                             float* out) {
+  const float4* p = reinterpret_cast<const float4*>(img + f.off);
+  const float4 c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + 2);
+  const float v[12] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
+  float t[10], q[8];
+  const bool s2 = (f.o & 2) != 0, s1 = (f.o & 1) != 0;
+#pragma unroll
+  for (int j = 0; j < 10; ++j) t[j] = s2 ? v[j + 2] : v[j];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) q[j] = s1 ? t[j + 1] : t[j];
+  float h[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) h[i] = fmaf(f.ax, q[i + 1] - q[i], q[i]);
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const float below = __shfl_down_sync(gmask, h[i], 1, 8);
+    out[i] = fmaf(f.ay, below - h[i], h[i]);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+track7_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, float* __restrict__ fx,
+              float* __restrict__ fy, int* __restrict__ fval,
+              unsigned long long* __restrict__ live_total) {
+  constexpr int WW = 7, hw = 3, hh = 3;
+  const int lane = threadIdx.x & 31;
+  const int r8 = lane & 7;
+  const bool rowlane = r8 < 7;                                // lane 7 only feeds the shuffle
+  const unsigned gmask = 0xFFu << (lane & 24);                // the 8 lanes of this feature group
+  const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+
+  bool alive = false;
+  float xloc = 0.0f, yloc = 0.0f;
+  if (f < n) {
+    alive = fval[f] >= 0;                                     // only features that are not lost (:1346)
+    if (alive) { xloc = fx[f]; yloc = fy[f]; }
+  }
+  {
+    const unsigned bal = __ballot_sync(0xffffffffu, alive && r8 == 0);
+    if (lane == 0 && bal) atomicAdd(live_total, (unsigned long long)__popc(bal));
+  }
+  if (!__any_sync(0xffffffffu, alive)) return;
+
+  for (int r = a.nlevels - 1; r >= 0; --r) { xloc = xloc / a.ss; yloc = yloc / a.ss; }
+  float xout = xloc, yout = yloc;
+  int status = KLT_TRACKED;
+  bool running = alive;
+
+  for (int r = a.nlevels - 1; r >= 0; --r) {
+    if (running) { xloc *= a.ss; yloc *= a.ss; xout *= a.ss; yout *= a.ss; }
+    const int nc = p1.ncols[r], nr = p1.nrows[r], pitch = p1.pitch[r];
+    const float* __restrict__ i1 = p1.img[r];
+    const float* __restrict__ gx1 = p1.gx[r];
+    const float* __restrict__ gy1 = p1.gy[r];
+    const float* __restrict__ i2 = p2.img[r];
+    const float* __restrict__ gx2 = p2.gx[r];
+    const float* __restrict__ gy2 = p2.gy[r];
+
+    if (running && r > 0) {                                   // L2 prefetch of the next finer level
+      const int pn = p1.pitch[r - 1], ncn = p1.ncols[r - 1], nrn = p1.nrows[r - 1];
+      const int px1 = (int)(xloc * a.ss) - hw, py1 = (int)(yloc * a.ss) - hh + r8;
+      const int px2 = (int)(xout * a.ss) - hw, py2 = (int)(yout * a.ss) - hh + r8;
+      if (px1 >= 0 && py1 >= 0 && px1 + WW < ncn && py1 < nrn) {
+        const size_t o = (size_t)py1 * pn + px1;
+        prefetch_l2(p1.img[r - 1] + o); prefetch_l2(p1.img[r - 1] + o + WW);
+        prefetch_l2(p1.gx[r - 1] + o);  prefetch_l2(p1.gx[r - 1] + o + WW);
+        prefetch_l2(p1.gy[r - 1] + o);  prefetch_l2(p1.gy[r - 1] + o + WW);
+      }
+      if (px2 >= 0 && py2 >= 0 && px2 + WW < ncn && py2 < nrn) {
+        const size_t o = (size_t)py2 * pn + px2;
+        prefetch_l2(p2.img[r - 1] + o); prefetch_l2(p2.img[r - 1] + o + WW);
+        prefetch_l2(p2.gx[r - 1] + o);  prefetch_l2(p2.gx[r - 1] + o + WW);
+        prefetch_l2(p2.gy[r - 1] + o);  prefetch_l2(p2.gy[r - 1] + o + WW);
+      }
+    }
+
+    const float x1 = xloc, y1 = yloc;
+    float x2 = xout, y2 = yout;
+    int iteration = 0;
+    float dx = 0.0f, dy = 0.0f;
+    float t_i[WW], t_gx[WW], t_gy[WW];
+    bool iterating = running;
+    int lvl_status = KLT_TRACKED;
+
+    if (iterating && window_oob(x1, y1, hw, hh, nc, nr)) { lvl_status = KLT_OOB; iterating = false; }
+    if (iterating && window_oob(x2, y2, hw, hh, nc, nr)) { lvl_status = KLT_OOB; iterating = false; }
+    // the sampling routines shuffle inside the 8-lane group, so whole groups enter them together
+    // (iterating is uniform within a group)
+    if (iterating) {
+      const Foot7 ft = foot7_setup(x1, y1, pitch, r8);
+      foot7_sample(i1, ft, gmask, t_i);
+      foot7_sample(gx1, ft, gmask, t_gx);
+      foot7_sample(gy1, ft, gmask, t_gy);
+    }
+
+    while (__any_sync(0xffffffffu, iterating)) {
+      float gxx = 0.0f, gxy = 0.0f, gyy = 0.0f, ex = 0.0f, ey = 0.0f;
+      if (iterating) {
+        const Foot7 ft = foot7_setup(x2, y2, pitch, r8);
+        float s_i[WW], s_gx[WW], s_gy[WW];
+        foot7_sample(i2, ft, gmask, s_i);
+        foot7_sample(gx2, ft, gmask, s_gx);
+        foot7_sample(gy2, ft, gmask, s_gy);
+        if (rowlane) {
+#pragma unroll
+          for (int i = 0; i < WW; ++i) {
+            const float df = t_i[i] - s_i[i];
+            const float sx = t_gx[i] + s_gx[i];
+            const float sy = t_gy[i] + s_gy[i];
+            gxx = fmaf(sx, sx, gxx); gxy = fmaf(sx, sy, gxy); gyy = fmaf(sy, sy, gyy);
+            ex = fmaf(df, sx, ex); ey = fmaf(df, sy, ey);
+          }
+        }
+      }
+      gxx = group_sum8(gxx); gxy = group_sum8(gxy); gyy = group_sum8(gyy);
+      ex = group_sum8(ex); ey = group_sum8(ey);
+      if (iterating) {
+        ex *= a.step_factor; ey *= a.step_factor;
+        const float det = gxx * gyy - gxy * gxy;
+        if (det < a.min_determinant) {
+          lvl_status = KLT_SMALL_DET; iterating = false;
+        } else {
+          dx = (gyy * ex - gxy * ey) / det;
+          dy = (gxx * ey - gxy * ex) / det;
+          x2 += dx; y2 += dy;
+          ++iteration;
+          const bool again = (fabsf(dx) >= a.min_displacement || fabsf(dy) >= a.min_displacement) &&
+                             iteration < a.max_iterations;
+          if (!again) iterating = false;
+          else if (window_oob(x2, y2, hw, hh, nc, nr)) { lvl_status = KLT_OOB; iterating = false; }
+        }
+      }
+    }
+
+    bool need_res = false;
+    if (running) {
+      if (window_oob(x2, y2, hw, hh, nc, nr)) lvl_status = KLT_OOB;
+      need_res = (lvl_status == KLT_TRACKED);
+    }
+    if (__any_sync(0xffffffffu, need_res)) {
+      float sum = 0.0f;
+      if (need_res) {
+        const Foot7 ft = foot7_setup(x2, y2, pitch, r8);
+        float s_i[WW];
+        foot7_sample(i2, ft, gmask, s_i);
+        if (rowlane) {
+#pragma unroll
+          for (int i = 0; i < WW; ++i) sum += fabsf(t_i[i] - s_i[i]);
+        }
+      }
+      sum = group_sum8(sum);
+      if (need_res && sum / 49.0f > a.max_residue) lvl_status = KLT_LARGE_RESIDUE;
+    }
+    if (running) {
+      int v;
+      if (lvl_status == KLT_SMALL_DET) v = KLT_SMALL_DET;
+      else if (lvl_status == KLT_OOB) v = KLT_OOB;
+      else if (lvl_status == KLT_LARGE_RESIDUE) v = KLT_LARGE_RESIDUE;
+      else if (iteration >= a.max_iterations) v = KLT_MAX_ITERATIONS;
+      else v = KLT_TRACKED;
+      status = v;
+      xout = x2; yout = y2;
+      if (v == KLT_SMALL_DET || v == KLT_OOB) running = false;
+    }
+    if (!__any_sync(0xffffffffu, running)) break;
+  }
+
+  if (alive && r8 == 0) {
+    const bool outside = (xout < (float)a.borderx || xout > (float)(a.ncols - 1 - a.borderx) ||
+                          yout < (float)a.bordery || yout > (float)(a.nrows - 1 - a.bordery));
+    if (status == KLT_OOB || outside) { fx[f] = -1.0f; fy[f] = -1.0f; fval[f] = KLT_OOB; }
+    else if (status != KLT_TRACKED) { fx[f] = -1.0f; fy[f] = -1.0f; fval[f] = status; }
+    else { fx[f] = xout; fy[f] = yout; fval[f] = KLT_TRACKED; }
+  }
+}

@@ -92,12 +92,13 @@ def test_golden_run_exact_mode(L, capi, oracle, oracle_mod, provided, golden_ft)
     L.KLTFreeTrackingContext(tc)
 
 
-def _teacher_forced(L, capi, oracle, oracle_mod, imgs, n, exact, tc_setup=None):
+def _teacher_forced(L, capi, oracle, oracle_mod, imgs, n, exact, tc_setup=None, no_fused=0):
     tc = L.KLTCreateTrackingContext()
     tc.contents.sequentialMode = 1
     if tc_setup:
         tc_setup(tc)
     L.KLTB200SetExact(tc, exact)
+    L.klt_dev_disable_fused(L.KLTB200Device(tc), no_fused)
     p = params_from_tc(oracle, tc)
     fl = L.KLTCreateFeatureList(n)
     ox, oy, ov = oracle.select(imgs[0], p, n, sort_kind=oracle_mod.SORT_STABLE)
@@ -221,3 +222,9 @@ def test_track_other_window_sizes(L, capi, oracle, oracle_mod, window, exact):
         L.KLTUpdateTCBorder(tc)
     rep = _teacher_forced(L, capi, oracle, oracle_mod, imgs, 200, exact, setup)
     assert rep[-1][3] > 60
+
+
+def test_track_7x7_generic_fast_kernel(L, capi, oracle, oracle_mod, provided):
+    """fma mode without the specialised kernels: tiled image kernels + track_fast_kernel<7,1>"""
+    rep = _teacher_forced(L, capi, oracle, oracle_mod, provided[:5], 150, 0, no_fused=1)
+    assert rep[-1][3] > 80
