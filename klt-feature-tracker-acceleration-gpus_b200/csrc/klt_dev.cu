@@ -1395,7 +1395,15 @@ static bool launch_track_fast(klt_dev* d, const PyrView& v1, const PyrView& v2, 
     case 7:
       if (d->track7_off) { launch_track_fast_t<7, 1>(d, v1, v2, a, n); return true; }
       { Launch l(d, KID_TRACK7);
-        track7_kernel<<<(8 * n + 127) / 128, 128, 0, d->stream>>>(v1, v2, a, n, d->d_x, d->d_y, d->d_val, d->d_live); }
+        static int fpw = getenv("KLT_TRACK_FPW") ? atoi(getenv("KLT_TRACK_FPW")) : 4;
+        const int warps_per_block = 4;
+        if (fpw == 1)
+          track7_kernel<1><<<(n + warps_per_block - 1) / warps_per_block, 128, 0, d->stream>>>(v1, v2, a, n, d->d_x, d->d_y, d->d_val, d->d_live);
+        else if (fpw == 4)
+          track7_kernel<4><<<(n + 4 * warps_per_block - 1) / (4 * warps_per_block), 128, 0, d->stream>>>(v1, v2, a, n, d->d_x, d->d_y, d->d_val, d->d_live);
+        else
+          track7_kernel<2><<<(n + 2 * warps_per_block - 1) / (2 * warps_per_block), 128, 0, d->stream>>>(v1, v2, a, n, d->d_x, d->d_y, d->d_val, d->d_live);
+      }
       return true;
     case 9: launch_track_fast_t<9, 2>(d, v1, v2, a, n); return true;
     case 11: launch_track_fast_t<11, 2>(d, v1, v2, a, n); return true;

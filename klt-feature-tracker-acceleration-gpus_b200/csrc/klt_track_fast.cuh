@@ -247,13 +247,20 @@ __device__ __forceinline__ Foot7 foot7_setup(float x, float y, int pitch, int r8
   f.ay = y - (float)yt;
   return f;
 }
-// window row r8 of the bilinear samples of one image (valid for r8 < 7)
-// gmask: the 8 lanes of this feature group (whole groups call this together)
-__device__ __forceinline__ void foot7_sample(const float* __restrict__ img, const Foot7& f, unsigned gmask,
-                                             float* out) {
-  const float4* p = reinterpret_cast<const float4*>(img + f.off);
-  const float4 c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + 2);
-  const float v[12] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
+// raw footprint row of this lane: three aligned 16 B chunks
+struct Row12 { float4 c0, c1, c2; };
+__device__ __forceinline__ Row12 foot7_load(const float* __restrict__ img, int off) {
+  const float4* p = reinterpret_cast<const float4*>(img + off);
+  Row12 r;
+  r.c0 = __ldg(p); r.c1 = __ldg(p + 1); r.c2 = __ldg(p + 2);
+  return r;
+}
+// window row r8 of the bilinear samples (valid for r8 < 7) from the raw row of this lane and,
+// through a shuffle, the row below.  gmask: the 8 lanes of this feature group (whole groups call
+// this together).
+__device__ __forceinline__ void foot7_interp(const Row12& r, const Foot7& f, unsigned gmask, float* out) {
+  const float v[12] = {r.c0.x, r.c0.y, r.c0.z, r.c0.w, r.c1.x, r.c1.y, r.c1.z, r.c1.w,
+                       r.c2.x, r.c2.y, r.c2.z, r.c2.w};
   float t[10], q[8];
   const bool s2 = (f.o & 2) != 0, s1 = (f.o & 1) != 0;
 #pragma unroll
@@ -269,7 +276,15 @@ __device__ __forceinline__ void foot7_sample(const float* __restrict__ img, cons
     out[i] = fmaf(f.ay, below - h[i], h[i]);
   }
 }
+__device__ __forceinline__ void foot7_sample(const float* __restrict__ img, const Foot7& f, unsigned gmask,
+                                             float* out) {
+  const Row12 r = foot7_load(img, f.off);
+  foot7_interp(r, f, gmask, out);
+}
 
+// FPW: features per warp (1, 2 or 4).  Fewer features per warp = more warps in flight for the
+// same work: the kernel is latency bound (issue slots are ~10 % used), so idle lanes are free.
+template <int FPW>
 __global__ void __launch_bounds__(128)
 track7_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, float* __restrict__ fx,
               float* __restrict__ fy, int* __restrict__ fval,
@@ -279,7 +294,9 @@ track7_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, float* __restrict__ fx
   const int r8 = lane & 7;
   const bool rowlane = r8 < 7;                                // lane 7 only feeds the shuffle
   const unsigned gmask = 0xFFu << (lane & 24);                // the 8 lanes of this feature group
-  const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int grp = lane >> 3;
+  const int f = grp < FPW ? warp_global * FPW + grp : n;      // groups >= FPW stay idle
 
   bool alive = false;
   float xloc = 0.0f, yloc = 0.0f;
@@ -308,24 +325,6 @@ track7_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, float* __restrict__ fx
     const float* __restrict__ gx2 = p2.gx[r];
     const float* __restrict__ gy2 = p2.gy[r];
 
-    if (running && r > 0) {                                   // L2 prefetch of the next finer level
-      const int pn = p1.pitch[r - 1], ncn = p1.ncols[r - 1], nrn = p1.nrows[r - 1];
-      const int px1 = (int)(xloc * a.ss) - hw, py1 = (int)(yloc * a.ss) - hh + r8;
-      const int px2 = (int)(xout * a.ss) - hw, py2 = (int)(yout * a.ss) - hh + r8;
-      if (px1 >= 0 && py1 >= 0 && px1 + WW < ncn && py1 < nrn) {
-        const size_t o = (size_t)py1 * pn + px1;
-        prefetch_l2(p1.img[r - 1] + o); prefetch_l2(p1.img[r - 1] + o + WW);
-        prefetch_l2(p1.gx[r - 1] + o);  prefetch_l2(p1.gx[r - 1] + o + WW);
-        prefetch_l2(p1.gy[r - 1] + o);  prefetch_l2(p1.gy[r - 1] + o + WW);
-      }
-      if (px2 >= 0 && py2 >= 0 && px2 + WW < ncn && py2 < nrn) {
-        const size_t o = (size_t)py2 * pn + px2;
-        prefetch_l2(p2.img[r - 1] + o); prefetch_l2(p2.img[r - 1] + o + WW);
-        prefetch_l2(p2.gx[r - 1] + o);  prefetch_l2(p2.gx[r - 1] + o + WW);
-        prefetch_l2(p2.gy[r - 1] + o);  prefetch_l2(p2.gy[r - 1] + o + WW);
-      }
-    }
-
     const float x1 = xloc, y1 = yloc;
     float x2 = xout, y2 = yout;
     int iteration = 0;
@@ -345,14 +344,22 @@ track7_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, float* __restrict__ fx
       foot7_sample(gy1, ft, gmask, t_gy);
     }
 
+    // raw footprint rows of frame 2, kept across iterations: sub-pixel Newton updates and the
+    // residue pass usually stay on the same 8x8 integer footprint, so nothing is re-read
+    Row12 c_i, c_gx, c_gy;
+    int c_off = -1;
     while (__any_sync(0xffffffffu, iterating)) {
       float gxx = 0.0f, gxy = 0.0f, gyy = 0.0f, ex = 0.0f, ey = 0.0f;
       if (iterating) {
         const Foot7 ft = foot7_setup(x2, y2, pitch, r8);
+        if (ft.off != c_off) {                               // uniform within the group
+          c_i = foot7_load(i2, ft.off); c_gx = foot7_load(gx2, ft.off); c_gy = foot7_load(gy2, ft.off);
+          c_off = ft.off;
+        }
         float s_i[WW], s_gx[WW], s_gy[WW];
-        foot7_sample(i2, ft, gmask, s_i);
-        foot7_sample(gx2, ft, gmask, s_gx);
-        foot7_sample(gy2, ft, gmask, s_gy);
+        foot7_interp(c_i, ft, gmask, s_i);
+        foot7_interp(c_gx, ft, gmask, s_gx);
+        foot7_interp(c_gy, ft, gmask, s_gy);
         if (rowlane) {
 #pragma unroll
           for (int i = 0; i < WW; ++i) {
@@ -393,8 +400,9 @@ track7_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, float* __restrict__ fx
       float sum = 0.0f;
       if (need_res) {
         const Foot7 ft = foot7_setup(x2, y2, pitch, r8);
+        if (ft.off != c_off) { c_i = foot7_load(i2, ft.off); c_off = ft.off; }
         float s_i[WW];
-        foot7_sample(i2, ft, gmask, s_i);
+        foot7_interp(c_i, ft, gmask, s_i);
         if (rowlane) {
 #pragma unroll
           for (int i = 0; i < WW; ++i) sum += fabsf(t_i[i] - s_i[i]);
