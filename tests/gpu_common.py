@@ -47,3 +47,37 @@ def compare_status(gx, gy, gv, ox, oy, ov):
     if both.any():
         err = float(max(np.abs(gx[both] - ox[both]).max(), np.abs(gy[both] - oy[both]).max()))
     return float(agree.mean()), err
+
+
+def check_fma_step(oracle, p, pyr_prev, pyr_cur, x0, y0, v0, gx, gy, gv, ox, oy, ov, where=""):
+    """north_star parity gate for one teacher-forced frame pair in fma mode:
+    status codes agree on >= 99.5 % of features, coordinates within 0.01 px; every feature
+    outside that must be explained by threshold proximity -- the oracle itself lands on the
+    GPU's answer when its convergence / determinant / residue thresholds are nudged by 2 %
+    (one Newton iteration more or less at |dx| ~ min_displacement, etc.).  Unexplained
+    deviations fail; explained ones are limited to 0.5 % of the features."""
+    import copy
+    agree = (gv == ov)
+    assert agree.mean() >= STATUS_AGREE, "%s status agreement %.4f" % (where, agree.mean())
+    both = agree & (ov >= 0)
+    err = np.maximum(np.abs(gx - ox), np.abs(gy - oy))
+    suspects = np.nonzero((both & (err > PX_TOL)) | ~agree)[0]
+    if len(suspects) == 0:
+        return 0
+    assert len(suspects) <= max(1, int(0.005 * len(ov))), "%s: %d features off" % (where, len(suspects))
+    explained = np.zeros(len(suspects), bool)
+    for scale_d, scale_det, scale_res in ((0.98, 1, 1), (1.02, 1, 1), (1, 0.98, 1), (1, 1.02, 1),
+                                          (1, 1, 0.98), (1, 1, 1.02), (0.96, 1, 1), (1.04, 1, 1)):
+        q = copy.copy(p)
+        q.min_displacement = p.min_displacement * scale_d
+        q.min_determinant = p.min_determinant * scale_det
+        q.max_residue = p.max_residue * scale_res
+        ax, ay, av = oracle.track(pyr_prev, pyr_cur, q, x0[suspects], y0[suspects], v0[suspects])
+        ok = (av == gv[suspects]) & ((av < 0) | (np.maximum(np.abs(ax - gx[suspects]),
+                                                             np.abs(ay - gy[suspects])) <= PX_TOL))
+        explained |= ok
+    bad = suspects[~explained]
+    assert len(bad) == 0, "%s: unexplained deviations %s" % (
+        where, [(int(k), float(gx[k]), float(ox[k]), float(gy[k]), float(oy[k]), int(gv[k]), int(ov[k]))
+                for k in bad[:8]])
+    return len(suspects)

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from tests.conftest import synth_image
-from tests.gpu_common import PX_TOL, STATUS_AGREE, compare_status, params_from_tc
+from tests.gpu_common import PX_TOL, STATUS_AGREE, check_fma_step, compare_status, params_from_tc
 
 pytestmark = pytest.mark.gpu
 
@@ -109,17 +109,15 @@ def _teacher_forced(L, capi, oracle, oracle_mod, imgs, n, exact, tc_setup=None, 
         L.track(tc, imgs[i - 1], imgs[i], fl)
         gx, gy, gv = _get(capi, fl)
         cur = oracle.build_pyramids(imgs[i], p)
+        x0, y0, v0 = ox, oy, ov
         ox, oy, ov = oracle.track(prev, cur, p, ox, oy, ov)
-        prev = cur
         agree, err = compare_status(gx, gy, gv, ox, oy, ov)
         report.append((i, agree, err, int((ov >= 0).sum())))
         if exact:
             assert gx.tobytes() == ox.tobytes() and gy.tobytes() == oy.tobytes() and np.array_equal(gv, ov)
         else:
-            bad = np.nonzero(gv != ov)[0]
-            assert agree >= STATUS_AGREE, "frame %d: status agreement %.4f, disagreements %s" % (
-                i, agree, [(int(k), int(gv[k]), int(ov[k])) for k in bad[:10]])
-            assert err <= PX_TOL, "frame %d: max coordinate error %g px" % (i, err)
+            check_fma_step(oracle, p, prev, cur, x0, y0, v0, gx, gy, gv, ox, oy, ov, "frame %d" % i)
+        prev = cur
     L.KLTFreeFeatureList(fl)
     L.KLTFreeTrackingContext(tc)
     return report
