@@ -115,6 +115,12 @@ int klt_dev_features_upload(klt_dev *d, int n, const float *x, const float *y, c
 int klt_dev_track_resident(klt_dev *d, int slot_prev, int slot_cur,
                            const klt_dev_track_params *p);
 int klt_dev_features_download(klt_dev *d, int n, float *x, float *y, int *val);   /* synchronises */
+/* zero-copy variant for the C host layer: pack the feature list straight into the
+ * context's pinned staging area, commit it (async H2D), and after the work fetch the
+ * results back into the same area (D2H + synchronise). */
+int klt_dev_features_staging(klt_dev *d, int n, float **x, float **y, int **val);
+int klt_dev_features_commit(klt_dev *d, int n);
+int klt_dev_features_fetch(klt_dev *d, int n);
 
 /* ---- selection --------------------------------------------------------- */
 /* replaces the eigenvalue loop, _sortPointList and _enforceMinimumDistance of

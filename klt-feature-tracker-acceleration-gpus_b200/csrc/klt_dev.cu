@@ -795,11 +795,14 @@ struct klt_dev {
   // features
   float *d_x, *d_y; int* d_val; int feat_cap; int feat_n;
   float *h_x, *h_y; int* h_val;   // pinned staging
+  int staging_busy;
   // selection
   int *c_val[2]; unsigned* c_idx[2]; size_t cand_cap;
   void* cub_tmp; size_t cub_bytes;
   unsigned char* fmap; size_t fmap_cap;
   int* open_slots; int open_cap;
+  // dynamic tile scheduler of the persistent kernels: one counter per launch site
+  unsigned* d_tile_ctr; unsigned tile_base[16];
   // timing
   cudaEvent_t ev_a, ev_b; int ev_made;
   // per-kernel profiling (klt_dev_profile_*)
@@ -899,6 +902,8 @@ extern "C" int klt_dev_create(int device, klt_dev** out) {
   if (e != cudaSuccess) { free(c); return fail(nullptr, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
   e = cudaMalloc(&c->d_live, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemsetAsync(c->d_live, 0, sizeof(unsigned long long), c->stream);
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_tile_ctr, 16 * sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMemsetAsync(c->d_tile_ctr, 0, 16 * sizeof(unsigned), c->stream);
   if (e != cudaSuccess) { cudaStreamDestroy(c->stream); free(c); return fail(nullptr, "cudaMalloc: %s", cudaGetErrorString(e)); }
   *out = c;
   return 0;
@@ -917,13 +922,14 @@ extern "C" void klt_dev_destroy(klt_dev* d) {
   cudaStreamSynchronize(d->stream);
   free_geometry(d);
   cudaFree(d->frame);
-  cudaFree(d->d_x); cudaFree(d->d_y); cudaFree(d->d_val);
-  cudaFreeHost(d->h_x); cudaFreeHost(d->h_y); cudaFreeHost(d->h_val);
+  cudaFree(d->d_x);
+  cudaFreeHost(d->h_x);
   for (int i = 0; i < 2; ++i) { cudaFree(d->c_val[i]); cudaFree(d->c_idx[i]); }
   cudaFree(d->cub_tmp); cudaFree(d->fmap); cudaFree(d->open_slots);
   if (d->ev_made) { cudaEventDestroy(d->ev_a); cudaEventDestroy(d->ev_b); }
   if (d->prof_ev) { for (int i = 0; i < 2 * PROF_POOL; ++i) cudaEventDestroy(d->prof_ev[i]); free(d->prof_ev); free(d->prof_kid); }
   cudaFree(d->d_live);
+  cudaFree(d->d_tile_ctr);
   cudaStreamDestroy(d->stream);
   free(d);
 }
@@ -1120,16 +1126,18 @@ static int l0_fused_dispatch(klt_dev* d, const unsigned char* src, int spitch, i
   const int ntiles = tiles_x * tiles_y;
   const int grid = ntiles < 3 * d->num_sms ? ntiles : 3 * d->num_sms;       // persistent, 3 CTAs / SM
   { Launch l(d, KID_L0_FUSED);
-    l0_fused_kernel<EXACT><<<grid, 256, L0Geo::SMEM, d->stream>>>(map, W, H, tiles_x, ntiles, ts, tg, td,
-                                                                  lv.img, lv.gx, lv.gy, lv.pitch); }
+    l0_fused_kernel<EXACT><<<grid, 256, L0Geo::SMEM, d->stream>>>(map, W, H, tiles_x, ntiles, d->d_tile_ctr,
+                                                                  d->tile_base[0], ts, tg, td, lv.img, lv.gx,
+                                                                  lv.gy, lv.pitch);
+    d->tile_base[0] += (unsigned)(ntiles + grid); }
   *done = true;
   return 0;
 }
 
 // fused coarser level (L_{l-1} -> L_l, gx_l, gy_l)
 template <int SS, int R, int TX, int TY, bool EXACT>
-static int launch_level_fused(klt_dev* d, const Level& a, const Level& b, const TapsR& tp, const TapsR& tg,
-                              const TapsR& td, bool* done) {
+static int launch_level_fused(klt_dev* d, int level, const Level& a, const Level& b, const TapsR& tp,
+                              const TapsR& tg, const TapsR& td, bool* done) {
   using G = LvGeo<SS, R, TX, TY>;
   *done = false;
   CUtensorMap map;
@@ -1146,18 +1154,20 @@ static int launch_level_fused(klt_dev* d, const Level& a, const Level& b, const 
   const int grid = ntiles < 2 * d->num_sms ? ntiles : 2 * d->num_sms;       // persistent, 2 CTAs / SM
   { Launch l(d, KID_LEVEL_FUSED);
     level_fused_kernel<SS, R, TX, TY, EXACT><<<grid, 256, G::SMEM, d->stream>>>(
-        map, a.w, a.h, b.w, b.h, tiles_x, ntiles, tp, tg, td, b.img, b.gx, b.gy, b.pitch); }
+        map, a.w, a.h, b.w, b.h, tiles_x, ntiles, d->d_tile_ctr + (level & 15), d->tile_base[level & 15], tp, tg,
+        td, b.img, b.gx, b.gy, b.pitch);
+    d->tile_base[level & 15] += (unsigned)(ntiles + grid); }
   *done = true;
   return 0;
 }
 template <bool EXACT>
-static int level_fused_dispatch(klt_dev* d, int ss, const Level& a, const Level& b, const TapsR& tp,
+static int level_fused_dispatch(klt_dev* d, int ss, int level, const Level& a, const Level& b, const TapsR& tp,
                                 const TapsR& tg, const TapsR& td, bool* done) {
   *done = false;
   if (!fused_grad_taps_ok(tg, td)) return 0;
   const int r = tp.w / 2;
-  if (ss == 2 && r == 5) return launch_level_fused<2, 5, 64, 32, EXACT>(d, a, b, tp, tg, td, done);
-  if (ss == 4 && r == 10) return launch_level_fused<4, 10, 32, 16, EXACT>(d, a, b, tp, tg, td, done);
+  if (ss == 2 && r == 5) return launch_level_fused<2, 5, 64, 32, EXACT>(d, level, a, b, tp, tg, td, done);
+  if (ss == 4 && r == 10) return launch_level_fused<4, 10, 32, 16, EXACT>(d, level, a, b, tp, tg, td, done);
   return 0;
 }
 
@@ -1221,7 +1231,7 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
       const Level& b = S.lv[l];
       done = false;
       if (!d->force_generic && !d->no_fused) {
-        if (level_fused_dispatch<EXACT>(d, q->subsampling, a, b, tp, tg, td, &done)) return 1;
+        if (level_fused_dispatch<EXACT>(d, q->subsampling, l, a, b, tp, tg, td, &done)) return 1;
         if (done) { grads_done[l] = true; d->last_fused += 1; continue; }
       }
       if (!d->force_generic)
@@ -1315,21 +1325,29 @@ extern "C" int klt_dev_read_level(klt_dev* d, int slot, int which, int level, fl
 }
 
 // ---- features --------------------------------------------------------------------
+// device and pinned-host staging hold x | y | val back to back (one copy each way)
 static int ensure_features(klt_dev* d, int n) {
   if (n <= d->feat_cap) return 0;
   CU(cudaStreamSynchronize(d->stream));
-  cudaFree(d->d_x); cudaFree(d->d_y); cudaFree(d->d_val);
-  cudaFreeHost(d->h_x); cudaFreeHost(d->h_y); cudaFreeHost(d->h_val);
+  cudaFree(d->d_x);
+  cudaFreeHost(d->h_x);
   d->d_x = d->d_y = nullptr; d->d_val = nullptr; d->h_x = d->h_y = nullptr; d->h_val = nullptr;
   d->feat_cap = 0;
   const int cap = (n + 1023) / 1024 * 1024;
-  CU(cudaMalloc(&d->d_x, cap * sizeof(float)));
-  CU(cudaMalloc(&d->d_y, cap * sizeof(float)));
-  CU(cudaMalloc(&d->d_val, cap * sizeof(int)));
-  CU(cudaMallocHost(&d->h_x, cap * sizeof(float)));
-  CU(cudaMallocHost(&d->h_y, cap * sizeof(float)));
-  CU(cudaMallocHost(&d->h_val, cap * sizeof(int)));
+  CU(cudaMalloc(&d->d_x, (size_t)cap * 12));
+  CU(cudaMallocHost(&d->h_x, (size_t)cap * 12));
+  d->d_y = d->d_x + cap; d->d_val = reinterpret_cast<int*>(d->d_y + cap);
+  d->h_y = d->h_x + cap; d->h_val = reinterpret_cast<int*>(d->h_y + cap);
   d->feat_cap = cap;
+  return 0;
+}
+
+// the pinned staging area is reused by every call: wait for copies that may still read/write it
+static int staging_quiesce(klt_dev* d) {
+  if (d->staging_busy) {
+    CU(cudaStreamSynchronize(d->stream));
+    d->staging_busy = 0;
+  }
   return 0;
 }
 
@@ -1337,25 +1355,43 @@ extern "C" int klt_dev_features_upload(klt_dev* d, int n, const float* x, const 
   CU(cudaSetDevice(d->device));
   if (n < 0) return fail(d, "negative feature count");
   if (ensure_features(d, n > 0 ? n : 1)) return 1;
-  // the pinned staging buffers may still be in flight from a previous call
-  CU(cudaStreamSynchronize(d->stream));
+  if (staging_quiesce(d)) return 1;
   memcpy(d->h_x, x, n * sizeof(float));
   memcpy(d->h_y, y, n * sizeof(float));
   memcpy(d->h_val, val, n * sizeof(int));
-  CU(cudaMemcpyAsync(d->d_x, d->h_x, n * sizeof(float), cudaMemcpyHostToDevice, d->stream));
-  CU(cudaMemcpyAsync(d->d_y, d->h_y, n * sizeof(float), cudaMemcpyHostToDevice, d->stream));
-  CU(cudaMemcpyAsync(d->d_val, d->h_val, n * sizeof(int), cudaMemcpyHostToDevice, d->stream));
+  CU(cudaMemcpyAsync(d->d_x, d->h_x, (size_t)d->feat_cap * 12, cudaMemcpyHostToDevice, d->stream));
+  d->staging_busy = 1;
   d->feat_n = n;
   return 0;
 }
 
-extern "C" int klt_dev_features_download(klt_dev* d, int n, float* x, float* y, int* val) {
+// staging access for the C host layer: it packs the feature list straight into pinned memory
+extern "C" int klt_dev_features_staging(klt_dev* d, int n, float** x, float** y, int** val) {
+  CU(cudaSetDevice(d->device));
+  if (ensure_features(d, n > 0 ? n : 1)) return 1;
+  if (staging_quiesce(d)) return 1;
+  *x = d->h_x; *y = d->h_y; *val = d->h_val;
+  return 0;
+}
+extern "C" int klt_dev_features_commit(klt_dev* d, int n) {      // H2D of the staging area (async)
+  CU(cudaSetDevice(d->device));
+  if (n > d->feat_cap) return fail(d, "commit of %d features, capacity %d", n, d->feat_cap);
+  CU(cudaMemcpyAsync(d->d_x, d->h_x, (size_t)d->feat_cap * 12, cudaMemcpyHostToDevice, d->stream));
+  d->staging_busy = 1;
+  d->feat_n = n;
+  return 0;
+}
+extern "C" int klt_dev_features_fetch(klt_dev* d, int n) {       // D2H into the staging area + sync
   CU(cudaSetDevice(d->device));
   if (n > d->feat_n) return fail(d, "download of %d features but %d resident", n, d->feat_n);
-  CU(cudaMemcpyAsync(d->h_x, d->d_x, n * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
-  CU(cudaMemcpyAsync(d->h_y, d->d_y, n * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
-  CU(cudaMemcpyAsync(d->h_val, d->d_val, n * sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+  CU(cudaMemcpyAsync(d->h_x, d->d_x, (size_t)d->feat_cap * 12, cudaMemcpyDeviceToHost, d->stream));
   CU(cudaStreamSynchronize(d->stream));
+  d->staging_busy = 0;
+  return 0;
+}
+
+extern "C" int klt_dev_features_download(klt_dev* d, int n, float* x, float* y, int* val) {
+  if (klt_dev_features_fetch(d, n)) return 1;
   memcpy(x, d->h_x, n * sizeof(float));
   memcpy(y, d->h_y, n * sizeof(float));
   memcpy(val, d->h_val, n * sizeof(int));

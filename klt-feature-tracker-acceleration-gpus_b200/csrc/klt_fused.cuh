@@ -8,7 +8,7 @@
 // 273-314, src/V1/pyramid.c:112-124 as sequenced by trackFeatures.c:1311-1321) without any
 // float input image, horizontal-pass temporary or smoothed-before-subsample image touching HBM.
 //
-// Both kernels are persistent (grid = resident CTAs, static round-robin over tiles): the
+// Both kernels are persistent (grid = resident CTAs, tiles claimed from an atomic counter): the
 // TMA load of the next tile's source box is issued as soon as the current one has been
 // consumed, so its latency hides behind the remaining stages.  All stages of a tile run in
 // shared memory:
@@ -322,25 +322,35 @@ __device__ __forceinline__ void l0_fused_tile_rest(unsigned char* smem, int W, i
                                                             x0, y0, W, H);
 }
 
+// Tiles are handed out dynamically: counter[0] - base is the next tile index.  Every CTA performs
+// (tiles it processed + 1) atomicAdds, so after the launch the counter stands at
+// base + ntiles + gridDim.x, which the host uses as the next launch's base (no reset needed).
+// The claim for the NEXT tile is made one tile ahead, so its TMA load can be issued early.
 template <bool EXACT>
 __global__ void __launch_bounds__(256, 3)
 l0_fused_kernel(const __grid_constant__ CUtensorMap map, int W, int H, int tiles_x, int ntiles,
+                unsigned* __restrict__ counter, unsigned base,
                 TapsR ts, TapsR tg, TapsR td, float* __restrict__ out_img,
                 float* __restrict__ out_gx, float* __restrict__ out_gy, int opitch) {
   using G = L0Geo;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + G::OFF_BAR);
+  volatile int* s_next = reinterpret_cast<volatile int*>(smem_raw + G::OFF_BAR + 8);
   const int tid = threadIdx.x;
-  if (tid == 0) mbar_init(bar, 1);
-  __syncthreads();
-  int tile = blockIdx.x;
-  if (tid == 0 && tile < ntiles) {
-    mbar_expect_tx(bar, G::U8_W * G::U8_H);
-    tma_load_2d(smem_raw + G::OFF_U8, &map, (tile % tiles_x) * G::TX - 16,
-                (tile / tiles_x) * G::TY - (G::RS + G::RG), bar);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    const int t = (int)(atomicAdd(counter, 1u) - base);
+    *s_next = t;
+    if (t < ntiles) {
+      mbar_expect_tx(bar, G::U8_W * G::U8_H);
+      tma_load_2d(smem_raw + G::OFF_U8, &map, (t % tiles_x) * G::TX - 16,
+                  (t / tiles_x) * G::TY - (G::RS + G::RG), bar);
+    }
   }
+  __syncthreads();
+  int tile = *s_next;
   unsigned phase = 0;
-  for (; tile < ntiles; tile += gridDim.x) {
+  while (tile < ntiles) {
     const int x0 = (tile % tiles_x) * G::TX, y0 = (tile / tiles_x) * G::TY;
     // tiles whose 8-pixel margin stays inside the image never meet a zero band
     const bool border = (x0 < 8) || (y0 < 8) || (x0 + G::TX + 8 > W) || (y0 + G::TY + 8 > H);
@@ -348,17 +358,21 @@ l0_fused_kernel(const __grid_constant__ CUtensorMap map, int W, int H, int tiles
     phase ^= 1;
     if (border) l0_fused_tile<EXACT, true>(smem_raw, W, ts, x0);
     else l0_fused_tile<EXACT, false>(smem_raw, W, ts, x0);
-    __syncthreads();                 // u8 tile consumed (and the previous tile's stage D is done)
-    const int next = tile + gridDim.x;
-    if (tid == 0 && next < ntiles) {
-      mbar_expect_tx(bar, G::U8_W * G::U8_H);
-      tma_load_2d(smem_raw + G::OFF_U8, &map, (next % tiles_x) * G::TX - 16,
-                  (next / tiles_x) * G::TY - (G::RS + G::RG), bar);
+    __syncthreads();                 // u8 tile consumed; everybody has read s_next
+    if (tid == 0) {
+      const int t = (int)(atomicAdd(counter, 1u) - base);
+      *s_next = t;
+      if (t < ntiles) {
+        mbar_expect_tx(bar, G::U8_W * G::U8_H);
+        tma_load_2d(smem_raw + G::OFF_U8, &map, (t % tiles_x) * G::TX - 16,
+                    (t / tiles_x) * G::TY - (G::RS + G::RG), bar);
+      }
     }
     if (border) l0_fused_tile_rest<EXACT, true>(smem_raw, W, H, ts, tg, td, out_img, out_gx, out_gy, opitch, x0, y0);
     else l0_fused_tile_rest<EXACT, false>(smem_raw, W, H, ts, tg, td, out_img, out_gx, out_gy, opitch, x0, y0);
     // stage D reads Hd (aliased on Hs) and Hg: the next tile's stage A must not start before
     __syncthreads();
+    tile = *s_next;
   }
 }
 
@@ -498,27 +512,34 @@ __device__ __forceinline__ void lv_stage_rest(unsigned char* smem, const TapsR& 
   stage_vgrad_both<EXACT, BORDER, TX, TY, PY, G::HP>(sHd, sHg, tg, td, out_gx, out_gy, opitch, x0, y0, W, H);
 }
 
-// W,H: size of the level being produced; Wsrc,Hsrc: size of the level it is made from
+// W,H: size of the level being produced; Wsrc,Hsrc: size of the level it is made from.
+// Dynamic tile scheduler as in l0_fused_kernel.
 template <int SS, int R, int TX, int TY, bool EXACT>
 __global__ void __launch_bounds__(256, 2)
 level_fused_kernel(const __grid_constant__ CUtensorMap map, int Wsrc, int Hsrc, int W, int H,
-                   int tiles_x, int ntiles, TapsR tp, TapsR tg, TapsR td,
+                   int tiles_x, int ntiles, unsigned* __restrict__ counter, unsigned base,
+                   TapsR tp, TapsR tg, TapsR td,
                    float* __restrict__ out_img, float* __restrict__ out_gx,
                    float* __restrict__ out_gy, int opitch) {
   using G = LvGeo<SS, R, TX, TY>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + G::OFF_BAR);
+  volatile int* s_next = reinterpret_cast<volatile int*>(smem_raw + G::OFF_BAR + 8);
   const int tid = threadIdx.x;
-  if (tid == 0) mbar_init(bar, 1);
-  __syncthreads();
-  int tile = blockIdx.x;
-  if (tid == 0 && tile < ntiles) {
-    mbar_expect_tx(bar, G::SW * G::SH * 4);
-    tma_load_2d(smem_raw + G::OFF_SRC, &map, SS * (tile % tiles_x) * TX + G::XOFF,
-                SS * (tile / tiles_x) * TY + G::YOFF, bar);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    const int t = (int)(atomicAdd(counter, 1u) - base);
+    *s_next = t;
+    if (t < ntiles) {
+      mbar_expect_tx(bar, G::SW * G::SH * 4);
+      tma_load_2d(smem_raw + G::OFF_SRC, &map, SS * (t % tiles_x) * TX + G::XOFF,
+                  SS * (t / tiles_x) * TY + G::YOFF, bar);
+    }
   }
+  __syncthreads();
+  int tile = *s_next;
   unsigned phase = 0;
-  for (; tile < ntiles; tile += gridDim.x) {
+  while (tile < ntiles) {
     const int x0 = (tile % tiles_x) * TX, y0 = (tile / tiles_x) * TY;
     // interior tiles (margins derived in DESIGN.md) never meet a zero band at either level
     const bool border = (x0 < 8) || (y0 < 8) || (x0 + TX + 16 > W) || (y0 + TY + 16 > H);
@@ -526,17 +547,21 @@ level_fused_kernel(const __grid_constant__ CUtensorMap map, int Wsrc, int Hsrc, 
     phase ^= 1;
     if (border) lv_stage_p1<EXACT, true, SS, R, TX, TY>(smem_raw, tp, x0, Wsrc);
     else lv_stage_p1<EXACT, false, SS, R, TX, TY>(smem_raw, tp, x0, Wsrc);
-    __syncthreads();                 // source box consumed
-    const int next = tile + gridDim.x;
-    if (tid == 0 && next < ntiles) {
-      mbar_expect_tx(bar, G::SW * G::SH * 4);
-      tma_load_2d(smem_raw + G::OFF_SRC, &map, SS * (next % tiles_x) * TX + G::XOFF,
-                  SS * (next / tiles_x) * TY + G::YOFF, bar);
+    __syncthreads();                 // source box consumed; everybody has read s_next
+    if (tid == 0) {
+      const int t = (int)(atomicAdd(counter, 1u) - base);
+      *s_next = t;
+      if (t < ntiles) {
+        mbar_expect_tx(bar, G::SW * G::SH * 4);
+        tma_load_2d(smem_raw + G::OFF_SRC, &map, SS * (t % tiles_x) * TX + G::XOFF,
+                    SS * (t / tiles_x) * TY + G::YOFF, bar);
+      }
     }
     if (border)
       lv_stage_rest<EXACT, true, SS, R, TX, TY>(smem_raw, tp, tg, td, Hsrc, W, H, out_img, out_gx, out_gy, opitch, x0, y0);
     else
       lv_stage_rest<EXACT, false, SS, R, TX, TY>(smem_raw, tp, tg, td, Hsrc, W, H, out_img, out_gx, out_gy, opitch, x0, y0);
     __syncthreads();                 // Hp / L / Hd / Hg free for the next tile
+    tile = *s_next;
   }
 }

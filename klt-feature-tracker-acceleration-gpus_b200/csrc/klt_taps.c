@@ -17,7 +17,28 @@
 static __thread klt_dev_taps t_cache;
 static __thread float t_sigma_last = -10.0f;
 
+/* generate() is a pure function of sigma; the last few results are remembered so that the
+ * per-frame sequence smooth -> pyramid -> gradient sigma does not redo ~200 exp() calls.
+ * (This memo is invisible: the reference's cache RULE lives in klt_taps_for below.) */
+#define MEMO 8
+static __thread struct { float sigma; int used; klt_dev_taps taps; } t_memo[MEMO];
+static __thread int t_memo_next = 0;
+
+static void generate_uncached(float sigma, klt_dev_taps *t);
+
 static void generate(float sigma, klt_dev_taps *t)
+{
+  int i;
+  for (i = 0; i < MEMO; i++)
+    if (t_memo[i].used && memcmp(&t_memo[i].sigma, &sigma, sizeof sigma) == 0) { *t = t_memo[i].taps; return; }
+  generate_uncached(sigma, t);
+  t_memo[t_memo_next].sigma = sigma;
+  t_memo[t_memo_next].used = 1;
+  t_memo[t_memo_next].taps = *t;
+  t_memo_next = (t_memo_next + 1) % MEMO;
+}
+
+static void generate_uncached(float sigma, klt_dev_taps *t)
 {
   const float cut = 0.01f;                 /* tails below 1 % of the peak are dropped */
   const int half = MAXW / 2;

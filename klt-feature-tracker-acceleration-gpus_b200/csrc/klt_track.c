@@ -104,30 +104,31 @@ static void track_common(KLT_TrackingContext tc, const KLT_PixelType *img1,
   check_supported(tc);
   dev = klt_state_device(s);
 
+  /* Everything below is queued on the context stream without waiting: feature upload,
+   * frame upload, pyramid kernels, tracker, result download; one synchronisation at the end. */
+  DEVCALL(s, klt_dev_features_staging(dev, n, &x, &y, &v));
+  klt_list_to_arrays(fl, x, y, v);
+  DEVCALL(s, klt_dev_features_commit(dev, n));
+
   slot_prev = prepare_previous(tc, s, img1, on_device, pitch, ncols, nrows);
   slot_cur = 1 - slot_prev;
   klt_fill_build_desc(tc, ncols, nrows, tc->nPyramidLevels, 1, s->exact, &q);
   DEVCALL(s, klt_dev_build(dev, slot_cur, img2, on_device, pitch, &q));
 
-  x = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
-  y = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
-  v = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
-  if (!x || !y || !v) KLTError("(KLTTrackFeatures) Out of memory");
-  klt_list_to_arrays(fl, x, y, v);
   fill_track_params(tc, s->exact, &tp);
-  DEVCALL(s, klt_dev_track(dev, slot_prev, slot_cur, &tp, n, x, y, v));
+  DEVCALL(s, klt_dev_track_resident(dev, slot_prev, slot_cur, &tp));
+  DEVCALL(s, klt_dev_features_fetch(dev, n));
   for (i = 0; i < n; i++) {
     KLT_Feature f = fl->feature[i];
     if (f->val < 0) continue;                 /* lost features are not touched (:1346) */
     f->x = x[i];
     f->y = y[i];
     f->val = v[i];
-    if (v[i] < 0) {                           /* lost now: drop affine templates (:1387-1392) */
-      free(f->aff_img); free(f->aff_img_gradx); free(f->aff_img_grady);
+    if (v[i] < 0 && (f->aff_img || f->aff_img_gradx || f->aff_img_grady)) {
+      free(f->aff_img); free(f->aff_img_gradx); free(f->aff_img_grady);   /* (:1387-1392) */
       f->aff_img = f->aff_img_gradx = f->aff_img_grady = NULL;
     }
   }
-  free(x); free(y); free(v);
 
   hand_over(tc, s, slot_cur);
 
