@@ -13,7 +13,8 @@
  * Data layout on the device: every float image is row-major with a row pitch
  * rounded up to 32 floats (128 B); one "pyramid set" holds, for each level l,
  * the smoothed image L_l and its gradients gx_l, gy_l.  A context owns two
- * sets (slots 0 and 1): the previous frame and the frame being built.
+ * sets (slots 0..2): the previous frame, the current frame and -- in the overlapped
+ * resident pipeline -- the frame being built while the tracker still reads the other two.
  */
 #ifndef KLT_CUDA_H
 #define KLT_CUDA_H
@@ -26,6 +27,7 @@ extern "C" {
 
 #define KLT_DEV_MAX_TAPS   71   /* reference src/V1/convolve.c:16 MAX_KERNEL_WIDTH */
 #define KLT_DEV_MAX_LEVELS 12
+#define KLT_DEV_SLOTS      3    /* pyramid sets per context: previous, current, being built */
 
 typedef struct klt_dev klt_dev;   /* opaque device context: stream, buffers */
 
@@ -140,6 +142,11 @@ int klt_dev_level_dims(const klt_dev *d, int level, int *ncols, int *nrows);
 int klt_dev_eigen_map(klt_dev *d, int slot, const klt_dev_select_params *p,
                       int *out, int *npoints);
 int klt_dev_sync(klt_dev *d);
+/* 1: the tracker and the feature copies run on a second stream, ordered against the
+ * pyramid builds with events, so build(k+1) overlaps track(k) (KLTB200Resident*);
+ * 0 (default): one stream, strictly in order.  Drains both streams. */
+int klt_dev_set_overlap(klt_dev *d, int on);
+int klt_dev_slots(void);
 /* number of kernels this context has launched so far */
 unsigned long long klt_dev_launch_count(const klt_dev *d);
 /* 1 if the last klt_dev_build used the fused tiled kernels, 0 if it took the

@@ -781,13 +781,20 @@ struct PyrSet {
 
 struct klt_dev {
   int device, num_sms;
-  cudaStream_t stream;
+  cudaStream_t stream;        // frame upload, pyramid kernels, selection
+  cudaStream_t tstream;       // tracker + feature copies; == stream unless overlap is on
+  cudaStream_t stream2;       // the second stream object (owned)
+  int overlap;                // 1: tracker of frame k runs concurrently with the build of frame k+1
+  cudaEvent_t ev_built[KLT_DEV_SLOTS];   // build of the slot finished (recorded on stream)
+  cudaEvent_t ev_read[KLT_DEV_SLOTS];    // last tracker reading the slot finished (recorded on tstream)
+  int read_pending[KLT_DEV_SLOTS], built_pending[KLT_DEV_SLOTS];
+  cudaEvent_t ev_join;
   char err[512];
   unsigned long long launches;
-  int last_path, force_generic, no_fused, last_fused, track7_off;
+  int last_path, force_generic, no_fused, last_fused, track7_off, overlap_l0_ctas;
   // geometry
   int W, H, L, ss;
-  PyrSet set[2];
+  PyrSet set[KLT_DEV_SLOTS];
   float* arena;
   float* tmp;                // generic path: horizontal-pass result, W*H floats
   unsigned char* frame;      // u8 staging of the frame being built, row pitch frame_pitch
@@ -819,7 +826,8 @@ struct klt_dev {
 // with CUDA events on the context stream.
 static void prof_fold(klt_dev* d) {
   if (d->prof_used == 0) return;
-  cudaEventSynchronize(d->prof_ev[2 * (d->prof_used - 1) + 1]);
+  cudaStreamSynchronize(d->stream);
+  if (d->stream2) cudaStreamSynchronize(d->stream2);
   for (int i = 0; i < d->prof_used; ++i) {
     float ms = 0.0f;
     if (cudaEventElapsedTime(&ms, d->prof_ev[2 * i], d->prof_ev[2 * i + 1]) == cudaSuccess) {
@@ -829,18 +837,24 @@ static void prof_fold(klt_dev* d) {
   }
   d->prof_used = 0;
 }
+static int sync_all(klt_dev* d) {
+  cudaError_t e = cudaStreamSynchronize(d->stream);
+  if (e == cudaSuccess && d->stream2) e = cudaStreamSynchronize(d->stream2);
+  d->staging_busy = 0;
+  return e == cudaSuccess ? 0 : 1;
+}
 struct Launch {
-  klt_dev* d; int slot;
-  Launch(klt_dev* d_, int kid) : d(d_), slot(-1) {
+  klt_dev* d; int slot; cudaStream_t st;
+  Launch(klt_dev* d_, int kid, cudaStream_t st_ = nullptr) : d(d_), slot(-1), st(st_ ? st_ : d_->stream) {
     d->launches++;
     if (d->prof_on) {
       if (d->prof_used == PROF_POOL) prof_fold(d);
       slot = d->prof_used++;
       d->prof_kid[slot] = kid;
-      cudaEventRecord(d->prof_ev[2 * slot], d->stream);
+      cudaEventRecord(d->prof_ev[2 * slot], st);
     }
   }
-  ~Launch() { if (slot >= 0) cudaEventRecord(d->prof_ev[2 * slot + 1], d->stream); }
+  ~Launch() { if (slot >= 0) cudaEventRecord(d->prof_ev[2 * slot + 1], st); }
 };
 
 static char g_create_err[512] = "";
@@ -899,7 +913,15 @@ extern "C" int klt_dev_create(int device, klt_dev** out) {
   cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
   if (c->num_sms < 1) c->num_sms = 1;
   e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
+  for (int i = 0; i < KLT_DEV_SLOTS && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&c->ev_built[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_read[i], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
   if (e != cudaSuccess) { free(c); return fail(nullptr, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+  c->tstream = c->stream;
+  c->overlap_l0_ctas = getenv("KLT_B200_OVERLAP_L0_CTAS") ? atoi(getenv("KLT_B200_OVERLAP_L0_CTAS")) : 0;
   e = cudaMalloc(&c->d_live, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemsetAsync(c->d_live, 0, sizeof(unsigned long long), c->stream);
   if (e == cudaSuccess) e = cudaMalloc(&c->d_tile_ctr, 16 * sizeof(unsigned));
@@ -919,7 +941,7 @@ static void free_geometry(klt_dev* d) {
 extern "C" void klt_dev_destroy(klt_dev* d) {
   if (!d) return;
   cudaSetDevice(d->device);
-  cudaStreamSynchronize(d->stream);
+  sync_all(d);
   free_geometry(d);
   cudaFree(d->frame);
   cudaFree(d->d_x);
@@ -930,7 +952,10 @@ extern "C" void klt_dev_destroy(klt_dev* d) {
   if (d->prof_ev) { for (int i = 0; i < 2 * PROF_POOL; ++i) cudaEventDestroy(d->prof_ev[i]); free(d->prof_ev); free(d->prof_kid); }
   cudaFree(d->d_live);
   cudaFree(d->d_tile_ctr);
+  for (int i = 0; i < KLT_DEV_SLOTS; ++i) { cudaEventDestroy(d->ev_built[i]); cudaEventDestroy(d->ev_read[i]); }
+  cudaEventDestroy(d->ev_join);
   cudaStreamDestroy(d->stream);
+  cudaStreamDestroy(d->stream2);
   free(d);
 }
 
@@ -940,7 +965,9 @@ static int ensure_geometry(klt_dev* d, int W, int H, int L, int ss) {
   if (L < 1 || L > KLT_DEV_MAX_LEVELS) return fail(d, "nPyramidLevels %d not in 1..%d", L, KLT_DEV_MAX_LEVELS);
   if (L > 1 && ss != 2 && ss != 4 && ss != 8 && ss != 16 && ss != 32)
     return fail(d, "Pyramid's subsampling must be either 2, 4, 8, 16, or 32");
-  CU(cudaStreamSynchronize(d->stream));
+  if (sync_all(d)) return fail(d, "stream synchronisation failed");
+  memset(d->read_pending, 0, sizeof(d->read_pending));
+  memset(d->built_pending, 0, sizeof(d->built_pending));
   free_geometry(d);
   size_t per_set = 0;
   int w = W, h = H;
@@ -951,10 +978,10 @@ static int ensure_geometry(klt_dev* d, int W, int H, int L, int ss) {
     per_set += 3 * (size_t)ps[l] * h;
     if (L > 1) { w /= ss; h /= ss; }
   }
-  CU(cudaMalloc(&d->arena, 2 * per_set * sizeof(float) + 256));   // + slack for aligned over-reads
+  CU(cudaMalloc(&d->arena, KLT_DEV_SLOTS * per_set * sizeof(float) + 256));   // + slack for aligned over-reads
   CU(cudaMalloc(&d->tmp, (size_t)ps[0] * H * sizeof(float)));
   float* p = d->arena;
-  for (int s = 0; s < 2; ++s)
+  for (int s = 0; s < KLT_DEV_SLOTS; ++s)
     for (int l = 0; l < L; ++l) {
       Level& lv = d->set[s].lv[l];
       lv.w = ws[l]; lv.h = hs[l]; lv.pitch = ps[l];
@@ -970,10 +997,10 @@ extern "C" int klt_dev_geometry(const klt_dev* d, int* W, int* H, int* L, int* s
   return d->arena != nullptr;
 }
 extern "C" int klt_dev_slot_valid(const klt_dev* d, int slot) {
-  return d->arena && slot >= 0 && slot < 2 && d->set[slot].built_levels == d->L;
+  return d->arena && slot >= 0 && slot < KLT_DEV_SLOTS && d->set[slot].built_levels == d->L;
 }
 extern "C" void klt_dev_invalidate(klt_dev* d, int slot) {
-  for (int s = 0; s < 2; ++s) if (slot < 0 || slot == s) d->set[s].built_levels = 0;
+  for (int s = 0; s < KLT_DEV_SLOTS; ++s) if (slot < 0 || slot == s) d->set[s].built_levels = 0;
 }
 extern "C" int klt_dev_level_dims(const klt_dev* d, int level, int* w, int* h) {
   if (!d->arena || level < 0 || level >= d->L) return 1;
@@ -982,9 +1009,22 @@ extern "C" int klt_dev_level_dims(const klt_dev* d, int level, int* w, int* h) {
 }
 extern "C" int klt_dev_sync(klt_dev* d) {
   CU(cudaSetDevice(d->device));
-  CU(cudaStreamSynchronize(d->stream));
+  if (sync_all(d)) return fail(d, "stream synchronisation failed");
   return 0;
 }
+
+// overlap on: the tracker and the feature copies move to a second stream, ordered against the
+// pyramid builds with events, so that build(k+1) can run while track(k) is still in flight.
+extern "C" int klt_dev_set_overlap(klt_dev* d, int on) {
+  CU(cudaSetDevice(d->device));
+  if (sync_all(d)) return fail(d, "stream synchronisation failed");
+  memset(d->read_pending, 0, sizeof(d->read_pending));
+  memset(d->built_pending, 0, sizeof(d->built_pending));
+  d->overlap = on ? 1 : 0;
+  d->tstream = on ? d->stream2 : d->stream;
+  return 0;
+}
+extern "C" int klt_dev_slots(void) { return KLT_DEV_SLOTS; }
 
 // ---- kernel dispatch ----------------------------------------------------------
 template <typename K>
@@ -1124,7 +1164,8 @@ static int l0_fused_dispatch(klt_dev* d, const unsigned char* src, int spitch, i
   }
   const int tiles_x = (W + L0Geo::TX - 1) / L0Geo::TX, tiles_y = (H + L0Geo::TY - 1) / L0Geo::TY;
   const int ntiles = tiles_x * tiles_y;
-  const int grid = ntiles < 3 * d->num_sms ? ntiles : 3 * d->num_sms;       // persistent, 3 CTAs / SM
+  const int cps = (d->overlap && d->overlap_l0_ctas > 0) ? d->overlap_l0_ctas : 3;
+  const int grid = ntiles < cps * d->num_sms ? ntiles : cps * d->num_sms;    // persistent, 3 CTAs / SM
   { Launch l(d, KID_L0_FUSED);
     l0_fused_kernel<EXACT><<<grid, 256, L0Geo::SMEM, d->stream>>>(map, W, H, tiles_x, ntiles, d->d_tile_ctr,
                                                                   d->tile_base[0], ts, tg, td, lv.img, lv.gx,
@@ -1151,7 +1192,10 @@ static int launch_level_fused(klt_dev* d, int level, const Level& a, const Level
   }
   const int tiles_x = (b.w + TX - 1) / TX, tiles_y = (b.h + TY - 1) / TY;
   const int ntiles = tiles_x * tiles_y;
-  const int grid = ntiles < 2 * d->num_sms ? ntiles : 2 * d->num_sms;       // persistent, 2 CTAs / SM
+  int cps = 0;                                                              // resident CTAs per SM
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, level_fused_kernel<SS, R, TX, TY, EXACT>, 256, G::SMEM));
+  if (cps < 1) cps = 1;
+  const int grid = ntiles < cps * d->num_sms ? ntiles : cps * d->num_sms;   // persistent
   { Launch l(d, KID_LEVEL_FUSED);
     level_fused_kernel<SS, R, TX, TY, EXACT><<<grid, 256, G::SMEM, d->stream>>>(
         map, a.w, a.h, b.w, b.h, tiles_x, ntiles, d->d_tile_ctr + (level & 15), d->tile_base[level & 15], tp, tg,
@@ -1166,7 +1210,16 @@ static int level_fused_dispatch(klt_dev* d, int ss, int level, const Level& a, c
   *done = false;
   if (!fused_grad_taps_ok(tg, td)) return 0;
   const int r = tp.w / 2;
-  if (ss == 2 && r == 5) return launch_level_fused<2, 5, 64, 32, EXACT>(d, level, a, b, tp, tg, td, done);
+  if (ss == 2 && r == 5) {
+    // tile shape by level size: big levels amortise the halo with 64x32 tiles, small levels
+    // need many small tiles to fill 148 SMs and to keep the per-CTA latency short
+    static int force = getenv("KLT_B200_LEVEL_TILE") ? atoi(getenv("KLT_B200_LEVEL_TILE")) : 0;
+    const long px = (long)b.w * b.h;
+    int shape = force ? force : (px >= 1500000 ? 1 : (px >= 300000 ? 2 : 3));
+    if (shape == 1) return launch_level_fused<2, 5, 64, 32, EXACT>(d, level, a, b, tp, tg, td, done);
+    if (shape == 2) return launch_level_fused<2, 5, 64, 16, EXACT>(d, level, a, b, tp, tg, td, done);
+    return launch_level_fused<2, 5, 32, 16, EXACT>(d, level, a, b, tp, tg, td, done);
+  }
   if (ss == 4 && r == 10) return launch_level_fused<4, 10, 32, 16, EXACT>(d, level, a, b, tp, tg, td, done);
   return 0;
 }
@@ -1275,7 +1328,7 @@ static int check_taps(klt_dev* d, const klt_dev_taps& t, const char* what) {
 extern "C" int klt_dev_build(klt_dev* d, int slot, const unsigned char* img, int img_is_device,
                              size_t img_pitch, const klt_dev_build_desc* q) {
   if (!d || !q || !img) return fail(d, "klt_dev_build: null argument");
-  if (slot < 0 || slot > 1) return fail(d, "klt_dev_build: slot %d", slot);
+  if (slot < 0 || slot >= KLT_DEV_SLOTS) return fail(d, "klt_dev_build: slot %d", slot);
   CU(cudaSetDevice(d->device));
   if (q->nlevels_built < 1 || q->nlevels_built > q->nlevels) return fail(d, "nlevels_built %d of %d", q->nlevels_built, q->nlevels);
   if (check_taps(d, q->grad_taps, "gradient")) return 1;
@@ -1289,7 +1342,7 @@ extern "C" int klt_dev_build(klt_dev* d, int slot, const unsigned char* img, int
     const int fp = (W + 15) / 16 * 16;          // TMA needs a 16 B multiple row pitch
     const size_t bytes = (size_t)fp * H;
     if (d->frame_cap < bytes) {
-      CU(cudaStreamSynchronize(d->stream));
+      if (sync_all(d)) return fail(d, "stream synchronisation failed");
       cudaFree(d->frame); d->frame = nullptr; d->frame_cap = 0;
       CU(cudaMalloc(&d->frame, bytes));
       d->frame_cap = bytes;
@@ -1306,15 +1359,23 @@ extern "C" int klt_dev_build(klt_dev* d, int slot, const unsigned char* img, int
   }
   PyrSet& S = d->set[slot];
   S.built_levels = 0;
+  if (d->overlap && d->read_pending[slot]) {          // a tracker on the other stream may still read it
+    CU(cudaStreamWaitEvent(d->stream, d->ev_read[slot], 0));
+    d->read_pending[slot] = 0;
+  }
   const int rc = q->exact ? build_impl<true>(d, S, src, spitch, q) : build_impl<false>(d, S, src, spitch, q);
   if (rc) return rc;
   CU(cudaGetLastError());
+  if (d->overlap) {
+    CU(cudaEventRecord(d->ev_built[slot], d->stream));
+    d->built_pending[slot] = 1;
+  }
   S.built_levels = q->nlevels_built;
   return 0;
 }
 
 extern "C" int klt_dev_read_level(klt_dev* d, int slot, int which, int level, float* out) {
-  if (!d->arena || slot < 0 || slot > 1 || level < 0 || level >= d->L) return fail(d, "read_level: bad slot/level");
+  if (!d->arena || slot < 0 || slot >= KLT_DEV_SLOTS || level < 0 || level >= d->L) return fail(d, "read_level: bad slot/level");
   CU(cudaSetDevice(d->device));
   const Level& lv = d->set[slot].lv[level];
   const float* src = which == 0 ? lv.img : which == 1 ? lv.gx : lv.gy;
@@ -1328,7 +1389,7 @@ extern "C" int klt_dev_read_level(klt_dev* d, int slot, int which, int level, fl
 // device and pinned-host staging hold x | y | val back to back (one copy each way)
 static int ensure_features(klt_dev* d, int n) {
   if (n <= d->feat_cap) return 0;
-  CU(cudaStreamSynchronize(d->stream));
+  if (sync_all(d)) return fail(d, "stream synchronisation failed");
   cudaFree(d->d_x);
   cudaFreeHost(d->h_x);
   d->d_x = d->d_y = nullptr; d->d_val = nullptr; d->h_x = d->h_y = nullptr; d->h_val = nullptr;
@@ -1345,7 +1406,7 @@ static int ensure_features(klt_dev* d, int n) {
 // the pinned staging area is reused by every call: wait for copies that may still read/write it
 static int staging_quiesce(klt_dev* d) {
   if (d->staging_busy) {
-    CU(cudaStreamSynchronize(d->stream));
+    CU(cudaStreamSynchronize(d->tstream));
     d->staging_busy = 0;
   }
   return 0;
@@ -1359,7 +1420,7 @@ extern "C" int klt_dev_features_upload(klt_dev* d, int n, const float* x, const 
   memcpy(d->h_x, x, n * sizeof(float));
   memcpy(d->h_y, y, n * sizeof(float));
   memcpy(d->h_val, val, n * sizeof(int));
-  CU(cudaMemcpyAsync(d->d_x, d->h_x, (size_t)d->feat_cap * 12, cudaMemcpyHostToDevice, d->stream));
+  CU(cudaMemcpyAsync(d->d_x, d->h_x, (size_t)d->feat_cap * 12, cudaMemcpyHostToDevice, d->tstream));
   d->staging_busy = 1;
   d->feat_n = n;
   return 0;
@@ -1376,7 +1437,7 @@ extern "C" int klt_dev_features_staging(klt_dev* d, int n, float** x, float** y,
 extern "C" int klt_dev_features_commit(klt_dev* d, int n) {      // H2D of the staging area (async)
   CU(cudaSetDevice(d->device));
   if (n > d->feat_cap) return fail(d, "commit of %d features, capacity %d", n, d->feat_cap);
-  CU(cudaMemcpyAsync(d->d_x, d->h_x, (size_t)d->feat_cap * 12, cudaMemcpyHostToDevice, d->stream));
+  CU(cudaMemcpyAsync(d->d_x, d->h_x, (size_t)d->feat_cap * 12, cudaMemcpyHostToDevice, d->tstream));
   d->staging_busy = 1;
   d->feat_n = n;
   return 0;
@@ -1384,8 +1445,9 @@ extern "C" int klt_dev_features_commit(klt_dev* d, int n) {      // H2D of the s
 extern "C" int klt_dev_features_fetch(klt_dev* d, int n) {       // D2H into the staging area + sync
   CU(cudaSetDevice(d->device));
   if (n > d->feat_n) return fail(d, "download of %d features but %d resident", n, d->feat_n);
-  CU(cudaMemcpyAsync(d->h_x, d->d_x, (size_t)d->feat_cap * 12, cudaMemcpyDeviceToHost, d->stream));
-  CU(cudaStreamSynchronize(d->stream));
+  CU(cudaMemcpyAsync(d->h_x, d->d_x, (size_t)d->feat_cap * 12, cudaMemcpyDeviceToHost, d->tstream));
+  CU(cudaStreamSynchronize(d->tstream));
+  if (d->overlap) CU(cudaStreamSynchronize(d->stream));
   d->staging_busy = 0;
   return 0;
 }
@@ -1411,16 +1473,16 @@ static int launch_track(klt_dev* d, const PyrView& v1, const PyrView& v2, const 
   const int warps = 4;
   const size_t smem = EXACT ? (size_t)warps * 3 * a.ww * a.wh * sizeof(float) : 0;
   if (set_smem(d, track_kernel<EXACT, PPL>, smem)) return 1;
-  { Launch l(d, KID_TRACK);
-    track_kernel<EXACT, PPL><<<(n + warps - 1) / warps, warps * 32, smem, d->stream>>>(
+  { Launch l(d, KID_TRACK, d->tstream);
+    track_kernel<EXACT, PPL><<<(n + warps - 1) / warps, warps * 32, smem, d->tstream>>>(
         v1, v2, a, n, d->d_x, d->d_y, d->d_val, d->d_live); }
   return 0;
 }
 
 template <int WW, int RPL>
 static void launch_track_fast_t(klt_dev* d, const PyrView& v1, const PyrView& v2, const TrackArgs& a, int n) {
-  Launch l(d, KID_TRACK_FAST);
-  track_fast_kernel<WW, RPL><<<(8 * n + 127) / 128, 128, 0, d->stream>>>(v1, v2, a, n, d->d_x, d->d_y,
+  Launch l(d, KID_TRACK_FAST, d->tstream);
+  track_fast_kernel<WW, RPL><<<(8 * n + 127) / 128, 128, 0, d->tstream>>>(v1, v2, a, n, d->d_x, d->d_y,
                                                                         d->d_val, d->d_live);
 }
 // square odd windows up to 15x15; returns false if this window has no instantiation
@@ -1430,15 +1492,15 @@ static bool launch_track_fast(klt_dev* d, const PyrView& v1, const PyrView& v2, 
     case 5: launch_track_fast_t<5, 1>(d, v1, v2, a, n); return true;
     case 7:
       if (d->track7_off) { launch_track_fast_t<7, 1>(d, v1, v2, a, n); return true; }
-      { Launch l(d, KID_TRACK7);
+      { Launch l(d, KID_TRACK7, d->tstream);
         static int fpw = getenv("KLT_TRACK_FPW") ? atoi(getenv("KLT_TRACK_FPW")) : 4;
         const int warps_per_block = 4;
         if (fpw == 1)
-          track7_kernel<1><<<(n + warps_per_block - 1) / warps_per_block, 128, 0, d->stream>>>(v1, v2, a, n, d->d_x, d->d_y, d->d_val, d->d_live);
+          track7_kernel<1><<<(n + warps_per_block - 1) / warps_per_block, 128, 0, d->tstream>>>(v1, v2, a, n, d->d_x, d->d_y, d->d_val, d->d_live);
         else if (fpw == 4)
-          track7_kernel<4><<<(n + 4 * warps_per_block - 1) / (4 * warps_per_block), 128, 0, d->stream>>>(v1, v2, a, n, d->d_x, d->d_y, d->d_val, d->d_live);
+          track7_kernel<4><<<(n + 4 * warps_per_block - 1) / (4 * warps_per_block), 128, 0, d->tstream>>>(v1, v2, a, n, d->d_x, d->d_y, d->d_val, d->d_live);
         else
-          track7_kernel<2><<<(n + 2 * warps_per_block - 1) / (2 * warps_per_block), 128, 0, d->stream>>>(v1, v2, a, n, d->d_x, d->d_y, d->d_val, d->d_live);
+          track7_kernel<2><<<(n + 2 * warps_per_block - 1) / (2 * warps_per_block), 128, 0, d->tstream>>>(v1, v2, a, n, d->d_x, d->d_y, d->d_val, d->d_live);
       }
       return true;
     case 9: launch_track_fast_t<9, 2>(d, v1, v2, a, n); return true;
@@ -1458,6 +1520,14 @@ extern "C" int klt_dev_track_resident(klt_dev* d, int slot_prev, int slot_cur,
     return fail(d, "tracking window %d x %d must be odd and >= 3", p->window_width, p->window_height);
   const int n = d->feat_n;
   if (n == 0) return 0;
+  if (d->overlap) {                                  // the pyramids are produced on the other stream
+    const int sl[2] = {slot_prev, slot_cur};
+    for (int k = 0; k < 2; ++k)
+      if (d->built_pending[sl[k]]) {                  // once waited for, stream order covers later trackers
+        CU(cudaStreamWaitEvent(d->tstream, d->ev_built[sl[k]], 0));
+        d->built_pending[sl[k]] = 0;
+      }
+  }
   PyrView v1, v2;
   make_view(d->set[slot_prev], d->L, &v1);
   make_view(d->set[slot_cur], d->L, &v2);
@@ -1487,6 +1557,11 @@ extern "C" int klt_dev_track_resident(klt_dev* d, int slot_prev, int slot_cur,
   }
   if (rc) return rc;
   CU(cudaGetLastError());
+  if (d->overlap) {
+    CU(cudaEventRecord(d->ev_read[slot_prev], d->tstream));
+    CU(cudaEventRecord(d->ev_read[slot_cur], d->tstream));
+    d->read_pending[slot_prev] = d->read_pending[slot_cur] = 1;
+  }
   return 0;
 }
 
@@ -1542,7 +1617,7 @@ static int run_mineig(klt_dev* d, int slot, const klt_dev_select_params* p, cons
 
 extern "C" int klt_dev_eigen_map(klt_dev* d, int slot, const klt_dev_select_params* p, int* out, int* npoints) {
   CU(cudaSetDevice(d->device));
-  if (!d->arena || slot < 0 || slot > 1 || d->set[slot].built_levels < 1) return fail(d, "eigen_map: slot %d has no level 0", slot);
+  if (!d->arena || slot < 0 || slot >= KLT_DEV_SLOTS || d->set[slot].built_levels < 1) return fail(d, "eigen_map: slot %d has no level 0", slot);
   const CandGeo g = cand_geometry(d, p);
   if (npoints) *npoints = (int)g.npoints;
   if (!out || g.npoints == 0) return 0;
@@ -1557,8 +1632,11 @@ extern "C" int klt_dev_eigen_map(klt_dev* d, int slot, const klt_dev_select_para
 extern "C" int klt_dev_select(klt_dev* d, int slot, const klt_dev_select_params* p, int n,
                               float* x, float* y, int* val) {
   CU(cudaSetDevice(d->device));
-  if (!d->arena || slot < 0 || slot > 1 || d->set[slot].built_levels < 1) return fail(d, "select: slot %d has no level 0", slot);
+  if (!d->arena || slot < 0 || slot >= KLT_DEV_SLOTS || d->set[slot].built_levels < 1) return fail(d, "select: slot %d has no level 0", slot);
   if (n <= 0) return 0;
+  cudaStream_t saved_t = d->tstream;
+  if (d->overlap) { if (sync_all(d)) return fail(d, "stream synchronisation failed"); d->tstream = d->stream; }
+  struct Restore { klt_dev* d; cudaStream_t t; ~Restore() { d->tstream = t; } } restore{d, saved_t};
   const CandGeo g = cand_geometry(d, p);
   int mindist = p->mindist < 0 ? 0 : p->mindist;
   const int dist = mindist - 1;                    // the reference works with mindist-1 (:157)
@@ -1606,13 +1684,18 @@ extern "C" int klt_dev_select(klt_dev* d, int slot, const klt_dev_select_params*
 extern "C" int klt_dev_timer_start(klt_dev* d) {
   CU(cudaSetDevice(d->device));
   if (!d->ev_made) { CU(cudaEventCreate(&d->ev_a)); CU(cudaEventCreate(&d->ev_b)); d->ev_made = 1; }
-  CU(cudaEventRecord(d->ev_a, d->stream));
+  if (sync_all(d)) return fail(d, "stream synchronisation failed");
+  CU(cudaEventRecord(d->ev_a, d->tstream));
   return 0;
 }
 extern "C" int klt_dev_timer_stop(klt_dev* d, float* ms) {
   CU(cudaSetDevice(d->device));
   if (!d->ev_made) return fail(d, "timer_stop without timer_start");
-  CU(cudaEventRecord(d->ev_b, d->stream));
+  if (d->overlap) {                 // everything queued on the build stream must be inside the interval
+    CU(cudaEventRecord(d->ev_join, d->stream));
+    CU(cudaStreamWaitEvent(d->tstream, d->ev_join, 0));
+  }
+  CU(cudaEventRecord(d->ev_b, d->tstream));
   CU(cudaEventSynchronize(d->ev_b));
   CU(cudaEventElapsedTime(ms, d->ev_a, d->ev_b));
   return 0;
@@ -1627,7 +1710,7 @@ extern "C" int klt_dev_profile_begin(klt_dev* d) {
     if (!d->prof_ev || !d->prof_kid) return fail(d, "out of host memory");
     for (int i = 0; i < 2 * PROF_POOL; ++i) CU(cudaEventCreate(&d->prof_ev[i]));
   }
-  CU(cudaStreamSynchronize(d->stream));
+  if (sync_all(d)) return fail(d, "stream synchronisation failed");
   memset(d->prof_ms, 0, sizeof(d->prof_ms));
   memset(d->prof_n, 0, sizeof(d->prof_n));
   d->prof_used = 0;
@@ -1636,7 +1719,7 @@ extern "C" int klt_dev_profile_begin(klt_dev* d) {
 }
 extern "C" int klt_dev_profile_end(klt_dev* d) {
   CU(cudaSetDevice(d->device));
-  CU(cudaStreamSynchronize(d->stream));
+  if (sync_all(d)) return fail(d, "stream synchronisation failed");
   prof_fold(d);
   d->prof_on = 0;
   return 0;
@@ -1650,8 +1733,9 @@ extern "C" const char* klt_dev_profile_get(const klt_dev* d, int kid, unsigned l
 }
 extern "C" int klt_dev_live_total(klt_dev* d, unsigned long long* out, int reset) {
   CU(cudaSetDevice(d->device));
-  CU(cudaMemcpyAsync(out, d->d_live, sizeof(*out), cudaMemcpyDeviceToHost, d->stream));
-  if (reset) CU(cudaMemsetAsync(d->d_live, 0, sizeof(*out), d->stream));
-  CU(cudaStreamSynchronize(d->stream));
+  if (sync_all(d)) return fail(d, "stream synchronisation failed");
+  CU(cudaMemcpyAsync(out, d->d_live, sizeof(*out), cudaMemcpyDeviceToHost, d->tstream));
+  if (reset) CU(cudaMemsetAsync(d->d_live, 0, sizeof(*out), d->tstream));
+  CU(cudaStreamSynchronize(d->tstream));
   return 0;
 }

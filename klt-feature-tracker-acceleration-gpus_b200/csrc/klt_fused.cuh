@@ -397,10 +397,11 @@ struct LvGeo {
   static_assert((LP / 4) % 2 == 1 && (HP / 4) % 2 == 1 && (SW / 4) % 2 == 1, "odd chunk pitches");
   static constexpr int OFF_SRC = 0;
   static constexpr int OFF_HP = SW * SH * 4;
-  static constexpr int OFF_L = OFF_HP + SH * LW * 4;
-  static constexpr int OFF_HD = OFF_L + LH * LP * 4;
+  static constexpr int HP_BYTES = SH * LW * 4, HDG_BYTES = 2 * LH * HP * 4;
+  static constexpr int OFF_L = OFF_HP + (HP_BYTES > HDG_BYTES ? HP_BYTES : HDG_BYTES);
+  static constexpr int OFF_HD = OFF_HP;                                // Hd, Hg reuse Hp (dead after P2)
   static constexpr int OFF_HG = OFF_HD + LH * HP * 4;
-  static constexpr int OFF_BAR = OFF_HG + LH * HP * 4;
+  static constexpr int OFF_BAR = OFF_L + LH * LP * 4;
   static constexpr int SMEM = OFF_BAR + 16;
 };
 
@@ -515,7 +516,7 @@ __device__ __forceinline__ void lv_stage_rest(unsigned char* smem, const TapsR& 
 // W,H: size of the level being produced; Wsrc,Hsrc: size of the level it is made from.
 // Dynamic tile scheduler as in l0_fused_kernel.
 template <int SS, int R, int TX, int TY, bool EXACT>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, (LvGeo<SS, R, TX, TY>::SMEM <= 56 * 1024) ? 3 : 2)
 level_fused_kernel(const __grid_constant__ CUtensorMap map, int Wsrc, int Hsrc, int W, int H,
                    int tiles_x, int ntiles, unsigned* __restrict__ counter, unsigned base,
                    TapsR tp, TapsR tg, TapsR td,

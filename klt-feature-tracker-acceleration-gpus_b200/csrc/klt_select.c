@@ -47,7 +47,7 @@ static void select_common(KLT_TrackingContext tc, const KLT_PixelType *img, int 
      * eigenvalues equal the CPU reference's.  Built in the slot that does not
      * hold the previous frame. */
     klt_dev_build_desc q;
-    slot = (tc->pyramid_last != NULL && s->last_slot >= 0) ? 1 - s->last_slot : 0;
+    slot = (tc->pyramid_last != NULL && s->last_slot >= 0) ? (s->last_slot + 1) % KLT_DEV_SLOTS : 0;
     klt_fill_build_desc(tc, ncols, nrows, 1, tc->smoothBeforeSelecting ? 1 : 0, 1, &q);
     DEVCALL(s, klt_dev_build(dev, slot, img, 0, (size_t)ncols, &q));
   }

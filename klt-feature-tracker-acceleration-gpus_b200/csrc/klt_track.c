@@ -111,7 +111,7 @@ static void track_common(KLT_TrackingContext tc, const KLT_PixelType *img1,
   DEVCALL(s, klt_dev_features_commit(dev, n));
 
   slot_prev = prepare_previous(tc, s, img1, on_device, pitch, ncols, nrows);
-  slot_cur = 1 - slot_prev;
+  slot_cur = (slot_prev + 1) % KLT_DEV_SLOTS;
   klt_fill_build_desc(tc, ncols, nrows, tc->nPyramidLevels, 1, s->exact, &q);
   DEVCALL(s, klt_dev_build(dev, slot_cur, img2, on_device, pitch, &q));
 
@@ -166,6 +166,12 @@ void KLTB200ResidentBegin(KLT_TrackingContext tc, const KLT_PixelType *img1, int
   check_supported(tc);
   if (!tc->sequentialMode)
     KLTError("(KLTB200ResidentBegin) the resident pipeline needs tc->sequentialMode = TRUE");
+  {
+    /* opt-in: measured on B200, the tracker and the level-0 kernel are both bound by the
+     * LSU / L1 data pipe, so running them concurrently stretches both */
+    const char *e = getenv("KLT_B200_OVERLAP");
+    DEVCALL(s, klt_dev_set_overlap(klt_state_device(s), (e != NULL && atoi(e) != 0) ? 1 : 0));
+  }
   slot = prepare_previous(tc, s, img1, on_device, pitch ? pitch : (size_t)ncols, ncols, nrows);
   hand_over(tc, s, slot);
   klt_list_to_arrays(fl, x, y, v);
@@ -183,7 +189,7 @@ void KLTB200ResidentStep(KLT_TrackingContext tc, const KLT_PixelType *img2, int 
   if (tc->pyramid_last == NULL || s->last_slot < 0)
     KLTError("(KLTB200ResidentStep) call KLTB200ResidentBegin first");
   slot_prev = s->last_slot;
-  slot_cur = 1 - slot_prev;
+  slot_cur = (slot_prev + 1) % KLT_DEV_SLOTS;      /* third slot: build(k+1) may overlap track(k) */
   klt_fill_build_desc(tc, ncols, nrows, tc->nPyramidLevels, 1, s->exact, &q);
   DEVCALL(s, klt_dev_build(s->dev, slot_cur, img2, on_device, pitch ? pitch : (size_t)ncols, &q));
   fill_track_params(tc, s->exact, &tp);
@@ -201,6 +207,7 @@ void KLTB200ResidentEnd(KLT_TrackingContext tc, KLT_FeatureList fl)
   int i;
   if (!x || !y || !v) KLTError("(KLTB200ResidentEnd) Out of memory");
   DEVCALL(s, klt_dev_features_download(klt_state_device(s), n, x, y, v));
+  DEVCALL(s, klt_dev_set_overlap(s->dev, 0));       /* back to the single in-order stream */
   for (i = 0; i < n; i++) {
     fl->feature[i]->x = x[i];
     fl->feature[i]->y = y[i];

@@ -75,6 +75,8 @@ DEV_API = {
     "klt_dev_level_dims": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "klt_dev_eigen_map": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(SelectParams), C.c_void_p, C.POINTER(C.c_int)]),
     "klt_dev_sync": (C.c_int, [C.c_void_p]),
+    "klt_dev_set_overlap": (C.c_int, [C.c_void_p, C.c_int]),
+    "klt_dev_slots": (C.c_int, []),
     "klt_dev_launch_count": (C.c_ulonglong, [C.c_void_p]),
     "klt_dev_last_build_path": (C.c_int, [C.c_void_p]),
     "klt_dev_force_generic": (None, [C.c_void_p, C.c_int]),
