@@ -159,6 +159,19 @@ void klt_dev_disable_fused(klt_dev *d, int on);
 /* number of pyramid levels the last klt_dev_build produced with the fused TMA kernels
  * (level 0: l0_fused_kernel, coarser levels: level_fused_kernel); 0 if none */
 int klt_dev_last_build_fused(const klt_dev *d);
+/* Host frames are uploaded in bands of `rows` image rows (rounded up to 64) on a copy stream and
+ * the fused kernels are launched over the tile rows each band completes, so the PCIe transfer
+ * hides the image pipeline; rows == 0: one copy, then the kernels; rows < 0 (default, or env
+ * KLT_B200_BAND_ROWS): automatic -- frames of >= 4 MB in two bands (60 % / 40 %), smaller ones in
+ * one copy.  klt_dev_last_build_bands: copies the last klt_dev_build issued (0 for a
+ * device-resident frame). */
+void klt_dev_set_band_rows(klt_dev *d, int rows);
+/* 1 if the last klt_dev_build ran the whole pyramid in one pyramid_mega_kernel launch (tile-level
+ * dataflow across levels, level-0 tiles gated on the uploaded bands).  Opt-in: klt_dev_disable_mega(d, 0)
+ * or env KLT_B200_MEGA=1; the default is the per-level fused kernels, which measure faster. */
+int klt_dev_last_build_mega(const klt_dev *d);
+void klt_dev_disable_mega(klt_dev *d, int on);
+int klt_dev_last_build_bands(const klt_dev *d);
 /* device time between the two calls, measured with CUDA events recorded on the
  * context's own stream (the stream the kernels run on) */
 int klt_dev_timer_start(klt_dev *d);
@@ -170,6 +183,11 @@ int klt_dev_profile_begin(klt_dev *d);
 int klt_dev_profile_end(klt_dev *d);
 int klt_dev_profile_kernels(void);
 const char *klt_dev_profile_get(const klt_dev *d, int kid, unsigned long long *launches, double *total_ms);
+/* timeline of the same profiling session: record i (launch order as folded) = class name, start
+ * and end in ms since klt_dev_profile_begin; also covers the frame / feature copies ("copy_h2d",
+ * "copy_d2h"), which are timed but never counted as kernel launches.  NULL past the end. */
+int klt_dev_trace_count(const klt_dev *d);
+const char *klt_dev_trace_get(const klt_dev *d, int i, float *t0_ms, float *t1_ms);
 /* number of features that entered klt_dev_track* with val >= 0 since the last
  * reset, counted on the device (the metric's numerator for resident pipelines) */
 int klt_dev_live_total(klt_dev *d, unsigned long long *out, int reset);

@@ -59,6 +59,7 @@ struct TapsR {
 static constexpr int NT = 256;   // threads per CTA of every tile kernel
 
 #include "klt_fused.cuh"
+#include "klt_mega.cuh"
 
 // ---------------------------------------------------------------------------
 // generic kernels: any radius, any subsampling.  One thread per output sample.
@@ -575,7 +576,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 template <bool EXACT, int PPL>
 __global__ void __launch_bounds__(128)
 track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n,
-             float* __restrict__ fx, float* __restrict__ fy, int* __restrict__ fval,
+             const float* __restrict__ fx, const float* __restrict__ fy, const int* __restrict__ fval,
+             float* __restrict__ ox, float* __restrict__ oy, int* __restrict__ oval,
              unsigned long long* __restrict__ live_total) {
   extern __shared__ float s_win[];     // EXACT only: [warps][3][npix]
   const int lane = threadIdx.x & 31;
@@ -744,11 +746,11 @@ track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n,
     const bool outside = (xout < (float)a.borderx || xout > (float)(a.ncols - 1 - a.borderx) ||
                           yout < (float)a.bordery || yout > (float)(a.nrows - 1 - a.bordery));
     if (status == KLT_OOB || outside) {
-      fx[f] = -1.0f; fy[f] = -1.0f; fval[f] = KLT_OOB;
+      ox[f] = -1.0f; oy[f] = -1.0f; oval[f] = KLT_OOB;
     } else if (status != KLT_TRACKED) {
-      fx[f] = -1.0f; fy[f] = -1.0f; fval[f] = status;
+      ox[f] = -1.0f; oy[f] = -1.0f; oval[f] = status;
     } else {
-      fx[f] = xout; fy[f] = yout; fval[f] = KLT_TRACKED;
+      ox[f] = xout; oy[f] = yout; oval[f] = KLT_TRACKED;
     }
   }
 }
@@ -761,14 +763,17 @@ track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n,
 // kernel classes, for launch accounting and per-kernel event timing
 enum KernelId {
   KID_SMOOTH_U8 = 0, KID_GRAD, KID_PYRDOWN, KID_TRACK, KID_MINEIG, KID_SORT, KID_STAMP,
-  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_L0_FUSED, KID_LEVEL_FUSED, KID_TRACK_FAST, KID_TRACK7, KID_COUNT
+  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_L0_FUSED, KID_LEVEL_FUSED, KID_TRACK_FAST, KID_TRACK7, KID_MEGA, KID_COPY_H2D, KID_COPY_D2H, KID_COUNT
 };
 static const char* const kKernelNames[KID_COUNT] = {
   "smooth_u8_tile", "grad_tile", "pyrdown_tile", "track_kernel", "mineig_kernel",
   "cub_radix_sort", "stamp_existing_kernel", "enforce_mindist_kernel",
-  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel", "l0_fused_kernel", "level_fused_kernel", "track_fast_kernel", "track7_kernel"
+  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel", "l0_fused_kernel", "level_fused_kernel", "track_fast_kernel", "track7_kernel", "pyramid_mega_kernel",
+  "copy_h2d", "copy_d2h"          // not kernels: timed in profiling mode, never counted as launches
 };
 static constexpr int PROF_POOL = 2048;     // event pairs in flight before folding
+static constexpr int TRACE_CAP = 8192;     // timeline records kept per profiling session
+static constexpr int KLT_BAND_EVENTS = 64; // events cycled by the banded frame upload
 
 struct Level {
   int w, h, pitch;           // pitch in floats
@@ -799,10 +804,23 @@ struct klt_dev {
   float* tmp;                // generic path: horizontal-pass result, W*H floats
   unsigned char* frame;      // u8 staging of the frame being built, row pitch frame_pitch
   size_t frame_cap; int frame_pitch;
+  // banded upload of host frames: copy stream, one event per band, "staging consumed" event
+  cudaStream_t cstream;
+  cudaEvent_t ev_band[KLT_BAND_EVENTS]; int band_ev_next;
+  cudaEvent_t ev_frame_free; int frame_busy;
+  int band_rows, last_bands;
+  // pyramid_mega_kernel: cached schedule + dependency counters (klt_mega.cuh)
+  int no_mega, last_mega;
+  MegaSeg* d_segs; int mega_nseg, mega_nitems, mega_key[8];
+  unsigned* d_done; int mega_done_off[MEGA_MAX_LEVELS + 1];
+  unsigned mega_epoch[MEGA_MAX_LEVELS];
+  unsigned* d_u8_flag; unsigned feed_epoch;
   // features
   float *d_x, *d_y; int* d_val; int feat_cap; int feat_n;
   float *h_x, *h_y; int* h_val;   // pinned staging
   int staging_busy;
+  int feat_out_host;            // 1: the next tracker writes its results into h_x/h_y/h_val (sync API)
+  cudaEvent_t ev_feat; int feat_pending;   // feature upload queued on the copy stream
   // selection
   int *c_val[2]; unsigned* c_idx[2]; size_t cand_cap;
   void* cub_tmp; size_t cub_bytes;
@@ -818,6 +836,9 @@ struct klt_dev {
   int* prof_kid;
   double prof_ms[KID_COUNT];
   unsigned long long prof_n[KID_COUNT];
+  // timeline of the profiled operations (klt_dev_trace_get): start/end in ms since profile_begin
+  cudaEvent_t ev_origin;
+  int trace_n; int* trace_kid; float* trace_t0; float* trace_t1;
   // features entering klt_dev_track* with val >= 0, accumulated on the device
   unsigned long long* d_live;
 };
@@ -828,11 +849,19 @@ static void prof_fold(klt_dev* d) {
   if (d->prof_used == 0) return;
   cudaStreamSynchronize(d->stream);
   if (d->stream2) cudaStreamSynchronize(d->stream2);
+  if (d->cstream) cudaStreamSynchronize(d->cstream);
   for (int i = 0; i < d->prof_used; ++i) {
     float ms = 0.0f;
     if (cudaEventElapsedTime(&ms, d->prof_ev[2 * i], d->prof_ev[2 * i + 1]) == cudaSuccess) {
       d->prof_ms[d->prof_kid[i]] += ms;
       d->prof_n[d->prof_kid[i]] += 1;
+      if (d->trace_n < TRACE_CAP) {
+        float t0 = 0.0f;
+        cudaEventElapsedTime(&t0, d->ev_origin, d->prof_ev[2 * i]);
+        d->trace_kid[d->trace_n] = d->prof_kid[i];
+        d->trace_t0[d->trace_n] = t0; d->trace_t1[d->trace_n] = t0 + ms;
+        d->trace_n += 1;
+      }
     }
   }
   d->prof_used = 0;
@@ -840,13 +869,14 @@ static void prof_fold(klt_dev* d) {
 static int sync_all(klt_dev* d) {
   cudaError_t e = cudaStreamSynchronize(d->stream);
   if (e == cudaSuccess && d->stream2) e = cudaStreamSynchronize(d->stream2);
+  if (e == cudaSuccess && d->cstream) e = cudaStreamSynchronize(d->cstream);
   d->staging_busy = 0;
   return e == cudaSuccess ? 0 : 1;
 }
 struct Launch {
   klt_dev* d; int slot; cudaStream_t st;
   Launch(klt_dev* d_, int kid, cudaStream_t st_ = nullptr) : d(d_), slot(-1), st(st_ ? st_ : d_->stream) {
-    d->launches++;
+    if (kid != KID_COPY_H2D && kid != KID_COPY_D2H) d->launches++;
     if (d->prof_on) {
       if (d->prof_used == PROF_POOL) prof_fold(d);
       slot = d->prof_used++;
@@ -895,6 +925,10 @@ extern "C" int klt_dev_last_build_path(const klt_dev* d) { return d->last_path; 
 extern "C" void klt_dev_force_generic(klt_dev* d, int on) { d->force_generic = on; }
 extern "C" void klt_dev_disable_fused(klt_dev* d, int on) { d->no_fused = on; d->track7_off = on; }
 extern "C" int klt_dev_last_build_fused(const klt_dev* d) { return d->last_fused; }
+extern "C" int klt_dev_last_build_bands(const klt_dev* d) { return d->last_bands; }
+extern "C" int klt_dev_last_build_mega(const klt_dev* d) { return d->last_mega; }
+extern "C" void klt_dev_disable_mega(klt_dev* d, int on) { d->no_mega = on; }
+extern "C" void klt_dev_set_band_rows(klt_dev* d, int rows) { d->band_rows = rows; }
 
 extern "C" int klt_dev_create(int device, klt_dev** out) {
   *out = nullptr;
@@ -919,11 +953,22 @@ extern "C" int klt_dev_create(int device, klt_dev** out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_read[i], cudaEventDisableTiming);
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->cstream, cudaStreamNonBlocking);
+  for (int i = 0; i < KLT_BAND_EVENTS && e == cudaSuccess; ++i)
+    e = cudaEventCreateWithFlags(&c->ev_band[i], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_frame_free, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_feat, cudaEventDisableTiming);
+  c->band_rows = getenv("KLT_B200_BAND_ROWS") ? atoi(getenv("KLT_B200_BAND_ROWS")) : -1;
   if (e != cudaSuccess) { free(c); return fail(nullptr, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
   c->tstream = c->stream;
   c->overlap_l0_ctas = getenv("KLT_B200_OVERLAP_L0_CTAS") ? atoi(getenv("KLT_B200_OVERLAP_L0_CTAS")) : 0;
   e = cudaMalloc(&c->d_live, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemsetAsync(c->d_live, 0, sizeof(unsigned long long), c->stream);
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_u8_flag, sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMemsetAsync(c->d_u8_flag, 0, sizeof(unsigned), c->stream);
+  // the single-launch pyramid (klt_mega.cuh) is opt-in: correct in both arithmetic modes, but measured
+  // slower than the per-level kernels on B200 (4K: 87 us vs 69 us resident)
+  c->no_mega = getenv("KLT_B200_MEGA") && atoi(getenv("KLT_B200_MEGA")) ? 0 : 1;
   if (e == cudaSuccess) e = cudaMalloc(&c->d_tile_ctr, 16 * sizeof(unsigned));
   if (e == cudaSuccess) e = cudaMemsetAsync(c->d_tile_ctr, 0, 16 * sizeof(unsigned), c->stream);
   if (e != cudaSuccess) { cudaStreamDestroy(c->stream); free(c); return fail(nullptr, "cudaMalloc: %s", cudaGetErrorString(e)); }
@@ -932,6 +977,10 @@ extern "C" int klt_dev_create(int device, klt_dev** out) {
 }
 
 static void free_geometry(klt_dev* d) {
+  cudaFree(d->d_segs); d->d_segs = nullptr; d->mega_nseg = 0;
+  cudaFree(d->d_done); d->d_done = nullptr;
+  memset(d->mega_key, 0, sizeof(d->mega_key));
+  memset(d->mega_epoch, 0, sizeof(d->mega_epoch));
   cudaFree(d->arena); d->arena = nullptr;
   cudaFree(d->tmp); d->tmp = nullptr;
   memset(d->set, 0, sizeof(d->set));
@@ -949,11 +998,17 @@ extern "C" void klt_dev_destroy(klt_dev* d) {
   for (int i = 0; i < 2; ++i) { cudaFree(d->c_val[i]); cudaFree(d->c_idx[i]); }
   cudaFree(d->cub_tmp); cudaFree(d->fmap); cudaFree(d->open_slots);
   if (d->ev_made) { cudaEventDestroy(d->ev_a); cudaEventDestroy(d->ev_b); }
-  if (d->prof_ev) { for (int i = 0; i < 2 * PROF_POOL; ++i) cudaEventDestroy(d->prof_ev[i]); free(d->prof_ev); free(d->prof_kid); }
+  if (d->prof_ev) { for (int i = 0; i < 2 * PROF_POOL; ++i) cudaEventDestroy(d->prof_ev[i]); free(d->prof_ev); free(d->prof_kid);
+    cudaEventDestroy(d->ev_origin); free(d->trace_kid); free(d->trace_t0); free(d->trace_t1); }
   cudaFree(d->d_live);
   cudaFree(d->d_tile_ctr);
+  cudaFree(d->d_u8_flag);
   for (int i = 0; i < KLT_DEV_SLOTS; ++i) { cudaEventDestroy(d->ev_built[i]); cudaEventDestroy(d->ev_read[i]); }
   cudaEventDestroy(d->ev_join);
+  for (int i = 0; i < KLT_BAND_EVENTS; ++i) cudaEventDestroy(d->ev_band[i]);
+  cudaEventDestroy(d->ev_frame_free);
+  cudaEventDestroy(d->ev_feat);
+  cudaStreamDestroy(d->cstream);
   cudaStreamDestroy(d->stream);
   cudaStreamDestroy(d->stream2);
   free(d);
@@ -1147,81 +1202,126 @@ static bool fused_grad_taps_ok(const TapsR& tg, const TapsR& td) {
   return tg.w == 2 * FUSED_RG + 1 && td.w == 2 * FUSED_RG + 1 && td.k[FUSED_RG] == 0.0f;
 }
 
-// fused level 0 (u8 -> L0, gx0, gy0); *done = false if this frame / these taps do not qualify
+// ---- fused kernels: plan (tensor maps, tile shapes) + launches over whole tile rows ------------
+// A launch covers the tile rows [jr0, jr1) of one level, so that a frame can be built band by band
+// behind its upload (klt_dev_build with a host frame) or in one go (jr0 = 0, jr1 = tiles_y).
+enum LevelShape { SHAPE_NONE = 0, SHAPE_2_5_64_32, SHAPE_2_5_64_16, SHAPE_2_5_32_16, SHAPE_4_10_32_16 };
+struct FusedPlan {
+  bool l0_ok;                                   // level 0 runs on l0_fused_kernel
+  int shape[KLT_DEV_MAX_LEVELS];                // LevelShape of level l >= 1 (SHAPE_NONE: not fused)
+  CUtensorMap map[KLT_DEV_MAX_LEVELS];          // source of level l (u8 frame for l = 0, L_{l-1} else)
+  int TX[KLT_DEV_MAX_LEVELS], TY[KLT_DEV_MAX_LEVELS], tiles_x[KLT_DEV_MAX_LEVELS], tiles_y[KLT_DEV_MAX_LEVELS];
+  int SS, R;                                    // pyramid step geometry of the fused level kernels
+};
+
+static int level_shape_for(int ss, int r, long px) {
+  if (ss == 2 && r == 5) {
+    // tile shape by level size: big levels amortise the halo with 64x32 tiles, small levels
+    // need many small tiles to fill 148 SMs and to keep the per-CTA latency short
+    static int force = getenv("KLT_B200_LEVEL_TILE") ? atoi(getenv("KLT_B200_LEVEL_TILE")) : 0;
+    const int shape = force ? force : (px >= 1500000 ? 1 : (px >= 300000 ? 2 : 3));
+    return shape == 1 ? SHAPE_2_5_64_32 : (shape == 2 ? SHAPE_2_5_64_16 : SHAPE_2_5_32_16);
+  }
+  if (ss == 4 && r == 10) return SHAPE_4_10_32_16;
+  return SHAPE_NONE;
+}
+template <int SS, int R, int TX, int TY>
+static bool level_map(CUtensorMap* m, const Level& a) {
+  using G = LvGeo<SS, R, TX, TY>;
+  return make_tensor_map(m, a.img, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.w, a.h, (size_t)a.pitch * 4, G::SW, G::SH);
+}
+
+// which levels of this build can run on the fused kernels, and their tensor maps
+static void fused_plan(klt_dev* d, const PyrSet& S, const unsigned char* src, int spitch,
+                       const klt_dev_build_desc* q, const TapsR& ts, const TapsR& tp, const TapsR& tg,
+                       const TapsR& td, FusedPlan* P, int force_shape) {
+  memset(P, 0, sizeof(*P));
+  if (d->force_generic || d->no_fused || !fused_grad_taps_ok(tg, td)) return;
+  const int W = q->ncols, H = q->nrows;
+  if (q->smooth && ts.w == 2 * L0Geo::RS + 1 &&
+      make_tensor_map(&P->map[0], src, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, W, H, (size_t)spitch, L0Geo::U8_W,
+                      L0Geo::U8_H)) {
+    P->l0_ok = true;
+    P->TX[0] = L0Geo::TX; P->TY[0] = L0Geo::TY;
+    P->tiles_x[0] = (W + L0Geo::TX - 1) / L0Geo::TX; P->tiles_y[0] = (H + L0Geo::TY - 1) / L0Geo::TY;
+  }
+  P->SS = q->subsampling; P->R = tp.w / 2;
+  for (int l = 1; l < q->nlevels_built; ++l) {
+    const Level& a = S.lv[l - 1];
+    const Level& b = S.lv[l];
+    int shape = force_shape != SHAPE_NONE ? force_shape : level_shape_for(q->subsampling, tp.w / 2, (long)b.w * b.h);
+    bool ok = false;
+    switch (shape) {
+      case SHAPE_2_5_64_32: ok = level_map<2, 5, 64, 32>(&P->map[l], a); P->TX[l] = 64; P->TY[l] = 32; break;
+      case SHAPE_2_5_64_16: ok = level_map<2, 5, 64, 16>(&P->map[l], a); P->TX[l] = 64; P->TY[l] = 16; break;
+      case SHAPE_2_5_32_16: ok = level_map<2, 5, 32, 16>(&P->map[l], a); P->TX[l] = 32; P->TY[l] = 16; break;
+      case SHAPE_4_10_32_16: ok = level_map<4, 10, 32, 16>(&P->map[l], a); P->TX[l] = 32; P->TY[l] = 16; break;
+      default: break;
+    }
+    if (!ok) { shape = SHAPE_NONE; continue; }
+    P->shape[l] = shape;
+    P->tiles_x[l] = (b.w + P->TX[l] - 1) / P->TX[l];
+    P->tiles_y[l] = (b.h + P->TY[l] - 1) / P->TY[l];
+  }
+}
+
+// fused level 0 (u8 -> L0, gx0, gy0), tile rows [jr0, jr1)
 template <bool EXACT>
-static int l0_fused_dispatch(klt_dev* d, const unsigned char* src, int spitch, int W, int H, const TapsR& ts,
-                             const TapsR& tg, const TapsR& td, const Level& lv, bool* done) {
-  *done = false;
-  if (ts.w != 2 * L0Geo::RS + 1 || !fused_grad_taps_ok(tg, td)) return 0;
-  CUtensorMap map;
-  if (!make_tensor_map(&map, src, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, W, H, (size_t)spitch, L0Geo::U8_W,
-                       L0Geo::U8_H))
-    return 0;
+static int l0_fused_launch(klt_dev* d, const FusedPlan& P, int W, int H, const TapsR& ts, const TapsR& tg,
+                           const TapsR& td, const Level& lv, int jr0, int jr1) {
+  if (jr1 <= jr0) return 0;
   static bool attr_set[2] = {false, false};
   if (!attr_set[EXACT]) {
     CU(cudaFuncSetAttribute(l0_fused_kernel<EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L0Geo::SMEM));
     attr_set[EXACT] = true;
   }
-  const int tiles_x = (W + L0Geo::TX - 1) / L0Geo::TX, tiles_y = (H + L0Geo::TY - 1) / L0Geo::TY;
-  const int ntiles = tiles_x * tiles_y;
+  const int tiles_x = P.tiles_x[0];
+  const int tile0 = jr0 * tiles_x, tile1 = jr1 * tiles_x, n = tile1 - tile0;
   const int cps = (d->overlap && d->overlap_l0_ctas > 0) ? d->overlap_l0_ctas : 3;
-  const int grid = ntiles < cps * d->num_sms ? ntiles : cps * d->num_sms;    // persistent, 3 CTAs / SM
+  const int grid = n < cps * d->num_sms ? n : cps * d->num_sms;               // persistent, 3 CTAs / SM
   { Launch l(d, KID_L0_FUSED);
-    l0_fused_kernel<EXACT><<<grid, 256, L0Geo::SMEM, d->stream>>>(map, W, H, tiles_x, ntiles, d->d_tile_ctr,
-                                                                  d->tile_base[0], ts, tg, td, lv.img, lv.gx,
-                                                                  lv.gy, lv.pitch);
-    d->tile_base[0] += (unsigned)(ntiles + grid); }
-  *done = true;
+    l0_fused_kernel<EXACT><<<grid, 256, L0Geo::SMEM, d->stream>>>(P.map[0], W, H, tiles_x, tile0, tile1,
+                                                                  d->d_tile_ctr, d->tile_base[0], ts, tg, td,
+                                                                  lv.img, lv.gx, lv.gy, lv.pitch);
+    d->tile_base[0] += (unsigned)(n + grid); }
   return 0;
 }
 
-// fused coarser level (L_{l-1} -> L_l, gx_l, gy_l)
+// fused coarser level (L_{l-1} -> L_l, gx_l, gy_l), tile rows [jr0, jr1)
 template <int SS, int R, int TX, int TY, bool EXACT>
-static int launch_level_fused(klt_dev* d, int level, const Level& a, const Level& b, const TapsR& tp,
-                              const TapsR& tg, const TapsR& td, bool* done) {
+static int level_fused_launch_t(klt_dev* d, const FusedPlan& P, int level, const Level& a, const Level& b,
+                                const TapsR& tp, const TapsR& tg, const TapsR& td, int jr0, int jr1) {
   using G = LvGeo<SS, R, TX, TY>;
-  *done = false;
-  CUtensorMap map;
-  if (!make_tensor_map(&map, a.img, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.w, a.h, (size_t)a.pitch * 4, G::SW, G::SH))
-    return 0;
   static bool attr_set = false;
+  static int cps = 0;                                                       // resident CTAs per SM
   if (!attr_set) {
     CU(cudaFuncSetAttribute(level_fused_kernel<SS, R, TX, TY, EXACT>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, level_fused_kernel<SS, R, TX, TY, EXACT>, 256, G::SMEM));
+    if (cps < 1) cps = 1;
     attr_set = true;
   }
-  const int tiles_x = (b.w + TX - 1) / TX, tiles_y = (b.h + TY - 1) / TY;
-  const int ntiles = tiles_x * tiles_y;
-  int cps = 0;                                                              // resident CTAs per SM
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, level_fused_kernel<SS, R, TX, TY, EXACT>, 256, G::SMEM));
-  if (cps < 1) cps = 1;
-  const int grid = ntiles < cps * d->num_sms ? ntiles : cps * d->num_sms;   // persistent
+  const int tiles_x = P.tiles_x[level];
+  const int tile0 = jr0 * tiles_x, tile1 = jr1 * tiles_x, n = tile1 - tile0;
+  const int grid = n < cps * d->num_sms ? n : cps * d->num_sms;             // persistent
   { Launch l(d, KID_LEVEL_FUSED);
     level_fused_kernel<SS, R, TX, TY, EXACT><<<grid, 256, G::SMEM, d->stream>>>(
-        map, a.w, a.h, b.w, b.h, tiles_x, ntiles, d->d_tile_ctr + (level & 15), d->tile_base[level & 15], tp, tg,
-        td, b.img, b.gx, b.gy, b.pitch);
-    d->tile_base[level & 15] += (unsigned)(ntiles + grid); }
-  *done = true;
+        P.map[level], a.w, a.h, b.w, b.h, tiles_x, tile0, tile1, d->d_tile_ctr + (level & 15),
+        d->tile_base[level & 15], tp, tg, td, b.img, b.gx, b.gy, b.pitch);
+    d->tile_base[level & 15] += (unsigned)(n + grid); }
   return 0;
 }
 template <bool EXACT>
-static int level_fused_dispatch(klt_dev* d, int ss, int level, const Level& a, const Level& b, const TapsR& tp,
-                                const TapsR& tg, const TapsR& td, bool* done) {
-  *done = false;
-  if (!fused_grad_taps_ok(tg, td)) return 0;
-  const int r = tp.w / 2;
-  if (ss == 2 && r == 5) {
-    // tile shape by level size: big levels amortise the halo with 64x32 tiles, small levels
-    // need many small tiles to fill 148 SMs and to keep the per-CTA latency short
-    static int force = getenv("KLT_B200_LEVEL_TILE") ? atoi(getenv("KLT_B200_LEVEL_TILE")) : 0;
-    const long px = (long)b.w * b.h;
-    int shape = force ? force : (px >= 1500000 ? 1 : (px >= 300000 ? 2 : 3));
-    if (shape == 1) return launch_level_fused<2, 5, 64, 32, EXACT>(d, level, a, b, tp, tg, td, done);
-    if (shape == 2) return launch_level_fused<2, 5, 64, 16, EXACT>(d, level, a, b, tp, tg, td, done);
-    return launch_level_fused<2, 5, 32, 16, EXACT>(d, level, a, b, tp, tg, td, done);
+static int level_fused_launch(klt_dev* d, const FusedPlan& P, int level, const Level& a, const Level& b,
+                              const TapsR& tp, const TapsR& tg, const TapsR& td, int jr0, int jr1) {
+  if (jr1 <= jr0) return 0;
+  switch (P.shape[level]) {
+    case SHAPE_2_5_64_32: return level_fused_launch_t<2, 5, 64, 32, EXACT>(d, P, level, a, b, tp, tg, td, jr0, jr1);
+    case SHAPE_2_5_64_16: return level_fused_launch_t<2, 5, 64, 16, EXACT>(d, P, level, a, b, tp, tg, td, jr0, jr1);
+    case SHAPE_2_5_32_16: return level_fused_launch_t<2, 5, 32, 16, EXACT>(d, P, level, a, b, tp, tg, td, jr0, jr1);
+    case SHAPE_4_10_32_16: return level_fused_launch_t<4, 10, 32, 16, EXACT>(d, P, level, a, b, tp, tg, td, jr0, jr1);
+    default: return fail(d, "level %d has no fused kernel", level);
   }
-  if (ss == 4 && r == 10) return launch_level_fused<4, 10, 32, 16, EXACT>(d, level, a, b, tp, tg, td, done);
-  return 0;
 }
 
 // generic two-kernel separable pass through d->tmp
@@ -1240,25 +1340,404 @@ static int generic_separable(klt_dev* d, const SrcT* src, int spitch, int W, int
   return 0;
 }
 
+// ---- pyramid_mega_kernel: schedule, dependency state, launch ------------------------------------
+typedef CUresult (*WriteValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static WriteValue32Fn stream_write_value32() {
+  static WriteValue32Fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (WriteValue32Fn)p;
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+// tile shape of the coarse levels inside the mega kernel: one shape per subsampling (all tile types
+// of a launch share one shared-memory footprint; 64x16 / 32x16 match level 0's 55 KB / fit 2 per SM)
+static int mega_shape_for(int ss, int r) {
+  if (ss == 2 && r == 5) return SHAPE_2_5_64_16;
+  if (ss == 4 && r == 10) return SHAPE_4_10_32_16;
+  return SHAPE_NONE;
+}
+
+// Coarse work list in topological order: walking the level-0 tile rows top to bottom, the tile
+// rows of the coarser levels each one completes (the same rule the per-level band loop uses).
+// Cached per geometry; the device checks the real dependencies, the order only has to be valid.
+static int mega_schedule(klt_dev* d, const FusedPlan& P, const PyrSet& S, int nb) {
+  const int key[8] = {d->W, d->H, d->L, d->ss, nb, P.shape[1], P.R, 1};
+  if (d->d_segs && memcmp(key, d->mega_key, sizeof(key)) == 0) return 0;
+  MegaSeg segs[MEGA_MAX_SEGS];
+  memset(segs, 0, sizeof(segs));
+  int nseg = 0, nitems = 0;
+  int rows_done[KLT_DEV_MAX_LEVELS] = {0}, valid[KLT_DEV_MAX_LEVELS] = {0};
+  const int SS = P.SS, R = P.R, RG = FUSED_RG, H = S.lv[0].h;
+  auto emit = [&](int level, int j0, int j1) -> bool {
+    if (j1 <= j0) return true;
+    if (nseg > 0 && segs[nseg - 1].level == level && segs[nseg - 1].jr0 + segs[nseg - 1].n / P.tiles_x[level] == j0) {
+      segs[nseg - 1].n += (j1 - j0) * P.tiles_x[level];          // extend the previous segment
+    } else {
+      if (nseg == MEGA_MAX_SEGS) return false;
+      segs[nseg].level = level; segs[nseg].jr0 = j0; segs[nseg].w0 = nitems; segs[nseg].n = (j1 - j0) * P.tiles_x[level];
+      ++nseg;
+    }
+    nitems += (j1 - j0) * P.tiles_x[level];
+    return true;
+  };
+  // A tile row is listed only once the rows it reads have been listed at least `lag` items
+  // earlier (about one wave of the CTAs serving this queue), so that in steady state its producers
+  // have finished by the time it is claimed and nobody waits; everything is flushed at the end.
+  static int lag_env = getenv("KLT_B200_MEGA_LAG") ? atoi(getenv("KLT_B200_MEGA_LAG")) : 160;
+  struct Pend { int j0, j1, ready_pos; };
+  static const int PQ = 4096;
+  Pend* pend[KLT_DEV_MAX_LEVELS] = {nullptr};
+  int ph[KLT_DEV_MAX_LEVELS] = {0}, pt[KLT_DEV_MAX_LEVELS] = {0};      // queue head / tail
+  int queued[KLT_DEV_MAX_LEVELS] = {0}, last_emit_pos[KLT_DEV_MAX_LEVELS] = {0};
+  for (int l = 1; l < nb; ++l) pend[l] = (Pend*)malloc(sizeof(Pend) * PQ);
+  bool overflow = false;
+  for (int step = 0; step <= P.tiles_y[0] && !overflow; ++step) {
+    const bool flush = step == P.tiles_y[0];
+    const int lag = flush ? 0 : lag_env;
+    if (!flush) {
+      rows_done[0] = step + 1;
+      valid[0] = P.TY[0] * (step + 1) < H ? P.TY[0] * (step + 1) : H;
+    }
+    bool progress = true;
+    while (progress && !overflow) {
+      progress = false;
+      for (int l = 1; l < nb && !overflow; ++l) {
+        const Level& a = S.lv[l - 1];
+        const Level& b = S.lv[l];
+        int j = queued[l];
+        while (j < P.tiles_y[l]) {
+          int need = SS * (P.TY[l] * (j + 1) - 1 + RG) + SS / 2 + R + 1;
+          if (need > a.h) need = a.h;
+          if (need > valid[l - 1]) break;
+          ++j;
+        }
+        if (j > queued[l]) {
+          if (pt[l] == PQ) { overflow = true; break; }
+          pend[l][pt[l]++] = Pend{queued[l], j, l == 1 ? 0 : last_emit_pos[l - 1] + lag_env};
+          queued[l] = j;
+        }
+        while (ph[l] < pt[l] && (flush || pend[l][ph[l]].ready_pos <= nitems)) {
+          const Pend q = pend[l][ph[l]++];
+          if (!emit(l, q.j0, q.j1)) { overflow = true; break; }
+          rows_done[l] = q.j1;
+          valid[l] = P.TY[l] * q.j1 < b.h ? P.TY[l] * q.j1 : b.h;
+          last_emit_pos[l] = nitems;
+          progress = true;
+        }
+      }
+    }
+    (void)lag;
+  }
+  for (int l = 1; l < nb; ++l) free(pend[l]);
+  if (overflow) return 2;                                    // caller falls back to the per-level kernels
+  for (int l = 0; l < nb; ++l)
+    if (rows_done[l] != P.tiles_y[l]) return fail(d, "mega schedule left level %d incomplete", l);
+  if (sync_all(d)) return fail(d, "stream synchronisation failed");
+  cudaFree(d->d_segs); d->d_segs = nullptr;
+  cudaFree(d->d_done); d->d_done = nullptr;
+  CU(cudaMalloc(&d->d_segs, sizeof(MegaSeg) * (nseg > 0 ? nseg : 1)));
+  if (nseg > 0) CU(cudaMemcpy(d->d_segs, segs, sizeof(MegaSeg) * nseg, cudaMemcpyHostToDevice));
+  int off = 0;
+  for (int l = 0; l < nb; ++l) { d->mega_done_off[l] = off; off += P.tiles_y[l]; }
+  d->mega_done_off[nb] = off;
+  CU(cudaMalloc(&d->d_done, sizeof(unsigned) * off));
+  CU(cudaMemset(d->d_done, 0, sizeof(unsigned) * off));
+  memset(d->mega_epoch, 0, sizeof(d->mega_epoch));
+  d->mega_nseg = nseg; d->mega_nitems = nitems;
+  memcpy(d->mega_key, key, sizeof(key));
+  return 0;
+}
+
+template <int SS, int R, int TX, int TY, bool EXACT>
+static int mega_launch_t(klt_dev* d, const MegaParams& MP) {
+  using MG = MegaGeo<SS, R, TX, TY>;
+  static bool attr_set = false;
+  static int cps = 0;
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(pyramid_mega_kernel<SS, R, TX, TY, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG::SMEM));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, pyramid_mega_kernel<SS, R, TX, TY, EXACT>, 288, MG::SMEM));
+    if (cps < 1) return fail(d, "pyramid_mega_kernel does not fit on an SM");
+    attr_set = true;
+  }
+  // the grid must be fully resident: CTAs wait on each other's tiles
+  const int cap = cps * d->num_sms;
+  const int items = MP.nitems0 + MP.nitems1;
+  const int grid = items < cap ? items : cap;
+  { Launch l(d, KID_MEGA);
+    pyramid_mega_kernel<SS, R, TX, TY, EXACT><<<grid, 288, MG::SMEM, d->stream>>>(MP); }
+  return 0;
+}
+
+// A host frame being uploaded band by band on the copy stream (klt_dev_build); the fused kernels
+// are launched over the tile rows each band completes, so the upload hides the image pipeline.
+// All copies are queued first (the host must never starve the copy engine), then the kernels,
+// each group gated by the event of the band that completes its source rows.
+static constexpr int KLT_MAX_BANDS = 48;
+struct BandFeed {
+  const unsigned char* host;     // tightly packed W x H
+  int W, H, fp;                  // fp: row pitch of d->frame
+  int nbands, next;              // bands queued / bands the compute stream has been gated on
+  int end_row[KLT_MAX_BANDS];    // band b covers rows [end_row[b-1], end_row[b])
+  cudaEvent_t ev[KLT_MAX_BANDS];
+};
+// band schedule: mode > 0: equal bands of `mode` rows; mode == 0: one copy; mode < 0: automatic --
+// frames of >= 4 MB go in two bands, 60 % / 40 % (everything behind the last band is exposed
+// latency, but every extra band costs four kernel boundaries at 7-12 us each while a copy is in
+// flight; measured best on B200), smaller frames in one copy
+static void feed_schedule(BandFeed* f, int mode) {
+  const int H = f->H;
+  f->nbands = 0;
+  if (mode > 0) {
+    const int rows = (mode + 63) / 64 * 64;
+    int r = 0;
+    while (r < H && f->nbands < KLT_MAX_BANDS - 1) {
+      int take = rows;
+      const int left = H - r;
+      if (left > rows && left < rows + rows / 2) take = left - rows / 2;   // keep the last band short
+      if (take > left) take = left;
+      r += take;
+      f->end_row[f->nbands++] = r;
+    }
+    if (r < H) f->end_row[f->nbands++] = H;
+  } else if (mode < 0 && (long)f->W * H >= 4L * 1000 * 1000) {
+    static float frac[8] = {0.6f};
+    static int nfrac = 1;
+    static bool parsed = false;
+    if (!parsed) {                 // tuning hook: KLT_B200_BAND_FRACS="0.3,0.6,0.85"
+      parsed = true;
+      const char* e = getenv("KLT_B200_BAND_FRACS");
+      if (e && *e) {
+        nfrac = 0;
+        while (*e && nfrac < 8) {
+          char* end = nullptr;
+          const float v = strtof(e, &end);
+          if (end == e) break;
+          frac[nfrac++] = v;
+          e = (*end == ',') ? end + 1 : end;
+        }
+      }
+    }
+    for (int i = 0; i < nfrac; ++i) {
+      int r = (int)(frac[i] * H) / 64 * 64;
+      if (r > 0 && r < H && (f->nbands == 0 || r > f->end_row[f->nbands - 1])) f->end_row[f->nbands++] = r;
+    }
+    f->end_row[f->nbands++] = H;
+  } else {
+    f->end_row[f->nbands++] = H;
+  }
+}
+static int feed_enqueue_copies(klt_dev* d, BandFeed* f) {
+  if (d->frame_busy) {          // the previous build's level-0 kernels may still read d->frame
+    CU(cudaStreamWaitEvent(d->cstream, d->ev_frame_free, 0));
+    d->frame_busy = 0;
+  }
+  int r0 = 0;
+  for (int b = 0; b < f->nbands; ++b) {
+    const int rows = f->end_row[b] - r0;
+    unsigned char* dst = d->frame + (size_t)r0 * f->fp;
+    const unsigned char* src = f->host + (size_t)r0 * f->W;
+    { Launch l(d, KID_COPY_H2D, d->cstream);
+      if (f->fp == f->W)
+        CU(cudaMemcpyAsync(dst, src, (size_t)rows * f->W, cudaMemcpyHostToDevice, d->cstream));
+      else
+        CU(cudaMemcpy2DAsync(dst, f->fp, src, f->W, f->W, rows, cudaMemcpyHostToDevice, d->cstream)); }
+    f->ev[b] = d->ev_band[d->band_ev_next];
+    d->band_ev_next = (d->band_ev_next + 1) % KLT_BAND_EVENTS;
+    CU(cudaEventRecord(f->ev[b], d->cstream));
+    r0 = f->end_row[b];
+  }
+  f->next = 0;
+  return 0;
+}
+// gate the compute stream on the next band (or on all of them); returns the rows then available
+static int feed_wait(klt_dev* d, BandFeed* f, bool all, int* rows) {
+  do {
+    CU(cudaStreamWaitEvent(d->stream, f->ev[f->next], 0));
+    f->next += 1;
+  } while (all && f->next < f->nbands);
+  *rows = f->end_row[f->next - 1];
+  return 0;
+}
+
+// all levels of one frame in one launch.  feed != nullptr: the frame is still on the host; its
+// bands are queued on the copy stream, each followed by a write of the device word the level-0
+// tiles wait on.  Returns 2 (nothing queued) if the frame has no schedule: the caller falls back.
+template <bool EXACT>
+static int mega_build(klt_dev* d, PyrSet& S, const FusedPlan& P, int nb, const TapsR& ts, const TapsR& tp,
+                      const TapsR& tg, const TapsR& td, BandFeed* feed) {
+  { const int rc = mega_schedule(d, P, S, nb); if (rc) return rc; }
+  MegaParams MP;
+  memset(&MP, 0, sizeof(MP));
+  for (int l = 0; l < nb; ++l) {
+    MP.map[l] = P.map[l];
+    MegaLevel& L = MP.lv[l];
+    L.W = S.lv[l].w; L.H = S.lv[l].h; L.pitch = S.lv[l].pitch;
+    L.img = S.lv[l].img; L.gx = S.lv[l].gx; L.gy = S.lv[l].gy;
+    L.tiles_x = P.tiles_x[l]; L.tiles_y = P.tiles_y[l];
+    L.done_off = d->mega_done_off[l];
+    d->mega_epoch[l] += 1;
+    L.target = d->mega_epoch[l] * (unsigned)P.tiles_x[l];
+  }
+  MP.nlev = nb; MP.nseg = d->mega_nseg;
+  MP.nitems0 = P.tiles_x[0] * P.tiles_y[0]; MP.nitems1 = d->mega_nitems;
+  MP.segs = d->d_segs;
+  MP.ctr = d->d_tile_ctr + 12;                   // three words, reset by the kernel itself
+  { static int every = getenv("KLT_B200_MEGA_COARSE_EVERY") ? atoi(getenv("KLT_B200_MEGA_COARSE_EVERY")) : 3;
+    MP.coarse_every = every < 1 ? 1 : every;
+    static int serial = getenv("KLT_B200_MEGA_SERIAL") ? atoi(getenv("KLT_B200_MEGA_SERIAL")) : 0;
+    MP.serial = serial; }
+  MP.done = d->d_done;
+  MP.u8_flag = d->d_u8_flag;
+  MP.ts = ts; MP.tp = tp; MP.tg = tg; MP.td = td;
+  if (feed) {
+    WriteValue32Fn wv = stream_write_value32();
+    d->feed_epoch += 1;
+    MP.u8_base = d->feed_epoch * 8192u;
+    bool flags_ok = wv != nullptr && feed->H < 8192;
+    if (d->frame_busy) {          // the previous build's level-0 tiles may still read d->frame
+      CU(cudaStreamWaitEvent(d->cstream, d->ev_frame_free, 0));
+      d->frame_busy = 0;
+    }
+    int r0 = 0;
+    for (int b = 0; b < feed->nbands; ++b) {
+      const int rows = feed->end_row[b] - r0;
+      unsigned char* dst = d->frame + (size_t)r0 * feed->fp;
+      const unsigned char* src = feed->host + (size_t)r0 * feed->W;
+      { Launch l(d, KID_COPY_H2D, d->cstream);
+        if (feed->fp == feed->W)
+          CU(cudaMemcpyAsync(dst, src, (size_t)rows * feed->W, cudaMemcpyHostToDevice, d->cstream));
+        else
+          CU(cudaMemcpy2DAsync(dst, feed->fp, src, feed->W, feed->W, rows, cudaMemcpyHostToDevice, d->cstream)); }
+      r0 = feed->end_row[b];
+      if (flags_ok && wv((CUstream)d->cstream, (CUdeviceptr)(uintptr_t)d->d_u8_flag, MP.u8_base + (unsigned)r0, 0) != CUDA_SUCCESS)
+        flags_ok = false;
+    }
+    if (flags_ok) {
+      MP.has_feed = 1;
+    } else {                      // no in-kernel flag: gate the whole launch on the end of the upload
+      cudaEvent_t ev = d->ev_band[d->band_ev_next];
+      d->band_ev_next = (d->band_ev_next + 1) % KLT_BAND_EVENTS;
+      CU(cudaEventRecord(ev, d->cstream));
+      CU(cudaStreamWaitEvent(d->stream, ev, 0));
+      MP.has_feed = 0;
+    }
+    d->last_bands = feed->nbands;
+  }
+  int rc;
+  switch (nb > 1 ? P.shape[1] : (int)SHAPE_2_5_64_16) {        // nb == 1: only level-0 tiles exist
+    case SHAPE_2_5_64_16: rc = mega_launch_t<2, 5, 64, 16, EXACT>(d, MP); break;
+    case SHAPE_4_10_32_16: rc = mega_launch_t<4, 10, 32, 16, EXACT>(d, MP); break;
+    default: return fail(d, "no mega kernel for this pyramid geometry");
+  }
+  if (rc) return rc;
+  if (feed) {
+    CU(cudaEventRecord(d->ev_frame_free, d->stream));
+    d->frame_busy = 1;
+  }
+  return 0;
+}
+
 template <bool EXACT>
 static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitch,
-                      const klt_dev_build_desc* q) {
+                      const klt_dev_build_desc* q, BandFeed* feed) {
   const int W = q->ncols, H = q->nrows;
   bool tiled_all = true, done = false;
+  const int nb = q->nlevels_built;
+  TapsR ts, tp;
+  memset(&ts, 0, sizeof(ts)); memset(&tp, 0, sizeof(tp));
+  if (q->smooth) ts = reversed(q->smooth_taps.gauss, q->smooth_taps.gauss_width);
+  if (nb > 1) tp = reversed(q->pyramid_taps.gauss, q->pyramid_taps.gauss_width);
+  const TapsR tg = reversed(q->grad_taps.gauss, q->grad_taps.gauss_width);
+  const TapsR td = reversed(q->grad_taps.deriv, q->grad_taps.deriv_width);
+  FusedPlan P;
+  d->last_fused = 0;
+  d->last_bands = 0;
+  d->last_mega = 0;
+  // one launch for the whole pyramid when every level qualifies (klt_mega.cuh)
+  if (!d->no_mega && nb <= MEGA_MAX_LEVELS && (nb == 1 || mega_shape_for(q->subsampling, tp.w / 2) != SHAPE_NONE)) {
+    fused_plan(d, S, src, spitch, q, ts, tp, tg, td, &P, nb > 1 ? mega_shape_for(q->subsampling, tp.w / 2) : SHAPE_NONE);
+    bool ok = P.l0_ok;
+    for (int l = 1; l < nb; ++l) ok = ok && P.shape[l] != SHAPE_NONE;
+    if (ok) {
+      const int rc = mega_build<EXACT>(d, S, P, nb, ts, tp, tg, td, feed);
+      if (rc == 1) return 1;
+      if (rc == 0) { d->last_fused = nb; d->last_path = 1; d->last_mega = 1; return 0; }
+    }
+  }
+  fused_plan(d, S, src, spitch, q, ts, tp, tg, td, &P, SHAPE_NONE);
+  bool all_fused = P.l0_ok;
+  for (int l = 1; l < nb; ++l) all_fused = all_fused && P.shape[l] != SHAPE_NONE;
+
+  if (all_fused) {
+    // every level runs on the fused kernels: launch whole tile rows as soon as their source rows
+    // exist -- all at once for a resident frame, band by band behind the upload of a host frame
+    int rows_done[KLT_DEV_MAX_LEVELS] = {0}, valid[KLT_DEV_MAX_LEVELS] = {0};
+    const int SS = P.SS, R = P.R, RG = FUSED_RG;
+    int u8_rows = feed ? 0 : H;
+    if (feed && feed_enqueue_copies(d, feed)) return 1;
+    do {
+      if (feed && feed_wait(d, feed, false, &u8_rows)) return 1;
+      int j = rows_done[0];
+      while (j < P.tiles_y[0]) {
+        int need = P.TY[0] * (j + 1) + L0Geo::RS + L0Geo::RG;
+        if (need > H) need = H;
+        if (need > u8_rows) break;
+        ++j;
+      }
+      if (l0_fused_launch<EXACT>(d, P, W, H, ts, tg, td, S.lv[0], rows_done[0], j)) return 1;
+      rows_done[0] = j;
+      valid[0] = P.TY[0] * j < H ? P.TY[0] * j : H;
+      for (int l = 1; l < nb; ++l) {
+        const Level& a = S.lv[l - 1];
+        const Level& b = S.lv[l];
+        j = rows_done[l];
+        while (j < P.tiles_y[l]) {
+          int need = SS * (P.TY[l] * (j + 1) - 1 + RG) + SS / 2 + R + 1;
+          if (need > a.h) need = a.h;
+          if (need > valid[l - 1]) break;
+          ++j;
+        }
+        if (level_fused_launch<EXACT>(d, P, l, a, b, tp, tg, td, rows_done[l], j)) return 1;
+        rows_done[l] = j;
+        valid[l] = P.TY[l] * j < b.h ? P.TY[l] * j : b.h;
+      }
+    } while (u8_rows < H);
+    if (feed) {
+      d->last_bands = feed->nbands;
+      CU(cudaEventRecord(d->ev_frame_free, d->stream));
+      d->frame_busy = 1;
+    }
+    for (int l = 0; l < nb; ++l)
+      if (rows_done[l] != P.tiles_y[l]) return fail(d, "banded build left level %d incomplete", l);
+    d->last_fused = nb;
+    d->last_path = 1;
+    return 0;
+  }
+
+  // ---- mixed / generic path: the whole frame must be on the device -----------------------------
+  if (feed) {
+    int rows = 0;
+    feed->nbands = 1; feed->end_row[0] = H;
+    if (feed_enqueue_copies(d, feed) || feed_wait(d, feed, true, &rows)) return 1;
+    d->last_bands = 1;
+  }
   int grad_from = 0;                 // first level whose gradients are still to be computed
-  // level 0: fused TMA kernel (smooth + both gradients) when the frame and taps qualify
-  if (q->smooth && !d->force_generic && !d->no_fused) {
-    const TapsR ts = reversed(q->smooth_taps.gauss, q->smooth_taps.gauss_width);
-    const TapsR tg = reversed(q->grad_taps.gauss, q->grad_taps.gauss_width);
-    const TapsR td = reversed(q->grad_taps.deriv, q->grad_taps.deriv_width);
-    if (l0_fused_dispatch<EXACT>(d, src, spitch, W, H, ts, tg, td, S.lv[0], &done)) return 1;
-    if (done) grad_from = 1;
+  if (P.l0_ok) {
+    if (l0_fused_launch<EXACT>(d, P, W, H, ts, tg, td, S.lv[0], 0, P.tiles_y[0])) return 1;
+    grad_from = 1;
   }
   d->last_fused = grad_from;
   if (grad_from == 1) {
     // nothing left to do for level 0
   } else if (q->smooth) {
-    const TapsR ts = reversed(q->smooth_taps.gauss, q->smooth_taps.gauss_width);
     done = false;
     if (!d->force_generic)
       if (smooth_u8_dispatch<EXACT>(d, src, spitch, W, H, ts, S.lv[0].img, S.lv[0].pitch, &done)) return 1;
@@ -1272,46 +1751,42 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
     Launch l(d, KID_U8_TO_F32);
     u8_to_f32_kernel<<<g, b, 0, d->stream>>>(src, spitch, W, H, S.lv[0].img, S.lv[0].pitch);
   }
+  if (feed) {                        // d->frame has been consumed by the level-0 kernel(s) above
+    CU(cudaEventRecord(d->ev_frame_free, d->stream));
+    d->frame_busy = 1;
+  }
   // coarser levels
   bool grads_done[KLT_DEV_MAX_LEVELS] = {false};
   grads_done[0] = (grad_from == 1);
-  if (q->nlevels_built > 1) {
-    const TapsR tp = reversed(q->pyramid_taps.gauss, q->pyramid_taps.gauss_width);
-    const TapsR tg = reversed(q->grad_taps.gauss, q->grad_taps.gauss_width);
-    const TapsR td = reversed(q->grad_taps.deriv, q->grad_taps.deriv_width);
-    for (int l = 1; l < q->nlevels_built; ++l) {
-      const Level& a = S.lv[l - 1];
-      const Level& b = S.lv[l];
-      done = false;
-      if (!d->force_generic && !d->no_fused) {
-        if (level_fused_dispatch<EXACT>(d, q->subsampling, l, a, b, tp, tg, td, &done)) return 1;
-        if (done) { grads_done[l] = true; d->last_fused += 1; continue; }
-      }
-      if (!d->force_generic)
-        if (pyrdown_dispatch<EXACT>(d, q->subsampling, a.img, a.pitch, a.w, a.h, tp, b.img, b.pitch,
-                                    b.w, b.h, &done)) return 1;
-      if (!done) {
-        tiled_all = false;
-        if (generic_separable<float, EXACT>(d, a.img, a.pitch, a.w, a.h, tp, tp, q->subsampling,
-                                            b.img, b.pitch, b.w, b.h)) return 1;
-      }
+  for (int l = 1; l < nb; ++l) {
+    const Level& a = S.lv[l - 1];
+    const Level& b = S.lv[l];
+    if (P.shape[l] != SHAPE_NONE) {
+      if (level_fused_launch<EXACT>(d, P, l, a, b, tp, tg, td, 0, P.tiles_y[l])) return 1;
+      grads_done[l] = true; d->last_fused += 1;
+      continue;
+    }
+    done = false;
+    if (!d->force_generic)
+      if (pyrdown_dispatch<EXACT>(d, q->subsampling, a.img, a.pitch, a.w, a.h, tp, b.img, b.pitch,
+                                  b.w, b.h, &done)) return 1;
+    if (!done) {
+      tiled_all = false;
+      if (generic_separable<float, EXACT>(d, a.img, a.pitch, a.w, a.h, tp, tp, q->subsampling,
+                                          b.img, b.pitch, b.w, b.h)) return 1;
     }
   }
   // gradients
-  {
-    const TapsR tg = reversed(q->grad_taps.gauss, q->grad_taps.gauss_width);
-    const TapsR td = reversed(q->grad_taps.deriv, q->grad_taps.deriv_width);
-    for (int l = 0; l < q->nlevels_built; ++l) {
-      if (grads_done[l]) continue;
-      const Level& a = S.lv[l];
-      done = false;
-      if (!d->force_generic)
-        if (grad_dispatch<EXACT>(d, a.img, a.pitch, a.w, a.h, tg, td, a.gx, a.gy, a.pitch, &done)) return 1;
-      if (!done) {
-        tiled_all = false;
-        if (generic_separable<float, EXACT>(d, a.img, a.pitch, a.w, a.h, td, tg, 1, a.gx, a.pitch, a.w, a.h)) return 1;
-        if (generic_separable<float, EXACT>(d, a.img, a.pitch, a.w, a.h, tg, td, 1, a.gy, a.pitch, a.w, a.h)) return 1;
-      }
+  for (int l = 0; l < nb; ++l) {
+    if (grads_done[l]) continue;
+    const Level& a = S.lv[l];
+    done = false;
+    if (!d->force_generic)
+      if (grad_dispatch<EXACT>(d, a.img, a.pitch, a.w, a.h, tg, td, a.gx, a.gy, a.pitch, &done)) return 1;
+    if (!done) {
+      tiled_all = false;
+      if (generic_separable<float, EXACT>(d, a.img, a.pitch, a.w, a.h, td, tg, 1, a.gx, a.pitch, a.w, a.h)) return 1;
+      if (generic_separable<float, EXACT>(d, a.img, a.pitch, a.w, a.h, tg, td, 1, a.gy, a.pitch, a.w, a.h)) return 1;
     }
   }
   d->last_path = tiled_all ? 1 : 0;
@@ -1338,6 +1813,8 @@ extern "C" int klt_dev_build(klt_dev* d, int slot, const unsigned char* img, int
   const int W = q->ncols, H = q->nrows;
   const unsigned char* src = img;
   int spitch = (int)img_pitch;
+  BandFeed feed;
+  memset(&feed, 0, sizeof(feed));
   if (!img_is_device) {
     const int fp = (W + 15) / 16 * 16;          // TMA needs a 16 B multiple row pitch
     const size_t bytes = (size_t)fp * H;
@@ -1346,11 +1823,11 @@ extern "C" int klt_dev_build(klt_dev* d, int slot, const unsigned char* img, int
       cudaFree(d->frame); d->frame = nullptr; d->frame_cap = 0;
       CU(cudaMalloc(&d->frame, bytes));
       d->frame_cap = bytes;
+      d->frame_busy = 0;
     }
-    if (fp == W)
-      CU(cudaMemcpyAsync(d->frame, img, bytes, cudaMemcpyHostToDevice, d->stream));
-    else
-      CU(cudaMemcpy2DAsync(d->frame, fp, img, W, W, H, cudaMemcpyHostToDevice, d->stream));
+    // uploaded inside build_impl: band by band on the copy stream when every level runs fused
+    feed.host = img; feed.W = W; feed.H = H; feed.fp = fp;
+    feed_schedule(&feed, d->band_rows);
     d->frame_pitch = fp;
     src = d->frame;
     spitch = fp;
@@ -1363,7 +1840,8 @@ extern "C" int klt_dev_build(klt_dev* d, int slot, const unsigned char* img, int
     CU(cudaStreamWaitEvent(d->stream, d->ev_read[slot], 0));
     d->read_pending[slot] = 0;
   }
-  const int rc = q->exact ? build_impl<true>(d, S, src, spitch, q) : build_impl<false>(d, S, src, spitch, q);
+  BandFeed* fp_ = img_is_device ? nullptr : &feed;
+  const int rc = q->exact ? build_impl<true>(d, S, src, spitch, q, fp_) : build_impl<false>(d, S, src, spitch, q, fp_);
   if (rc) return rc;
   CU(cudaGetLastError());
   if (d->overlap) {
@@ -1422,6 +1900,7 @@ extern "C" int klt_dev_features_upload(klt_dev* d, int n, const float* x, const 
   memcpy(d->h_val, val, n * sizeof(int));
   CU(cudaMemcpyAsync(d->d_x, d->h_x, (size_t)d->feat_cap * 12, cudaMemcpyHostToDevice, d->tstream));
   d->staging_busy = 1;
+  d->feat_out_host = 0;
   d->feat_n = n;
   return 0;
 }
@@ -1437,16 +1916,26 @@ extern "C" int klt_dev_features_staging(klt_dev* d, int n, float** x, float** y,
 extern "C" int klt_dev_features_commit(klt_dev* d, int n) {      // H2D of the staging area (async)
   CU(cudaSetDevice(d->device));
   if (n > d->feat_cap) return fail(d, "commit of %d features, capacity %d", n, d->feat_cap);
-  CU(cudaMemcpyAsync(d->d_x, d->h_x, (size_t)d->feat_cap * 12, cudaMemcpyHostToDevice, d->tstream));
+  // on the copy stream, ahead of the frame bands: the tracker is gated on ev_feat, the image
+  // kernels are not (on the compute stream this small copy would sit behind the whole frame upload)
+  { Launch l(d, KID_COPY_H2D, d->cstream);
+    CU(cudaMemcpyAsync(d->d_x, d->h_x, (size_t)d->feat_cap * 12, cudaMemcpyHostToDevice, d->cstream)); }
+  CU(cudaEventRecord(d->ev_feat, d->cstream));
+  d->feat_pending = 1;
   d->staging_busy = 1;
+  d->feat_out_host = 1;
   d->feat_n = n;
   return 0;
 }
 extern "C" int klt_dev_features_fetch(klt_dev* d, int n) {       // D2H into the staging area + sync
   CU(cudaSetDevice(d->device));
   if (n > d->feat_n) return fail(d, "download of %d features but %d resident", n, d->feat_n);
-  CU(cudaMemcpyAsync(d->h_x, d->d_x, (size_t)d->feat_cap * 12, cudaMemcpyDeviceToHost, d->tstream));
+  if (!d->feat_out_host) {
+    Launch l(d, KID_COPY_D2H, d->tstream);
+    CU(cudaMemcpyAsync(d->h_x, d->d_x, (size_t)d->feat_cap * 12, cudaMemcpyDeviceToHost, d->tstream));
+  }                                   // else: the tracker wrote its results into the staging area
   CU(cudaStreamSynchronize(d->tstream));
+  if (d->feat_pending) { CU(cudaStreamSynchronize(d->cstream)); d->feat_pending = 0; }
   if (d->overlap) CU(cudaStreamSynchronize(d->stream));
   d->staging_busy = 0;
   return 0;
@@ -1468,6 +1957,12 @@ static void make_view(const PyrSet& S, int L, PyrView* v) {
   }
 }
 
+// where the tracker records its results: the device arrays (resident pipelines) or, for the
+// synchronous API, straight into the pinned host staging area (posted writes over PCIe, no D2H copy)
+static float* feat_out_x(klt_dev* d) { return d->feat_out_host ? d->h_x : d->d_x; }
+static float* feat_out_y(klt_dev* d) { return d->feat_out_host ? d->h_y : d->d_y; }
+static int* feat_out_val(klt_dev* d) { return d->feat_out_host ? d->h_val : d->d_val; }
+
 template <bool EXACT, int PPL>
 static int launch_track(klt_dev* d, const PyrView& v1, const PyrView& v2, const TrackArgs& a, int n) {
   const int warps = 4;
@@ -1475,15 +1970,15 @@ static int launch_track(klt_dev* d, const PyrView& v1, const PyrView& v2, const 
   if (set_smem(d, track_kernel<EXACT, PPL>, smem)) return 1;
   { Launch l(d, KID_TRACK, d->tstream);
     track_kernel<EXACT, PPL><<<(n + warps - 1) / warps, warps * 32, smem, d->tstream>>>(
-        v1, v2, a, n, d->d_x, d->d_y, d->d_val, d->d_live); }
+        v1, v2, a, n, d->d_x, d->d_y, d->d_val, feat_out_x(d), feat_out_y(d), feat_out_val(d), d->d_live); }
   return 0;
 }
 
 template <int WW, int RPL>
 static void launch_track_fast_t(klt_dev* d, const PyrView& v1, const PyrView& v2, const TrackArgs& a, int n) {
   Launch l(d, KID_TRACK_FAST, d->tstream);
-  track_fast_kernel<WW, RPL><<<(8 * n + 127) / 128, 128, 0, d->tstream>>>(v1, v2, a, n, d->d_x, d->d_y,
-                                                                        d->d_val, d->d_live);
+  track_fast_kernel<WW, RPL><<<(8 * n + 127) / 128, 128, 0, d->tstream>>>(
+      v1, v2, a, n, d->d_x, d->d_y, d->d_val, feat_out_x(d), feat_out_y(d), feat_out_val(d), d->d_live);
 }
 // square odd windows up to 15x15; returns false if this window has no instantiation
 static bool launch_track_fast(klt_dev* d, const PyrView& v1, const PyrView& v2, const TrackArgs& a, int n) {
@@ -1496,11 +1991,11 @@ static bool launch_track_fast(klt_dev* d, const PyrView& v1, const PyrView& v2, 
         static int fpw = getenv("KLT_TRACK_FPW") ? atoi(getenv("KLT_TRACK_FPW")) : 4;
         const int warps_per_block = 4;
         if (fpw == 1)
-          track7_kernel<1><<<(n + warps_per_block - 1) / warps_per_block, 128, 0, d->tstream>>>(v1, v2, a, n, d->d_x, d->d_y, d->d_val, d->d_live);
+          track7_kernel<1><<<(n + warps_per_block - 1) / warps_per_block, 128, 0, d->tstream>>>(v1, v2, a, n, d->d_x, d->d_y, d->d_val, feat_out_x(d), feat_out_y(d), feat_out_val(d), d->d_live);
         else if (fpw == 4)
-          track7_kernel<4><<<(n + 4 * warps_per_block - 1) / (4 * warps_per_block), 128, 0, d->tstream>>>(v1, v2, a, n, d->d_x, d->d_y, d->d_val, d->d_live);
+          track7_kernel<4><<<(n + 4 * warps_per_block - 1) / (4 * warps_per_block), 128, 0, d->tstream>>>(v1, v2, a, n, d->d_x, d->d_y, d->d_val, feat_out_x(d), feat_out_y(d), feat_out_val(d), d->d_live);
         else
-          track7_kernel<2><<<(n + 2 * warps_per_block - 1) / (2 * warps_per_block), 128, 0, d->tstream>>>(v1, v2, a, n, d->d_x, d->d_y, d->d_val, d->d_live);
+          track7_kernel<2><<<(n + 2 * warps_per_block - 1) / (2 * warps_per_block), 128, 0, d->tstream>>>(v1, v2, a, n, d->d_x, d->d_y, d->d_val, feat_out_x(d), feat_out_y(d), feat_out_val(d), d->d_live);
       }
       return true;
     case 9: launch_track_fast_t<9, 2>(d, v1, v2, a, n); return true;
@@ -1520,6 +2015,10 @@ extern "C" int klt_dev_track_resident(klt_dev* d, int slot_prev, int slot_cur,
     return fail(d, "tracking window %d x %d must be odd and >= 3", p->window_width, p->window_height);
   const int n = d->feat_n;
   if (n == 0) return 0;
+  if (d->feat_pending) {                             // features uploaded on the copy stream
+    CU(cudaStreamWaitEvent(d->tstream, d->ev_feat, 0));
+    d->feat_pending = 0;
+  }
   if (d->overlap) {                                  // the pyramids are produced on the other stream
     const int sl[2] = {slot_prev, slot_cur};
     for (int k = 0; k < 2; ++k)
@@ -1709,11 +2208,18 @@ extern "C" int klt_dev_profile_begin(klt_dev* d) {
     d->prof_kid = (int*)calloc(PROF_POOL, sizeof(int));
     if (!d->prof_ev || !d->prof_kid) return fail(d, "out of host memory");
     for (int i = 0; i < 2 * PROF_POOL; ++i) CU(cudaEventCreate(&d->prof_ev[i]));
+    CU(cudaEventCreate(&d->ev_origin));
+    d->trace_kid = (int*)calloc(TRACE_CAP, sizeof(int));
+    d->trace_t0 = (float*)calloc(TRACE_CAP, sizeof(float));
+    d->trace_t1 = (float*)calloc(TRACE_CAP, sizeof(float));
+    if (!d->trace_kid || !d->trace_t0 || !d->trace_t1) return fail(d, "out of host memory");
   }
   if (sync_all(d)) return fail(d, "stream synchronisation failed");
   memset(d->prof_ms, 0, sizeof(d->prof_ms));
   memset(d->prof_n, 0, sizeof(d->prof_n));
   d->prof_used = 0;
+  d->trace_n = 0;
+  CU(cudaEventRecord(d->ev_origin, d->stream));
   d->prof_on = 1;
   return 0;
 }
@@ -1725,6 +2231,13 @@ extern "C" int klt_dev_profile_end(klt_dev* d) {
   return 0;
 }
 extern "C" int klt_dev_profile_kernels(void) { return KID_COUNT; }
+extern "C" int klt_dev_trace_count(const klt_dev* d) { return d->trace_n; }
+extern "C" const char* klt_dev_trace_get(const klt_dev* d, int i, float* t0_ms, float* t1_ms) {
+  if (i < 0 || i >= d->trace_n) return nullptr;
+  if (t0_ms) *t0_ms = d->trace_t0[i];
+  if (t1_ms) *t1_ms = d->trace_t1[i];
+  return kKernelNames[d->trace_kid[i]];
+}
 extern "C" const char* klt_dev_profile_get(const klt_dev* d, int kid, unsigned long long* launches, double* total_ms) {
   if (kid < 0 || kid >= KID_COUNT) return nullptr;
   if (launches) *launches = d->prof_n[kid];

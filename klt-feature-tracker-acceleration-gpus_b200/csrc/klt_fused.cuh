@@ -90,6 +90,10 @@ __device__ __forceinline__ void fma4(float4& a, const float4& v, float k, bool e
 
 static constexpr int FUSED_RG = 3;       // gradient radius the fused kernels are built for
 
+// barrier among the 256 threads that compute a tile (== __syncthreads() in the 256-thread kernels;
+// pyramid_mega_kernel carries a ninth, scheduling warp that must stay out of it)
+__device__ __forceinline__ void tile_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 // ---- stage C: horizontal DoG and Gaussian of a level tile ---------------------------------
 // sL [LH][LP]: tile col c <-> global x0-4+c.   sHd, sHg [LH][HP]: col c <-> global x0+c.
 // 8 outputs per thread from a 16-float window (4 x LDS.128); a warp covers 8 groups x 4 rows
@@ -314,21 +318,23 @@ __device__ __forceinline__ void l0_fused_tile_rest(unsigned char* smem, int W, i
       }
     }
   }
-  __syncthreads();
+  tile_sync();
 
   stage_hgrad<EXACT, BORDER, G::TX, G::L0_H, G::L0_P, G::HG_P>(sL0, sHd, sHg, tg, td, x0, W);
-  __syncthreads();
+  tile_sync();
   stage_vgrad_both<EXACT, BORDER, G::TX, G::TY, 8, G::HG_P>(sHd, sHg, tg, td, out_gx, out_gy, opitch,
                                                             x0, y0, W, H);
 }
 
-// Tiles are handed out dynamically: counter[0] - base is the next tile index.  Every CTA performs
-// (tiles it processed + 1) atomicAdds, so after the launch the counter stands at
-// base + ntiles + gridDim.x, which the host uses as the next launch's base (no reset needed).
+// Tiles are handed out dynamically: a launch covers the tiles [tile0, ntiles) (whole tile rows when
+// a frame is built band by band behind its upload); tile0 + counter[0] - base is the next tile
+// index.  Every CTA performs (tiles it processed + 1) atomicAdds, so after the launch the counter
+// stands at base + (ntiles - tile0) + gridDim.x, which the host uses as the next launch's base (no
+// reset needed).
 // The claim for the NEXT tile is made one tile ahead, so its TMA load can be issued early.
 template <bool EXACT>
 __global__ void __launch_bounds__(256, 3)
-l0_fused_kernel(const __grid_constant__ CUtensorMap map, int W, int H, int tiles_x, int ntiles,
+l0_fused_kernel(const __grid_constant__ CUtensorMap map, int W, int H, int tiles_x, int tile0, int ntiles,
                 unsigned* __restrict__ counter, unsigned base,
                 TapsR ts, TapsR tg, TapsR td, float* __restrict__ out_img,
                 float* __restrict__ out_gx, float* __restrict__ out_gy, int opitch) {
@@ -339,7 +345,7 @@ l0_fused_kernel(const __grid_constant__ CUtensorMap map, int W, int H, int tiles
   const int tid = threadIdx.x;
   if (tid == 0) {
     mbar_init(bar, 1);
-    const int t = (int)(atomicAdd(counter, 1u) - base);
+    const int t = tile0 + (int)(atomicAdd(counter, 1u) - base);
     *s_next = t;
     if (t < ntiles) {
       mbar_expect_tx(bar, G::U8_W * G::U8_H);
@@ -360,7 +366,7 @@ l0_fused_kernel(const __grid_constant__ CUtensorMap map, int W, int H, int tiles
     else l0_fused_tile<EXACT, false>(smem_raw, W, ts, x0);
     __syncthreads();                 // u8 tile consumed; everybody has read s_next
     if (tid == 0) {
-      const int t = (int)(atomicAdd(counter, 1u) - base);
+      const int t = tile0 + (int)(atomicAdd(counter, 1u) - base);
       *s_next = t;
       if (t < ntiles) {
         mbar_expect_tx(bar, G::U8_W * G::U8_H);
@@ -506,9 +512,9 @@ __device__ __forceinline__ void lv_stage_rest(unsigned char* smem, const TapsR& 
       }
     }
   }
-  __syncthreads();
+  tile_sync();
   stage_hgrad<EXACT, BORDER, TX, G::LH, G::LP, G::HP>(sL, sHd, sHg, tg, td, x0, W);
-  __syncthreads();
+  tile_sync();
   constexpr int PY = (TX / 4) * (TY / 4) <= 128 ? 4 : 8;
   stage_vgrad_both<EXACT, BORDER, TX, TY, PY, G::HP>(sHd, sHg, tg, td, out_gx, out_gy, opitch, x0, y0, W, H);
 }
@@ -518,7 +524,7 @@ __device__ __forceinline__ void lv_stage_rest(unsigned char* smem, const TapsR& 
 template <int SS, int R, int TX, int TY, bool EXACT>
 __global__ void __launch_bounds__(256, (LvGeo<SS, R, TX, TY>::SMEM <= 56 * 1024) ? 3 : 2)
 level_fused_kernel(const __grid_constant__ CUtensorMap map, int Wsrc, int Hsrc, int W, int H,
-                   int tiles_x, int ntiles, unsigned* __restrict__ counter, unsigned base,
+                   int tiles_x, int tile0, int ntiles, unsigned* __restrict__ counter, unsigned base,
                    TapsR tp, TapsR tg, TapsR td,
                    float* __restrict__ out_img, float* __restrict__ out_gx,
                    float* __restrict__ out_gy, int opitch) {
@@ -529,7 +535,7 @@ level_fused_kernel(const __grid_constant__ CUtensorMap map, int Wsrc, int Hsrc, 
   const int tid = threadIdx.x;
   if (tid == 0) {
     mbar_init(bar, 1);
-    const int t = (int)(atomicAdd(counter, 1u) - base);
+    const int t = tile0 + (int)(atomicAdd(counter, 1u) - base);
     *s_next = t;
     if (t < ntiles) {
       mbar_expect_tx(bar, G::SW * G::SH * 4);
@@ -550,7 +556,7 @@ level_fused_kernel(const __grid_constant__ CUtensorMap map, int Wsrc, int Hsrc, 
     else lv_stage_p1<EXACT, false, SS, R, TX, TY>(smem_raw, tp, x0, Wsrc);
     __syncthreads();                 // source box consumed; everybody has read s_next
     if (tid == 0) {
-      const int t = (int)(atomicAdd(counter, 1u) - base);
+      const int t = tile0 + (int)(atomicAdd(counter, 1u) - base);
       *s_next = t;
       if (t < ntiles) {
         mbar_expect_tx(bar, G::SW * G::SH * 4);

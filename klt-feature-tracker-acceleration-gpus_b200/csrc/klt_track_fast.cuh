@@ -45,8 +45,9 @@ __device__ __forceinline__ void sample_row(const float* __restrict__ img, int pi
 // WW: window width (odd, <= 15); RPL: window rows per lane (window height <= 8 * RPL)
 template <int WW, int RPL>
 __global__ void __launch_bounds__(128)
-track_fast_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, float* __restrict__ fx,
-                  float* __restrict__ fy, int* __restrict__ fval,
+track_fast_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, const float* __restrict__ fx,
+                  const float* __restrict__ fy, const int* __restrict__ fval,
+                  float* __restrict__ ox, float* __restrict__ oy, int* __restrict__ oval,
                   unsigned long long* __restrict__ live_total) {
   const int lane = threadIdx.x & 31;
   const int r8 = lane & 7;                                   // lane within the feature group
@@ -214,9 +215,9 @@ track_fast_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, float* __restrict_
   if (alive && r8 == 0) {                                   // record (:1383-1437)
     const bool outside = (xout < (float)a.borderx || xout > (float)(a.ncols - 1 - a.borderx) ||
                           yout < (float)a.bordery || yout > (float)(a.nrows - 1 - a.bordery));
-    if (status == KLT_OOB || outside) { fx[f] = -1.0f; fy[f] = -1.0f; fval[f] = KLT_OOB; }
-    else if (status != KLT_TRACKED) { fx[f] = -1.0f; fy[f] = -1.0f; fval[f] = status; }
-    else { fx[f] = xout; fy[f] = yout; fval[f] = KLT_TRACKED; }
+    if (status == KLT_OOB || outside) { ox[f] = -1.0f; oy[f] = -1.0f; oval[f] = KLT_OOB; }
+    else if (status != KLT_TRACKED) { ox[f] = -1.0f; oy[f] = -1.0f; oval[f] = status; }
+    else { ox[f] = xout; oy[f] = yout; oval[f] = KLT_TRACKED; }
   }
 }
 
@@ -286,8 +287,9 @@ __device__ __forceinline__ void foot7_sample(const float* __restrict__ img, cons
 // same work: the kernel is latency bound (issue slots are ~10 % used), so idle lanes are free.
 template <int FPW>
 __global__ void __launch_bounds__(128)
-track7_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, float* __restrict__ fx,
-              float* __restrict__ fy, int* __restrict__ fval,
+track7_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, const float* __restrict__ fx,
+              const float* __restrict__ fy, const int* __restrict__ fval,
+              float* __restrict__ ox, float* __restrict__ oy, int* __restrict__ oval,
               unsigned long long* __restrict__ live_total) {
   constexpr int WW = 7, hw = 3, hh = 3;
   const int lane = threadIdx.x & 31;
@@ -428,8 +430,8 @@ track7_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, float* __restrict__ fx
   if (alive && r8 == 0) {
     const bool outside = (xout < (float)a.borderx || xout > (float)(a.ncols - 1 - a.borderx) ||
                           yout < (float)a.bordery || yout > (float)(a.nrows - 1 - a.bordery));
-    if (status == KLT_OOB || outside) { fx[f] = -1.0f; fy[f] = -1.0f; fval[f] = KLT_OOB; }
-    else if (status != KLT_TRACKED) { fx[f] = -1.0f; fy[f] = -1.0f; fval[f] = status; }
-    else { fx[f] = xout; fy[f] = yout; fval[f] = KLT_TRACKED; }
+    if (status == KLT_OOB || outside) { ox[f] = -1.0f; oy[f] = -1.0f; oval[f] = KLT_OOB; }
+    else if (status != KLT_TRACKED) { ox[f] = -1.0f; oy[f] = -1.0f; oval[f] = status; }
+    else { ox[f] = xout; oy[f] = yout; oval[f] = KLT_TRACKED; }
   }
 }

@@ -82,12 +82,18 @@ DEV_API = {
     "klt_dev_force_generic": (None, [C.c_void_p, C.c_int]),
     "klt_dev_disable_fused": (None, [C.c_void_p, C.c_int]),
     "klt_dev_last_build_fused": (C.c_int, [C.c_void_p]),
+    "klt_dev_set_band_rows": (None, [C.c_void_p, C.c_int]),
+    "klt_dev_last_build_bands": (C.c_int, [C.c_void_p]),
+    "klt_dev_last_build_mega": (C.c_int, [C.c_void_p]),
+    "klt_dev_disable_mega": (None, [C.c_void_p, C.c_int]),
     "klt_dev_timer_start": (C.c_int, [C.c_void_p]),
     "klt_dev_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "klt_dev_profile_begin": (C.c_int, [C.c_void_p]),
     "klt_dev_profile_end": (C.c_int, [C.c_void_p]),
     "klt_dev_profile_kernels": (C.c_int, []),
     "klt_dev_profile_get": (C.c_char_p, [C.c_void_p, C.c_int, C.POINTER(C.c_ulonglong), C.POINTER(C.c_double)]),
+    "klt_dev_trace_count": (C.c_int, [C.c_void_p]),
+    "klt_dev_trace_get": (C.c_char_p, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "klt_dev_live_total": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]),
     # include/klt_b200.h
     "KLTB200SetDevice": (None, [_TC, C.c_int]),
@@ -190,6 +196,16 @@ class B200Library(capi.KLTLibrary):
             name = self.lib.klt_dev_profile_get(dev, k, C.byref(n), C.byref(ms))
             if name and n.value:
                 out[name.decode()] = (int(n.value), float(ms.value))
+        return out
+
+
+    def trace(self, dev) -> list:
+        """[(class name, start ms, end ms)] of the last profiling session, launch order"""
+        out = []
+        for i in range(self.lib.klt_dev_trace_count(dev)):
+            t0, t1 = C.c_float(0), C.c_float(0)
+            name = self.lib.klt_dev_trace_get(dev, i, C.byref(t0), C.byref(t1))
+            out.append((name.decode(), float(t0.value), float(t1.value)))
         return out
 
 

@@ -178,3 +178,68 @@ def test_eigenvalue_map_is_integer_exact(L, oracle, provided, shape, window, ski
     if shape == (240, 320):
         assert len(got) == 52224          # gprof call count of the golden run
     L.KLTFreeTrackingContext(tc)
+
+
+# ---- banded upload: host frames are copied in bands, kernels follow tile row by tile row -------
+@pytest.mark.parametrize("mega", [1, 0])
+@pytest.mark.parametrize("band_rows", [64, 128, 192, 0])
+@pytest.mark.parametrize("cfg", [(4, 2, (700, 900)), (2, 4, (480, 640)), (3, 2, (333, 517)), (4, 2, (64, 200)),
+                                 (1, 2, (300, 400))])
+def test_banded_build_matches_oracle(L, oracle, band_rows, cfg, mega):
+    """klt_dev_build with a host frame uploads it in bands on the copy stream.  mega = 1: one
+    pyramid_mega_kernel launch whose level-0 tiles wait for the band flag and whose coarser tiles
+    wait for the tile rows below them; mega = 0: the per-level fused kernels launched over the
+    tile rows each band completes.  Whatever the band size, the pyramids are bit-identical to
+    the oracle in exact mode (same tile code, different schedule)."""
+    nlev, ss, (h, w) = cfg
+    img = synth_image(w, h, seed=17 * h + w)
+    tc = L.KLTCreateTrackingContext()
+    tc.contents.nPyramidLevels, tc.contents.subsampling = nlev, ss
+    L.KLTUpdateTCBorder(tc)
+    dev = L.KLTB200Device(tc)
+    L.klt_dev_set_band_rows(dev, band_rows)
+    L.klt_dev_disable_mega(dev, 1 - mega)
+    _check_build(L, oracle, img, tc, exact=1, generic=0, expect_tiled=True, expect_fused=True)
+    assert L.klt_dev_last_build_mega(dev) == mega
+    expect = 1 if band_rows == 0 else -(-h // band_rows)
+    got = L.klt_dev_last_build_bands(dev)
+    if band_rows < 0:
+        expect = got
+    assert abs(got - expect) <= 1 and (got > 1) == (band_rows != 0 and h > band_rows + band_rows // 2), (got, expect)
+    # fma mode: banded == single-shot bit for bit (same kernels)
+    q = L.build_desc(tc, w, h, exact=0)
+    L.dev_build(dev, 0, img, q)
+    a = device_pyramids(L, dev, 0, nlev)
+    L.klt_dev_set_band_rows(dev, 0)
+    L.klt_dev_disable_mega(dev, mega)              # ... and the other scheduler
+    L.dev_build(dev, 1, img, q)
+    assert L.klt_dev_last_build_mega(dev) == 1 - mega
+    b = device_pyramids(L, dev, 1, nlev)
+    for which in range(3):
+        for l in range(nlev):
+            assert np.array_equal(a[which][l], b[which][l])
+    L.KLTFreeTrackingContext(tc)
+
+
+def test_mega_repeated_frames_and_level_counts(L, oracle):
+    """The mega kernel's completion counters are never reset (targets advance per level and per
+    frame): alternate full-pyramid builds and level-0-only builds (selection) of different frames
+    on one context and check every result against the oracle."""
+    h, w = 521, 777
+    tc = L.KLTCreateTrackingContext()
+    tc.contents.nPyramidLevels, tc.contents.subsampling = 3, 2
+    L.KLTUpdateTCBorder(tc)
+    dev = L.KLTB200Device(tc)
+    L.klt_dev_disable_mega(dev, 0)
+    p = params_from_tc(oracle, tc)
+    for it, nb in enumerate([3, 1, 3, 3, 1, 1, 3]):
+        img = synth_image(w, h, seed=100 + it)
+        q = L.build_desc(tc, w, h, nlevels_built=nb, exact=1)
+        L.klt_dev_set_band_rows(dev, [0, 64, 128][it % 3])
+        L.dev_build(dev, it % 3, img, q)
+        assert L.klt_dev_last_build_mega(dev) == 1
+        want = oracle.build_pyramids(img, p)
+        for which in range(3):
+            for l in range(nb):
+                assert np.array_equal(L.dev_level(dev, it % 3, which, l), want.level(which, l)), (it, which, l)
+    L.KLTFreeTrackingContext(tc)
