@@ -171,6 +171,11 @@ void klt_dev_set_band_rows(klt_dev *d, int rows);
  * or env KLT_B200_MEGA=1; the default is the per-level fused kernels, which measure faster. */
 int klt_dev_last_build_mega(const klt_dev *d);
 void klt_dev_disable_mega(klt_dev *d, int on);
+/* first_level > 0 (env KLT_B200_MEGA_TAIL; default 0 = off, it measures slower): levels >=
+ * first_level of a pyramid with more than first_level + 1 levels are built by ONE
+ * pyramid_mega_kernel launch in tail mode instead of one launch each
+ * (klt_dev_last_build_mega then returns 2). */
+void klt_dev_set_mega_tail(klt_dev *d, int first_level);
 int klt_dev_last_build_bands(const klt_dev *d);
 /* device time between the two calls, measured with CUDA events recorded on the
  * context's own stream (the stream the kernels run on) */

@@ -810,7 +810,7 @@ struct klt_dev {
   cudaEvent_t ev_frame_free; int frame_busy;
   int band_rows, last_bands;
   // pyramid_mega_kernel: cached schedule + dependency counters (klt_mega.cuh)
-  int no_mega, last_mega;
+  int no_mega, last_mega, mega_tail_from;
   MegaSeg* d_segs; int mega_nseg, mega_nitems, mega_key[8];
   unsigned* d_done; int mega_done_off[MEGA_MAX_LEVELS + 1];
   unsigned mega_epoch[MEGA_MAX_LEVELS];
@@ -928,6 +928,7 @@ extern "C" int klt_dev_last_build_fused(const klt_dev* d) { return d->last_fused
 extern "C" int klt_dev_last_build_bands(const klt_dev* d) { return d->last_bands; }
 extern "C" int klt_dev_last_build_mega(const klt_dev* d) { return d->last_mega; }
 extern "C" void klt_dev_disable_mega(klt_dev* d, int on) { d->no_mega = on; }
+extern "C" void klt_dev_set_mega_tail(klt_dev* d, int first_level) { d->mega_tail_from = first_level; }
 extern "C" void klt_dev_set_band_rows(klt_dev* d, int rows) { d->band_rows = rows; }
 
 extern "C" int klt_dev_create(int device, klt_dev** out) {
@@ -969,6 +970,7 @@ extern "C" int klt_dev_create(int device, klt_dev** out) {
   // the single-launch pyramid (klt_mega.cuh) is opt-in: correct in both arithmetic modes, but measured
   // slower than the per-level kernels on B200 (4K: 87 us vs 69 us resident)
   c->no_mega = getenv("KLT_B200_MEGA") && atoi(getenv("KLT_B200_MEGA")) ? 0 : 1;
+  c->mega_tail_from = getenv("KLT_B200_MEGA_TAIL") ? atoi(getenv("KLT_B200_MEGA_TAIL")) : 0;   // opt-in too (4K: 30 us vs 21 us for levels 2+3)
   if (e == cudaSuccess) e = cudaMalloc(&c->d_tile_ctr, 16 * sizeof(unsigned));
   if (e == cudaSuccess) e = cudaMemsetAsync(c->d_tile_ctr, 0, 16 * sizeof(unsigned), c->stream);
   if (e != cudaSuccess) { cudaStreamDestroy(c->stream); free(c); return fail(nullptr, "cudaMalloc: %s", cudaGetErrorString(e)); }
@@ -1368,8 +1370,10 @@ static int mega_shape_for(int ss, int r) {
 // Coarse work list in topological order: walking the level-0 tile rows top to bottom, the tile
 // rows of the coarser levels each one completes (the same rule the per-level band loop uses).
 // Cached per geometry; the device checks the real dependencies, the order only has to be valid.
-static int mega_schedule(klt_dev* d, const FusedPlan& P, const PyrSet& S, int nb) {
-  const int key[8] = {d->W, d->H, d->L, d->ss, nb, P.shape[1], P.R, 1};
+// first > 0 ("tail mode"): levels < first are built by the per-level kernels before the launch; only
+// the levels >= first are listed.
+static int mega_schedule(klt_dev* d, const FusedPlan& P, const PyrSet& S, int nb, int first) {
+  const int key[8] = {d->W, d->H, d->L, d->ss, nb, P.shape[nb > 1 ? nb - 1 : 1], P.R, 1 + first};
   if (d->d_segs && memcmp(key, d->mega_key, sizeof(key)) == 0) return 0;
   MegaSeg segs[MEGA_MAX_SEGS];
   memset(segs, 0, sizeof(segs));
@@ -1399,7 +1403,11 @@ static int mega_schedule(klt_dev* d, const FusedPlan& P, const PyrSet& S, int nb
   int queued[KLT_DEV_MAX_LEVELS] = {0}, last_emit_pos[KLT_DEV_MAX_LEVELS] = {0};
   for (int l = 1; l < nb; ++l) pend[l] = (Pend*)malloc(sizeof(Pend) * PQ);
   bool overflow = false;
-  for (int step = 0; step <= P.tiles_y[0] && !overflow; ++step) {
+  for (int l = 0; l < first; ++l) {                          // complete before the launch
+    rows_done[l] = queued[l] = P.tiles_y[l];
+    valid[l] = S.lv[l].h;
+  }
+  for (int step = first > 0 ? P.tiles_y[0] : 0; step <= P.tiles_y[0] && !overflow; ++step) {
     const bool flush = step == P.tiles_y[0];
     const int lag = flush ? 0 : lag_env;
     if (!flush) {
@@ -1409,7 +1417,7 @@ static int mega_schedule(klt_dev* d, const FusedPlan& P, const PyrSet& S, int nb
     bool progress = true;
     while (progress && !overflow) {
       progress = false;
-      for (int l = 1; l < nb && !overflow; ++l) {
+      for (int l = first > 1 ? first : 1; l < nb && !overflow; ++l) {
         const Level& a = S.lv[l - 1];
         const Level& b = S.lv[l];
         int j = queued[l];
@@ -1421,7 +1429,7 @@ static int mega_schedule(klt_dev* d, const FusedPlan& P, const PyrSet& S, int nb
         }
         if (j > queued[l]) {
           if (pt[l] == PQ) { overflow = true; break; }
-          pend[l][pt[l]++] = Pend{queued[l], j, l == 1 ? 0 : last_emit_pos[l - 1] + lag_env};
+          pend[l][pt[l]++] = Pend{queued[l], j, l <= first || l == 1 ? 0 : last_emit_pos[l - 1] + lag_env};
           queued[l] = j;
         }
         while (ph[l] < pt[l] && (flush || pend[l][ph[l]].ready_pos <= nitems)) {
@@ -1572,8 +1580,8 @@ static int feed_wait(klt_dev* d, BandFeed* f, bool all, int* rows) {
 // tiles wait on.  Returns 2 (nothing queued) if the frame has no schedule: the caller falls back.
 template <bool EXACT>
 static int mega_build(klt_dev* d, PyrSet& S, const FusedPlan& P, int nb, const TapsR& ts, const TapsR& tp,
-                      const TapsR& tg, const TapsR& td, BandFeed* feed) {
-  { const int rc = mega_schedule(d, P, S, nb); if (rc) return rc; }
+                      const TapsR& tg, const TapsR& td, BandFeed* feed, int first = 0) {
+  { const int rc = mega_schedule(d, P, S, nb, first); if (rc) return rc; }
   MegaParams MP;
   memset(&MP, 0, sizeof(MP));
   for (int l = 0; l < nb; ++l) {
@@ -1583,11 +1591,12 @@ static int mega_build(klt_dev* d, PyrSet& S, const FusedPlan& P, int nb, const T
     L.img = S.lv[l].img; L.gx = S.lv[l].gx; L.gy = S.lv[l].gy;
     L.tiles_x = P.tiles_x[l]; L.tiles_y = P.tiles_y[l];
     L.done_off = d->mega_done_off[l];
-    d->mega_epoch[l] += 1;
+    if (l >= first) d->mega_epoch[l] += 1;
     L.target = d->mega_epoch[l] * (unsigned)P.tiles_x[l];
   }
+  MP.ready_below = first;
   MP.nlev = nb; MP.nseg = d->mega_nseg;
-  MP.nitems0 = P.tiles_x[0] * P.tiles_y[0]; MP.nitems1 = d->mega_nitems;
+  MP.nitems0 = first == 0 ? P.tiles_x[0] * P.tiles_y[0] : 0; MP.nitems1 = d->mega_nitems;
   MP.segs = d->d_segs;
   MP.ctr = d->d_tile_ctr + 12;                   // three words, reset by the kernel itself
   { static int every = getenv("KLT_B200_MEGA_COARSE_EVERY") ? atoi(getenv("KLT_B200_MEGA_COARSE_EVERY")) : 3;
@@ -1632,7 +1641,7 @@ static int mega_build(klt_dev* d, PyrSet& S, const FusedPlan& P, int nb, const T
     d->last_bands = feed->nbands;
   }
   int rc;
-  switch (nb > 1 ? P.shape[1] : (int)SHAPE_2_5_64_16) {        // nb == 1: only level-0 tiles exist
+  switch (nb > 1 ? P.shape[nb - 1] : (int)SHAPE_2_5_64_16) {   // nb == 1: only level-0 tiles exist
     case SHAPE_2_5_64_16: rc = mega_launch_t<2, 5, 64, 16, EXACT>(d, MP); break;
     case SHAPE_4_10_32_16: rc = mega_launch_t<4, 10, 32, 16, EXACT>(d, MP); break;
     default: return fail(d, "no mega kernel for this pyramid geometry");
@@ -1681,6 +1690,18 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
     // exist -- all at once for a resident frame, band by band behind the upload of a host frame
     int rows_done[KLT_DEV_MAX_LEVELS] = {0}, valid[KLT_DEV_MAX_LEVELS] = {0};
     const int SS = P.SS, R = P.R, RG = FUSED_RG;
+    // "tail" levels (small: a launch each would be all fixed latency, ~8 us) go into one
+    // pyramid_mega_kernel launch in tail mode: tiles of level l+1 start as soon as the tile rows of
+    // level l under them are complete
+    int nl = nb;                                   // levels built by the per-level kernels
+    FusedPlan PT;
+    if (d->mega_tail_from > 0 && nb > d->mega_tail_from + 1 && nb <= MEGA_MAX_LEVELS &&
+        mega_shape_for(q->subsampling, tp.w / 2) != SHAPE_NONE) {
+      fused_plan(d, S, src, spitch, q, ts, tp, tg, td, &PT, mega_shape_for(q->subsampling, tp.w / 2));
+      bool ok = true;
+      for (int l = d->mega_tail_from; l < nb; ++l) ok = ok && PT.shape[l] != SHAPE_NONE;
+      if (ok) nl = d->mega_tail_from;
+    }
     int u8_rows = feed ? 0 : H;
     if (feed && feed_enqueue_copies(d, feed)) return 1;
     do {
@@ -1695,7 +1716,7 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
       if (l0_fused_launch<EXACT>(d, P, W, H, ts, tg, td, S.lv[0], rows_done[0], j)) return 1;
       rows_done[0] = j;
       valid[0] = P.TY[0] * j < H ? P.TY[0] * j : H;
-      for (int l = 1; l < nb; ++l) {
+      for (int l = 1; l < nl; ++l) {
         const Level& a = S.lv[l - 1];
         const Level& b = S.lv[l];
         j = rows_done[l];
@@ -1710,6 +1731,17 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
         valid[l] = P.TY[l] * j < b.h ? P.TY[l] * j : b.h;
       }
     } while (u8_rows < H);
+    if (nl < nb) {
+      const int rc = mega_build<EXACT>(d, S, PT, nb, ts, tp, tg, td, nullptr, nl);
+      if (rc == 1) return 1;
+      if (rc == 2) {                               // no schedule: per-level kernels after all
+        for (int l = nl; l < nb; ++l)
+          if (level_fused_launch<EXACT>(d, P, l, S.lv[l - 1], S.lv[l], tp, tg, td, 0, P.tiles_y[l])) return 1;
+      } else {
+        d->last_mega = 2;
+      }
+      for (int l = nl; l < nb; ++l) rows_done[l] = P.tiles_y[l];
+    }
     if (feed) {
       d->last_bands = feed->nbands;
       CU(cudaEventRecord(d->ev_frame_free, d->stream));

@@ -58,6 +58,7 @@ struct MegaParams {
   unsigned* done;                     // per tile row completion counters (never reset: see target)
   const unsigned* u8_flag;            // rows of the u8 frame on the device: *u8_flag - u8_base
   unsigned u8_base; int has_feed;
+  int ready_below;                    // levels < ready_below were complete before the launch (tail mode)
   int serial;                         // debug: no prefetch, tile k is loaded after tile k-1 is finished
   int coarse_every;                   // CTA b starts on the coarse queue iff b % coarse_every == coarse_every - 1
   TapsR ts, tp, tg, td;
@@ -105,6 +106,7 @@ __device__ __forceinline__ bool mega_deps_ready(const MegaParams& P, int level, 
     return (int)(ld_relaxed_sys_u32(P.u8_flag) - P.u8_base) >= need;
   }
   using GL = LvGeo<SS, R, TX, TY>;
+  if (level - 1 < P.ready_below) return true;
   const MegaLevel& s = P.lv[level - 1];
   int ylo = SS * y0 + GL::YOFF, yhi = ylo + GL::SH - 1;          // source rows under the TMA box
   if (ylo < 0) ylo = 0;
@@ -252,7 +254,8 @@ pyramid_mega_kernel(const __grid_constant__ MegaParams P) {
     if (tid != 256) return;
     MegaSched st;
     st.on_coarse = P.nitems1 > 0 && (int)(blockIdx.x % (unsigned)P.coarse_every) == P.coarse_every - 1;
-    st.l0_empty = false; st.coarse_empty = P.nitems1 == 0;
+    st.l0_empty = P.nitems0 == 0; st.coarse_empty = P.nitems1 == 0;
+    if (st.l0_empty) st.on_coarse = true;
     st.seg_cursor = 0; st.h_level = -1; st.h_x0 = st.h_y0 = 0;
     st.p_ctr = nullptr; st.p_next = nullptr; st.n_published = 0;
     unsigned ph_empty = 0;

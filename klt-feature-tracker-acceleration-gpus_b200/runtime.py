@@ -86,6 +86,7 @@ DEV_API = {
     "klt_dev_last_build_bands": (C.c_int, [C.c_void_p]),
     "klt_dev_last_build_mega": (C.c_int, [C.c_void_p]),
     "klt_dev_disable_mega": (None, [C.c_void_p, C.c_int]),
+    "klt_dev_set_mega_tail": (None, [C.c_void_p, C.c_int]),
     "klt_dev_timer_start": (C.c_int, [C.c_void_p]),
     "klt_dev_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "klt_dev_profile_begin": (C.c_int, [C.c_void_p]),

@@ -199,6 +199,7 @@ def test_banded_build_matches_oracle(L, oracle, band_rows, cfg, mega):
     dev = L.KLTB200Device(tc)
     L.klt_dev_set_band_rows(dev, band_rows)
     L.klt_dev_disable_mega(dev, 1 - mega)
+    L.klt_dev_set_mega_tail(dev, 0)
     _check_build(L, oracle, img, tc, exact=1, generic=0, expect_tiled=True, expect_fused=True)
     assert L.klt_dev_last_build_mega(dev) == mega
     expect = 1 if band_rows == 0 else -(-h // band_rows)
@@ -218,6 +219,27 @@ def test_banded_build_matches_oracle(L, oracle, band_rows, cfg, mega):
     for which in range(3):
         for l in range(nlev):
             assert np.array_equal(a[which][l], b[which][l])
+    L.KLTFreeTrackingContext(tc)
+
+
+@pytest.mark.parametrize("tail_from", [1, 2, 3])
+@pytest.mark.parametrize("band_rows", [0, 64])
+@pytest.mark.parametrize("cfg", [(4, 2, (700, 900)), (5, 2, (1000, 777)), (3, 4, (600, 800)), (4, 2, (2160, 3840))])
+def test_tail_levels_in_one_launch(L, oracle, cfg, band_rows, tail_from):
+    """Default build path: per-level fused kernels for the big levels, ONE pyramid_mega_kernel launch
+    (tail mode) for the levels >= tail_from; bit-identical to the oracle in exact mode."""
+    nlev, ss, (h, w) = cfg
+    img = synth_image(w, h, seed=5 * h + w)
+    tc = L.KLTCreateTrackingContext()
+    tc.contents.nPyramidLevels, tc.contents.subsampling = nlev, ss
+    L.KLTUpdateTCBorder(tc)
+    dev = L.KLTB200Device(tc)
+    L.klt_dev_set_band_rows(dev, band_rows)
+    L.klt_dev_disable_mega(dev, 1)
+    L.klt_dev_set_mega_tail(dev, tail_from)
+    for rep in range(2):                              # second build: counters carry over
+        _check_build(L, oracle, img, tc, exact=1, generic=0, expect_tiled=True, expect_fused=True)
+        assert L.klt_dev_last_build_mega(dev) == (2 if nlev > tail_from + 1 else 0)
     L.KLTFreeTrackingContext(tc)
 
 
