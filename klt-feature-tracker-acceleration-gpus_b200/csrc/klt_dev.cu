@@ -522,6 +522,7 @@ struct TrackArgs {
   float min_determinant, min_displacement, max_residue;
   int   borderx, bordery;
   int   ncols, nrows;
+  int   prefetch;            // track7: L2 prefetch of the finer levels' footprints at kernel start
 };
 
 // bilinear weights of _interpolate (trackFeatures.c:31-57): the four products
@@ -811,6 +812,7 @@ struct klt_dev {
   int band_rows, last_bands;
   // pyramid_mega_kernel: cached schedule + dependency counters (klt_mega.cuh)
   int no_mega, last_mega, mega_tail_from;
+  int pdl;                     // programmatic dependent launch along the per-frame kernel chain
   MegaSeg* d_segs; int mega_nseg, mega_nitems, mega_key[8];
   unsigned* d_done; int mega_done_off[MEGA_MAX_LEVELS + 1];
   unsigned mega_epoch[MEGA_MAX_LEVELS];
@@ -886,6 +888,21 @@ struct Launch {
   }
   ~Launch() { if (slot >= 0) cudaEventRecord(d->prof_ev[2 * slot + 1], st); }
 };
+
+// kernel launch with (optionally) programmatic stream serialisation: the kernel may start before
+// its predecessor in the stream has finished and synchronises itself with griddepcontrol.wait
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                            Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 static char g_create_err[512] = "";
 
@@ -970,6 +987,7 @@ extern "C" int klt_dev_create(int device, klt_dev** out) {
   // the single-launch pyramid (klt_mega.cuh) is opt-in: correct in both arithmetic modes, but measured
   // slower than the per-level kernels on B200 (4K: 87 us vs 69 us resident)
   c->no_mega = getenv("KLT_B200_MEGA") && atoi(getenv("KLT_B200_MEGA")) ? 0 : 1;
+  c->pdl = getenv("KLT_B200_PDL") ? atoi(getenv("KLT_B200_PDL")) : 1;
   c->mega_tail_from = getenv("KLT_B200_MEGA_TAIL") ? atoi(getenv("KLT_B200_MEGA_TAIL")) : 0;   // opt-in too (4K: 30 us vs 21 us for levels 2+3)
   if (e == cudaSuccess) e = cudaMalloc(&c->d_tile_ctr, 16 * sizeof(unsigned));
   if (e == cudaSuccess) e = cudaMemsetAsync(c->d_tile_ctr, 0, 16 * sizeof(unsigned), c->stream);
@@ -1282,9 +1300,8 @@ static int l0_fused_launch(klt_dev* d, const FusedPlan& P, int W, int H, const T
   const int cps = (d->overlap && d->overlap_l0_ctas > 0) ? d->overlap_l0_ctas : 3;
   const int grid = n < cps * d->num_sms ? n : cps * d->num_sms;               // persistent, 3 CTAs / SM
   { Launch l(d, KID_L0_FUSED);
-    l0_fused_kernel<EXACT><<<grid, 256, L0Geo::SMEM, d->stream>>>(P.map[0], W, H, tiles_x, tile0, tile1,
-                                                                  d->d_tile_ctr, d->tile_base[0], ts, tg, td,
-                                                                  lv.img, lv.gx, lv.gy, lv.pitch);
+    CU(launch_k(l0_fused_kernel<EXACT>, dim3(grid), dim3(256), L0Geo::SMEM, d->stream, d->pdl != 0, P.map[0], W, H,
+                tiles_x, tile0, tile1, d->d_tile_ctr, d->tile_base[0], ts, tg, td, lv.img, lv.gx, lv.gy, lv.pitch));
     d->tile_base[0] += (unsigned)(n + grid); }
   return 0;
 }
@@ -1307,9 +1324,9 @@ static int level_fused_launch_t(klt_dev* d, const FusedPlan& P, int level, const
   const int tile0 = jr0 * tiles_x, tile1 = jr1 * tiles_x, n = tile1 - tile0;
   const int grid = n < cps * d->num_sms ? n : cps * d->num_sms;             // persistent
   { Launch l(d, KID_LEVEL_FUSED);
-    level_fused_kernel<SS, R, TX, TY, EXACT><<<grid, 256, G::SMEM, d->stream>>>(
-        P.map[level], a.w, a.h, b.w, b.h, tiles_x, tile0, tile1, d->d_tile_ctr + (level & 15),
-        d->tile_base[level & 15], tp, tg, td, b.img, b.gx, b.gy, b.pitch);
+    CU(launch_k(level_fused_kernel<SS, R, TX, TY, EXACT>, dim3(grid), dim3(256), G::SMEM, d->stream, d->pdl != 0,
+                P.map[level], a.w, a.h, b.w, b.h, tiles_x, tile0, tile1, d->d_tile_ctr + (level & 15),
+                d->tile_base[level & 15], tp, tg, td, b.img, b.gx, b.gy, b.pitch));
     d->tile_base[level & 15] += (unsigned)(n + grid); }
   return 0;
 }
@@ -2025,7 +2042,9 @@ static bool launch_track_fast(klt_dev* d, const PyrView& v1, const PyrView& v2, 
         if (fpw == 1)
           track7_kernel<1><<<(n + warps_per_block - 1) / warps_per_block, 128, 0, d->tstream>>>(v1, v2, a, n, d->d_x, d->d_y, d->d_val, feat_out_x(d), feat_out_y(d), feat_out_val(d), d->d_live);
         else if (fpw == 4)
-          track7_kernel<4><<<(n + 4 * warps_per_block - 1) / (4 * warps_per_block), 128, 0, d->tstream>>>(v1, v2, a, n, d->d_x, d->d_y, d->d_val, feat_out_x(d), feat_out_y(d), feat_out_val(d), d->d_live);
+          launch_k(track7_kernel<4>, dim3((n + 4 * warps_per_block - 1) / (4 * warps_per_block)), dim3(128), 0, d->tstream,
+                   d->pdl != 0 && !d->overlap, v1, v2, a, n, d->d_x, d->d_y, d->d_val, feat_out_x(d), feat_out_y(d),
+                   feat_out_val(d), d->d_live);
         else
           track7_kernel<2><<<(n + 2 * warps_per_block - 1) / (2 * warps_per_block), 128, 0, d->tstream>>>(v1, v2, a, n, d->d_x, d->d_y, d->d_val, feat_out_x(d), feat_out_y(d), feat_out_val(d), d->d_live);
       }
@@ -2068,6 +2087,7 @@ extern "C" int klt_dev_track_resident(klt_dev* d, int slot_prev, int slot_cur,
   a.min_determinant = p->min_determinant; a.min_displacement = p->min_displacement;
   a.max_residue = p->max_residue; a.borderx = p->borderx; a.bordery = p->bordery;
   a.ncols = d->W; a.nrows = d->H;
+  { static int pf = getenv("KLT_TRACK_PREFETCH") ? atoi(getenv("KLT_TRACK_PREFETCH")) : 0; a.prefetch = pf; }
   const int npix = a.ww * a.wh;
   const int ppl = (npix + 31) / 32;
   int rc;

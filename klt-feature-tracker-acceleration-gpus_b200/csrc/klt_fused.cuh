@@ -90,6 +90,16 @@ __device__ __forceinline__ void fma4(float4& a, const float4& v, float k, bool e
 
 static constexpr int FUSED_RG = 3;       // gradient radius the fused kernels are built for
 
+// Programmatic dependent launch: a CTA of the per-frame chain that finds its tile queue empty lets
+// the successor kernel start launching (its CTAs become resident as ours retire and run their
+// prologue), and every kernel waits for its predecessor's memory before it touches any of it.
+// Hides the launch latency and the drain / fill bubble at each kernel boundary of a frame: 94.3 ->
+// 82.2 us per 4K step on B200.  The trigger point matters (measured): at kernel start the step
+// takes 132 us, at the claim of the last tile 94.7 us (no gain), at queue-empty 82.2 us.  Both
+// instructions are no-ops when the launch did not ask for programmatic serialisation.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // barrier among the 256 threads that compute a tile (== __syncthreads() in the 256-thread kernels;
 // pyramid_mega_kernel carries a ninth, scheduling warp that must stay out of it)
 __device__ __forceinline__ void tile_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -343,8 +353,9 @@ l0_fused_kernel(const __grid_constant__ CUtensorMap map, int W, int H, int tiles
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + G::OFF_BAR);
   volatile int* s_next = reinterpret_cast<volatile int*>(smem_raw + G::OFF_BAR + 8);
   const int tid = threadIdx.x;
+  if (tid == 0) mbar_init(bar, 1);
+  pdl_wait();                         // the u8 frame / the pyramid slot we overwrite may still be in use
   if (tid == 0) {
-    mbar_init(bar, 1);
     const int t = tile0 + (int)(atomicAdd(counter, 1u) - base);
     *s_next = t;
     if (t < ntiles) {
@@ -380,6 +391,7 @@ l0_fused_kernel(const __grid_constant__ CUtensorMap map, int W, int H, int tiles
     __syncthreads();
     tile = *s_next;
   }
+  pdl_launch_dependents();            // queue empty: the next kernel of the chain may move in
 }
 
 // ============================================================================================
@@ -533,8 +545,9 @@ level_fused_kernel(const __grid_constant__ CUtensorMap map, int Wsrc, int Hsrc, 
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + G::OFF_BAR);
   volatile int* s_next = reinterpret_cast<volatile int*>(smem_raw + G::OFF_BAR + 8);
   const int tid = threadIdx.x;
+  if (tid == 0) mbar_init(bar, 1);
+  pdl_wait();                         // the source level is written by the previous kernel
   if (tid == 0) {
-    mbar_init(bar, 1);
     const int t = tile0 + (int)(atomicAdd(counter, 1u) - base);
     *s_next = t;
     if (t < ntiles) {
@@ -571,4 +584,5 @@ level_fused_kernel(const __grid_constant__ CUtensorMap map, int Wsrc, int Hsrc, 
     __syncthreads();                 // Hp / L / Hd / Hg free for the next tile
     tile = *s_next;
   }
+  pdl_launch_dependents();            // queue empty: the next kernel of the chain may move in
 }

@@ -283,6 +283,21 @@ __device__ __forceinline__ void foot7_sample(const float* __restrict__ img, cons
   foot7_interp(r, f, gmask, out);
 }
 
+// L2 prefetch of this lane's footprint row of one level, both frames, around (x, y): the three
+// 32 B sectors around the aligned 48 B the loads will touch if the feature moves by a few pixels.
+__device__ __forceinline__ void foot7_prefetch(const PyrView& p1, const PyrView& p2, int r, float x, float y,
+                                               int r8) {
+  const int pitch = p1.pitch[r];
+  const int xs = (((int)x) - 3) & ~3, row = ((int)y) - 3 + r8;
+  if (xs < 4 || row < 0 || row >= p1.nrows[r] || xs + 16 > pitch) return;
+  const size_t o = (size_t)row * pitch + xs;
+#pragma unroll
+  for (int k = -4; k <= 12; k += 8) {
+    prefetch_l2(p1.img[r] + o + k); prefetch_l2(p1.gx[r] + o + k); prefetch_l2(p1.gy[r] + o + k);
+    prefetch_l2(p2.img[r] + o + k); prefetch_l2(p2.gx[r] + o + k); prefetch_l2(p2.gy[r] + o + k);
+  }
+}
+
 // FPW: features per warp (1, 2 or 4).  Fewer features per warp = more warps in flight for the
 // same work: the kernel is latency bound (issue slots are ~10 % used), so idle lanes are free.
 template <int FPW>
@@ -300,6 +315,7 @@ track7_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, const float* __restric
   const int grp = lane >> 3;
   const int f = grp < FPW ? warp_global * FPW + grp : n;      // groups >= FPW stay idle
 
+  pdl_wait();                                                 // pyramids and features come from earlier kernels
   bool alive = false;
   float xloc = 0.0f, yloc = 0.0f;
   if (f < n) {
@@ -312,6 +328,16 @@ track7_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, const float* __restric
   }
   if (!__any_sync(0xffffffffu, alive)) return;
 
+  // Every first touch of a level is a DRAM miss (two 132 MB pyramid sets do not fit in L2) and the
+  // levels are a dependent chain: pull the footprints of all the finer levels towards L2 now, while
+  // the coarsest level is being worked on.  The feature moves by a few pixels at most.
+  if (alive && a.prefetch) {
+    float px = xloc, py = yloc;
+    for (int r = 0; r < a.nlevels - 1; ++r) {
+      foot7_prefetch(p1, p2, r, px, py, r8);
+      px = px / a.ss; py = py / a.ss;
+    }
+  }
   for (int r = a.nlevels - 1; r >= 0; --r) { xloc = xloc / a.ss; yloc = yloc / a.ss; }
   float xout = xloc, yout = yloc;
   int status = KLT_TRACKED;
@@ -337,19 +363,25 @@ track7_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, const float* __restric
 
     if (iterating && window_oob(x1, y1, hw, hh, nc, nr)) { lvl_status = KLT_OOB; iterating = false; }
     if (iterating && window_oob(x2, y2, hw, hh, nc, nr)) { lvl_status = KLT_OOB; iterating = false; }
-    // the sampling routines shuffle inside the 8-lane group, so whole groups enter them together
-    // (iterating is uniform within a group)
-    if (iterating) {
-      const Foot7 ft = foot7_setup(x1, y1, pitch, r8);
-      foot7_sample(i1, ft, gmask, t_i);
-      foot7_sample(gx1, ft, gmask, t_gx);
-      foot7_sample(gy1, ft, gmask, t_gy);
-    }
-
     // raw footprint rows of frame 2, kept across iterations: sub-pixel Newton updates and the
     // residue pass usually stay on the same 8x8 integer footprint, so nothing is re-read
     Row12 c_i, c_gx, c_gy;
     int c_off = -1;
+    // the sampling routines shuffle inside the 8-lane group, so whole groups enter them together
+    // (iterating is uniform within a group)
+    if (iterating) {
+      // all 18 loads of the level (template + first frame-2 footprint) are issued before the first
+      // use, so the level pays one memory round trip instead of two
+      const Foot7 ft = foot7_setup(x1, y1, pitch, r8);
+      const Foot7 f2 = foot7_setup(x2, y2, pitch, r8);
+      const Row12 r_i = foot7_load(i1, ft.off), r_gx = foot7_load(gx1, ft.off), r_gy = foot7_load(gy1, ft.off);
+      c_i = foot7_load(i2, f2.off); c_gx = foot7_load(gx2, f2.off); c_gy = foot7_load(gy2, f2.off);
+      c_off = f2.off;
+      foot7_interp(r_i, ft, gmask, t_i);
+      foot7_interp(r_gx, ft, gmask, t_gx);
+      foot7_interp(r_gy, ft, gmask, t_gy);
+    }
+
     while (__any_sync(0xffffffffu, iterating)) {
       float gxx = 0.0f, gxy = 0.0f, gyy = 0.0f, ex = 0.0f, ey = 0.0f;
       if (iterating) {
@@ -381,8 +413,9 @@ track7_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, const float* __restric
         if (det < a.min_determinant) {
           lvl_status = KLT_SMALL_DET; iterating = false;
         } else {
-          dx = (gyy * ex - gxy * ey) / det;
-          dy = (gxx * ey - gxy * ex) / det;
+          const float inv = __frcp_rn(det);                   // one reciprocal instead of two divisions
+          dx = (gyy * ex - gxy * ey) * inv;
+          dy = (gxx * ey - gxy * ex) * inv;
           x2 += dx; y2 += dy;
           ++iteration;
           const bool again = (fabsf(dx) >= a.min_displacement || fabsf(dy) >= a.min_displacement) &&
@@ -411,7 +444,7 @@ track7_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, const float* __restric
         }
       }
       sum = group_sum8(sum);
-      if (need_res && sum / 49.0f > a.max_residue) lvl_status = KLT_LARGE_RESIDUE;
+      if (need_res && sum * (1.0f / 49.0f) > a.max_residue) lvl_status = KLT_LARGE_RESIDUE;
     }
     if (running) {
       int v;
