@@ -56,6 +56,15 @@ struct TapsR {
   float k[KLT_DEV_MAX_TAPS];
 };
 
+// taps of the fused kernels (radius <= 11): plain (k) and duplicated (kk[m] = {k[m], k[m]}) so that
+// a packed FFMA2 can take its multiplier pair straight from a 64-bit constant / uniform register
+static constexpr int FUSED_MAX_TAPS = 24;
+struct TapsF {
+  int    w, pad;
+  float  k[FUSED_MAX_TAPS];
+  float2 kk[FUSED_MAX_TAPS];
+};
+
 static constexpr int NT = 256;   // threads per CTA of every tile kernel
 
 #include "klt_fused.cuh"
@@ -920,6 +929,13 @@ static int fail(klt_dev* d, const char* fmt, ...) {
       return fail(d, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
+static TapsF to_fused(const TapsR& t) {
+  TapsF f;
+  memset(&f, 0, sizeof(f));
+  f.w = t.w;
+  for (int m = 0; m < t.w && m < FUSED_MAX_TAPS; ++m) { f.k[m] = t.k[m]; f.kk[m] = make_float2(t.k[m], t.k[m]); }
+  return f;
+}
 static TapsR reversed(const float* k, int w) {
   TapsR t;
   memset(&t, 0, sizeof(t));
@@ -1301,7 +1317,8 @@ static int l0_fused_launch(klt_dev* d, const FusedPlan& P, int W, int H, const T
   const int grid = n < cps * d->num_sms ? n : cps * d->num_sms;               // persistent, 3 CTAs / SM
   { Launch l(d, KID_L0_FUSED);
     CU(launch_k(l0_fused_kernel<EXACT>, dim3(grid), dim3(256), L0Geo::SMEM, d->stream, d->pdl != 0, P.map[0], W, H,
-                tiles_x, tile0, tile1, d->d_tile_ctr, d->tile_base[0], ts, tg, td, lv.img, lv.gx, lv.gy, lv.pitch));
+                tiles_x, tile0, tile1, d->d_tile_ctr, d->tile_base[0], to_fused(ts), to_fused(tg), to_fused(td), lv.img,
+                lv.gx, lv.gy, lv.pitch));
     d->tile_base[0] += (unsigned)(n + grid); }
   return 0;
 }
@@ -1326,7 +1343,7 @@ static int level_fused_launch_t(klt_dev* d, const FusedPlan& P, int level, const
   { Launch l(d, KID_LEVEL_FUSED);
     CU(launch_k(level_fused_kernel<SS, R, TX, TY, EXACT>, dim3(grid), dim3(256), G::SMEM, d->stream, d->pdl != 0,
                 P.map[level], a.w, a.h, b.w, b.h, tiles_x, tile0, tile1, d->d_tile_ctr + (level & 15),
-                d->tile_base[level & 15], tp, tg, td, b.img, b.gx, b.gy, b.pitch));
+                d->tile_base[level & 15], to_fused(tp), to_fused(tg), to_fused(td), b.img, b.gx, b.gy, b.pitch));
     d->tile_base[level & 15] += (unsigned)(n + grid); }
   return 0;
 }
@@ -1622,7 +1639,7 @@ static int mega_build(klt_dev* d, PyrSet& S, const FusedPlan& P, int nb, const T
     MP.serial = serial; }
   MP.done = d->d_done;
   MP.u8_flag = d->d_u8_flag;
-  MP.ts = ts; MP.tp = tp; MP.tg = tg; MP.td = td;
+  MP.ts = to_fused(ts); MP.tp = to_fused(tp); MP.tg = to_fused(tg); MP.td = to_fused(td);
   if (feed) {
     WriteValue32Fn wv = stream_write_value32();
     d->feed_epoch += 1;

@@ -78,13 +78,25 @@ __device__ __forceinline__ float u8_to_float(unsigned word, unsigned byte_sel) {
   return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7440u + byte_sel)) - 8388608.0f;
 }
 
-__device__ __forceinline__ void fma4(float4& a, const float4& v, float k, bool exact) {
+// packed FP32 FMA (Blackwell FFMA2): (ax, ay) += (vx, vy) * (kk.x, kk.y), each half an ordinary
+// IEEE fma -- bit-identical to two fmaf, half the issue slots.  The packs are register renames.
+__device__ __forceinline__ void ffma2(float& ax, float& ay, float vx, float vy, float2 kk) {
+  unsigned long long a, v, k;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(ax), "f"(ay));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(vx), "f"(vy));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(k) : "f"(kk.x), "f"(kk.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(v), "l"(k));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(ax), "=f"(ay) : "l"(a));
+}
+// a += v * t.k[m] on four columns: the vertical passes (scatter form)
+__device__ __forceinline__ void fma4(float4& a, const float4& v, const TapsF& t, int m, bool exact) {
   if (exact) {
+    const float k = t.k[m];
     a.x = __fadd_rn(a.x, __fmul_rn(v.x, k)); a.y = __fadd_rn(a.y, __fmul_rn(v.y, k));
     a.z = __fadd_rn(a.z, __fmul_rn(v.z, k)); a.w = __fadd_rn(a.w, __fmul_rn(v.w, k));
   } else {
-    a.x = fmaf(v.x, k, a.x); a.y = fmaf(v.y, k, a.y);
-    a.z = fmaf(v.z, k, a.z); a.w = fmaf(v.w, k, a.w);
+    ffma2(a.x, a.y, v.x, v.y, t.kk[m]);
+    ffma2(a.z, a.w, v.z, v.w, t.kk[m]);
   }
 }
 
@@ -110,8 +122,8 @@ __device__ __forceinline__ void tile_sync() { asm volatile("bar.sync 1, 256;" ::
 // (TX = 64) or 4 groups x 8 rows (TX = 32); a quarter warp is 4 groups x 2 rows, conflict free
 // because LP/4 and HP/4 are odd.
 template <bool EXACT, bool BORDER, int TX, int LH, int LP, int HP>
-__device__ __forceinline__ void stage_hgrad(const float* sL, float* sHd, float* sHg, const TapsR& tg,
-                                            const TapsR& td, int x0, int W) {
+__device__ __forceinline__ void stage_hgrad(const float* sL, float* sHd, float* sHg, const TapsF& tg,
+                                            const TapsF& td, int x0, int W) {
   constexpr int RG = FUSED_RG;
   constexpr int NGC = TX / 8;                       // groups per row: 8 or 4
   constexpr int RPW = 32 / NGC;                     // rows per warp: 4 or 8
@@ -158,7 +170,7 @@ __device__ __forceinline__ void stage_hgrad(const float* sL, float* sHd, float* 
 // scatter form: every loaded row feeds the outputs it belongs to, taps in increasing order
 // (== the reference's summation order for each output).
 template <bool EXACT, bool BORDER, int PY, int HP, bool SKIP_CENTRE>
-__device__ __forceinline__ void stage_vgrad(const float* __restrict__ src, const TapsR& tk,
+__device__ __forceinline__ void stage_vgrad(const float* __restrict__ src, const TapsF& tk,
                                             float* __restrict__ out, int opitch, int xg, int yg0,
                                             int W, int H) {
   constexpr int R = FUSED_RG;
@@ -171,7 +183,7 @@ __device__ __forceinline__ void stage_vgrad(const float* __restrict__ src, const
 #pragma unroll
     for (int q = 0; q < PY; ++q) {
       const int m = i - q;
-      if (m >= 0 && m <= 2 * R && !(SKIP_CENTRE && m == R)) fma4(acc[q], v, tk.k[m], EXACT);
+      if (m >= 0 && m <= 2 * R && !(SKIP_CENTRE && m == R)) fma4(acc[q], v, tk, m, EXACT);
     }
   }
 #pragma unroll
@@ -188,8 +200,8 @@ __device__ __forceinline__ void stage_vgrad(const float* __restrict__ src, const
 
 // gx = V_gauss(Hd), gy = V_deriv(Hg); first half of the CTA does gx, second half gy (warp uniform)
 template <bool EXACT, bool BORDER, int TX, int TY, int PY, int HP>
-__device__ __forceinline__ void stage_vgrad_both(const float* sHd, const float* sHg, const TapsR& tg,
-                                                 const TapsR& td, float* out_gx, float* out_gy,
+__device__ __forceinline__ void stage_vgrad_both(const float* sHd, const float* sHg, const TapsF& tg,
+                                                 const TapsF& td, float* out_gx, float* out_gy,
                                                  int opitch, int x0, int y0, int W, int H) {
   constexpr int NCG = TX / 4, NRB = TY / PY, ITEMS = NCG * NRB;       // per output image
   static_assert(ITEMS <= 128 && 128 % ITEMS == 0, "stage D mapping");
@@ -227,7 +239,7 @@ struct L0Geo {
 
 // stage A item: 8 outputs (Hs cols 8g..8g+7 <-> global x0-4+8g+q) of row r from 12 u8 pixels
 template <bool EXACT, bool BORDER>
-__device__ __forceinline__ void l0_stage_a_item(const unsigned char* sU8, float* sHs, const TapsR& ts,
+__device__ __forceinline__ void l0_stage_a_item(const unsigned char* sU8, float* sHs, const TapsF& ts,
                                                 int r, int g, int x0, int W) {
   using G = L0Geo;
   constexpr int RS = G::RS;
@@ -258,7 +270,7 @@ __device__ __forceinline__ void l0_stage_a_item(const unsigned char* sU8, float*
 }
 
 template <bool EXACT, bool BORDER>
-__device__ __forceinline__ void l0_fused_tile(unsigned char* smem, int W, const TapsR& ts, int x0) {
+__device__ __forceinline__ void l0_fused_tile(unsigned char* smem, int W, const TapsF& ts, int x0) {
   using G = L0Geo;
   const unsigned char* sU8 = smem + G::OFF_U8;
   float* sHs = reinterpret_cast<float*>(smem + G::OFF_HS);
@@ -277,8 +289,8 @@ __device__ __forceinline__ void l0_fused_tile(unsigned char* smem, int W, const 
 }
 
 template <bool EXACT, bool BORDER>
-__device__ __forceinline__ void l0_fused_tile_rest(unsigned char* smem, int W, int H, const TapsR& ts,
-                                                   const TapsR& tg, const TapsR& td,
+__device__ __forceinline__ void l0_fused_tile_rest(unsigned char* smem, int W, int H, const TapsF& ts,
+                                                   const TapsF& tg, const TapsF& td,
                                                    float* __restrict__ out_img,
                                                    float* __restrict__ out_gx,
                                                    float* __restrict__ out_gy, int opitch, int x0,
@@ -310,7 +322,7 @@ __device__ __forceinline__ void l0_fused_tile_rest(unsigned char* smem, int W, i
 #pragma unroll
       for (int q = 0; q < PY; ++q) {
         const int m = i - q;
-        if (m >= 0 && m <= 2 * RS) fma4(acc[q], v, ts.k[m], EXACT);
+        if (m >= 0 && m <= 2 * RS) fma4(acc[q], v, ts, m, EXACT);
       }
     }
     const int xg = x0 - 4 + 4 * j;
@@ -346,7 +358,7 @@ template <bool EXACT>
 __global__ void __launch_bounds__(256, 3)
 l0_fused_kernel(const __grid_constant__ CUtensorMap map, int W, int H, int tiles_x, int tile0, int ntiles,
                 unsigned* __restrict__ counter, unsigned base,
-                TapsR ts, TapsR tg, TapsR td, float* __restrict__ out_img,
+                TapsF ts, TapsF tg, TapsF td, float* __restrict__ out_img,
                 float* __restrict__ out_gx, float* __restrict__ out_gy, int opitch) {
   using G = L0Geo;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -425,7 +437,7 @@ struct LvGeo {
 
 // P1 item: 4 kept outputs (tile cols 4g..4g+3) of source row r
 template <bool EXACT, bool BORDER, int SS, int R, int TX, int TY>
-__device__ __forceinline__ void lv_p1_item(const float* sSrc, float* sHp, const TapsR& tp, int r, int g,
+__device__ __forceinline__ void lv_p1_item(const float* sSrc, float* sHp, const TapsF& tp, int r, int g,
                                            int x0, int Wsrc) {
   using G = LvGeo<SS, R, TX, TY>;
   float win[4 * G::NV1];
@@ -451,7 +463,7 @@ __device__ __forceinline__ void lv_p1_item(const float* sSrc, float* sHp, const 
 }
 
 template <bool EXACT, bool BORDER, int SS, int R, int TX, int TY>
-__device__ __forceinline__ void lv_stage_p1(const unsigned char* smem, const TapsR& tp, int x0, int Wsrc) {
+__device__ __forceinline__ void lv_stage_p1(const unsigned char* smem, const TapsF& tp, int x0, int Wsrc) {
   using G = LvGeo<SS, R, TX, TY>;
   const float* sSrc = reinterpret_cast<const float*>(smem + G::OFF_SRC);
   float* sHp = const_cast<float*>(reinterpret_cast<const float*>(smem + G::OFF_HP));
@@ -474,8 +486,8 @@ __device__ __forceinline__ void lv_stage_p1(const unsigned char* smem, const Tap
 }
 
 template <bool EXACT, bool BORDER, int SS, int R, int TX, int TY>
-__device__ __forceinline__ void lv_stage_rest(unsigned char* smem, const TapsR& tp, const TapsR& tg,
-                                              const TapsR& td, int Hsrc, int W, int H,
+__device__ __forceinline__ void lv_stage_rest(unsigned char* smem, const TapsF& tp, const TapsF& tg,
+                                              const TapsF& td, int Hsrc, int W, int H,
                                               float* __restrict__ out_img, float* __restrict__ out_gx,
                                               float* __restrict__ out_gy, int opitch, int x0, int y0) {
   using G = LvGeo<SS, R, TX, TY>;
@@ -504,7 +516,7 @@ __device__ __forceinline__ void lv_stage_rest(unsigned char* smem, const TapsR& 
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int m = i - SS * q;
-          if (m >= 0 && m <= 2 * R) fma4(acc[q], v, tp.k[m], EXACT);
+          if (m >= 0 && m <= 2 * R) fma4(acc[q], v, tp, m, EXACT);
         }
       }
       const int xg = x0 - 4 + 4 * j;
@@ -537,7 +549,7 @@ template <int SS, int R, int TX, int TY, bool EXACT>
 __global__ void __launch_bounds__(256, (LvGeo<SS, R, TX, TY>::SMEM <= 56 * 1024) ? 3 : 2)
 level_fused_kernel(const __grid_constant__ CUtensorMap map, int Wsrc, int Hsrc, int W, int H,
                    int tiles_x, int tile0, int ntiles, unsigned* __restrict__ counter, unsigned base,
-                   TapsR tp, TapsR tg, TapsR td,
+                   TapsF tp, TapsF tg, TapsF td,
                    float* __restrict__ out_img, float* __restrict__ out_gx,
                    float* __restrict__ out_gy, int opitch) {
   using G = LvGeo<SS, R, TX, TY>;

@@ -61,7 +61,7 @@ struct MegaParams {
   int ready_below;                    // levels < ready_below were complete before the launch (tail mode)
   int serial;                         // debug: no prefetch, tile k is loaded after tile k-1 is finished
   int coarse_every;                   // CTA b starts on the coarse queue iff b % coarse_every == coarse_every - 1
-  TapsR ts, tp, tg, td;
+  TapsF ts, tp, tg, td;
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {

@@ -11,6 +11,7 @@
  */
 #include <stdio.h>
 #include <stdlib.h>
+#include <time.h>
 
 #include "klt_internal.h"
 
@@ -18,6 +19,20 @@
   do {                                                                       \
     if ((call) != 0) KLTError("(KLT/B200) %s", klt_dev_error((s)->dev));      \
   } while (0)
+
+/* KLT_B200_TIMING=1: host-side phase times of the synchronous call, printed every 64 calls */
+static double now_us(void)
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
+static int timing_on(void)
+{
+  static int on = -1;
+  if (on < 0) { const char *e = getenv("KLT_B200_TIMING"); on = (e && atoi(e)) ? 1 : 0; }
+  return on;
+}
 
 static void fill_track_params(KLT_TrackingContext tc, int exact, klt_dev_track_params *p)
 {
@@ -106,18 +121,26 @@ static void track_common(KLT_TrackingContext tc, const KLT_PixelType *img1,
 
   /* Everything below is queued on the context stream without waiting: feature upload,
    * frame upload, pyramid kernels, tracker, result download; one synchronisation at the end. */
-  DEVCALL(s, klt_dev_features_staging(dev, n, &x, &y, &v));
-  klt_list_to_arrays(fl, x, y, v);
-  DEVCALL(s, klt_dev_features_commit(dev, n));
-
+  const int timing = timing_on();
+  static double acc[5]; static int calls;
+  double t0 = timing ? now_us() : 0, t1 = 0, t2 = 0, t3 = 0;
+  /* the frame upload is the long pole: queue it (and the pyramid kernels behind it) first, then
+   * pack the feature list into the pinned staging area while the copy engine is already busy */
   slot_prev = prepare_previous(tc, s, img1, on_device, pitch, ncols, nrows);
   slot_cur = (slot_prev + 1) % KLT_DEV_SLOTS;
   klt_fill_build_desc(tc, ncols, nrows, tc->nPyramidLevels, 1, s->exact, &q);
   DEVCALL(s, klt_dev_build(dev, slot_cur, img2, on_device, pitch, &q));
+  if (timing) t1 = now_us();
+
+  DEVCALL(s, klt_dev_features_staging(dev, n, &x, &y, &v));
+  klt_list_to_arrays(fl, x, y, v);
+  DEVCALL(s, klt_dev_features_commit(dev, n));
 
   fill_track_params(tc, s->exact, &tp);
   DEVCALL(s, klt_dev_track_resident(dev, slot_prev, slot_cur, &tp));
+  if (timing) t2 = now_us();
   DEVCALL(s, klt_dev_features_fetch(dev, n));
+  if (timing) t3 = now_us();
   for (i = 0; i < n; i++) {
     KLT_Feature f = fl->feature[i];
     if (f->val < 0) continue;                 /* lost features are not touched (:1346) */
@@ -131,6 +154,15 @@ static void track_common(KLT_TrackingContext tc, const KLT_PixelType *img1,
   }
 
   hand_over(tc, s, slot_cur);
+  if (timing) {
+    const double t4 = now_us();
+    acc[0] += t1 - t0; acc[1] += t2 - t1; acc[2] += t3 - t2; acc[3] += t4 - t3; acc[4] += t4 - t0;
+    if (++calls % 64 == 0) {
+      fprintf(stderr, "(KLT/B200 timing, us/call over 64 calls) build enqueue %.1f  pack+commit+track enqueue %.1f  wait %.1f  unpack %.1f  total %.1f\n",
+              acc[0] / 64, acc[1] / 64, acc[2] / 64, acc[3] / 64, acc[4] / 64);
+      acc[0] = acc[1] = acc[2] = acc[3] = acc[4] = 0;
+    }
+  }
 
   if (KLT_verbose >= 1) {
     fprintf(stderr, "\n\t%d features successfully tracked.\n", KLTCountRemainingFeatures(fl));
