@@ -123,6 +123,15 @@ int klt_dev_features_download(klt_dev *d, int n, float *x, float *y, int *val); 
 int klt_dev_features_staging(klt_dev *d, int n, float **x, float **y, int **val);
 int klt_dev_features_commit(klt_dev *d, int n);
 int klt_dev_features_fetch(klt_dev *d, int n);
+/* record mode, for feature lists that live in pinned host memory (klt_dev_host_alloc: what
+ * KLTCreateFeatureList uses when a CUDA device is present): first_record points at an array of n
+ * records of stride_bytes each with x | y | val (float, float, int) in their first 12 bytes -- the
+ * layout of KLT_FeatureRec.  One H2D copy mirrors them, the next tracker reads the mirror and
+ * writes x | y | val of every live feature straight into the caller's records (posted PCIe
+ * writes); klt_dev_features_fetch then only synchronises.  No pack / unpack on the host. */
+int klt_dev_features_commit_records(klt_dev *d, int n, void *first_record, size_t stride_bytes);
+void *klt_dev_host_alloc(size_t bytes);     /* portable pinned host memory; NULL without a device */
+void klt_dev_host_free(void *p);
 
 /* ---- selection --------------------------------------------------------- */
 /* replaces the eigenvalue loop, _sortPointList and _enforceMinimumDistance of

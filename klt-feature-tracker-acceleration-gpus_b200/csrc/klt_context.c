@@ -188,13 +188,55 @@ static void feature_defaults(KLT_Feature f)
 }
 
 /* one block: header, pointer array, records (klt.c:148-167) */
+/* Feature lists are one block (header, pointer array, records: reference klt.c:148-167).  When a
+ * CUDA device is present the block is pinned host memory, so that KLTTrackFeatures can mirror the
+ * records to the device in one copy and let the tracker write x | y | val of every feature straight
+ * back into them (klt_dev_features_commit_records): no pack / unpack pass on the host.  Pinned
+ * blocks are remembered here; anything else (no device, or a list built by hand) takes the
+ * staging path. */
+typedef struct pinned_block { void *p; struct pinned_block *next; } pinned_block;
+static pinned_block *g_pinned = NULL;
+static pthread_mutex_t g_pinned_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static void pinned_remember(void *p)
+{
+  pinned_block *b = (pinned_block *)malloc(sizeof(pinned_block));
+  if (!b) KLTError("(KLTCreateFeatureList) Out of memory");
+  pthread_mutex_lock(&g_pinned_lock);
+  b->p = p; b->next = g_pinned; g_pinned = b;
+  pthread_mutex_unlock(&g_pinned_lock);
+}
+int klt_list_is_pinned(const void *p)
+{
+  pinned_block *b;
+  int found = 0;
+  pthread_mutex_lock(&g_pinned_lock);
+  for (b = g_pinned; b; b = b->next) if (b->p == p) { found = 1; break; }
+  pthread_mutex_unlock(&g_pinned_lock);
+  return found;
+}
+static int pinned_forget(void *p)
+{
+  pinned_block **pp, *b;
+  int found = 0;
+  pthread_mutex_lock(&g_pinned_lock);
+  for (pp = &g_pinned; *pp; pp = &(*pp)->next)
+    if ((*pp)->p == p) { b = *pp; *pp = b->next; free(b); found = 1; break; }
+  pthread_mutex_unlock(&g_pinned_lock);
+  return found;
+}
+
 KLT_FeatureList KLTCreateFeatureList(int nFeatures)
 {
   const size_t bytes = sizeof(KLT_FeatureListRec) + (size_t)nFeatures * sizeof(KLT_Feature) +
                        (size_t)nFeatures * sizeof(KLT_FeatureRec);
-  KLT_FeatureList fl = (KLT_FeatureList)malloc(bytes);
+  const char *env = getenv("KLT_B200_PINNED_LISTS");
+  KLT_FeatureList fl = NULL;
   KLT_Feature recs;
   int i;
+  if (env == NULL || atoi(env) != 0) fl = (KLT_FeatureList)klt_dev_host_alloc(bytes);
+  if (fl) pinned_remember(fl);
+  else fl = (KLT_FeatureList)malloc(bytes);
   if (!fl) KLTError("(KLTCreateFeatureList) Out of memory");
   fl->nFeatures = nFeatures;
   fl->feature = (KLT_Feature *)(fl + 1);
@@ -314,7 +356,8 @@ void KLTFreeFeatureList(KLT_FeatureList fl)
     free(fl->feature[i]->aff_img_grady);
     feature_defaults(fl->feature[i]);
   }
-  free(fl);
+  if (pinned_forget(fl)) klt_dev_host_free(fl);
+  else free(fl);
 }
 
 void KLTFreeFeatureHistory(KLT_FeatureHistory fh) { free(fh); }

@@ -534,6 +534,16 @@ struct TrackArgs {
   int   prefetch;            // track7: L2 prefetch of the finer levels' footprints at kernel start
 };
 
+// Where a tracker kernel reads the features and where it records the results (element strides in
+// 4-byte words): SoA device arrays (stride 1), the pinned SoA staging area, or -- for feature lists
+// that live in pinned host memory -- a device mirror of the KLT_FeatureRec array for the input and
+// the caller's own records for the output (stride = sizeof(KLT_FeatureRec) / 4, x | y | val at
+// words 0 | 1 | 2), so that the synchronous API needs no pack / unpack pass on the host.
+struct FeatIO {
+  const float* x; const float* y; const int* val; int istride;
+  float* ox; float* oy; int* oval; int ostride;
+};
+
 // bilinear weights of _interpolate (trackFeatures.c:31-57): the four products
 // (1-ax)(1-ay), ax(1-ay), (1-ax)ay, ax*ay are rounded first, then multiplied by
 // the pixels and summed left to right.
@@ -585,16 +595,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 // level and kept in registers.
 template <bool EXACT, int PPL>
 __global__ void __launch_bounds__(128)
-track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n,
-             const float* __restrict__ fx, const float* __restrict__ fy, const int* __restrict__ fval,
-             float* __restrict__ ox, float* __restrict__ oy, int* __restrict__ oval,
+track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
              unsigned long long* __restrict__ live_total) {
   extern __shared__ float s_win[];     // EXACT only: [warps][3][npix]
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int f = blockIdx.x * (blockDim.x >> 5) + wib;
   if (f >= n) return;
-  if (fval[f] < 0) return;             // only features that are not lost (:1346)
+  if (io.val[(size_t)f * io.istride] < 0) return;             // only features that are not lost (:1346)
   if (lane == 0) atomicAdd(live_total, 1ULL);
 
   const int ww = a.ww, wh = a.wh, hw = ww / 2, hh = wh / 2, npix = ww * wh;
@@ -602,7 +610,7 @@ track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n,
   float* swy = swx + npix;
   float* swd = swy + npix;
 
-  float xloc = fx[f], yloc = fy[f];
+  float xloc = io.x[(size_t)f * io.istride], yloc = io.y[(size_t)f * io.istride];
   for (int r = a.nlevels - 1; r >= 0; --r) { xloc = __fdiv_rn(xloc, a.ss); yloc = __fdiv_rn(yloc, a.ss); }
   float xout = xloc, yout = yloc;
   int status = KLT_TRACKED;
@@ -755,12 +763,13 @@ track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n,
   if (lane == 0) {
     const bool outside = (xout < (float)a.borderx || xout > (float)(a.ncols - 1 - a.borderx) ||
                           yout < (float)a.bordery || yout > (float)(a.nrows - 1 - a.bordery));
+    const size_t o = (size_t)f * io.ostride;
     if (status == KLT_OOB || outside) {
-      ox[f] = -1.0f; oy[f] = -1.0f; oval[f] = KLT_OOB;
+      io.ox[o] = -1.0f; io.oy[o] = -1.0f; io.oval[o] = KLT_OOB;
     } else if (status != KLT_TRACKED) {
-      ox[f] = -1.0f; oy[f] = -1.0f; oval[f] = status;
+      io.ox[o] = -1.0f; io.oy[o] = -1.0f; io.oval[o] = status;
     } else {
-      ox[f] = xout; oy[f] = yout; oval[f] = KLT_TRACKED;
+      io.ox[o] = xout; io.oy[o] = yout; io.oval[o] = KLT_TRACKED;
     }
   }
 }
@@ -830,7 +839,8 @@ struct klt_dev {
   float *d_x, *d_y; int* d_val; int feat_cap; int feat_n;
   float *h_x, *h_y; int* h_val;   // pinned staging
   int staging_busy;
-  int feat_out_host;            // 1: the next tracker writes its results into h_x/h_y/h_val (sync API)
+  int feat_out_host;            // 1: the next tracker writes its results into h_x/h_y/h_val (sync API); 2: record mode
+  unsigned char* d_rec; size_t d_rec_cap; void* h_rec; int rec_stride;   // record mode (klt_dev_features_commit_records)
   cudaEvent_t ev_feat; int feat_pending;   // feature upload queued on the copy stream
   // selection
   int *c_val[2]; unsigned* c_idx[2]; size_t cand_cap;
@@ -1039,6 +1049,7 @@ extern "C" void klt_dev_destroy(klt_dev* d) {
   cudaFree(d->d_live);
   cudaFree(d->d_tile_ctr);
   cudaFree(d->d_u8_flag);
+  cudaFree(d->d_rec);
   for (int i = 0; i < KLT_DEV_SLOTS; ++i) { cudaEventDestroy(d->ev_built[i]); cudaEventDestroy(d->ev_read[i]); }
   cudaEventDestroy(d->ev_join);
   for (int i = 0; i < KLT_BAND_EVENTS; ++i) cudaEventDestroy(d->ev_band[i]);
@@ -1993,10 +2004,43 @@ extern "C" int klt_dev_features_commit(klt_dev* d, int n) {      // H2D of the s
   d->feat_n = n;
   return 0;
 }
+// record mode: the feature list lives in pinned host memory (klt_dev_host_alloc).  The records are
+// mirrored to the device in one copy (behind the frame bands on the copy stream), the tracker reads
+// the mirror and writes x | y | val of every live feature straight into the caller's records.
+extern "C" int klt_dev_features_commit_records(klt_dev* d, int n, void* first_record, size_t stride_bytes) {
+  CU(cudaSetDevice(d->device));
+  if (n < 0 || (stride_bytes & 3) || stride_bytes < 12) return fail(d, "commit_records: bad count / stride");
+  const size_t bytes = (size_t)n * stride_bytes;
+  if (d->d_rec_cap < bytes) {
+    if (sync_all(d)) return fail(d, "stream synchronisation failed");
+    cudaFree(d->d_rec); d->d_rec = nullptr; d->d_rec_cap = 0;
+    CU(cudaMalloc(&d->d_rec, bytes ? bytes : 16));
+    d->d_rec_cap = bytes ? bytes : 16;
+  }
+  if (n > 0) {
+    Launch l(d, KID_COPY_H2D, d->cstream);
+    CU(cudaMemcpyAsync(d->d_rec, first_record, bytes, cudaMemcpyHostToDevice, d->cstream));
+  }
+  CU(cudaEventRecord(d->ev_feat, d->cstream));
+  d->feat_pending = 1;
+  d->feat_out_host = 2;
+  d->h_rec = first_record;
+  d->rec_stride = (int)(stride_bytes / 4);
+  d->feat_n = n;
+  return 0;
+}
+extern "C" void* klt_dev_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (klt_dev_count() < 1) return nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+extern "C" void klt_dev_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 extern "C" int klt_dev_features_fetch(klt_dev* d, int n) {       // D2H into the staging area + sync
   CU(cudaSetDevice(d->device));
   if (n > d->feat_n) return fail(d, "download of %d features but %d resident", n, d->feat_n);
-  if (!d->feat_out_host) {
+  if (d->feat_out_host == 0) {
     Launch l(d, KID_COPY_D2H, d->tstream);
     CU(cudaMemcpyAsync(d->h_x, d->d_x, (size_t)d->feat_cap * 12, cudaMemcpyDeviceToHost, d->tstream));
   }                                   // else: the tracker wrote its results into the staging area
@@ -2025,9 +2069,22 @@ static void make_view(const PyrSet& S, int L, PyrView* v) {
 
 // where the tracker records its results: the device arrays (resident pipelines) or, for the
 // synchronous API, straight into the pinned host staging area (posted writes over PCIe, no D2H copy)
-static float* feat_out_x(klt_dev* d) { return d->feat_out_host ? d->h_x : d->d_x; }
-static float* feat_out_y(klt_dev* d) { return d->feat_out_host ? d->h_y : d->d_y; }
-static int* feat_out_val(klt_dev* d) { return d->feat_out_host ? d->h_val : d->d_val; }
+static FeatIO feat_io(klt_dev* d) {
+  FeatIO io;
+  if (d->feat_out_host == 2) {              // record mode: device mirror in, the caller's pinned records out
+    const float* in = reinterpret_cast<const float*>(d->d_rec);
+    float* out = reinterpret_cast<float*>(d->h_rec);
+    io.x = in; io.y = in + 1; io.val = reinterpret_cast<const int*>(in + 2); io.istride = d->rec_stride;
+    io.ox = out; io.oy = out + 1; io.oval = reinterpret_cast<int*>(out + 2); io.ostride = d->rec_stride;
+  } else {
+    io.x = d->d_x; io.y = d->d_y; io.val = d->d_val; io.istride = 1;
+    io.ox = d->feat_out_host ? d->h_x : d->d_x;
+    io.oy = d->feat_out_host ? d->h_y : d->d_y;
+    io.oval = d->feat_out_host ? d->h_val : d->d_val;
+    io.ostride = 1;
+  }
+  return io;
+}
 
 template <bool EXACT, int PPL>
 static int launch_track(klt_dev* d, const PyrView& v1, const PyrView& v2, const TrackArgs& a, int n) {
@@ -2036,7 +2093,7 @@ static int launch_track(klt_dev* d, const PyrView& v1, const PyrView& v2, const 
   if (set_smem(d, track_kernel<EXACT, PPL>, smem)) return 1;
   { Launch l(d, KID_TRACK, d->tstream);
     track_kernel<EXACT, PPL><<<(n + warps - 1) / warps, warps * 32, smem, d->tstream>>>(
-        v1, v2, a, n, d->d_x, d->d_y, d->d_val, feat_out_x(d), feat_out_y(d), feat_out_val(d), d->d_live); }
+        v1, v2, a, n, feat_io(d), d->d_live); }
   return 0;
 }
 
@@ -2044,7 +2101,7 @@ template <int WW, int RPL>
 static void launch_track_fast_t(klt_dev* d, const PyrView& v1, const PyrView& v2, const TrackArgs& a, int n) {
   Launch l(d, KID_TRACK_FAST, d->tstream);
   track_fast_kernel<WW, RPL><<<(8 * n + 127) / 128, 128, 0, d->tstream>>>(
-      v1, v2, a, n, d->d_x, d->d_y, d->d_val, feat_out_x(d), feat_out_y(d), feat_out_val(d), d->d_live);
+      v1, v2, a, n, feat_io(d), d->d_live);
 }
 // square odd windows up to 15x15; returns false if this window has no instantiation
 static bool launch_track_fast(klt_dev* d, const PyrView& v1, const PyrView& v2, const TrackArgs& a, int n) {
@@ -2057,13 +2114,12 @@ static bool launch_track_fast(klt_dev* d, const PyrView& v1, const PyrView& v2, 
         static int fpw = getenv("KLT_TRACK_FPW") ? atoi(getenv("KLT_TRACK_FPW")) : 4;
         const int warps_per_block = 4;
         if (fpw == 1)
-          track7_kernel<1><<<(n + warps_per_block - 1) / warps_per_block, 128, 0, d->tstream>>>(v1, v2, a, n, d->d_x, d->d_y, d->d_val, feat_out_x(d), feat_out_y(d), feat_out_val(d), d->d_live);
+          track7_kernel<1><<<(n + warps_per_block - 1) / warps_per_block, 128, 0, d->tstream>>>(v1, v2, a, n, feat_io(d), d->d_live);
         else if (fpw == 4)
           launch_k(track7_kernel<4>, dim3((n + 4 * warps_per_block - 1) / (4 * warps_per_block)), dim3(128), 0, d->tstream,
-                   d->pdl != 0 && !d->overlap, v1, v2, a, n, d->d_x, d->d_y, d->d_val, feat_out_x(d), feat_out_y(d),
-                   feat_out_val(d), d->d_live);
+                   d->pdl != 0 && !d->overlap, v1, v2, a, n, feat_io(d), d->d_live);
         else
-          track7_kernel<2><<<(n + 2 * warps_per_block - 1) / (2 * warps_per_block), 128, 0, d->tstream>>>(v1, v2, a, n, d->d_x, d->d_y, d->d_val, feat_out_x(d), feat_out_y(d), feat_out_val(d), d->d_live);
+          track7_kernel<2><<<(n + 2 * warps_per_block - 1) / (2 * warps_per_block), 128, 0, d->tstream>>>(v1, v2, a, n, feat_io(d), d->d_live);
       }
       return true;
     case 9: launch_track_fast_t<9, 2>(d, v1, v2, a, n); return true;

@@ -35,6 +35,9 @@ void klt_fill_build_desc(KLT_TrackingContext tc, int ncols, int nrows,
                          int nlevels_built, int smooth, int exact,
                          klt_dev_build_desc *q);
 
+/* 1 if fl is a pinned block made by KLTCreateFeatureList (record mode of the tracker) */
+int klt_list_is_pinned(const void *p);
+
 /* list <-> SoA staging */
 void klt_list_to_arrays(KLT_FeatureList fl, float *x, float *y, int *v);
 

@@ -106,9 +106,9 @@ static void track_common(KLT_TrackingContext tc, const KLT_PixelType *img1,
   klt_dev *dev;
   klt_dev_build_desc q;
   klt_dev_track_params tp;
-  int slot_prev, slot_cur, n = fl->nFeatures, i;
-  float *x, *y;
-  int *v;
+  int slot_prev, slot_cur, n = fl->nFeatures, i, records;
+  float *x = NULL, *y = NULL;
+  int *v = NULL;
 
   if (KLT_verbose >= 1) {
     fprintf(stderr, "(KLT) Tracking %d features in a %d by %d image...  ",
@@ -132,16 +132,26 @@ static void track_common(KLT_TrackingContext tc, const KLT_PixelType *img1,
   DEVCALL(s, klt_dev_build(dev, slot_cur, img2, on_device, pitch, &q));
   if (timing) t1 = now_us();
 
-  DEVCALL(s, klt_dev_features_staging(dev, n, &x, &y, &v));
-  klt_list_to_arrays(fl, x, y, v);
-  DEVCALL(s, klt_dev_features_commit(dev, n));
+  /* record mode: a list made by KLTCreateFeatureList is pinned and its records are contiguous --
+   * mirror them in one copy and let the tracker write the results straight back into them */
+  records = n > 0 && klt_list_is_pinned(fl) && fl->feature[n - 1] == fl->feature[0] + (n - 1);
+  if (records) {
+    DEVCALL(s, klt_dev_features_commit_records(dev, n, fl->feature[0], sizeof(KLT_FeatureRec)));
+  } else {
+    DEVCALL(s, klt_dev_features_staging(dev, n, &x, &y, &v));
+    klt_list_to_arrays(fl, x, y, v);
+    DEVCALL(s, klt_dev_features_commit(dev, n));
+  }
 
   fill_track_params(tc, s->exact, &tp);
   DEVCALL(s, klt_dev_track_resident(dev, slot_prev, slot_cur, &tp));
   if (timing) t2 = now_us();
   DEVCALL(s, klt_dev_features_fetch(dev, n));
   if (timing) t3 = now_us();
-  for (i = 0; i < n; i++) {
+  /* (record mode: nothing to unpack.  The reference frees a lost feature's affine images here,
+   * trackFeatures.c:1387-1392; this library never allocates them -- the affine check is a
+   * KLTError -- and KLTFreeFeatureList releases whatever a caller attached.) */
+  for (i = 0; !records && i < n; i++) {
     KLT_Feature f = fl->feature[i];
     if (f->val < 0) continue;                 /* lost features are not touched (:1346) */
     f->x = x[i];

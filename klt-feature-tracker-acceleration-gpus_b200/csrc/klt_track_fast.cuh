@@ -45,9 +45,7 @@ __device__ __forceinline__ void sample_row(const float* __restrict__ img, int pi
 // WW: window width (odd, <= 15); RPL: window rows per lane (window height <= 8 * RPL)
 template <int WW, int RPL>
 __global__ void __launch_bounds__(128)
-track_fast_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, const float* __restrict__ fx,
-                  const float* __restrict__ fy, const int* __restrict__ fval,
-                  float* __restrict__ ox, float* __restrict__ oy, int* __restrict__ oval,
+track_fast_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
                   unsigned long long* __restrict__ live_total) {
   const int lane = threadIdx.x & 31;
   const int r8 = lane & 7;                                   // lane within the feature group
@@ -59,9 +57,9 @@ track_fast_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, const float* __res
   bool alive = false;                                        // feature still being tracked
   float xloc = 0.0f, yloc = 0.0f;
   if (f < n) {
-    const int v0 = fval[f];
+    const int v0 = io.val[(size_t)f * io.istride];
     alive = v0 >= 0;                                         // only features that are not lost (:1346)
-    if (alive) { xloc = fx[f]; yloc = fy[f]; }
+    if (alive) { xloc = io.x[(size_t)f * io.istride]; yloc = io.y[(size_t)f * io.istride]; }
   }
   {
     const unsigned bal = __ballot_sync(0xffffffffu, alive && r8 == 0);
@@ -215,9 +213,10 @@ track_fast_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, const float* __res
   if (alive && r8 == 0) {                                   // record (:1383-1437)
     const bool outside = (xout < (float)a.borderx || xout > (float)(a.ncols - 1 - a.borderx) ||
                           yout < (float)a.bordery || yout > (float)(a.nrows - 1 - a.bordery));
-    if (status == KLT_OOB || outside) { ox[f] = -1.0f; oy[f] = -1.0f; oval[f] = KLT_OOB; }
-    else if (status != KLT_TRACKED) { ox[f] = -1.0f; oy[f] = -1.0f; oval[f] = status; }
-    else { ox[f] = xout; oy[f] = yout; oval[f] = KLT_TRACKED; }
+    const size_t o = (size_t)f * io.ostride;
+    if (status == KLT_OOB || outside) { io.ox[o] = -1.0f; io.oy[o] = -1.0f; io.oval[o] = KLT_OOB; }
+    else if (status != KLT_TRACKED) { io.ox[o] = -1.0f; io.oy[o] = -1.0f; io.oval[o] = status; }
+    else { io.ox[o] = xout; io.oy[o] = yout; io.oval[o] = KLT_TRACKED; }
   }
 }
 
@@ -302,9 +301,7 @@ __device__ __forceinline__ void foot7_prefetch(const PyrView& p1, const PyrView&
 // same work: the kernel is latency bound (issue slots are ~10 % used), so idle lanes are free.
 template <int FPW>
 __global__ void __launch_bounds__(128)
-track7_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, const float* __restrict__ fx,
-              const float* __restrict__ fy, const int* __restrict__ fval,
-              float* __restrict__ ox, float* __restrict__ oy, int* __restrict__ oval,
+track7_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
               unsigned long long* __restrict__ live_total) {
   constexpr int WW = 7, hw = 3, hh = 3;
   const int lane = threadIdx.x & 31;
@@ -319,8 +316,8 @@ track7_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, const float* __restric
   bool alive = false;
   float xloc = 0.0f, yloc = 0.0f;
   if (f < n) {
-    alive = fval[f] >= 0;                                     // only features that are not lost (:1346)
-    if (alive) { xloc = fx[f]; yloc = fy[f]; }
+    alive = io.val[(size_t)f * io.istride] >= 0;              // only features that are not lost (:1346)
+    if (alive) { xloc = io.x[(size_t)f * io.istride]; yloc = io.y[(size_t)f * io.istride]; }
   }
   {
     const unsigned bal = __ballot_sync(0xffffffffu, alive && r8 == 0);
@@ -463,8 +460,9 @@ track7_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, const float* __restric
   if (alive && r8 == 0) {
     const bool outside = (xout < (float)a.borderx || xout > (float)(a.ncols - 1 - a.borderx) ||
                           yout < (float)a.bordery || yout > (float)(a.nrows - 1 - a.bordery));
-    if (status == KLT_OOB || outside) { ox[f] = -1.0f; oy[f] = -1.0f; oval[f] = KLT_OOB; }
-    else if (status != KLT_TRACKED) { ox[f] = -1.0f; oy[f] = -1.0f; oval[f] = status; }
-    else { ox[f] = xout; oy[f] = yout; oval[f] = KLT_TRACKED; }
+    const size_t o = (size_t)f * io.ostride;
+    if (status == KLT_OOB || outside) { io.ox[o] = -1.0f; io.oy[o] = -1.0f; io.oval[o] = KLT_OOB; }
+    else if (status != KLT_TRACKED) { io.ox[o] = -1.0f; io.oy[o] = -1.0f; io.oval[o] = status; }
+    else { io.ox[o] = xout; io.oy[o] = yout; io.oval[o] = KLT_TRACKED; }
   }
 }

@@ -70,6 +70,9 @@ DEV_API = {
                                            C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.POINTER(C.c_int))]),
     "klt_dev_features_commit": (C.c_int, [C.c_void_p, C.c_int]),
     "klt_dev_features_fetch": (C.c_int, [C.c_void_p, C.c_int]),
+    "klt_dev_features_commit_records": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "klt_dev_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "klt_dev_host_free": (None, [C.c_void_p]),
     "klt_dev_select": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(SelectParams), C.c_int, _f32p, _f32p, _i32p]),
     "klt_dev_read_level": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _f32p]),
     "klt_dev_level_dims": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

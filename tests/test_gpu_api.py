@@ -226,3 +226,31 @@ def test_track_7x7_generic_fast_kernel(L, capi, oracle, oracle_mod, provided):
     """fma mode without the specialised kernels: tiled image kernels + track_fast_kernel<7,1>"""
     rep = _teacher_forced(L, capi, oracle, oracle_mod, provided[:5], 150, 0, no_fused=1)
     assert rep[-1][3] > 80
+
+
+def test_record_mode_equals_staging_mode(L, capi, provided, monkeypatch):
+    """KLTCreateFeatureList pins its block when a device is present; KLTTrackFeatures then mirrors the
+    records in one copy and the tracker writes x | y | val straight back into them.  A list in
+    ordinary memory (KLT_B200_PINNED_LISTS=0) takes the pack / staging / unpack path.  Both must give
+    the same features bit for bit, including the untouched lost ones."""
+    import ctypes as C
+    res = []
+    for pinned in ("1", "0"):
+        monkeypatch.setenv("KLT_B200_PINNED_LISTS", pinned)
+        tc = L.KLTCreateTrackingContext()
+        tc.contents.sequentialMode = 1
+        fl = L.KLTCreateFeatureList(200)
+        L.select(tc, provided[0], fl)
+        x, y, v = capi.featurelist_to_arrays(fl)
+        v[::7] = -3                                   # some features already lost: must stay as they are
+        x[::7] = -1.0
+        y[::7] = -1.0
+        capi.arrays_to_featurelist(fl, x, y, v)
+        for k in range(1, 4):
+            L.track(tc, provided[k - 1], provided[k], fl)
+        res.append(capi.featurelist_to_arrays(fl))
+        L.KLTFreeFeatureList(fl)
+        L.KLTFreeTrackingContext(tc)
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a, b)
+    assert (res[0][2][::7] == -3).all() and (res[0][0][::7] == -1.0).all()
