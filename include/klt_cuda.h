@@ -180,6 +180,12 @@ void klt_dev_set_band_rows(klt_dev *d, int rows);
  * or env KLT_B200_MEGA=1; the default is the per-level fused kernels, which measure faster. */
 int klt_dev_last_build_mega(const klt_dev *d);
 void klt_dev_disable_mega(klt_dev *d, int on);
+/* level 0 on the TMA tile kernel l0_fused_kernel (default) or, with klt_dev_disable_stream(d, 0) /
+ * env KLT_B200_L0_STREAM=1, on l0_stream_kernel (warp-synchronous column streaming: no shared
+ * memory, no CTA barrier).  Same bits either way; the tile kernel measures faster.
+ * klt_dev_last_build_stream: which one the last build used. */
+void klt_dev_disable_stream(klt_dev *d, int on);
+int klt_dev_last_build_stream(const klt_dev *d);
 /* first_level > 0 (env KLT_B200_MEGA_TAIL; default 0 = off, it measures slower): levels >=
  * first_level of a pyramid with more than first_level + 1 levels are built by ONE
  * pyramid_mega_kernel launch in tail mode instead of one launch each

@@ -69,6 +69,7 @@ static constexpr int NT = 256;   // threads per CTA of every tile kernel
 
 #include "klt_fused.cuh"
 #include "klt_mega.cuh"
+#include "klt_stream.cuh"
 
 // ---------------------------------------------------------------------------
 // generic kernels: any radius, any subsampling.  One thread per output sample.
@@ -782,12 +783,12 @@ track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
 // kernel classes, for launch accounting and per-kernel event timing
 enum KernelId {
   KID_SMOOTH_U8 = 0, KID_GRAD, KID_PYRDOWN, KID_TRACK, KID_MINEIG, KID_SORT, KID_STAMP,
-  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_L0_FUSED, KID_LEVEL_FUSED, KID_TRACK_FAST, KID_TRACK7, KID_MEGA, KID_COPY_H2D, KID_COPY_D2H, KID_COUNT
+  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_L0_FUSED, KID_LEVEL_FUSED, KID_TRACK_FAST, KID_TRACK7, KID_MEGA, KID_L0_STREAM, KID_COPY_H2D, KID_COPY_D2H, KID_COUNT
 };
 static const char* const kKernelNames[KID_COUNT] = {
   "smooth_u8_tile", "grad_tile", "pyrdown_tile", "track_kernel", "mineig_kernel",
   "cub_radix_sort", "stamp_existing_kernel", "enforce_mindist_kernel",
-  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel", "l0_fused_kernel", "level_fused_kernel", "track_fast_kernel", "track7_kernel", "pyramid_mega_kernel",
+  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel", "l0_fused_kernel", "level_fused_kernel", "track_fast_kernel", "track7_kernel", "pyramid_mega_kernel", "l0_stream_kernel",
   "copy_h2d", "copy_d2h"          // not kernels: timed in profiling mode, never counted as launches
 };
 static constexpr int PROF_POOL = 2048;     // event pairs in flight before folding
@@ -831,6 +832,7 @@ struct klt_dev {
   // pyramid_mega_kernel: cached schedule + dependency counters (klt_mega.cuh)
   int no_mega, last_mega, mega_tail_from;
   int pdl;                     // programmatic dependent launch along the per-frame kernel chain
+  int no_stream, stream_hs, last_stream;    // l0_stream_kernel off / output rows per segment
   MegaSeg* d_segs; int mega_nseg, mega_nitems, mega_key[8];
   unsigned* d_done; int mega_done_off[MEGA_MAX_LEVELS + 1];
   unsigned mega_epoch[MEGA_MAX_LEVELS];
@@ -971,6 +973,8 @@ extern "C" int klt_dev_last_build_fused(const klt_dev* d) { return d->last_fused
 extern "C" int klt_dev_last_build_bands(const klt_dev* d) { return d->last_bands; }
 extern "C" int klt_dev_last_build_mega(const klt_dev* d) { return d->last_mega; }
 extern "C" void klt_dev_disable_mega(klt_dev* d, int on) { d->no_mega = on; }
+extern "C" void klt_dev_disable_stream(klt_dev* d, int on) { d->no_stream = on; }
+extern "C" int klt_dev_last_build_stream(const klt_dev* d) { return d->last_stream; }
 extern "C" void klt_dev_set_mega_tail(klt_dev* d, int first_level) { d->mega_tail_from = first_level; }
 extern "C" void klt_dev_set_band_rows(klt_dev* d, int rows) { d->band_rows = rows; }
 
@@ -1014,6 +1018,11 @@ extern "C" int klt_dev_create(int device, klt_dev** out) {
   // slower than the per-level kernels on B200 (4K: 87 us vs 69 us resident)
   c->no_mega = getenv("KLT_B200_MEGA") && atoi(getenv("KLT_B200_MEGA")) ? 0 : 1;
   c->pdl = getenv("KLT_B200_PDL") ? atoi(getenv("KLT_B200_PDL")) : 1;
+  // the streaming level-0 kernel (klt_stream.cuh) is opt-in: bit-identical, but 32.7 us vs 28.6 us for
+  // the tile kernel on a 4K frame (FMA pipe 44 % busy at 2 CTAs / SM of 230 registers)
+  c->no_stream = getenv("KLT_B200_L0_STREAM") && atoi(getenv("KLT_B200_L0_STREAM")) ? 0 : 1;
+  c->stream_hs = getenv("KLT_B200_STREAM_HS") ? atoi(getenv("KLT_B200_STREAM_HS")) : 67;
+  if (c->stream_hs < 4) c->stream_hs = 4;
   c->mega_tail_from = getenv("KLT_B200_MEGA_TAIL") ? atoi(getenv("KLT_B200_MEGA_TAIL")) : 0;   // opt-in too (4K: 30 us vs 21 us for levels 2+3)
   if (e == cudaSuccess) e = cudaMalloc(&c->d_tile_ctr, 16 * sizeof(unsigned));
   if (e == cudaSuccess) e = cudaMemsetAsync(c->d_tile_ctr, 0, 16 * sizeof(unsigned), c->stream);
@@ -1254,6 +1263,8 @@ static bool fused_grad_taps_ok(const TapsR& tg, const TapsR& td) {
 // behind its upload (klt_dev_build with a host frame) or in one go (jr0 = 0, jr1 = tiles_y).
 enum LevelShape { SHAPE_NONE = 0, SHAPE_2_5_64_32, SHAPE_2_5_64_16, SHAPE_2_5_32_16, SHAPE_4_10_32_16 };
 struct FusedPlan {
+  bool l0_stream;                               // level 0 runs on l0_stream_kernel (no tensor map; TY[0] = rows per segment)
+  const unsigned char* src; int spitch;
   bool l0_ok;                                   // level 0 runs on l0_fused_kernel
   int shape[KLT_DEV_MAX_LEVELS];                // LevelShape of level l >= 1 (SHAPE_NONE: not fused)
   CUtensorMap map[KLT_DEV_MAX_LEVELS];          // source of level l (u8 frame for l = 0, L_{l-1} else)
@@ -1281,10 +1292,18 @@ static bool level_map(CUtensorMap* m, const Level& a) {
 // which levels of this build can run on the fused kernels, and their tensor maps
 static void fused_plan(klt_dev* d, const PyrSet& S, const unsigned char* src, int spitch,
                        const klt_dev_build_desc* q, const TapsR& ts, const TapsR& tp, const TapsR& tg,
-                       const TapsR& td, FusedPlan* P, int force_shape) {
+                       const TapsR& td, FusedPlan* P, int force_shape, bool allow_stream = true) {
   memset(P, 0, sizeof(*P));
   if (d->force_generic || d->no_fused || !fused_grad_taps_ok(tg, td)) return;
   const int W = q->ncols, H = q->nrows;
+  P->src = src; P->spitch = spitch;
+  if (allow_stream && !d->no_stream && q->smooth && ts.w == 2 * StreamGeo::RS + 1 && ((uintptr_t)src & 3) == 0 &&
+      (spitch & 3) == 0 && W >= 16 && H >= 8) {
+    P->l0_stream = true; P->l0_ok = true;
+    P->TX[0] = StreamGeo::OWN; P->TY[0] = d->stream_hs;
+    P->tiles_x[0] = (W + StreamGeo::OWN - 1) / StreamGeo::OWN;
+    P->tiles_y[0] = (H + d->stream_hs - 1) / d->stream_hs;
+  } else
   if (q->smooth && ts.w == 2 * L0Geo::RS + 1 &&
       make_tensor_map(&P->map[0], src, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, W, H, (size_t)spitch, L0Geo::U8_W,
                       L0Geo::U8_H)) {
@@ -1317,6 +1336,16 @@ template <bool EXACT>
 static int l0_fused_launch(klt_dev* d, const FusedPlan& P, int W, int H, const TapsR& ts, const TapsR& tg,
                            const TapsR& td, const Level& lv, int jr0, int jr1) {
   if (jr1 <= jr0) return 0;
+  if (P.l0_stream) {                             // one warp per (strip, segment), 4 warps per CTA
+    const int nstrips = P.tiles_x[0];
+    const int task0 = jr0 * nstrips, task1 = jr1 * nstrips;
+    const int grid = (task1 - task0 + 3) / 4;
+    Launch l(d, KID_L0_STREAM);
+    CU(launch_k(l0_stream_kernel<EXACT>, dim3(grid), dim3(128), 0, d->stream, d->pdl != 0, P.src, P.spitch, W, H,
+                nstrips, P.TY[0], task0, task1, to_fused(ts), to_fused(tg), to_fused(td), lv.img, lv.gx, lv.gy,
+                lv.pitch));
+    return 0;
+  }
   static bool attr_set[2] = {false, false};
   if (!attr_set[EXACT]) {
     CU(cudaFuncSetAttribute(l0_fused_kernel<EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L0Geo::SMEM));
@@ -1715,9 +1744,10 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
   d->last_fused = 0;
   d->last_bands = 0;
   d->last_mega = 0;
+  d->last_stream = 0;
   // one launch for the whole pyramid when every level qualifies (klt_mega.cuh)
   if (!d->no_mega && nb <= MEGA_MAX_LEVELS && (nb == 1 || mega_shape_for(q->subsampling, tp.w / 2) != SHAPE_NONE)) {
-    fused_plan(d, S, src, spitch, q, ts, tp, tg, td, &P, nb > 1 ? mega_shape_for(q->subsampling, tp.w / 2) : SHAPE_NONE);
+    fused_plan(d, S, src, spitch, q, ts, tp, tg, td, &P, nb > 1 ? mega_shape_for(q->subsampling, tp.w / 2) : SHAPE_NONE, false);
     bool ok = P.l0_ok;
     for (int l = 1; l < nb; ++l) ok = ok && P.shape[l] != SHAPE_NONE;
     if (ok) {
@@ -1742,7 +1772,7 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
     FusedPlan PT;
     if (d->mega_tail_from > 0 && nb > d->mega_tail_from + 1 && nb <= MEGA_MAX_LEVELS &&
         mega_shape_for(q->subsampling, tp.w / 2) != SHAPE_NONE) {
-      fused_plan(d, S, src, spitch, q, ts, tp, tg, td, &PT, mega_shape_for(q->subsampling, tp.w / 2));
+      fused_plan(d, S, src, spitch, q, ts, tp, tg, td, &PT, mega_shape_for(q->subsampling, tp.w / 2), false);
       bool ok = true;
       for (int l = d->mega_tail_from; l < nb; ++l) ok = ok && PT.shape[l] != SHAPE_NONE;
       if (ok) nl = d->mega_tail_from;
@@ -1796,6 +1826,7 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
       if (rows_done[l] != P.tiles_y[l]) return fail(d, "banded build left level %d incomplete", l);
     d->last_fused = nb;
     d->last_path = 1;
+    d->last_stream = P.l0_stream ? 1 : 0;
     return 0;
   }
 
@@ -1810,6 +1841,7 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
   if (P.l0_ok) {
     if (l0_fused_launch<EXACT>(d, P, W, H, ts, tg, td, S.lv[0], 0, P.tiles_y[0])) return 1;
     grad_from = 1;
+    d->last_stream = P.l0_stream ? 1 : 0;
   }
   d->last_fused = grad_from;
   if (grad_from == 1) {

@@ -14,7 +14,7 @@ import numpy as np
 from . import capi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libklt_b200.so")
+LIB_PATH = os.environ.get("KLT_B200_LIB") or os.path.join(HERE, "lib", "libklt_b200.so")   # (env: A/B builds)
 MAX_TAPS = 71
 
 
@@ -90,6 +90,8 @@ DEV_API = {
     "klt_dev_last_build_mega": (C.c_int, [C.c_void_p]),
     "klt_dev_disable_mega": (None, [C.c_void_p, C.c_int]),
     "klt_dev_set_mega_tail": (None, [C.c_void_p, C.c_int]),
+    "klt_dev_disable_stream": (None, [C.c_void_p, C.c_int]),
+    "klt_dev_last_build_stream": (C.c_int, [C.c_void_p]),
     "klt_dev_timer_start": (C.c_int, [C.c_void_p]),
     "klt_dev_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "klt_dev_profile_begin": (C.c_int, [C.c_void_p]),

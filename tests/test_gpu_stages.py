@@ -265,3 +265,36 @@ def test_mega_repeated_frames_and_level_counts(L, oracle):
             for l in range(nb):
                 assert np.array_equal(L.dev_level(dev, it % 3, which, l), want.level(which, l)), (it, which, l)
     L.KLTFreeTrackingContext(tc)
+
+
+# ---- streaming level-0 kernel (opt-in) == tile kernel, bit for bit ---------------------------------
+@pytest.mark.parametrize("exact", [1, 0])
+@pytest.mark.parametrize("band_rows", [0, 128])
+@pytest.mark.parametrize("shape", [(240, 320), (243, 321), (37, 1000), (600, 33), (130, 257), (64, 64), (700, 900),
+                                   (1080, 1920), (67, 112), (68, 113), (8, 16)])
+def test_stream_level0_equals_tile_kernel(L, oracle, shape, band_rows, exact):
+    """l0_stream_kernel (one warp per 128-column strip marching down the rows, rings in registers)
+    applies the taps in the same order as l0_fused_kernel: identical bits in both arithmetic
+    modes, for any strip / segment / band partition; exact mode also equals the oracle."""
+    h, w = shape
+    img = synth_image(w, h, seed=3 * h + w)
+    tc = L.KLTCreateTrackingContext()
+    tc.contents.nPyramidLevels, tc.contents.subsampling = 2, 2
+    L.KLTUpdateTCBorder(tc)
+    dev = L.KLTB200Device(tc)
+    L.klt_dev_set_band_rows(dev, band_rows)
+    q = L.build_desc(tc, w, h, exact=exact)
+    got = []
+    for stream in (1, 0):
+        L.klt_dev_disable_stream(dev, 1 - stream)
+        L.dev_build(dev, stream, img, q)
+        assert L.klt_dev_last_build_stream(dev) == stream
+        got.append(device_pyramids(L, dev, stream, 2))
+    for which in range(3):
+        for l in range(2):
+            assert np.array_equal(got[0][which][l], got[1][which][l]), (which, l)
+    if exact:
+        want = oracle.build_pyramids(img, params_from_tc(oracle, tc))
+        for which in range(3):
+            assert np.array_equal(got[0][which][0], want.level(which, 0))
+    L.KLTFreeTrackingContext(tc)
