@@ -148,6 +148,8 @@ def run_b200(args, rank, local_rank, world):
     L.KLTSetVerbosity(0)
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL's version banner / debug lines go to stdout by default: keep stdout for the JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():

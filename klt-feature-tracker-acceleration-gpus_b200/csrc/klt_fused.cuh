@@ -365,7 +365,11 @@ l0_fused_kernel(const __grid_constant__ CUtensorMap map, int W, int H, int tiles
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + G::OFF_BAR);
   volatile int* s_next = reinterpret_cast<volatile int*>(smem_raw + G::OFF_BAR + 8);
   const int tid = threadIdx.x;
-  if (tid == 0) mbar_init(bar, 1);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    // descriptor fetch overlaps the predecessor's tail (we may be resident before it has finished)
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(&map)) : "memory");
+  }
   pdl_wait();                         // the u8 frame / the pyramid slot we overwrite may still be in use
   if (tid == 0) {
     const int t = tile0 + (int)(atomicAdd(counter, 1u) - base);
@@ -557,7 +561,10 @@ level_fused_kernel(const __grid_constant__ CUtensorMap map, int Wsrc, int Hsrc, 
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + G::OFF_BAR);
   volatile int* s_next = reinterpret_cast<volatile int*>(smem_raw + G::OFF_BAR + 8);
   const int tid = threadIdx.x;
-  if (tid == 0) mbar_init(bar, 1);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(&map)) : "memory");
+  }
   pdl_wait();                         // the source level is written by the previous kernel
   if (tid == 0) {
     const int t = tile0 + (int)(atomicAdd(counter, 1u) - base);
