@@ -69,6 +69,8 @@ typedef struct {
   float max_residue;
   int   borderx, bordery;
   int   exact;
+  int   lighting_insensitive;  /* tc->lighting_insensitive: gain / bias normalised windows
+                                  (reference src/V1/trackFeatures.c:125-220, :433-437, :466-468) */
 } klt_dev_track_params;
 
 /* replaces the scalar arguments of _KLTSelectGoodFeatures /

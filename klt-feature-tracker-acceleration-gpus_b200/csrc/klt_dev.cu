@@ -532,6 +532,7 @@ struct TrackArgs {
   float min_determinant, min_displacement, max_residue;
   int   borderx, bordery;
   int   ncols, nrows;
+  int   lighting;            // tc->lighting_insensitive: gain / bias normalised windows (track_kernel only)
   int   prefetch;            // track7: L2 prefetch of the finer levels' footprints at kernel start
 };
 
@@ -589,6 +590,49 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// Gain / bias of the lighting-insensitive windows (trackFeatures.c:132-167, :178-220) from the
+// window samples g1 (frame 1) and g2 (frame 2):
+//   alpha  = sqrt(mean(g1^2) / mean(g2^2)),  belta = mean(g1) - alpha * mean(g2)   (intensity difference)
+//   alphag = sqrt(mean(g1) / mean(g2))                                             (gradient sum: the
+//            reference accumulates g, not g*g, in its "sum*_squared" variables, :202 -- kept as it is)
+// EXACT: the four sums run sequentially in raster order, one per lane, over the shared arrays.
+struct LiGain { float alpha, belta, alphag; };
+template <bool EXACT, int PPL>
+__device__ __forceinline__ LiGain li_gain(const float (&g1)[PPL], const float (&g2)[PPL], int lane, int npix,
+                                          float* sa, float* sb) {
+  float s1 = 0.0f, s2 = 0.0f, q1 = 0.0f, q2 = 0.0f;
+  if (EXACT) {
+#pragma unroll
+    for (int k = 0; k < PPL; ++k) {
+      const int p = lane + 32 * k;
+      if (p < npix) { sa[p] = g1[k]; sb[p] = g2[k]; }
+    }
+    __syncwarp();
+    float acc = 0.0f;
+    if (lane < 4) {
+      const float* A = (lane & 1) ? sb : sa;
+      if (lane < 2) { for (int p = 0; p < npix; ++p) acc = __fadd_rn(acc, A[p]); }
+      else          { for (int p = 0; p < npix; ++p) acc = __fadd_rn(acc, __fmul_rn(A[p], A[p])); }
+    }
+    s1 = __shfl_sync(0xffffffffu, acc, 0); s2 = __shfl_sync(0xffffffffu, acc, 1);
+    q1 = __shfl_sync(0xffffffffu, acc, 2); q2 = __shfl_sync(0xffffffffu, acc, 3);
+    __syncwarp();
+  } else {
+#pragma unroll
+    for (int k = 0; k < PPL; ++k) {
+      if (lane + 32 * k < npix) { s1 += g1[k]; s2 += g2[k]; q1 = fmaf(g1[k], g1[k], q1); q2 = fmaf(g2[k], g2[k], q2); }
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2); q1 = warp_sum(q1); q2 = warp_sum(q2);
+  }
+  const float n = (float)npix;
+  LiGain g;
+  g.alpha = (float)sqrt((double)__fdiv_rn(__fdiv_rn(q1, n), __fdiv_rn(q2, n)));
+  const float m1 = __fdiv_rn(s1, n), m2 = __fdiv_rn(s2, n);
+  g.belta = __fsub_rn(m1, __fmul_rn(g.alpha, m2));
+  g.alphag = (float)sqrt((double)__fdiv_rn(m1, m2));
+  return g;
 }
 
 // PPL = window pixels per lane (ceil(ww*wh / 32)); the frame-1 samples of the
@@ -661,15 +705,38 @@ track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
         have_template = true;
       }
       float gxx = 0.0f, gxy = 0.0f, gyy = 0.0f, ex = 0.0f, ey = 0.0f;
+      float s_i2[PPL], s_gx2[PPL], s_gy2[PPL];      // frame-2 samples (lighting-insensitive mode)
+      LiGain lg;
+      lg.alpha = 1.0f; lg.belta = 0.0f; lg.alphag = 1.0f;
+      if (a.lighting) {
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+          s_i2[k] = 0.0f; s_gx2[k] = 0.0f; s_gy2[k] = 0.0f;
+          if (lane + 32 * k < npix) {
+            const Bilin b = EXACT ? bilin_setup<EXACT>(__fadd_rn(x2, offi[k]), __fadd_rn(y2, offj[k]), pitch)
+                                  : bilin_setup<EXACT>(x2 + offi[k], y2 + offj[k], pitch);
+            s_i2[k] = bilin_fetch<EXACT>(i2, pitch, b);
+            s_gx2[k] = bilin_fetch<EXACT>(gx2, pitch, b);
+            s_gy2[k] = bilin_fetch<EXACT>(gy2, pitch, b);
+          }
+        }
+        lg = li_gain<EXACT, PPL>(t_i, s_i2, lane, npix, swx, swy);
+      }
       if (EXACT) {
 #pragma unroll
         for (int k = 0; k < PPL; ++k) {
           const int p = lane + 32 * k;
           if (p < npix) {
-            const Bilin b = bilin_setup<EXACT>(__fadd_rn(x2, offi[k]), __fadd_rn(y2, offj[k]), pitch);
-            swd[p] = __fsub_rn(t_i[k], bilin_fetch<EXACT>(i2, pitch, b));
-            swx[p] = __fadd_rn(t_gx[k], bilin_fetch<EXACT>(gx2, pitch, b));
-            swy[p] = __fadd_rn(t_gy[k], bilin_fetch<EXACT>(gy2, pitch, b));
+            if (a.lighting) {          // g1 - g2*alpha - belta;  g1 + g2*alphag   (:165, :213-216)
+              swd[p] = __fsub_rn(__fsub_rn(t_i[k], __fmul_rn(s_i2[k], lg.alpha)), lg.belta);
+              swx[p] = __fadd_rn(t_gx[k], __fmul_rn(s_gx2[k], lg.alphag));
+              swy[p] = __fadd_rn(t_gy[k], __fmul_rn(s_gy2[k], lg.alphag));
+            } else {
+              const Bilin b = bilin_setup<EXACT>(__fadd_rn(x2, offi[k]), __fadd_rn(y2, offj[k]), pitch);
+              swd[p] = __fsub_rn(t_i[k], bilin_fetch<EXACT>(i2, pitch, b));
+              swx[p] = __fadd_rn(t_gx[k], bilin_fetch<EXACT>(gx2, pitch, b));
+              swy[p] = __fadd_rn(t_gy[k], bilin_fetch<EXACT>(gy2, pitch, b));
+            }
           }
         }
         __syncwarp();
@@ -690,10 +757,17 @@ track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
 #pragma unroll
         for (int k = 0; k < PPL; ++k) {
           if (lane + 32 * k < npix) {
-            const Bilin b = bilin_setup<EXACT>(x2 + offi[k], y2 + offj[k], pitch);
-            const float df = t_i[k] - bilin_fetch<EXACT>(i2, pitch, b);
-            const float sx = t_gx[k] + bilin_fetch<EXACT>(gx2, pitch, b);
-            const float sy = t_gy[k] + bilin_fetch<EXACT>(gy2, pitch, b);
+            float df, sx, sy;
+            if (a.lighting) {
+              df = t_i[k] - s_i2[k] * lg.alpha - lg.belta;
+              sx = fmaf(s_gx2[k], lg.alphag, t_gx[k]);
+              sy = fmaf(s_gy2[k], lg.alphag, t_gy[k]);
+            } else {
+              const Bilin b = bilin_setup<EXACT>(x2 + offi[k], y2 + offj[k], pitch);
+              df = t_i[k] - bilin_fetch<EXACT>(i2, pitch, b);
+              sx = t_gx[k] + bilin_fetch<EXACT>(gx2, pitch, b);
+              sy = t_gy[k] + bilin_fetch<EXACT>(gy2, pitch, b);
+            }
             gxx = fmaf(sx, sx, gxx); gxy = fmaf(sx, sy, gxy); gyy = fmaf(sy, sy, gyy);
             ex = fmaf(df, sx, ex); ey = fmaf(df, sy, ey);
           }
@@ -721,13 +795,32 @@ track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
     // :464-474 residue of the final alignment
     if (status == KLT_TRACKED) {
       float sum = 0.0f;
+      float r_i2[PPL];
+      LiGain lg;
+      lg.alpha = 1.0f; lg.belta = 0.0f; lg.alphag = 1.0f;
+      if (a.lighting) {                 // the residue uses the normalised difference too (:466-468)
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+          r_i2[k] = 0.0f;
+          if (lane + 32 * k < npix) {
+            const Bilin b = EXACT ? bilin_setup<EXACT>(__fadd_rn(x2, offi[k]), __fadd_rn(y2, offj[k]), pitch)
+                                  : bilin_setup<EXACT>(x2 + offi[k], y2 + offj[k], pitch);
+            r_i2[k] = bilin_fetch<EXACT>(i2, pitch, b);
+          }
+        }
+        lg = li_gain<EXACT, PPL>(t_i, r_i2, lane, npix, swx, swy);
+      }
       if (EXACT) {
 #pragma unroll
         for (int k = 0; k < PPL; ++k) {
           const int p = lane + 32 * k;
           if (p < npix) {
-            const Bilin b = bilin_setup<EXACT>(__fadd_rn(x2, offi[k]), __fadd_rn(y2, offj[k]), pitch);
-            swd[p] = fabsf(__fsub_rn(t_i[k], bilin_fetch<EXACT>(i2, pitch, b)));
+            if (a.lighting) {
+              swd[p] = fabsf(__fsub_rn(__fsub_rn(t_i[k], __fmul_rn(r_i2[k], lg.alpha)), lg.belta));
+            } else {
+              const Bilin b = bilin_setup<EXACT>(__fadd_rn(x2, offi[k]), __fadd_rn(y2, offj[k]), pitch);
+              swd[p] = fabsf(__fsub_rn(t_i[k], bilin_fetch<EXACT>(i2, pitch, b)));
+            }
           }
         }
         __syncwarp();
@@ -739,8 +832,12 @@ track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
 #pragma unroll
         for (int k = 0; k < PPL; ++k) {
           if (lane + 32 * k < npix) {
-            const Bilin b = bilin_setup<EXACT>(x2 + offi[k], y2 + offj[k], pitch);
-            sum += fabsf(t_i[k] - bilin_fetch<EXACT>(i2, pitch, b));
+            if (a.lighting) {
+              sum += fabsf(t_i[k] - r_i2[k] * lg.alpha - lg.belta);
+            } else {
+              const Bilin b = bilin_setup<EXACT>(x2 + offi[k], y2 + offj[k], pitch);
+              sum += fabsf(t_i[k] - bilin_fetch<EXACT>(i2, pitch, b));
+            }
           }
         }
         sum = warp_sum(sum);
@@ -2192,6 +2289,7 @@ extern "C" int klt_dev_track_resident(klt_dev* d, int slot_prev, int slot_cur,
   a.min_determinant = p->min_determinant; a.min_displacement = p->min_displacement;
   a.max_residue = p->max_residue; a.borderx = p->borderx; a.bordery = p->bordery;
   a.ncols = d->W; a.nrows = d->H;
+  a.lighting = p->lighting_insensitive ? 1 : 0;
   { static int pf = getenv("KLT_TRACK_PREFETCH") ? atoi(getenv("KLT_TRACK_PREFETCH")) : 0; a.prefetch = pf; }
   const int npix = a.ww * a.wh;
   const int ppl = (npix + 31) / 32;
@@ -2202,7 +2300,7 @@ extern "C" int klt_dev_track_resident(klt_dev* d, int slot_prev, int slot_cur,
     else if (ppl <= 8) rc = launch_track<true, 8>(d, v1, v2, a, n);
     else if (ppl <= 16) rc = launch_track<true, 16>(d, v1, v2, a, n);
     else return fail(d, "tracking window %d x %d too large (max 512 pixels)", a.ww, a.wh);
-  } else if (!d->force_generic && a.ww == a.wh && a.ww <= 15 && launch_track_fast(d, v1, v2, a, n)) {
+  } else if (!d->force_generic && !a.lighting && a.ww == a.wh && a.ww <= 15 && launch_track_fast(d, v1, v2, a, n)) {
     rc = 0;
   } else {
     if (ppl <= 2) rc = launch_track<false, 2>(d, v1, v2, a, n);

@@ -5,9 +5,9 @@
  * pyramids in sequentialMode (:1285-1294) or building them from img1
  * (:1295-1308), building the pyramids of img2 (:1311-1321), the feature loop
  * (:1343-1437, one warp per feature in csrc/klt_dev.cu), and the pyramid
- * hand-over (:1503-1519).  The lighting-insensitive and affine-consistency
- * variants (:125-220, :506-1224) are not on the accelerated path: asking for
- * them is a KLTError rather than a silent CPU fallback.
+ * hand-over (:1503-1519).  tc->lighting_insensitive (:125-220) runs on the generic
+ * warp-per-feature kernel.  The affine-consistency check (:506-1224) is not on the
+ * accelerated path: asking for it is a KLTError rather than a silent CPU fallback.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -46,13 +46,11 @@ static void fill_track_params(KLT_TrackingContext tc, int exact, klt_dev_track_p
   p->borderx = tc->borderx;
   p->bordery = tc->bordery;
   p->exact = exact;
+  p->lighting_insensitive = tc->lighting_insensitive ? 1 : 0;
 }
 
 static void check_supported(KLT_TrackingContext tc)
 {
-  if (tc->lighting_insensitive)
-    KLTError("(KLTTrackFeatures) lighting_insensitive tracking is not implemented "
-             "on the GPU path (and there is no CPU path)");
   if (tc->affineConsistencyCheck >= 0)
     KLTError("(KLTTrackFeatures) affineConsistencyCheck >= 0 is not implemented "
              "on the GPU path (and there is no CPU path)");

@@ -35,7 +35,7 @@ class TrackParams(C.Structure):       # klt_dev_track_params
                 ("step_factor", C.c_float), ("max_iterations", C.c_int),
                 ("min_determinant", C.c_float), ("min_displacement", C.c_float),
                 ("max_residue", C.c_float), ("borderx", C.c_int), ("bordery", C.c_int),
-                ("exact", C.c_int)]
+                ("exact", C.c_int), ("lighting_insensitive", C.c_int)]
 
 
 class SelectParams(C.Structure):      # klt_dev_select_params
@@ -177,7 +177,7 @@ class B200Library(capi.KLTLibrary):
         t = tc.contents
         return TrackParams(t.window_width, t.window_height, t.step_factor, t.max_iterations,
                            t.min_determinant, t.min_displacement, t.max_residue,
-                           t.borderx, t.bordery, exact)
+                           t.borderx, t.bordery, exact, t.lighting_insensitive)
 
     def select_params(self, tc, overwrite_all=1) -> SelectParams:
         t = tc.contents

@@ -271,6 +271,7 @@ void klto_default_params(klto_params *p)
   p->nSkippedPixels = 0;
   p->nPyramidLevels = 0;
   p->subsampling = 0;
+  p->lighting_insensitive = 0;
   klto_change_pyramid(p, 15);
   klto_update_border(p);
 }
@@ -354,13 +355,92 @@ static int window_oob(float x, float y, int hw, int hh, int nc, int nr)
           y - hh < 0.0f || nr - (y + hh) < one_plus_eps);
 }
 
-/* reference trackFeatures.c:381-486 (_trackFeature), translation model only
- * (lighting_insensitive == FALSE, the default). */
+/* reference trackFeatures.c:132-167 (_computeIntensityDifferenceLightingInsensitive):
+ * gain alpha = sqrt(mean(g1^2) / mean(g2^2)), bias belta = mean(g1) - alpha * mean(g2) over the
+ * window, imgdiff = g1 - g2 * alpha - belta.  All sums are sequential float sums in raster order;
+ * the sqrt is the double sqrt of a float quotient. */
+static void intensity_difference_li(const float *img1, const float *img2, int nc, float x1, float y1,
+                                    float x2, float y2, int ww, int wh, float *diff)
+{
+  const int hw = ww / 2, hh = wh / 2;
+  float g1, g2, sum1_squared = 0, sum2_squared = 0, sum1 = 0, sum2 = 0;
+  float mean1, mean2, alpha, belta;
+  int i, j;
+  for (j = -hh; j <= hh; j++)
+    for (i = -hw; i <= hw; i++) {
+      g1 = bilinear(x1 + i, y1 + j, img1, nc);
+      g2 = bilinear(x2 + i, y2 + j, img2, nc);
+      sum1 += g1; sum2 += g2;
+      sum1_squared += g1 * g1;
+      sum2_squared += g2 * g2;
+    }
+  mean1 = sum1_squared / (ww * wh);
+  mean2 = sum2_squared / (ww * wh);
+  alpha = (float)sqrt(mean1 / mean2);
+  mean1 = sum1 / (ww * wh);
+  mean2 = sum2 / (ww * wh);
+  belta = mean1 - alpha * mean2;
+  for (j = -hh; j <= hh; j++)
+    for (i = -hw; i <= hw; i++) {
+      g1 = bilinear(x1 + i, y1 + j, img1, nc);
+      g2 = bilinear(x2 + i, y2 + j, img2, nc);
+      *diff++ = g1 - g2 * alpha - belta;
+    }
+}
+
+/* reference trackFeatures.c:178-220 (_computeGradientSumLightingInsensitive).  Its gain is the
+ * square root of the ratio of the window MEANS (the variables are called sum*_squared but
+ * accumulate g, not g*g, :202) -- restated as it is. */
+static void gradient_sum_li(const float *gx1, const float *gy1, const float *gx2, const float *gy2,
+                            const float *img1, const float *img2, int nc, float x1, float y1,
+                            float x2, float y2, int ww, int wh, float *wx, float *wy)
+{
+  const int hw = ww / 2, hh = wh / 2;
+  float g1, g2, sum1_squared = 0, sum2_squared = 0, mean1, mean2, alpha;
+  int i, j;
+  for (j = -hh; j <= hh; j++)
+    for (i = -hw; i <= hw; i++) {
+      g1 = bilinear(x1 + i, y1 + j, img1, nc);
+      g2 = bilinear(x2 + i, y2 + j, img2, nc);
+      sum1_squared += g1; sum2_squared += g2;
+    }
+  mean1 = sum1_squared / (ww * wh);
+  mean2 = sum2_squared / (ww * wh);
+  alpha = (float)sqrt(mean1 / mean2);
+  for (j = -hh; j <= hh; j++)
+    for (i = -hw; i <= hw; i++) {
+      g1 = bilinear(x1 + i, y1 + j, gx1, nc);
+      g2 = bilinear(x2 + i, y2 + j, gx2, nc);
+      *wx++ = g1 + g2 * alpha;
+      g1 = bilinear(x1 + i, y1 + j, gy1, nc);
+      g2 = bilinear(x2 + i, y2 + j, gy2, nc);
+      *wy++ = g1 + g2 * alpha;
+    }
+}
+
+/* reference trackFeatures.c:381-486 (_trackFeature), translation model; lighting != 0 takes the
+ * gain / bias normalised windows (:433-437, :466-468). */
+int klto_track_level_li(float x1, float y1, float *x2, float *y2,
+                        const float *img1, const float *gx1, const float *gy1,
+                        const float *img2, const float *gx2, const float *gy2,
+                        int nc, int nr, int ww, int wh, float step_factor,
+                        int max_iterations, float small, float th, float max_residue, int lighting);
+
 int klto_track_level(float x1, float y1, float *x2, float *y2,
                      const float *img1, const float *gx1, const float *gy1,
                      const float *img2, const float *gx2, const float *gy2,
                      int nc, int nr, int ww, int wh, float step_factor,
                      int max_iterations, float small, float th, float max_residue)
+{
+  return klto_track_level_li(x1, y1, x2, y2, img1, gx1, gy1, img2, gx2, gy2, nc, nr, ww, wh, step_factor,
+                             max_iterations, small, th, max_residue, 0);
+}
+
+int klto_track_level_li(float x1, float y1, float *x2, float *y2,
+                        const float *img1, const float *gx1, const float *gy1,
+                        const float *img2, const float *gx2, const float *gy2,
+                        int nc, int nr, int ww, int wh, float step_factor,
+                        int max_iterations, float small, float th, float max_residue, int lighting)
 {
   const int hw = ww / 2, hh = wh / 2, npix = ww * wh;
   float *diff = (float *)malloc(sizeof(float) * npix);
@@ -377,6 +457,10 @@ int klto_track_level(float x1, float y1, float *x2, float *y2,
     }
     /* :68-87 and :98-123 intensity difference and gradient sum windows */
     k = 0;
+    if (lighting) {
+      intensity_difference_li(img1, img2, nc, x1, y1, *x2, *y2, ww, wh, diff);
+      gradient_sum_li(gx1, gy1, gx2, gy2, img1, img2, nc, x1, y1, *x2, *y2, ww, wh, wx, wy);
+    } else
     for (j = -hh; j <= hh; j++)
       for (i = -hw; i <= hw; i++, k++) {
         float a = bilinear(x1 + i, y1 + j, img1, nc);
@@ -424,6 +508,9 @@ int klto_track_level(float x1, float y1, float *x2, float *y2,
   if (status == KLTO_TRACKED) {
     float sum = 0.0f;
     k = 0;
+    if (lighting)
+      intensity_difference_li(img1, img2, nc, x1, y1, *x2, *y2, ww, wh, diff);
+    else
     for (j = -hh; j <= hh; j++)
       for (i = -hw; i <= hw; i++, k++)
         diff[k] = bilinear(x1 + i, y1 + j, img1, nc) - bilinear(*x2 + i, *y2 + j, img2, nc);
@@ -459,13 +546,13 @@ void klto_track(const klto_pyramids *p1, const klto_pyramids *p2,
     xout = xloc; yout = yloc;
     for (r = L - 1; r >= 0; r--) {
       xloc *= ss; yloc *= ss; xout *= ss; yout *= ss;
-      v = klto_track_level(xloc, yloc, &xout, &yout,
-                           p1->img[r], p1->gx[r], p1->gy[r],
-                           p2->img[r], p2->gx[r], p2->gy[r],
-                           p1->ncols[r], p1->nrows[r],
-                           p->window_width, p->window_height, p->step_factor,
-                           p->max_iterations, p->min_determinant,
-                           p->min_displacement, p->max_residue);
+      v = klto_track_level_li(xloc, yloc, &xout, &yout,
+                              p1->img[r], p1->gx[r], p1->gy[r],
+                              p2->img[r], p2->gx[r], p2->gy[r],
+                              p1->ncols[r], p1->nrows[r],
+                              p->window_width, p->window_height, p->step_factor,
+                              p->max_iterations, p->min_determinant,
+                              p->min_displacement, p->max_residue, p->lighting_insensitive);
       if (v == KLTO_SMALL_DET || v == KLTO_OOB) break;
     }
     if (v == KLTO_OOB ||

@@ -52,6 +52,7 @@ typedef struct {
   int   borderx, bordery;
   int   nPyramidLevels;
   int   subsampling;
+  int   lighting_insensitive;   /* tc->lighting_insensitive (klt.h:50), default FALSE */
 } klto_params;
 
 /* parameter derivation (klt.c:20-44, :288-343, :362-431) */

@@ -29,6 +29,7 @@ class Params(C.Structure):
         ("pyramid_sigma_fact", C.c_float), ("step_factor", C.c_float),
         ("nSkippedPixels", C.c_int), ("borderx", C.c_int), ("bordery", C.c_int),
         ("nPyramidLevels", C.c_int), ("subsampling", C.c_int),
+        ("lighting_insensitive", C.c_int),
     ]
 
 

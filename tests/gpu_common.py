@@ -30,7 +30,7 @@ def params_from_tc(oracle, tc):
     for f in ("mindist", "window_width", "window_height", "smoothBeforeSelecting", "min_eigenvalue",
               "min_determinant", "min_displacement", "max_iterations", "max_residue", "grad_sigma",
               "smooth_sigma_fact", "pyramid_sigma_fact", "step_factor", "nSkippedPixels",
-              "borderx", "bordery", "nPyramidLevels", "subsampling"):
+              "borderx", "bordery", "nPyramidLevels", "subsampling", "lighting_insensitive"):
         setattr(p, f, getattr(t, f))
     return p
 

@@ -254,3 +254,27 @@ def test_record_mode_equals_staging_mode(L, capi, provided, monkeypatch):
     for a, b in zip(res[0], res[1]):
         assert np.array_equal(a, b)
     assert (res[0][2][::7] == -3).all() and (res[0][0][::7] == -1.0).all()
+
+
+@pytest.mark.parametrize("window", [7, 5])
+@pytest.mark.parametrize("exact", [1, 0])
+def test_lighting_insensitive_tracking(L, capi, oracle, oracle_mod, provided, exact, window):
+    """tc->lighting_insensitive = TRUE (reference trackFeatures.c:125-220, :433-437, :466-468) on the
+    GPU: gain / bias normalised windows, with the reference's own gain formula for the gradient sum.
+    Frames get brighter over time so that the normalisation matters; exact mode reproduces the
+    oracle bit for bit, fma mode meets the north_star tolerance."""
+    imgs = [provided[0]]
+    for k in range(1, 5):
+        f = provided[k].astype(np.float32) * (1.0 + 0.08 * k) + 6.0 * k
+        imgs.append(np.clip(f, 0, 255).astype(np.uint8))
+
+    def setup(tc):
+        tc.contents.lighting_insensitive = 1
+        tc.contents.window_width = tc.contents.window_height = window
+    rep = _teacher_forced(L, capi, oracle, oracle_mod, imgs, 150, exact, setup)
+    assert rep[-1][3] > 50
+    # and it is a different computation from the plain tracker on these frames
+    def plain(tc):
+        tc.contents.window_width = tc.contents.window_height = window
+    rep2 = _teacher_forced(L, capi, oracle, oracle_mod, imgs, 150, exact, plain)
+    assert rep != rep2

@@ -196,3 +196,27 @@ def test_quicksort_permutation_matches_reference(oracle, ref):
         oracle.lib.klto_sort_points(c, n, 0)
         order = np.argsort(-pts[:, 2], kind="stable")
         assert np.array_equal(c, pts[order])
+
+
+def test_lighting_insensitive_tracking_bit_exact_vs_reference(oracle, oracle_mod, ref_qsort, provided):
+    """tc->lighting_insensitive = TRUE (trackFeatures.c:125-220): gain / bias normalised windows,
+    including the reference's quirk that the gradient sum's gain is sqrt(mean(g1) / mean(g2)).
+    A brightness ramp is added to the later frames so that the normalisation matters."""
+    imgs = [provided[0]]
+    for k in range(1, 4):
+        f = provided[k].astype(np.float32) * (1.0 + 0.08 * k) + 6.0 * k
+        imgs.append(np.clip(f, 0, 255).astype(np.uint8))
+    want = _ref_flow(ref_qsort, imgs, 150, lighting_insensitive=1)
+    plain = _ref_flow(ref_qsort, imgs, 150)
+    assert any(not np.array_equal(a[0], b[0]) for a, b in zip(want[1:], plain[1:]))   # the flag matters
+    p = oracle.default_params()
+    p.lighting_insensitive = 1
+    x, y, v = oracle.select(imgs[0], p, 150, sort_kind=oracle_mod.SORT_STABLE)
+    prev = oracle.build_pyramids(imgs[0], p)
+    for i in range(1, len(imgs)):
+        cur = oracle.build_pyramids(imgs[i], p)
+        x, y, v = oracle.track(prev, cur, p, x, y, v)
+        assert x.tobytes() == want[i][0].tobytes()
+        assert y.tobytes() == want[i][1].tobytes()
+        assert np.array_equal(v, want[i][2])
+        prev = cur
