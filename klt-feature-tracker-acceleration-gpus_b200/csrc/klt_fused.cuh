@@ -431,7 +431,12 @@ struct LvGeo {
   static_assert((LP / 4) % 2 == 1 && (HP / 4) % 2 == 1 && (SW / 4) % 2 == 1, "odd chunk pitches");
   static constexpr int OFF_SRC = 0;
   static constexpr int OFF_HP = SW * SH * 4;
-  static constexpr int HP_BYTES = SH * LW * 4, HDG_BYTES = 2 * LH * HP * 4;
+  // pitch of the horizontal-pass buffer: 64 B more than a multiple of 128 B, so that the two rows a
+  // quarter warp stores in P1 (4 groups x 16 B each) fall into disjoint bank halves (ncu: the 72-float
+  // pitch cost 88 % extra wavefronts on that store)
+  static constexpr int HPP = ((LW * 4 + 127) / 128) * 32 + (((LW * 4) % 128) <= 64 && ((LW * 4) % 128) != 0 ? -16 : 16);
+  static_assert(HPP >= LW && (HPP * 4) % 128 == 64, "Hp pitch");
+  static constexpr int HP_BYTES = SH * HPP * 4, HDG_BYTES = 2 * LH * HP * 4;
   static constexpr int OFF_L = OFF_HP + (HP_BYTES > HDG_BYTES ? HP_BYTES : HDG_BYTES);
   static constexpr int OFF_HD = OFF_HP;                                // Hd, Hg reuse Hp (dead after P2)
   static constexpr int OFF_HG = OFF_HD + LH * HP * 4;
@@ -463,7 +468,7 @@ __device__ __forceinline__ void lv_p1_item(const float* sSrc, float* sHp, const 
     }
     o[q] = acc;
   }
-  *reinterpret_cast<float4*>(sHp + r * G::LW + 4 * g) = make_float4(o[0], o[1], o[2], o[3]);
+  *reinterpret_cast<float4*>(sHp + r * G::HPP + 4 * g) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 template <bool EXACT, bool BORDER, int SS, int R, int TX, int TY>
@@ -513,10 +518,10 @@ __device__ __forceinline__ void lv_stage_rest(unsigned char* smem, const TapsF& 
       if (it < NPAIR * NMAIN) { pr = it / NMAIN; j = it - pr * NMAIN; }
       else { const int t2 = it - NPAIR * NMAIN; pr = t2 / NTAIL; j = NMAIN + t2 - pr * NTAIL; }
       float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
-      const float* src = sHp + (SS * 2 * pr) * G::LW + 4 * j;
+      const float* src = sHp + (SS * 2 * pr) * G::HPP + 4 * j;
 #pragma unroll
       for (int i = 0; i < NR2; ++i) {
-        const float4 v = lds128(src + i * G::LW);
+        const float4 v = lds128(src + i * G::HPP);
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int m = i - SS * q;
@@ -550,7 +555,7 @@ __device__ __forceinline__ void lv_stage_rest(unsigned char* smem, const TapsF& 
 // W,H: size of the level being produced; Wsrc,Hsrc: size of the level it is made from.
 // Dynamic tile scheduler as in l0_fused_kernel.
 template <int SS, int R, int TX, int TY, bool EXACT>
-__global__ void __launch_bounds__(256, (LvGeo<SS, R, TX, TY>::SMEM <= 56 * 1024) ? 3 : 2)
+__global__ void __launch_bounds__(256, (LvGeo<SS, R, TX, TY>::SMEM <= 58 * 1024) ? 3 : 2)
 level_fused_kernel(const __grid_constant__ CUtensorMap map, int Wsrc, int Hsrc, int W, int H,
                    int tiles_x, int tile0, int ntiles, unsigned* __restrict__ counter, unsigned base,
                    TapsF tp, TapsF tg, TapsF td,
