@@ -119,6 +119,20 @@ int klt_dev_features_upload(klt_dev *d, int n, const float *x, const float *y, c
 int klt_dev_track_resident(klt_dev *d, int slot_prev, int slot_cur,
                            const klt_dev_track_params *p);
 int klt_dev_features_download(klt_dev *d, int n, float *x, float *y, int *val);   /* synchronises */
+/* Arm an early tracker pass for the next klt_dev_build of a HOST frame (features already
+ * committed, slot_prev valid): if the frame goes up in bands and the 7x7 fma tracker applies, its
+ * first pass is launched right behind the first band's pyramid rows -- while the rest of the frame
+ * is still on the bus -- and defers every feature whose footprint would touch a row that does not
+ * exist yet; the following klt_dev_track_resident then only tracks the deferred features.
+ * Results are identical to one pass.  Opt-in (env KLT_B200_EARLY_TRACK=1 or
+ * klt_dev_disable_early_track(d, 0)): measured no gain, the tracker's time is a latency chain and
+ * does not shrink with the number of features. */
+int klt_dev_arm_early_track(klt_dev *d, int slot_prev, const klt_dev_track_params *p);
+void klt_dev_disable_early_track(klt_dev *d, int on);
+/* 7x7 fma tracking runs on track7w_kernel (one warp per feature; default) or, with
+ * klt_dev_disable_track7w(d, 1) / env KLT_B200_TRACK7W=0, on track7_kernel (8 lanes per feature) */
+void klt_dev_disable_track7w(klt_dev *d, int on);
+int klt_dev_last_track_passes(const klt_dev *d);     /* 2 if the last tracking ran in two passes */
 /* zero-copy variant for the C host layer: pack the feature list straight into the
  * context's pinned staging area, commit it (async H2D), and after the work fetch the
  * results back into the same area (D2H + synchronise). */

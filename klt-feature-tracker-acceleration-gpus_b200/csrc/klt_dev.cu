@@ -534,6 +534,13 @@ struct TrackArgs {
   int   ncols, nrows;
   int   lighting;            // tc->lighting_insensitive: gain / bias normalised windows (track_kernel only)
   int   prefetch;            // track7: L2 prefetch of the finer levels' footprints at kernel start
+  // track7 behind a banded frame upload: pass 1 runs when only the first band's pyramid rows exist
+  // (row_limit[l] = complete rows of level l of the NEW frame) and gives up on -- "defers" -- any
+  // feature whose footprint would touch a later row; pass 2, after the last band, tracks exactly
+  // the deferred ones from scratch.  done[f]: 1 once feature f has its final answer.  pass 0: one pass.
+  int   pass;
+  int   row_limit[KLT_DEV_MAX_LEVELS];
+  unsigned char* done;
 };
 
 // Where a tracker kernel reads the features and where it records the results (element strides in
@@ -880,12 +887,12 @@ track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
 // kernel classes, for launch accounting and per-kernel event timing
 enum KernelId {
   KID_SMOOTH_U8 = 0, KID_GRAD, KID_PYRDOWN, KID_TRACK, KID_MINEIG, KID_SORT, KID_STAMP,
-  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_L0_FUSED, KID_LEVEL_FUSED, KID_TRACK_FAST, KID_TRACK7, KID_MEGA, KID_L0_STREAM, KID_COPY_H2D, KID_COPY_D2H, KID_COUNT
+  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_L0_FUSED, KID_LEVEL_FUSED, KID_TRACK_FAST, KID_TRACK7, KID_TRACK7W, KID_MEGA, KID_L0_STREAM, KID_COPY_H2D, KID_COPY_D2H, KID_COUNT
 };
 static const char* const kKernelNames[KID_COUNT] = {
   "smooth_u8_tile", "grad_tile", "pyrdown_tile", "track_kernel", "mineig_kernel",
   "cub_radix_sort", "stamp_existing_kernel", "enforce_mindist_kernel",
-  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel", "l0_fused_kernel", "level_fused_kernel", "track_fast_kernel", "track7_kernel", "pyramid_mega_kernel", "l0_stream_kernel",
+  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel", "l0_fused_kernel", "level_fused_kernel", "track_fast_kernel", "track7_kernel", "track7w_kernel", "pyramid_mega_kernel", "l0_stream_kernel",
   "copy_h2d", "copy_d2h"          // not kernels: timed in profiling mode, never counted as launches
 };
 static constexpr int PROF_POOL = 2048;     // event pairs in flight before folding
@@ -925,7 +932,7 @@ struct klt_dev {
   cudaStream_t cstream;
   cudaEvent_t ev_band[KLT_BAND_EVENTS]; int band_ev_next;
   cudaEvent_t ev_frame_free; int frame_busy;
-  int band_rows, last_bands;
+  int band_rows, last_bands, building_slot;
   // pyramid_mega_kernel: cached schedule + dependency counters (klt_mega.cuh)
   int no_mega, last_mega, mega_tail_from;
   int pdl;                     // programmatic dependent launch along the per-frame kernel chain
@@ -938,6 +945,11 @@ struct klt_dev {
   float *d_x, *d_y; int* d_val; int feat_cap; int feat_n;
   float *h_x, *h_y; int* h_val;   // pinned staging
   int staging_busy;
+  // early tracker pass behind the first uploaded band (klt_dev_arm_early_track)
+  int no_track7w;
+  int early_armed, early_done, early_slot_prev, early_slot_cur, no_early, last_passes;
+  klt_dev_track_params early_p;
+  unsigned char* d_fdone; int fdone_cap;
   int feat_out_host;            // 1: the next tracker writes its results into h_x/h_y/h_val (sync API); 2: record mode
   unsigned char* d_rec; size_t d_rec_cap; void* h_rec; int rec_stride;   // record mode (klt_dev_features_commit_records)
   cudaEvent_t ev_feat; int feat_pending;   // feature upload queued on the copy stream
@@ -1115,6 +1127,10 @@ extern "C" int klt_dev_create(int device, klt_dev** out) {
   // slower than the per-level kernels on B200 (4K: 87 us vs 69 us resident)
   c->no_mega = getenv("KLT_B200_MEGA") && atoi(getenv("KLT_B200_MEGA")) ? 0 : 1;
   c->pdl = getenv("KLT_B200_PDL") ? atoi(getenv("KLT_B200_PDL")) : 1;
+  c->no_track7w = getenv("KLT_B200_TRACK7W") ? !atoi(getenv("KLT_B200_TRACK7W")) : 0;
+  // opt-in: measured no gain (the tracker is a latency chain: a pass over half the features takes
+  // as long as a pass over all of them)
+  c->no_early = getenv("KLT_B200_EARLY_TRACK") && atoi(getenv("KLT_B200_EARLY_TRACK")) ? 0 : 1;
   // the streaming level-0 kernel (klt_stream.cuh) is opt-in: bit-identical, but 32.7 us vs 28.6 us for
   // the tile kernel on a 4K frame (FMA pipe 44 % busy at 2 CTAs / SM of 230 registers)
   c->no_stream = getenv("KLT_B200_L0_STREAM") && atoi(getenv("KLT_B200_L0_STREAM")) ? 0 : 1;
@@ -1156,6 +1172,7 @@ extern "C" void klt_dev_destroy(klt_dev* d) {
   cudaFree(d->d_tile_ctr);
   cudaFree(d->d_u8_flag);
   cudaFree(d->d_rec);
+  cudaFree(d->d_fdone);
   for (int i = 0; i < KLT_DEV_SLOTS; ++i) { cudaEventDestroy(d->ev_built[i]); cudaEventDestroy(d->ev_read[i]); }
   cudaEventDestroy(d->ev_join);
   for (int i = 0; i < KLT_BAND_EVENTS; ++i) cudaEventDestroy(d->ev_band[i]);
@@ -1825,6 +1842,8 @@ static int mega_build(klt_dev* d, PyrSet& S, const FusedPlan& P, int nb, const T
   return 0;
 }
 
+static int early_track_launch(klt_dev* d, int slot_cur, const int* valid_rows, int nb);   // (tracker section)
+
 template <bool EXACT>
 static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitch,
                       const klt_dev_build_desc* q, BandFeed* feed) {
@@ -1901,6 +1920,9 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
         if (level_fused_launch<EXACT>(d, P, l, a, b, tp, tg, td, rows_done[l], j)) return 1;
         rows_done[l] = j;
         valid[l] = P.TY[l] * j < b.h ? P.TY[l] * j : b.h;
+      }
+      if (feed && feed->next == 1 && feed->nbands >= 2 && nl == nb) {
+        if (early_track_launch(d, d->building_slot, valid, nb)) return 1;
       }
     } while (u8_rows < H);
     if (nl < nb) {
@@ -2042,6 +2064,7 @@ extern "C" int klt_dev_build(klt_dev* d, int slot, const unsigned char* img, int
   }
   PyrSet& S = d->set[slot];
   S.built_levels = 0;
+  d->building_slot = slot;
   if (d->overlap && d->read_pending[slot]) {          // a tracker on the other stream may still read it
     CU(cudaStreamWaitEvent(d->stream, d->ev_read[slot], 0));
     d->read_pending[slot] = 0;
@@ -2239,6 +2262,12 @@ static bool launch_track_fast(klt_dev* d, const PyrView& v1, const PyrView& v2, 
     case 5: launch_track_fast_t<5, 1>(d, v1, v2, a, n); return true;
     case 7:
       if (d->track7_off) { launch_track_fast_t<7, 1>(d, v1, v2, a, n); return true; }
+      if (!d->no_track7w) {                                  // one warp per feature: shortest latency chain
+        Launch l(d, KID_TRACK7W, d->tstream);
+        launch_k(track7w_kernel, dim3((n + 3) / 4), dim3(128), 0, d->tstream, d->pdl != 0 && !d->overlap, v1, v2, a, n,
+                 feat_io(d), d->d_live);
+        return true;
+      }
       { Launch l(d, KID_TRACK7, d->tstream);
         static int fpw = getenv("KLT_TRACK_FPW") ? atoi(getenv("KLT_TRACK_FPW")) : 4;
         const int warps_per_block = 4;
@@ -2257,6 +2286,68 @@ static bool launch_track_fast(klt_dev* d, const PyrView& v1, const PyrView& v2, 
     case 15: launch_track_fast_t<15, 2>(d, v1, v2, a, n); return true;
     default: return false;
   }
+}
+
+static void fill_track_args(const klt_dev* d, const klt_dev_track_params* p, TrackArgs* a) {
+  memset(a, 0, sizeof(*a));
+  a->nlevels = d->L; a->ss = (float)d->ss; a->ww = p->window_width; a->wh = p->window_height;
+  a->step_factor = p->step_factor; a->max_iterations = p->max_iterations;
+  a->min_determinant = p->min_determinant; a->min_displacement = p->min_displacement;
+  a->max_residue = p->max_residue; a->borderx = p->borderx; a->bordery = p->bordery;
+  a->ncols = d->W; a->nrows = d->H;
+  a->lighting = p->lighting_insensitive ? 1 : 0;
+  { static int pf = getenv("KLT_TRACK_PREFETCH") ? atoi(getenv("KLT_TRACK_PREFETCH")) : 0; a->prefetch = pf; }
+}
+// can this call be served by track7_kernel (the only tracker with the two-pass mode)?
+static bool track7_applies(const klt_dev* d, const klt_dev_track_params* p) {
+  return !p->exact && !p->lighting_insensitive && !d->force_generic && !d->track7_off && !d->overlap &&
+         p->window_width == 7 && p->window_height == 7;
+}
+static int launch_track7(klt_dev* d, const PyrView& v1, const PyrView& v2, const TrackArgs& a, int n) {
+  Launch l(d, KID_TRACK7, d->tstream);
+  const int warps_per_block = 4;
+  CU(launch_k(track7_kernel<4>, dim3((n + 4 * warps_per_block - 1) / (4 * warps_per_block)), dim3(128), 0, d->tstream,
+              d->pdl != 0 && !d->overlap, v1, v2, a, n, feat_io(d), d->d_live));
+  return 0;
+}
+
+// The synchronous API arms this before klt_dev_build: if the frame then goes up in bands and
+// track7_kernel applies, the tracker's first pass is launched right behind the first band's
+// pyramid rows -- while the second band is still on the bus and the GPU would be idle -- and the
+// later klt_dev_track_resident only finishes the features that pass had to defer.
+extern "C" void klt_dev_disable_early_track(klt_dev* d, int on) { d->no_early = on; }
+extern "C" void klt_dev_disable_track7w(klt_dev* d, int on) { d->no_track7w = on; }
+extern "C" int klt_dev_last_track_passes(const klt_dev* d) { return d->last_passes; }
+extern "C" int klt_dev_arm_early_track(klt_dev* d, int slot_prev, const klt_dev_track_params* p) {
+  d->early_armed = 0; d->early_done = 0;
+  if (!p || d->no_early || !track7_applies(d, p) || !klt_dev_slot_valid(d, slot_prev) || d->feat_n <= 0) return 0;
+  d->early_armed = 1; d->early_slot_prev = slot_prev; d->early_p = *p;
+  return 0;
+}
+static int early_track_launch(klt_dev* d, int slot_cur, const int* valid_rows, int nb) {
+  if (!d->early_armed || nb != d->L) return 0;
+  d->early_armed = 0;
+  const int n = d->feat_n;
+  if (d->fdone_cap < n) {
+    CU(cudaStreamSynchronize(d->stream));
+    cudaFree(d->d_fdone); d->d_fdone = nullptr; d->fdone_cap = 0;
+    CU(cudaMalloc(&d->d_fdone, (size_t)n));
+    d->fdone_cap = n;
+  }
+  if (d->feat_pending) {
+    CU(cudaStreamWaitEvent(d->tstream, d->ev_feat, 0));
+    d->feat_pending = 0;
+  }
+  PyrView v1, v2;
+  make_view(d->set[d->early_slot_prev], d->L, &v1);
+  make_view(d->set[slot_cur], d->L, &v2);
+  TrackArgs a;
+  fill_track_args(d, &d->early_p, &a);
+  a.pass = 1; a.done = d->d_fdone;
+  for (int l = 0; l < nb; ++l) a.row_limit[l] = valid_rows[l];
+  if (launch_track7(d, v1, v2, a, n)) return 1;
+  d->early_done = 1; d->early_slot_cur = slot_cur;
+  return 0;
 }
 
 extern "C" int klt_dev_track_resident(klt_dev* d, int slot_prev, int slot_cur,
@@ -2284,13 +2375,19 @@ extern "C" int klt_dev_track_resident(klt_dev* d, int slot_prev, int slot_cur,
   make_view(d->set[slot_prev], d->L, &v1);
   make_view(d->set[slot_cur], d->L, &v2);
   TrackArgs a;
-  a.nlevels = d->L; a.ss = (float)d->ss; a.ww = p->window_width; a.wh = p->window_height;
-  a.step_factor = p->step_factor; a.max_iterations = p->max_iterations;
-  a.min_determinant = p->min_determinant; a.min_displacement = p->min_displacement;
-  a.max_residue = p->max_residue; a.borderx = p->borderx; a.bordery = p->bordery;
-  a.ncols = d->W; a.nrows = d->H;
-  a.lighting = p->lighting_insensitive ? 1 : 0;
-  { static int pf = getenv("KLT_TRACK_PREFETCH") ? atoi(getenv("KLT_TRACK_PREFETCH")) : 0; a.prefetch = pf; }
+  fill_track_args(d, p, &a);
+  if (d->early_done) {                               // pass 1 ran behind the first band: finish the deferred ones
+    const bool same = d->early_slot_prev == slot_prev && d->early_slot_cur == slot_cur && track7_applies(d, p);
+    d->early_done = 0;
+    if (!same) return fail(d, "early tracker pass does not match this call");
+    a.pass = 2; a.done = d->d_fdone;
+    if (launch_track7(d, v1, v2, a, n)) return 1;
+    CU(cudaGetLastError());
+    d->last_passes = 2;
+    return 0;
+  }
+  d->early_armed = 0;
+  d->last_passes = 1;
   const int npix = a.ww * a.wh;
   const int ppl = (npix + 31) / 32;
   int rc;

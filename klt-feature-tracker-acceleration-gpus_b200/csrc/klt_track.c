@@ -122,16 +122,12 @@ static void track_common(KLT_TrackingContext tc, const KLT_PixelType *img1,
   const int timing = timing_on();
   static double acc[5]; static int calls;
   double t0 = timing ? now_us() : 0, t1 = 0, t2 = 0, t3 = 0;
-  /* the frame upload is the long pole: queue it (and the pyramid kernels behind it) first, then
-   * pack the feature list into the pinned staging area while the copy engine is already busy */
+  /* The frame upload is the long pole.  With a pinned feature list nothing has to be packed:
+   * queue the one-copy mirror of the records, arm the tracker's early pass (it runs behind the
+   * first uploaded band), then queue the frame and the pyramid kernels.  An ordinary list is
+   * packed into the staging area first (a few microseconds) for the same order on the copy stream. */
   slot_prev = prepare_previous(tc, s, img1, on_device, pitch, ncols, nrows);
   slot_cur = (slot_prev + 1) % KLT_DEV_SLOTS;
-  klt_fill_build_desc(tc, ncols, nrows, tc->nPyramidLevels, 1, s->exact, &q);
-  DEVCALL(s, klt_dev_build(dev, slot_cur, img2, on_device, pitch, &q));
-  if (timing) t1 = now_us();
-
-  /* record mode: a list made by KLTCreateFeatureList is pinned and its records are contiguous --
-   * mirror them in one copy and let the tracker write the results straight back into them */
   records = n > 0 && klt_list_is_pinned(fl) && fl->feature[n - 1] == fl->feature[0] + (n - 1);
   if (records) {
     DEVCALL(s, klt_dev_features_commit_records(dev, n, fl->feature[0], sizeof(KLT_FeatureRec)));
@@ -140,6 +136,11 @@ static void track_common(KLT_TrackingContext tc, const KLT_PixelType *img1,
     klt_list_to_arrays(fl, x, y, v);
     DEVCALL(s, klt_dev_features_commit(dev, n));
   }
+  fill_track_params(tc, s->exact, &tp);
+  if (!on_device) DEVCALL(s, klt_dev_arm_early_track(dev, slot_prev, &tp));
+  klt_fill_build_desc(tc, ncols, nrows, tc->nPyramidLevels, 1, s->exact, &q);
+  DEVCALL(s, klt_dev_build(dev, slot_cur, img2, on_device, pitch, &q));
+  if (timing) t1 = now_us();
 
   fill_track_params(tc, s->exact, &tp);
   DEVCALL(s, klt_dev_track_resident(dev, slot_prev, slot_cur, &tp));

@@ -317,12 +317,15 @@ track7_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
   float xloc = 0.0f, yloc = 0.0f;
   if (f < n) {
     alive = io.val[(size_t)f * io.istride] >= 0;              // only features that are not lost (:1346)
+    if (a.pass == 2 && a.done[f]) alive = false;              // answered by the early pass
+    if (a.pass == 1 && !alive && r8 == 0) a.done[f] = 1;      // nothing to do for a lost feature
     if (alive) { xloc = io.x[(size_t)f * io.istride]; yloc = io.y[(size_t)f * io.istride]; }
   }
-  {
+  if (a.pass != 2) {
     const unsigned bal = __ballot_sync(0xffffffffu, alive && r8 == 0);
     if (lane == 0 && bal) atomicAdd(live_total, (unsigned long long)__popc(bal));
   }
+  bool deferred = false;                                      // pass 1: footprint beyond the rows that exist
   if (!__any_sync(0xffffffffu, alive)) return;
 
   // Every first touch of a level is a DRAM miss (two 132 MB pyramid sets do not fit in L2) and the
@@ -360,6 +363,9 @@ track7_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
 
     if (iterating && window_oob(x1, y1, hw, hh, nc, nr)) { lvl_status = KLT_OOB; iterating = false; }
     if (iterating && window_oob(x2, y2, hw, hh, nc, nr)) { lvl_status = KLT_OOB; iterating = false; }
+    // pass 1: the footprint rows (int)y2 - 3 .. (int)y2 + 4 of the new frame must already exist
+    const int row_lim = a.pass == 1 ? a.row_limit[r] : 0x7fffffff;
+    if (iterating && (int)y2 + 4 >= row_lim) { deferred = true; iterating = false; running = false; }
     // raw footprint rows of frame 2, kept across iterations: sub-pixel Newton updates and the
     // residue pass usually stay on the same 8x8 integer footprint, so nothing is re-read
     Row12 c_i, c_gx, c_gy;
@@ -384,9 +390,15 @@ track7_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
       if (iterating) {
         const Foot7 ft = foot7_setup(x2, y2, pitch, r8);
         if (ft.off != c_off) {                               // uniform within the group
-          c_i = foot7_load(i2, ft.off); c_gx = foot7_load(gx2, ft.off); c_gy = foot7_load(gy2, ft.off);
-          c_off = ft.off;
+          if ((int)y2 + 4 >= row_lim) { deferred = true; iterating = false; running = false; }
+          else {
+            c_i = foot7_load(i2, ft.off); c_gx = foot7_load(gx2, ft.off); c_gy = foot7_load(gy2, ft.off);
+            c_off = ft.off;
+          }
         }
+      }
+      if (iterating) {
+        const Foot7 ft = foot7_setup(x2, y2, pitch, r8);
         float s_i[WW], s_gx[WW], s_gy[WW];
         foot7_interp(c_i, ft, gmask, s_i);
         foot7_interp(c_gx, ft, gmask, s_gx);
@@ -427,6 +439,9 @@ track7_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
     if (running) {
       if (window_oob(x2, y2, hw, hh, nc, nr)) lvl_status = KLT_OOB;
       need_res = (lvl_status == KLT_TRACKED);
+      if (need_res && foot7_setup(x2, y2, pitch, r8).off != c_off && (int)y2 + 4 >= row_lim) {
+        deferred = true; running = false; need_res = false;   // the residue footprint does not exist yet
+      }
     }
     if (__any_sync(0xffffffffu, need_res)) {
       float sum = 0.0f;
@@ -457,7 +472,159 @@ track7_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
     if (!__any_sync(0xffffffffu, running)) break;
   }
 
-  if (alive && r8 == 0) {
+  if (alive && r8 == 0 && a.pass == 1) a.done[f] = deferred ? 0 : 1;
+  if (alive && r8 == 0 && !deferred) {
+    const bool outside = (xout < (float)a.borderx || xout > (float)(a.ncols - 1 - a.borderx) ||
+                          yout < (float)a.bordery || yout > (float)(a.nrows - 1 - a.bordery));
+    const size_t o = (size_t)f * io.ostride;
+    if (status == KLT_OOB || outside) { io.ox[o] = -1.0f; io.oy[o] = -1.0f; io.oval[o] = KLT_OOB; }
+    else if (status != KLT_TRACKED) { io.ox[o] = -1.0f; io.oy[o] = -1.0f; io.oval[o] = status; }
+    else { io.ox[o] = xout; io.oy[o] = yout; io.oval[o] = KLT_TRACKED; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 7x7 window, one WARP per feature (track7w_kernel): the latency-optimised tracker.
+//
+// track7_kernel (8 lanes per feature) issues ~350 dependent-ish instructions per Newton iteration
+// from each warp at 1.7 warps per scheduler: measured, a pass over half of the features takes as
+// long as a pass over all of them (27 us) -- the kernel is a latency chain, not a throughput
+// problem, and the GPU is idle otherwise.  Here the 8x8 pixel footprint is spread over all 32
+// lanes (lane = 4 * row + column pair): each lane holds the three pixels it needs per image,
+// interpolates two window columns (10 instructions per image instead of ~53), the five sums are
+// reduced with 5 xor-shuffles, every lane solves the 2x2 system.  ~135 instructions per iteration
+// and 4x as many warps in flight.  Same per-sample arithmetic as track7_kernel; the sums are
+// added in a different (tree) order.
+// ---------------------------------------------------------------------------------------------
+struct Pix3 { float a, b, c; };
+__device__ __forceinline__ Pix3 pix3_load(const float* __restrict__ img, int off) {
+  const float* p = img + off;
+  Pix3 r;
+  r.a = __ldg(p); r.b = __ldg(p + 1); r.c = __ldg(p + 2);
+  return r;
+}
+// bilinear samples of this lane's two window columns in its window row; the row below comes from
+// lane + 4 (lanes 28..31 hold footprint row 7 and only feed the shuffle)
+__device__ __forceinline__ void pix3_interp(const Pix3& p, float ax, float ay, float& o0, float& o1) {
+  const float h0 = fmaf(ax, p.b - p.a, p.a), h1 = fmaf(ax, p.c - p.b, p.b);
+  const float b0 = __shfl_down_sync(0xffffffffu, h0, 4), b1 = __shfl_down_sync(0xffffffffu, h1, 4);
+  o0 = fmaf(ay, b0 - h0, h0);
+  o1 = fmaf(ay, b1 - h1, h1);
+}
+__device__ __forceinline__ float warp_sum32(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(128)
+track7w_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
+               unsigned long long* __restrict__ live_total) {
+  constexpr int hw = 3, hh = 3;
+  const int lane = threadIdx.x & 31;
+  const int r = lane >> 2, c = lane & 3;                     // footprint row, column pair
+  const bool v0 = r < 7, v1 = r < 7 && c < 3;                // window samples (2c, r) and (2c + 1, r)
+  const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  pdl_wait();                                                 // pyramids and features come from earlier kernels
+  if (f >= n) return;
+  if (io.val[(size_t)f * io.istride] < 0) return;             // only features that are not lost (:1346)
+  if (lane == 0) atomicAdd(live_total, 1ULL);
+  float xloc = io.x[(size_t)f * io.istride], yloc = io.y[(size_t)f * io.istride];
+  for (int l = a.nlevels - 1; l >= 0; --l) { xloc = xloc / a.ss; yloc = yloc / a.ss; }
+  float xout = xloc, yout = yloc;
+  int status = KLT_TRACKED;
+
+  for (int l = a.nlevels - 1; l >= 0; --l) {
+    xloc *= a.ss; yloc *= a.ss; xout *= a.ss; yout *= a.ss;
+    const int nc = p1.ncols[l], nr = p1.nrows[l], pitch = p1.pitch[l];
+    const float* __restrict__ i2 = p2.img[l];
+    const float* __restrict__ gx2 = p2.gx[l];
+    const float* __restrict__ gy2 = p2.gy[l];
+    const float x1 = xloc, y1 = yloc;
+    float x2 = xout, y2 = yout;
+    int iteration = 0, lvl_status = KLT_TRACKED;
+    bool iterating = true;
+    if (window_oob(x1, y1, hw, hh, nc, nr) || window_oob(x2, y2, hw, hh, nc, nr)) { lvl_status = KLT_OOB; iterating = false; }
+
+    float t_i0 = 0.f, t_i1 = 0.f, t_gx0 = 0.f, t_gx1 = 0.f, t_gy0 = 0.f, t_gy1 = 0.f;
+    Pix3 c_i, c_gx, c_gy;
+    c_i.a = c_i.b = c_i.c = 0.f; c_gx = c_i; c_gy = c_i;
+    int c_xt = -1000000, c_yt = -1000000;
+    if (iterating) {
+      // all 18 loads of the level are issued before the first use
+      const int xt1 = (int)x1, yt1 = (int)y1, xt2 = (int)x2, yt2 = (int)y2;
+      const int o1 = (yt1 - 3 + r) * pitch + (xt1 - 3 + 2 * c), o2 = (yt2 - 3 + r) * pitch + (xt2 - 3 + 2 * c);
+      const Pix3 r_i = pix3_load(p1.img[l], o1), r_gx = pix3_load(p1.gx[l], o1), r_gy = pix3_load(p1.gy[l], o1);
+      c_i = pix3_load(i2, o2); c_gx = pix3_load(gx2, o2); c_gy = pix3_load(gy2, o2);
+      c_xt = xt2; c_yt = yt2;
+      const float ax = x1 - (float)xt1, ay = y1 - (float)yt1;
+      pix3_interp(r_i, ax, ay, t_i0, t_i1);
+      pix3_interp(r_gx, ax, ay, t_gx0, t_gx1);
+      pix3_interp(r_gy, ax, ay, t_gy0, t_gy1);
+    }
+
+    float dx = 0.0f, dy = 0.0f;
+    while (iterating) {                                       // warp uniform
+      const int xt = (int)x2, yt = (int)y2;
+      if (xt != c_xt || yt != c_yt) {                         // the integer footprint moved: re-read it
+        const int o2 = (yt - 3 + r) * pitch + (xt - 3 + 2 * c);
+        c_i = pix3_load(i2, o2); c_gx = pix3_load(gx2, o2); c_gy = pix3_load(gy2, o2);
+        c_xt = xt; c_yt = yt;
+      }
+      const float ax = x2 - (float)xt, ay = y2 - (float)yt;
+      float s_i0, s_i1, s_gx0, s_gx1, s_gy0, s_gy1;
+      pix3_interp(c_i, ax, ay, s_i0, s_i1);
+      pix3_interp(c_gx, ax, ay, s_gx0, s_gx1);
+      pix3_interp(c_gy, ax, ay, s_gy0, s_gy1);
+      float gxx = 0.0f, gxy = 0.0f, gyy = 0.0f, ex = 0.0f, ey = 0.0f;
+      {
+        const float df = v0 ? t_i0 - s_i0 : 0.0f, sx = v0 ? t_gx0 + s_gx0 : 0.0f, sy = v0 ? t_gy0 + s_gy0 : 0.0f;
+        gxx = sx * sx; gxy = sx * sy; gyy = sy * sy; ex = df * sx; ey = df * sy;
+      }
+      {
+        const float df = v1 ? t_i1 - s_i1 : 0.0f, sx = v1 ? t_gx1 + s_gx1 : 0.0f, sy = v1 ? t_gy1 + s_gy1 : 0.0f;
+        gxx = fmaf(sx, sx, gxx); gxy = fmaf(sx, sy, gxy); gyy = fmaf(sy, sy, gyy);
+        ex = fmaf(df, sx, ex); ey = fmaf(df, sy, ey);
+      }
+      gxx = warp_sum32(gxx); gxy = warp_sum32(gxy); gyy = warp_sum32(gyy);
+      ex = warp_sum32(ex); ey = warp_sum32(ey);
+      ex *= a.step_factor; ey *= a.step_factor;
+      const float det = gxx * gyy - gxy * gxy;
+      if (det < a.min_determinant) { lvl_status = KLT_SMALL_DET; break; }
+      const float inv = __frcp_rn(det);
+      dx = (gyy * ex - gxy * ey) * inv;
+      dy = (gxx * ey - gxy * ex) * inv;
+      x2 += dx; y2 += dy;
+      ++iteration;
+      const bool again = (fabsf(dx) >= a.min_displacement || fabsf(dy) >= a.min_displacement) &&
+                         iteration < a.max_iterations;
+      if (!again) break;
+      if (window_oob(x2, y2, hw, hh, nc, nr)) { lvl_status = KLT_OOB; break; }
+    }
+
+    // after the loop (:459-474): bounds of the final position, then the residue
+    if (lvl_status == KLT_TRACKED && window_oob(x2, y2, hw, hh, nc, nr)) lvl_status = KLT_OOB;
+    if (lvl_status == KLT_TRACKED) {
+      const int xt = (int)x2, yt = (int)y2;
+      if (xt != c_xt || yt != c_yt) c_i = pix3_load(i2, (yt - 3 + r) * pitch + (xt - 3 + 2 * c));
+      float s_i0, s_i1;
+      pix3_interp(c_i, x2 - (float)xt, y2 - (float)yt, s_i0, s_i1);
+      float sum = (v0 ? fabsf(t_i0 - s_i0) : 0.0f) + (v1 ? fabsf(t_i1 - s_i1) : 0.0f);
+      sum = warp_sum32(sum);
+      if (sum * (1.0f / 49.0f) > a.max_residue) lvl_status = KLT_LARGE_RESIDUE;
+    }
+    int v;                                                   // return value of _trackFeature (:479-484)
+    if (lvl_status == KLT_SMALL_DET) v = KLT_SMALL_DET;
+    else if (lvl_status == KLT_OOB) v = KLT_OOB;
+    else if (lvl_status == KLT_LARGE_RESIDUE) v = KLT_LARGE_RESIDUE;
+    else if (iteration >= a.max_iterations) v = KLT_MAX_ITERATIONS;
+    else v = KLT_TRACKED;
+    status = v;
+    xout = x2; yout = y2;
+    if (v == KLT_SMALL_DET || v == KLT_OOB) break;           // :1378
+  }
+
+  if (lane == 0) {                                           // record (:1383-1437)
     const bool outside = (xout < (float)a.borderx || xout > (float)(a.ncols - 1 - a.borderx) ||
                           yout < (float)a.bordery || yout > (float)(a.nrows - 1 - a.bordery));
     const size_t o = (size_t)f * io.ostride;

@@ -65,6 +65,10 @@ DEV_API = {
     "klt_dev_track": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(TrackParams), C.c_int, _f32p, _f32p, _i32p]),
     "klt_dev_features_upload": (C.c_int, [C.c_void_p, C.c_int, _f32p, _f32p, _i32p]),
     "klt_dev_track_resident": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(TrackParams)]),
+    "klt_dev_arm_early_track": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(TrackParams)]),
+    "klt_dev_disable_early_track": (None, [C.c_void_p, C.c_int]),
+    "klt_dev_last_track_passes": (C.c_int, [C.c_void_p]),
+    "klt_dev_disable_track7w": (None, [C.c_void_p, C.c_int]),
     "klt_dev_features_download": (C.c_int, [C.c_void_p, C.c_int, _f32p, _f32p, _i32p]),
     "klt_dev_features_staging": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.POINTER(C.c_float)),
                                            C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.POINTER(C.c_int))]),

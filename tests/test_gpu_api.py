@@ -278,3 +278,36 @@ def test_lighting_insensitive_tracking(L, capi, oracle, oracle_mod, provided, ex
         tc.contents.window_width = tc.contents.window_height = window
     rep2 = _teacher_forced(L, capi, oracle, oracle_mod, imgs, 150, exact, plain)
     assert rep != rep2
+
+
+@pytest.mark.parametrize("band_rows", [64, 192, 320])
+def test_two_pass_tracking_behind_banded_upload(L, capi, band_rows):
+    """With a banded frame upload the 7x7 tracker's first pass runs behind the first band and defers
+    every feature whose footprint would touch a row that is not built yet; the second pass finishes
+    them.  The result must equal single-pass tracking bit for bit, whatever the band size."""
+    imgs = [synth_image(900, 700, seed=21, shift=(2.3 * t, -1.4 * t)) for t in range(4)]
+    res = []
+    for early in (1, 0):
+        tc = L.KLTCreateTrackingContext()
+        tc.contents.sequentialMode = 1
+        tc.contents.nPyramidLevels, tc.contents.subsampling = 4, 2
+        L.KLTUpdateTCBorder(tc)
+        dev = L.KLTB200Device(tc)
+        L.klt_dev_set_band_rows(dev, band_rows)
+        L.klt_dev_disable_early_track(dev, 1 - early)
+        L.klt_dev_disable_track7w(dev, 1)             # the two-pass mode lives in track7_kernel
+        fl = L.KLTCreateFeatureList(700)
+        L.select(tc, imgs[0], fl)
+        out = []
+        for k in range(1, 4):
+            L.track(tc, imgs[k - 1], imgs[k], fl)
+            if k > 1:                                    # (the first call also builds frame 0's pyramid)
+                assert L.klt_dev_last_track_passes(dev) == (2 if early else 1)
+            out.append(_get(capi, fl))
+        res.append(out)
+        L.KLTFreeFeatureList(fl)
+        L.KLTFreeTrackingContext(tc)
+    for a, b in zip(res[0], res[1]):
+        for u, v in zip(a, b):
+            assert u.tobytes() == v.tobytes()
+    assert (res[0][-1][2] >= 0).sum() > 300
