@@ -201,6 +201,12 @@ void klt_dev_disable_mega(klt_dev *d, int on);
  * memory, no CTA barrier).  Same bits either way; the tile kernel measures faster.
  * klt_dev_last_build_stream: which one the last build used. */
 void klt_dev_disable_stream(klt_dev *d, int on);
+/* klt_dev_disable_chain(d, 0) / env KLT_B200_CHAIN=1: levels >= 1 of a pyramid with more than two
+ * levels are built by ONE levels_chain_kernel launch (one tile shape, grid barrier between levels)
+ * instead of one level_fused_kernel launch per level (default: the per-level launches overlap
+ * through programmatic dependent launch and measure faster).  Same bits either way. */
+void klt_dev_disable_chain(klt_dev *d, int on);
+int klt_dev_last_build_chain(const klt_dev *d);
 int klt_dev_last_build_stream(const klt_dev *d);
 /* first_level > 0 (env KLT_B200_MEGA_TAIL; default 0 = off, it measures slower): levels >=
  * first_level of a pyramid with more than first_level + 1 levels are built by ONE

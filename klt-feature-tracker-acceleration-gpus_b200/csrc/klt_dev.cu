@@ -887,12 +887,12 @@ track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
 // kernel classes, for launch accounting and per-kernel event timing
 enum KernelId {
   KID_SMOOTH_U8 = 0, KID_GRAD, KID_PYRDOWN, KID_TRACK, KID_MINEIG, KID_SORT, KID_STAMP,
-  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_L0_FUSED, KID_LEVEL_FUSED, KID_TRACK_FAST, KID_TRACK7, KID_TRACK7W, KID_MEGA, KID_L0_STREAM, KID_COPY_H2D, KID_COPY_D2H, KID_COUNT
+  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_L0_FUSED, KID_LEVEL_FUSED, KID_TRACK_FAST, KID_TRACK7, KID_TRACK7W, KID_LEVELS_CHAIN, KID_MEGA, KID_L0_STREAM, KID_COPY_H2D, KID_COPY_D2H, KID_COUNT
 };
 static const char* const kKernelNames[KID_COUNT] = {
   "smooth_u8_tile", "grad_tile", "pyrdown_tile", "track_kernel", "mineig_kernel",
   "cub_radix_sort", "stamp_existing_kernel", "enforce_mindist_kernel",
-  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel", "l0_fused_kernel", "level_fused_kernel", "track_fast_kernel", "track7_kernel", "track7w_kernel", "pyramid_mega_kernel", "l0_stream_kernel",
+  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel", "l0_fused_kernel", "level_fused_kernel", "track_fast_kernel", "track7_kernel", "track7w_kernel", "levels_chain_kernel", "pyramid_mega_kernel", "l0_stream_kernel",
   "copy_h2d", "copy_d2h"          // not kernels: timed in profiling mode, never counted as launches
 };
 static constexpr int PROF_POOL = 2048;     // event pairs in flight before folding
@@ -935,6 +935,7 @@ struct klt_dev {
   int band_rows, last_bands, building_slot;
   // pyramid_mega_kernel: cached schedule + dependency counters (klt_mega.cuh)
   int no_mega, last_mega, mega_tail_from;
+  int no_chain, last_chain; unsigned chain_barrier_base;   // levels >= 1 in one launch (levels_chain_kernel)
   int pdl;                     // programmatic dependent launch along the per-frame kernel chain
   int no_stream, stream_hs, last_stream;    // l0_stream_kernel off / output rows per segment
   MegaSeg* d_segs; int mega_nseg, mega_nitems, mega_key[8];
@@ -1083,6 +1084,8 @@ extern "C" int klt_dev_last_build_bands(const klt_dev* d) { return d->last_bands
 extern "C" int klt_dev_last_build_mega(const klt_dev* d) { return d->last_mega; }
 extern "C" void klt_dev_disable_mega(klt_dev* d, int on) { d->no_mega = on; }
 extern "C" void klt_dev_disable_stream(klt_dev* d, int on) { d->no_stream = on; }
+extern "C" void klt_dev_disable_chain(klt_dev* d, int on) { d->no_chain = on; }
+extern "C" int klt_dev_last_build_chain(const klt_dev* d) { return d->last_chain; }
 extern "C" int klt_dev_last_build_stream(const klt_dev* d) { return d->last_stream; }
 extern "C" void klt_dev_set_mega_tail(klt_dev* d, int first_level) { d->mega_tail_from = first_level; }
 extern "C" void klt_dev_set_band_rows(klt_dev* d, int rows) { d->band_rows = rows; }
@@ -1127,6 +1130,10 @@ extern "C" int klt_dev_create(int device, klt_dev** out) {
   // slower than the per-level kernels on B200 (4K: 87 us vs 69 us resident)
   c->no_mega = getenv("KLT_B200_MEGA") && atoi(getenv("KLT_B200_MEGA")) ? 0 : 1;
   c->pdl = getenv("KLT_B200_PDL") ? atoi(getenv("KLT_B200_PDL")) : 1;
+  // opt-in: 39 us against 46 us for the three launches when timed alone, but in the real chain the
+  // per-level launches overlap each other's tails through PDL and the grid barriers do not (4K
+  // build 62.2 us vs 58.7 us)
+  c->no_chain = getenv("KLT_B200_CHAIN") && atoi(getenv("KLT_B200_CHAIN")) ? 0 : 1;
   c->no_track7w = getenv("KLT_B200_TRACK7W") ? !atoi(getenv("KLT_B200_TRACK7W")) : 0;
   // opt-in: measured no gain (the tracker is a latency chain: a pass over half the features takes
   // as long as a pass over all of them)
@@ -1514,6 +1521,59 @@ static int level_fused_launch(klt_dev* d, const FusedPlan& P, int level, const L
   }
 }
 
+// levels first .. nb-1 in one launch (levels_chain_kernel); jr0 / jr1: tile-row range per level
+template <int SS, int R, int TX, int TY, bool EXACT>
+static int levels_chain_launch_t(klt_dev* d, const FusedPlan& P, const PyrSet& S, int first, int nb, const TapsR& tp,
+                                 const TapsR& tg, const TapsR& td, const int* jr0, const int* jr1) {
+  using G = LvGeo<SS, R, TX, TY>;
+  static bool attr_set = false;
+  static int cps = 0;
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(levels_chain_kernel<SS, R, TX, TY, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, levels_chain_kernel<SS, R, TX, TY, EXACT>, 256, G::SMEM));
+    if (cps < 1) return fail(d, "levels_chain_kernel does not fit on an SM");
+    attr_set = true;
+  }
+  ChainParams CP;
+  memset(&CP, 0, sizeof(CP));
+  int maxtiles = 0;
+  CP.nlev = nb - first;
+  for (int l = first; l < nb; ++l) {
+    const int k = l - first;
+    const Level& a = S.lv[l - 1];
+    const Level& b = S.lv[l];
+    CP.map[k] = P.map[l];
+    ChainLevel& L = CP.lv[k];
+    L.Wsrc = a.w; L.Hsrc = a.h; L.W = b.w; L.H = b.h; L.tiles_x = P.tiles_x[l];
+    L.tile0 = jr0[l] * P.tiles_x[l]; L.ntiles = jr1[l] * P.tiles_x[l];
+    L.base = d->tile_base[l & 15];
+    L.img = b.img; L.gx = b.gx; L.gy = b.gy; L.pitch = b.pitch;
+    if (L.ntiles - L.tile0 > maxtiles) maxtiles = L.ntiles - L.tile0;
+  }
+  if (maxtiles == 0) return 0;
+  const int cap = cps * d->num_sms;                        // the grid barrier needs every CTA resident
+  const int grid = maxtiles < cap ? maxtiles : cap;
+  CP.counters = d->d_tile_ctr + first;                     // the per-level counters, consecutive
+  CP.barrier = d->d_tile_ctr + 15;                        // (0..11: per-level queues, 12..14: mega kernel)
+  CP.barrier_base = d->chain_barrier_base;
+  CP.tp = to_fused(tp); CP.tg = to_fused(tg); CP.td = to_fused(td);
+  { Launch l(d, KID_LEVELS_CHAIN);
+    CU(launch_k(levels_chain_kernel<SS, R, TX, TY, EXACT>, dim3(grid), dim3(256), G::SMEM, d->stream, d->pdl != 0, CP)); }
+  for (int l = first; l < nb; ++l)
+    d->tile_base[l & 15] += (unsigned)((jr1[l] - jr0[l]) * P.tiles_x[l] + grid);
+  d->chain_barrier_base += (unsigned)(CP.nlev - 1) * (unsigned)grid;
+  return 0;
+}
+template <bool EXACT>
+static int levels_chain_launch(klt_dev* d, const FusedPlan& P, const PyrSet& S, int first, int nb, const TapsR& tp,
+                               const TapsR& tg, const TapsR& td, const int* jr0, const int* jr1) {
+  switch (P.shape[first]) {
+    case SHAPE_2_5_64_16: return levels_chain_launch_t<2, 5, 64, 16, EXACT>(d, P, S, first, nb, tp, tg, td, jr0, jr1);
+    case SHAPE_4_10_32_16: return levels_chain_launch_t<4, 10, 32, 16, EXACT>(d, P, S, first, nb, tp, tg, td, jr0, jr1);
+    default: return fail(d, "no chained kernel for this pyramid geometry");
+  }
+}
+
 // generic two-kernel separable pass through d->tmp
 template <typename SrcT, bool EXACT>
 static int generic_separable(klt_dev* d, const SrcT* src, int spitch, int W, int H, const TapsR& kh,
@@ -1861,6 +1921,7 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
   d->last_bands = 0;
   d->last_mega = 0;
   d->last_stream = 0;
+  d->last_chain = 0;
   // one launch for the whole pyramid when every level qualifies (klt_mega.cuh)
   if (!d->no_mega && nb <= MEGA_MAX_LEVELS && (nb == 1 || mega_shape_for(q->subsampling, tp.w / 2) != SHAPE_NONE)) {
     fused_plan(d, S, src, spitch, q, ts, tp, tg, td, &P, nb > 1 ? mega_shape_for(q->subsampling, tp.w / 2) : SHAPE_NONE, false);
@@ -1893,6 +1954,16 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
       for (int l = d->mega_tail_from; l < nb; ++l) ok = ok && PT.shape[l] != SHAPE_NONE;
       if (ok) nl = d->mega_tail_from;
     }
+    // levels >= 1: one chained launch (uniform tile shape) or one launch per level
+    FusedPlan PC;
+    bool use_chain = false;
+    if (!d->no_chain && nl > 2 && nl - 1 <= CHAIN_MAX_LEVELS && mega_shape_for(q->subsampling, tp.w / 2) != SHAPE_NONE) {
+      fused_plan(d, S, src, spitch, q, ts, tp, tg, td, &PC, mega_shape_for(q->subsampling, tp.w / 2), false);
+      use_chain = true;
+      for (int l = 1; l < nl; ++l) use_chain = use_chain && PC.shape[l] != SHAPE_NONE;
+    }
+    const FusedPlan& PL = use_chain ? PC : P;
+    d->last_chain = use_chain ? 1 : 0;
     int u8_rows = feed ? 0 : H;
     if (feed && feed_enqueue_copies(d, feed)) return 1;
     do {
@@ -1907,20 +1978,23 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
       if (l0_fused_launch<EXACT>(d, P, W, H, ts, tg, td, S.lv[0], rows_done[0], j)) return 1;
       rows_done[0] = j;
       valid[0] = P.TY[0] * j < H ? P.TY[0] * j : H;
+      int jr0[KLT_DEV_MAX_LEVELS] = {0}, jr1[KLT_DEV_MAX_LEVELS] = {0};
       for (int l = 1; l < nl; ++l) {
         const Level& a = S.lv[l - 1];
         const Level& b = S.lv[l];
         j = rows_done[l];
-        while (j < P.tiles_y[l]) {
-          int need = SS * (P.TY[l] * (j + 1) - 1 + RG) + SS / 2 + R + 1;
+        while (j < PL.tiles_y[l]) {
+          int need = SS * (PL.TY[l] * (j + 1) - 1 + RG) + SS / 2 + R + 1;
           if (need > a.h) need = a.h;
           if (need > valid[l - 1]) break;
           ++j;
         }
-        if (level_fused_launch<EXACT>(d, P, l, a, b, tp, tg, td, rows_done[l], j)) return 1;
+        jr0[l] = rows_done[l]; jr1[l] = j;
+        if (!use_chain && level_fused_launch<EXACT>(d, PL, l, a, b, tp, tg, td, rows_done[l], j)) return 1;
         rows_done[l] = j;
-        valid[l] = P.TY[l] * j < b.h ? P.TY[l] * j : b.h;
+        valid[l] = PL.TY[l] * j < b.h ? PL.TY[l] * j : b.h;
       }
+      if (use_chain && levels_chain_launch<EXACT>(d, PL, S, 1, nl, tp, tg, td, jr0, jr1)) return 1;
       if (feed && feed->next == 1 && feed->nbands >= 2 && nl == nb) {
         if (early_track_launch(d, d->building_slot, valid, nb)) return 1;
       }
@@ -1942,7 +2016,7 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
       d->frame_busy = 1;
     }
     for (int l = 0; l < nb; ++l)
-      if (rows_done[l] != P.tiles_y[l]) return fail(d, "banded build left level %d incomplete", l);
+      if (rows_done[l] != (l == 0 || l >= nl ? P.tiles_y[l] : PL.tiles_y[l])) return fail(d, "banded build left level %d incomplete", l);
     d->last_fused = nb;
     d->last_path = 1;
     d->last_stream = P.l0_stream ? 1 : 0;

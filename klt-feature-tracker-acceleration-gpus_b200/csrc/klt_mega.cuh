@@ -64,11 +64,6 @@ struct MegaParams {
   TapsF ts, tp, tg, td;
 };
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ unsigned ld_relaxed_sys_u32(const unsigned* p) {
   unsigned v;
   asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

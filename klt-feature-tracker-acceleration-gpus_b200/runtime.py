@@ -95,6 +95,8 @@ DEV_API = {
     "klt_dev_disable_mega": (None, [C.c_void_p, C.c_int]),
     "klt_dev_set_mega_tail": (None, [C.c_void_p, C.c_int]),
     "klt_dev_disable_stream": (None, [C.c_void_p, C.c_int]),
+    "klt_dev_disable_chain": (None, [C.c_void_p, C.c_int]),
+    "klt_dev_last_build_chain": (C.c_int, [C.c_void_p]),
     "klt_dev_last_build_stream": (C.c_int, [C.c_void_p]),
     "klt_dev_timer_start": (C.c_int, [C.c_void_p]),
     "klt_dev_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),

@@ -298,3 +298,38 @@ def test_stream_level0_equals_tile_kernel(L, oracle, shape, band_rows, exact):
         for which in range(3):
             assert np.array_equal(got[0][which][0], want.level(which, 0))
     L.KLTFreeTrackingContext(tc)
+
+
+# ---- levels >= 1 in one launch (levels_chain_kernel) == one launch per level ------------------------
+@pytest.mark.parametrize("exact", [1, 0])
+@pytest.mark.parametrize("band_rows", [0, 64, 192])
+@pytest.mark.parametrize("cfg", [(4, 2, (700, 900)), (5, 2, (1000, 777)), (3, 4, (600, 800)), (3, 2, (130, 257)),
+                                 (6, 2, (1080, 1920))])
+def test_levels_chain_equals_per_level_kernels(L, oracle, cfg, band_rows, exact):
+    """levels_chain_kernel walks the coarse levels inside one persistent launch (grid barrier between
+    levels); its pyramids equal the per-level kernels' bit for bit in both arithmetic modes, for whole
+    frames and for banded uploads, and repeated builds keep the barrier / queue counters consistent."""
+    nlev, ss, (h, w) = cfg
+    tc = L.KLTCreateTrackingContext()
+    tc.contents.nPyramidLevels, tc.contents.subsampling = nlev, ss
+    L.KLTUpdateTCBorder(tc)
+    dev = L.KLTB200Device(tc)
+    L.klt_dev_set_band_rows(dev, band_rows)
+    q = L.build_desc(tc, w, h, exact=exact)
+    for rep in range(3):
+        img = synth_image(w, h, seed=7 * h + w + rep)
+        got = []
+        for chain in (1, 0):
+            L.klt_dev_disable_chain(dev, 1 - chain)
+            L.dev_build(dev, chain, img, q)
+            assert L.klt_dev_last_build_chain(dev) == chain
+            got.append(device_pyramids(L, dev, chain, nlev))
+        for which in range(3):
+            for l in range(nlev):
+                assert np.array_equal(got[0][which][l], got[1][which][l]), (rep, which, l)
+    if exact:
+        want = oracle.build_pyramids(img, params_from_tc(oracle, tc))
+        for which in range(3):
+            for l in range(nlev):
+                assert np.array_equal(got[0][which][l], want.level(which, l))
+    L.KLTFreeTrackingContext(tc)
