@@ -42,8 +42,20 @@ METRIC = "tracked_features_per_s"
 UNIT = "features/s"
 
 
+_JSON_FD = None          # the real stdout when fd 1 has been pointed at stderr (multi-rank runs)
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def emit_json(obj):
+    line = json.dumps(obj) + "\n"
+    if _JSON_FD is None:
+        sys.stdout.write(line)
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line.encode())
 
 
 def algorithmic_bytes(ncols, nrows, nlevels, ss):
@@ -148,8 +160,12 @@ def run_b200(args, rank, local_rank, world):
     L.KLTSetVerbosity(0)
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # NCCL's version banner / debug lines go to stdout by default: keep stdout for the JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL prints its version banner / debug lines on the process's stdout (fd 1, from C): point
+        # fd 1 at stderr for the whole run and keep the real stdout for the one JSON line
+        global _JSON_FD
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -330,7 +346,7 @@ def run_b200(args, rank, local_rank, world):
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(capi, fh, ncols, nrows, nfeat, nlevels, ss, window,
                                                budget_s=args.cpu_budget)
-        print(json.dumps(out), flush=True)
+        emit_json(out)
     barrier()
     L.KLTFreeFeatureList(fl)
     L.KLTFreeTrackingContext(tc)
