@@ -1138,10 +1138,10 @@ extern "C" int klt_dev_create(int device, klt_dev** out) {
   // opt-in: measured no gain (the tracker is a latency chain: a pass over half the features takes
   // as long as a pass over all of them)
   c->no_early = getenv("KLT_B200_EARLY_TRACK") && atoi(getenv("KLT_B200_EARLY_TRACK")) ? 0 : 1;
-  // the streaming level-0 kernel (klt_stream.cuh) is opt-in: bit-identical, but 32.7 us vs 28.6 us for
-  // the tile kernel on a 4K frame (FMA pipe 44 % busy at 2 CTAs / SM of 230 registers)
+  // the streaming level-0 kernel (klt_stream.cuh) is opt-in: bit-identical, but 31.5 us vs 28.5 us for
+  // the tile kernel on a 4K frame
   c->no_stream = getenv("KLT_B200_L0_STREAM") && atoi(getenv("KLT_B200_L0_STREAM")) ? 0 : 1;
-  c->stream_hs = getenv("KLT_B200_STREAM_HS") ? atoi(getenv("KLT_B200_STREAM_HS")) : 67;
+  c->stream_hs = getenv("KLT_B200_STREAM_HS") ? atoi(getenv("KLT_B200_STREAM_HS")) : 46;
   if (c->stream_hs < 4) c->stream_hs = 4;
   c->mega_tail_from = getenv("KLT_B200_MEGA_TAIL") ? atoi(getenv("KLT_B200_MEGA_TAIL")) : 0;   // opt-in too (4K: 30 us vs 21 us for levels 2+3)
   if (e == cudaSuccess) e = cudaMalloc(&c->d_tile_ctr, 16 * sizeof(unsigned));

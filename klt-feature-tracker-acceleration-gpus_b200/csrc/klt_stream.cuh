@@ -18,8 +18,8 @@
 //
 // The row loop is unrolled by 7 so that every ring index is a compile-time constant (the rings are
 // registers).  Taps are applied in increasing order, i.e. in the reference's summation order: the
-// results are bit-identical to the tile kernels in both arithmetic modes.  Vertical passes use the
-// packed FFMA2 (column pairs), the horizontal 7-tap passes too (output pairs, shifted input pairs).
+// results are bit-identical to the tile kernels in both arithmetic modes.  (A packed-FFMA2 variant
+// of the vertical and 7-tap passes is kept behind KLT_STREAM_FFMA2: measured slower, see sfma2.)
 //
 // Cost of the formulation: a strip yields 112 of its 128 columns (5-pixel halo, float4 alignment)
 // and a segment of HS rows needs 10 warm-up rows.
@@ -36,6 +36,20 @@ struct StreamGeo {
 
 template <bool EXACT>
 __device__ __forceinline__ float smac(float acc, float a, float k) { return mac<EXACT>(acc, a, k); }
+
+// (ax, ay) += (vx, vy) * k.  Packed FFMA2 with a uniform-register multiplier pair issues in half the
+// slots but runs at 96 FMA/clk/SM; two scalar FFMA with a uniform multiplier run at 116
+// (tools/ffma2_probe.cu) -- this kernel is limited by the FMA pipe, not by issue slots.
+#ifndef KLT_STREAM_FFMA2
+#define KLT_STREAM_FFMA2 0
+#endif
+__device__ __forceinline__ void sfma2(float& ax, float& ay, float vx, float vy, const TapsF& t, int m) {
+#if KLT_STREAM_FFMA2
+  ffma2(ax, ay, vx, vy, t.kk[m]);
+#else
+  ax = fmaf(vx, t.k[m], ax); ay = fmaf(vy, t.k[m], ay);
+#endif
+}
 
 // Per-warp state that advances by one row per step: the four row pointers (so that no row needs
 // an integer multiply) and the rings.
@@ -92,8 +106,8 @@ __device__ __forceinline__ void l0_stream_row(StreamRow& p, unsigned w, int opit
 #pragma unroll
       for (int c = 0; c < 4; ++c) L[c] = smac<true>(L[c], S[s][c], ts.k[m]);
     } else {
-      ffma2(L[0], L[1], S[s][0], S[s][1], ts.kk[m]);
-      ffma2(L[2], L[3], S[s][2], S[s][3], ts.kk[m]);
+      sfma2(L[0], L[1], S[s][0], S[s][1], ts, m);
+      sfma2(L[2], L[3], S[s][2], S[s][3], ts, m);
     }
   }
   if (BORDER) { if (yl < RS || yl >= H - RS) { L[0] = L[1] = L[2] = L[3] = 0.0f; } }
@@ -117,11 +131,11 @@ __device__ __forceinline__ void l0_stream_row(StreamRow& p, unsigned w, int opit
       }
     } else {
       if (m != RG) {
-        ffma2(hd[0], hd[1], Lw[m], Lw[m + 1], td.kk[m]);
-        ffma2(hd[2], hd[3], Lw[m + 2], Lw[m + 3], td.kk[m]);
+        sfma2(hd[0], hd[1], Lw[m], Lw[m + 1], td, m);
+        sfma2(hd[2], hd[3], Lw[m + 2], Lw[m + 3], td, m);
       }
-      ffma2(hg[0], hg[1], Lw[m], Lw[m + 1], tg.kk[m]);
-      ffma2(hg[2], hg[3], Lw[m + 2], Lw[m + 3], tg.kk[m]);
+      sfma2(hg[0], hg[1], Lw[m], Lw[m + 1], tg, m);
+      sfma2(hg[2], hg[3], Lw[m + 2], Lw[m + 3], tg, m);
     }
   }
 #pragma unroll
@@ -142,11 +156,11 @@ __device__ __forceinline__ void l0_stream_row(StreamRow& p, unsigned w, int opit
         if (m != RG) gy[c] = smac<true>(gy[c], HG[s][c], td.k[m]);
       }
     } else {
-      ffma2(gx[0], gx[1], HD[s][0], HD[s][1], tg.kk[m]);
-      ffma2(gx[2], gx[3], HD[s][2], HD[s][3], tg.kk[m]);
+      sfma2(gx[0], gx[1], HD[s][0], HD[s][1], tg, m);
+      sfma2(gx[2], gx[3], HD[s][2], HD[s][3], tg, m);
       if (m != RG) {
-        ffma2(gy[0], gy[1], HG[s][0], HG[s][1], td.kk[m]);
-        ffma2(gy[2], gy[3], HG[s][2], HG[s][3], td.kk[m]);
+        sfma2(gy[0], gy[1], HG[s][0], HG[s][1], td, m);
+        sfma2(gy[2], gy[3], HG[s][2], HG[s][3], td, m);
       }
     }
   }
