@@ -180,7 +180,9 @@ def run_b200(args, rank, local_rank, world):
 
     # ---- synthetic sequence: pinned host copy + HBM-resident copy -------------------
     t0 = time.time()
-    frames_h = torch.empty((nframes, nrows, ncols), dtype=torch.uint8, pin_memory=True)
+    # (KLT_BENCH_PAGEABLE=1: ordinary host memory, what a driver that mallocs its frames gets)
+    frames_h = torch.empty((nframes, nrows, ncols), dtype=torch.uint8,
+                           pin_memory=not os.environ.get("KLT_BENCH_PAGEABLE"))
     fh = frames_h.numpy()
     make_frames(synth, ncols, nrows, nframes, 12345 + rank, fh)
     frames_d = frames_h.cuda(non_blocking=False)
