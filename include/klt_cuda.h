@@ -214,6 +214,11 @@ int klt_dev_last_build_stream(const klt_dev *d);
  * (klt_dev_last_build_mega then returns 2). */
 void klt_dev_set_mega_tail(klt_dev *d, int first_level);
 int klt_dev_last_build_bands(const klt_dev *d);
+/* Pageable host frames of >= 1 MB are copied into a pinned staging buffer by n host threads
+ * (OpenMP; default 4, env KLT_B200_STAGE_THREADS; 0 = leave the staging to cudaMemcpyAsync), ~1 MB
+ * chunk by chunk ahead of the DMA.  klt_dev_last_build_staged: 1 if the last build did that. */
+void klt_dev_set_stage_threads(klt_dev *d, int n);
+int klt_dev_last_build_staged(const klt_dev *d);
 /* device time between the two calls, measured with CUDA events recorded on the
  * context's own stream (the stream the kernels run on) */
 int klt_dev_timer_start(klt_dev *d);

@@ -25,6 +25,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <omp.h>
 
 #include "klt_cuda.h"
 
@@ -933,6 +934,8 @@ struct klt_dev {
   cudaEvent_t ev_band[KLT_BAND_EVENTS]; int band_ev_next;
   cudaEvent_t ev_frame_free; int frame_busy;
   int band_rows, last_bands, building_slot;
+  // pageable host frames: parallel memcpy into pinned staging, chunk by chunk ahead of the DMA
+  unsigned char* h_frame; size_t h_frame_cap; cudaEvent_t ev_stage_free; int stage_busy, stage_threads, last_staged;
   // pyramid_mega_kernel: cached schedule + dependency counters (klt_mega.cuh)
   int no_mega, last_mega, mega_tail_from;
   int no_chain, last_chain; unsigned chain_barrier_base;   // levels >= 1 in one launch (levels_chain_kernel)
@@ -1081,6 +1084,8 @@ extern "C" void klt_dev_force_generic(klt_dev* d, int on) { d->force_generic = o
 extern "C" void klt_dev_disable_fused(klt_dev* d, int on) { d->no_fused = on; d->track7_off = on; }
 extern "C" int klt_dev_last_build_fused(const klt_dev* d) { return d->last_fused; }
 extern "C" int klt_dev_last_build_bands(const klt_dev* d) { return d->last_bands; }
+extern "C" int klt_dev_last_build_staged(const klt_dev* d) { return d->last_staged; }
+extern "C" void klt_dev_set_stage_threads(klt_dev* d, int n) { d->stage_threads = n; }
 extern "C" int klt_dev_last_build_mega(const klt_dev* d) { return d->last_mega; }
 extern "C" void klt_dev_disable_mega(klt_dev* d, int on) { d->no_mega = on; }
 extern "C" void klt_dev_disable_stream(klt_dev* d, int on) { d->no_stream = on; }
@@ -1118,6 +1123,12 @@ extern "C" int klt_dev_create(int device, klt_dev** out) {
     e = cudaEventCreateWithFlags(&c->ev_band[i], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_frame_free, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_feat, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_stage_free, cudaEventDisableTiming);
+  // default: up to 4 threads, but never more than the process was told to use (torchrun exports
+  // OMP_NUM_THREADS=1 per rank so that 8 ranks do not oversubscribe the host)
+  c->stage_threads = getenv("KLT_B200_STAGE_THREADS") ? atoi(getenv("KLT_B200_STAGE_THREADS"))
+                                                      : (omp_get_max_threads() < 4 ? omp_get_max_threads() : 4);
+  if (c->stage_threads > omp_get_num_procs()) c->stage_threads = omp_get_num_procs();
   c->band_rows = getenv("KLT_B200_BAND_ROWS") ? atoi(getenv("KLT_B200_BAND_ROWS")) : -1;
   if (e != cudaSuccess) { free(c); return fail(nullptr, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
   c->tstream = c->stream;
@@ -1185,6 +1196,8 @@ extern "C" void klt_dev_destroy(klt_dev* d) {
   for (int i = 0; i < KLT_BAND_EVENTS; ++i) cudaEventDestroy(d->ev_band[i]);
   cudaEventDestroy(d->ev_frame_free);
   cudaEventDestroy(d->ev_feat);
+  cudaEventDestroy(d->ev_stage_free);
+  cudaFreeHost(d->h_frame);
   cudaStreamDestroy(d->cstream);
   cudaStreamDestroy(d->stream);
   cudaStreamDestroy(d->stream2);
@@ -1741,6 +1754,8 @@ struct BandFeed {
   const unsigned char* host;     // tightly packed W x H
   int W, H, fp;                  // fp: row pitch of d->frame
   int nbands, next;              // bands queued / bands the compute stream has been gated on
+  int enqueued;                  // bands whose copies have been queued (pageable frames: one at a time)
+  bool staged;                   // pageable frame: goes through the pinned staging buffer
   int end_row[KLT_MAX_BANDS];    // band b covers rows [end_row[b-1], end_row[b])
   cudaEvent_t ev[KLT_MAX_BANDS];
 };
@@ -1790,32 +1805,90 @@ static void feed_schedule(BandFeed* f, int mode) {
     f->end_row[f->nbands++] = H;
   }
 }
+// Pageable host memory: cudaMemcpyAsync would stage it through the driver's own bounce buffers
+// synchronously at ~10 GB/s (905 us per 4K frame, measured).  One host thread copies at 17 GB/s,
+// four at 62 GB/s (tools/memcpy_probe.c), so the frame is copied into a pinned staging buffer by
+// a few OpenMP threads in 2 MB chunks, each chunk's DMA queued as soon as it is staged
+// (4K call: 867 us -> 412 us with 4 threads, 380 us with 8; pinned frames: 241 us).
+static bool host_ptr_is_pageable(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return at.type == cudaMemoryTypeUnregistered;
+}
+static void parallel_memcpy(unsigned char* dst, const unsigned char* src, size_t bytes, int nthreads) {
+  if (nthreads <= 1 || bytes < (256u << 10)) { memcpy(dst, src, bytes); return; }
+  const int parts = nthreads;
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+  for (int p = 0; p < parts; ++p) {
+    const size_t a = bytes / parts * p, b = p == parts - 1 ? bytes : bytes / parts * (p + 1);
+    memcpy(dst + a, src + a, b - a);
+  }
+}
+static int feed_enqueue_band(klt_dev* d, BandFeed* f, int b) {
+  const int r0 = b == 0 ? 0 : f->end_row[b - 1], r1 = f->end_row[b];
+  if (!f->staged) {
+    const int rows = r1 - r0;
+    unsigned char* dst = d->frame + (size_t)r0 * f->fp;
+    const unsigned char* src = f->host + (size_t)r0 * f->W;
+    Launch l(d, KID_COPY_H2D, d->cstream);
+    if (f->fp == f->W)
+      CU(cudaMemcpyAsync(dst, src, (size_t)rows * f->W, cudaMemcpyHostToDevice, d->cstream));
+    else
+      CU(cudaMemcpy2DAsync(dst, f->fp, src, f->W, f->W, rows, cudaMemcpyHostToDevice, d->cstream));
+  } else {
+    static unsigned chunk_kb = getenv("KLT_B200_STAGE_CHUNK_KB") ? (unsigned)atoi(getenv("KLT_B200_STAGE_CHUNK_KB")) : 2048u;
+    int chunk_rows = (int)((chunk_kb << 10) / (unsigned)f->W);
+    if (chunk_rows < 1) chunk_rows = 1;
+    for (int y = r0; y < r1; y += chunk_rows) {
+      const int rows = (y + chunk_rows < r1 ? y + chunk_rows : r1) - y;
+      unsigned char* stage = d->h_frame + (size_t)y * f->W;
+      parallel_memcpy(stage, f->host + (size_t)y * f->W, (size_t)rows * f->W, d->stage_threads);
+      unsigned char* dst = d->frame + (size_t)y * f->fp;
+      Launch l(d, KID_COPY_H2D, d->cstream);
+      if (f->fp == f->W)
+        CU(cudaMemcpyAsync(dst, stage, (size_t)rows * f->W, cudaMemcpyHostToDevice, d->cstream));
+      else
+        CU(cudaMemcpy2DAsync(dst, f->fp, stage, f->W, f->W, rows, cudaMemcpyHostToDevice, d->cstream));
+    }
+    if (b == f->nbands - 1) {                 // staging buffer free again once the last DMA has read it
+      CU(cudaEventRecord(d->ev_stage_free, d->cstream));
+      d->stage_busy = 1;
+    }
+  }
+  f->ev[b] = d->ev_band[d->band_ev_next];
+  d->band_ev_next = (d->band_ev_next + 1) % KLT_BAND_EVENTS;
+  CU(cudaEventRecord(f->ev[b], d->cstream));
+  f->enqueued = b + 1;
+  return 0;
+}
 static int feed_enqueue_copies(klt_dev* d, BandFeed* f) {
   if (d->frame_busy) {          // the previous build's level-0 kernels may still read d->frame
     CU(cudaStreamWaitEvent(d->cstream, d->ev_frame_free, 0));
     d->frame_busy = 0;
   }
-  int r0 = 0;
-  for (int b = 0; b < f->nbands; ++b) {
-    const int rows = f->end_row[b] - r0;
-    unsigned char* dst = d->frame + (size_t)r0 * f->fp;
-    const unsigned char* src = f->host + (size_t)r0 * f->W;
-    { Launch l(d, KID_COPY_H2D, d->cstream);
-      if (f->fp == f->W)
-        CU(cudaMemcpyAsync(dst, src, (size_t)rows * f->W, cudaMemcpyHostToDevice, d->cstream));
-      else
-        CU(cudaMemcpy2DAsync(dst, f->fp, src, f->W, f->W, rows, cudaMemcpyHostToDevice, d->cstream)); }
-    f->ev[b] = d->ev_band[d->band_ev_next];
-    d->band_ev_next = (d->band_ev_next + 1) % KLT_BAND_EVENTS;
-    CU(cudaEventRecord(f->ev[b], d->cstream));
-    r0 = f->end_row[b];
+  f->next = 0; f->enqueued = 0;
+  const size_t bytes = (size_t)f->W * f->H;
+  f->staged = d->stage_threads > 0 && bytes >= (1u << 20) && host_ptr_is_pageable(f->host);
+  d->last_staged = f->staged ? 1 : 0;
+  if (f->staged) {
+    if (d->h_frame_cap < bytes) {
+      if (sync_all(d)) return fail(d, "stream synchronisation failed");
+      cudaFreeHost(d->h_frame); d->h_frame = nullptr; d->h_frame_cap = 0;
+      CU(cudaHostAlloc(&d->h_frame, bytes, cudaHostAllocDefault));
+      d->h_frame_cap = bytes;
+      d->stage_busy = 0;
+    }
+    if (d->stage_busy) { CU(cudaEventSynchronize(d->ev_stage_free)); d->stage_busy = 0; }
+    return 0;                   // bands are staged and queued one at a time, each followed by its kernels
   }
-  f->next = 0;
+  for (int b = 0; b < f->nbands; ++b)
+    if (feed_enqueue_band(d, f, b)) return 1;
   return 0;
 }
 // gate the compute stream on the next band (or on all of them); returns the rows then available
 static int feed_wait(klt_dev* d, BandFeed* f, bool all, int* rows) {
   do {
+    if (f->next >= f->enqueued && feed_enqueue_band(d, f, f->next)) return 1;
     CU(cudaStreamWaitEvent(d->stream, f->ev[f->next], 0));
     f->next += 1;
   } while (all && f->next < f->nbands);

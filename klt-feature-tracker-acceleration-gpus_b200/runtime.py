@@ -91,6 +91,8 @@ DEV_API = {
     "klt_dev_last_build_fused": (C.c_int, [C.c_void_p]),
     "klt_dev_set_band_rows": (None, [C.c_void_p, C.c_int]),
     "klt_dev_last_build_bands": (C.c_int, [C.c_void_p]),
+    "klt_dev_set_stage_threads": (None, [C.c_void_p, C.c_int]),
+    "klt_dev_last_build_staged": (C.c_int, [C.c_void_p]),
     "klt_dev_last_build_mega": (C.c_int, [C.c_void_p]),
     "klt_dev_disable_mega": (None, [C.c_void_p, C.c_int]),
     "klt_dev_set_mega_tail": (None, [C.c_void_p, C.c_int]),

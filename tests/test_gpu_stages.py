@@ -333,3 +333,28 @@ def test_levels_chain_equals_per_level_kernels(L, oracle, cfg, band_rows, exact)
             for l in range(nlev):
                 assert np.array_equal(got[0][which][l], want.level(which, l))
     L.KLTFreeTrackingContext(tc)
+
+
+def test_pageable_frame_staging_matches(L, oracle):
+    """A pageable host frame of >= 1 MB is copied into pinned staging by a few host threads, chunk
+    by chunk ahead of the DMA; the pyramids are the same as with cudaMemcpyAsync's own staging."""
+    h, w = 1000, 1300
+    img = synth_image(w, h, seed=99)
+    tc = L.KLTCreateTrackingContext()
+    tc.contents.nPyramidLevels, tc.contents.subsampling = 3, 2
+    L.KLTUpdateTCBorder(tc)
+    dev = L.KLTB200Device(tc)
+    q = L.build_desc(tc, w, h, exact=1)
+    got = []
+    for threads, bands in ((4, 256), (1, 0), (0, 256)):
+        L.klt_dev_set_stage_threads(dev, threads)
+        L.klt_dev_set_band_rows(dev, bands)
+        L.dev_build(dev, 0, img, q)
+        assert L.klt_dev_last_build_staged(dev) == (1 if threads > 0 else 0)
+        got.append(device_pyramids(L, dev, 0, 3))
+    want = oracle.build_pyramids(img, params_from_tc(oracle, tc))
+    for g in got:
+        for which in range(3):
+            for l in range(3):
+                assert np.array_equal(g[which][l], want.level(which, l))
+    L.KLTFreeTrackingContext(tc)
