@@ -311,3 +311,84 @@ def test_two_pass_tracking_behind_banded_upload(L, capi, band_rows):
         for u, v in zip(a, b):
             assert u.tobytes() == v.tobytes()
     assert (res[0][-1][2] >= 0).sum() > 300
+
+
+# ---- edge cases ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(40, 44), (49, 49), (30, 200), (64, 52)])
+def test_tiny_images_select_and_track(L, capi, oracle, oracle_mod, shape):
+    """images barely larger than (or smaller than) twice the default border of 24: few or no
+    candidates, every slot padded with NOT_FOUND exactly as the reference does, tracking a list with
+    nothing alive is a no-op."""
+    h, w = shape
+    imgs = [synth_image(w, h, seed=5 + t, shift=(0.7 * t, 0.3 * t)) for t in range(2)]
+    tc = L.KLTCreateTrackingContext()
+    fl = L.KLTCreateFeatureList(20)
+    L.select(tc, imgs[0], fl)
+    x, y, v = _get(capi, fl)
+    p = params_from_tc(oracle, tc)
+    ox, oy, ov = oracle.select(imgs[0], p, 20, sort_kind=oracle_mod.SORT_STABLE)
+    assert np.array_equal(v, ov) and np.array_equal(x, ox) and np.array_equal(y, oy)
+    L.KLTB200SetExact(tc, 1)
+    L.track(tc, imgs[0], imgs[1], fl)
+    gx, gy, gv = _get(capi, fl)
+    tx, ty, tv = oracle.track(oracle.build_pyramids(imgs[0], p), oracle.build_pyramids(imgs[1], p), p, ox, oy, ov)
+    assert np.array_equal(gv, tv) and gx.tobytes() == tx.tobytes() and gy.tobytes() == ty.tobytes()
+    L.KLTFreeFeatureList(fl)
+    L.KLTFreeTrackingContext(tc)
+
+
+def test_even_and_small_windows_are_repaired(L, capi, oracle, oracle_mod, provided):
+    """window 6x4 -> 7x5 and 2x2 -> 3x3, silently, as trackFeatures.c:1258-1278 /
+    selectGoodFeatures.c:313-333 do; results equal the oracle run with the repaired sizes."""
+    for (ww, wh), (rw, rh) in (((6, 4), (7, 5)), ((2, 2), (3, 3))):
+        tc = L.KLTCreateTrackingContext()
+        tc.contents.window_width, tc.contents.window_height = ww, wh
+        L.KLTB200SetExact(tc, 1)
+        fl = L.KLTCreateFeatureList(100)
+        L.select(tc, provided[0], fl)
+        assert (tc.contents.window_width, tc.contents.window_height) == (rw, rh)
+        p = params_from_tc(oracle, tc)
+        ox, oy, ov = oracle.select(provided[0], p, 100, sort_kind=oracle_mod.SORT_STABLE)
+        x, y, v = _get(capi, fl)
+        assert np.array_equal(v, ov) and np.array_equal(x, ox) and np.array_equal(y, oy)
+        L.track(tc, provided[0], provided[1], fl)
+        gx, gy, gv = _get(capi, fl)
+        tx, ty, tv = oracle.track(oracle.build_pyramids(provided[0], p), oracle.build_pyramids(provided[1], p),
+                                  p, ox, oy, ov)
+        assert np.array_equal(gv, tv) and gx.tobytes() == tx.tobytes() and gy.tobytes() == ty.tobytes()
+        L.KLTFreeFeatureList(fl)
+        L.KLTFreeTrackingContext(tc)
+
+
+def test_device_frames_with_odd_pitch_and_offset(L, capi):
+    """KLTTrackFeaturesDevice with a frame that is neither 16 B aligned nor 16 B pitched (no TMA
+    descriptor possible): the tiled kernels take over, same result as the host-frame call."""
+    import ctypes as C
+    import torch
+    h, w = 300, 403
+    imgs = [synth_image(w, h, seed=31, shift=(1.3 * t, -0.6 * t)) for t in range(3)]
+    res = []
+    for mode in ("host", "device"):
+        tc = L.KLTCreateTrackingContext()
+        tc.contents.sequentialMode = 1
+        fl = L.KLTCreateFeatureList(120)
+        L.select(tc, imgs[0], fl)
+        if mode == "host":
+            for k in (1, 2):
+                L.track(tc, imgs[k - 1], imgs[k], fl)
+        else:
+            pitch = w + 5
+            bufs = []
+            for im in imgs:
+                buf = torch.zeros(h * pitch + 3, dtype=torch.uint8, device="cuda")
+                view = buf[3:3 + h * pitch].view(h, pitch)
+                view[:, :w] = torch.from_numpy(im).cuda()
+                bufs.append(buf)
+            torch.cuda.synchronize()
+            for k in (1, 2):
+                L.KLTTrackFeaturesDevice(tc, C.c_void_p(bufs[k - 1].data_ptr() + 3), C.c_void_p(bufs[k].data_ptr() + 3),
+                                         pitch, w, h, fl)
+        res.append(tuple(a.tobytes() for a in capi.featurelist_to_arrays(fl)))
+        L.KLTFreeFeatureList(fl)
+        L.KLTFreeTrackingContext(tc)
+    assert res[0] == res[1]
