@@ -1395,7 +1395,7 @@ static bool fused_grad_taps_ok(const TapsR& tg, const TapsR& td) {
 // ---- fused kernels: plan (tensor maps, tile shapes) + launches over whole tile rows ------------
 // A launch covers the tile rows [jr0, jr1) of one level, so that a frame can be built band by band
 // behind its upload (klt_dev_build with a host frame) or in one go (jr0 = 0, jr1 = tiles_y).
-enum LevelShape { SHAPE_NONE = 0, SHAPE_2_5_64_32, SHAPE_2_5_64_16, SHAPE_2_5_32_16, SHAPE_4_10_32_16 };
+enum LevelShape { SHAPE_NONE = 0, SHAPE_2_5_64_32, SHAPE_2_5_64_16, SHAPE_2_5_32_16, SHAPE_4_10_32_16, SHAPE_2_5_64_24 };
 struct FusedPlan {
   bool l0_stream;                               // level 0 runs on l0_stream_kernel (no tensor map; TY[0] = rows per segment)
   const unsigned char* src; int spitch;
@@ -1412,7 +1412,7 @@ static int level_shape_for(int ss, int r, long px) {
     // need many small tiles to fill 148 SMs and to keep the per-CTA latency short
     static int force = getenv("KLT_B200_LEVEL_TILE") ? atoi(getenv("KLT_B200_LEVEL_TILE")) : 0;
     const int shape = force ? force : (px >= 1500000 ? 1 : (px >= 300000 ? 2 : 3));
-    return shape == 1 ? SHAPE_2_5_64_32 : (shape == 2 ? SHAPE_2_5_64_16 : SHAPE_2_5_32_16);
+    return shape == 1 ? SHAPE_2_5_64_32 : (shape == 2 ? SHAPE_2_5_64_16 : (shape == 4 ? SHAPE_2_5_64_24 : SHAPE_2_5_32_16));
   }
   if (ss == 4 && r == 10) return SHAPE_4_10_32_16;
   return SHAPE_NONE;
@@ -1453,6 +1453,7 @@ static void fused_plan(klt_dev* d, const PyrSet& S, const unsigned char* src, in
     bool ok = false;
     switch (shape) {
       case SHAPE_2_5_64_32: ok = level_map<2, 5, 64, 32>(&P->map[l], a); P->TX[l] = 64; P->TY[l] = 32; break;
+      case SHAPE_2_5_64_24: ok = level_map<2, 5, 64, 24>(&P->map[l], a); P->TX[l] = 64; P->TY[l] = 24; break;
       case SHAPE_2_5_64_16: ok = level_map<2, 5, 64, 16>(&P->map[l], a); P->TX[l] = 64; P->TY[l] = 16; break;
       case SHAPE_2_5_32_16: ok = level_map<2, 5, 32, 16>(&P->map[l], a); P->TX[l] = 32; P->TY[l] = 16; break;
       case SHAPE_4_10_32_16: ok = level_map<4, 10, 32, 16>(&P->map[l], a); P->TX[l] = 32; P->TY[l] = 16; break;
@@ -1527,6 +1528,7 @@ static int level_fused_launch(klt_dev* d, const FusedPlan& P, int level, const L
   if (jr1 <= jr0) return 0;
   switch (P.shape[level]) {
     case SHAPE_2_5_64_32: return level_fused_launch_t<2, 5, 64, 32, EXACT>(d, P, level, a, b, tp, tg, td, jr0, jr1);
+    case SHAPE_2_5_64_24: return level_fused_launch_t<2, 5, 64, 24, EXACT>(d, P, level, a, b, tp, tg, td, jr0, jr1);
     case SHAPE_2_5_64_16: return level_fused_launch_t<2, 5, 64, 16, EXACT>(d, P, level, a, b, tp, tg, td, jr0, jr1);
     case SHAPE_2_5_32_16: return level_fused_launch_t<2, 5, 32, 16, EXACT>(d, P, level, a, b, tp, tg, td, jr0, jr1);
     case SHAPE_4_10_32_16: return level_fused_launch_t<4, 10, 32, 16, EXACT>(d, P, level, a, b, tp, tg, td, jr0, jr1);

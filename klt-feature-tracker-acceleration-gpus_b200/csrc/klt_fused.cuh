@@ -209,7 +209,7 @@ __device__ __forceinline__ void stage_vgrad_both(const float* sHd, const float* 
                                                  const TapsF& td, float* out_gx, float* out_gy,
                                                  int opitch, int x0, int y0, int W, int H) {
   constexpr int NCG = TX / 4, NRB = TY / PY, ITEMS = NCG * NRB;       // per output image
-  static_assert(ITEMS <= 128 && 128 % ITEMS == 0, "stage D mapping");
+  static_assert(ITEMS <= 128, "stage D mapping");
   const int tid = threadIdx.x;
   const int t = tid & 127;
   if (t < ITEMS) {
@@ -560,7 +560,7 @@ __device__ __forceinline__ void lv_stage_rest(unsigned char* smem, const TapsF& 
 // W,H: size of the level being produced; Wsrc,Hsrc: size of the level it is made from.
 // Dynamic tile scheduler as in l0_fused_kernel.
 template <int SS, int R, int TX, int TY, bool EXACT>
-__global__ void __launch_bounds__(256, (LvGeo<SS, R, TX, TY>::SMEM <= 58 * 1024) ? 3 : 2)
+__global__ void __launch_bounds__(256, (LvGeo<SS, R, TX, TY>::SMEM <= 75 * 1024) ? 3 : 2)
 level_fused_kernel(const __grid_constant__ CUtensorMap map, int Wsrc, int Hsrc, int W, int H,
                    int tiles_x, int tile0, int ntiles, unsigned* __restrict__ counter, unsigned base,
                    TapsF tp, TapsF tg, TapsF td,
