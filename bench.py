@@ -213,6 +213,9 @@ def run_b200(args, rank, local_rank, world):
     idx = lambda s: synth.pingpong_index(s, nframes)
 
     # ---- (1) value: frames resident in HBM, features resident, no host sync ----------
+    # (nvidia-smi is sampled every 100 ms from here to the end of the e2e legs; the rows taken are
+    # those between the start of the first timed region and the end of the last)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     restart()
     L.KLTB200ResidentBegin(tc, C.c_void_p(d_ptr(0)), 1, ncols, ncols, nrows, fl)
     step = 1
@@ -223,7 +226,6 @@ def run_b200(args, rank, local_rank, world):
     L.klt_dev_live_total(dev, C.byref(live), 1)
     launches0 = L.klt_dev_launch_count(dev)
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     wall0 = time.time()
     L.klt_dev_timer_start(dev)
     for _ in range(K):
@@ -232,8 +234,6 @@ def run_b200(args, rank, local_rank, world):
     ms = C.c_float(0)
     L.klt_dev_timer_stop(dev, C.byref(ms))
     barrier()
-    wall1 = time.time()
-    clocks = sampler.stop(wall0, wall1) if sampler else None
     launches = int(L.klt_dev_launch_count(dev) - launches0)
     L.klt_dev_live_total(dev, C.byref(live), 1)
     L.KLTB200ResidentEnd(tc, fl)
@@ -258,6 +258,28 @@ def run_b200(args, rank, local_rank, world):
     L.klt_dev_live_total(dev, C.byref(live), 1)
     e2e_feats = int(live.value)
 
+    # ---- (2b) e2e, batched: KLTTrackFeaturesSequence over the same pinned HOST frames -----
+    # (one call for K frames, per-frame results into a feature table; frame k+1 crosses PCIe while
+    # frame k is processed; the call returns after its single synchronisation)
+    restart()
+    ft = L.KLTCreateFeatureTable(K + 1, nfeat)
+    C.memset(C.cast(ft.contents.feature[0][0], C.c_void_p), 0,          # map the table's pages now
+             (K + 1) * nfeat * C.sizeof(capi.KLT_FeatureRec))
+    warm = (C.c_void_p * (W + 1))(*[h_ptr(idx(s)) for s in range(W + 1)])
+    L.KLTTrackFeaturesSequence(tc, warm, W + 1, ncols, nrows, fl, None, 0, 0)
+    seq = (C.c_void_p * (K + 1))(*[h_ptr(idx(W + s)) for s in range(K + 1)])
+    L.klt_dev_live_total(dev, C.byref(live), 1)
+    barrier()
+    t0 = time.perf_counter()
+    L.KLTTrackFeaturesSequence(tc, seq, K + 1, ncols, nrows, fl, ft, 0, 0)
+    seq_s = time.perf_counter() - t0
+    barrier()
+    L.klt_dev_live_total(dev, C.byref(live), 1)
+    seq_feats = int(live.value)
+    L.KLTFreeFeatureTable(ft)
+    wall1 = time.time()
+    clocks = sampler.stop(wall0, wall1) if sampler else None
+
     # ---- (3) per-kernel device time (CUDA events on the launching stream) ------------
     restart()
     L.KLTB200ResidentBegin(tc, C.c_void_p(d_ptr(0)), 1, ncols, ncols, nrows, fl)
@@ -275,12 +297,12 @@ def run_b200(args, rank, local_rank, world):
 
     # ---- reduce over ranks: sum of features, max of time -------------------------------
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dev_ms, e2e_s, seq_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        c = torch.tensor([dev_feats, e2e_feats], dtype=torch.float64, device="cuda")
+        c = torch.tensor([dev_feats, e2e_feats, seq_feats], dtype=torch.float64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        dev_ms, e2e_s = float(t[0]), float(t[1])
-        dev_feats, e2e_feats = int(c[0]), int(c[1])
+        dev_ms, e2e_s, seq_s = float(t[0]), float(t[1]), float(t[2])
+        dev_feats, e2e_feats, seq_feats = int(c[0]), int(c[1]), int(c[2])
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -343,6 +365,13 @@ def run_b200(args, rank, local_rank, world):
                            "goes up in 2 bands behind which the pyramid kernels run, the feature records "
                            "(64 B each) are mirrored in one copy and the tracker writes x|y|val (12 B) of "
                            "every feature straight into the caller's pinned feature list"},
+            "e2e_sequence": {"value": round(seq_feats / seq_s, 1), "unit": UNIT,
+                             "frames_per_s": round(K * world / seq_s, 1), "ms_per_step": round(seq_s / K * 1e3, 4),
+                             "h2d_bytes_per_step": fbytes, "d2h_bytes_per_step": 12 * nfeat,
+                             "api": "KLTTrackFeaturesSequence(tc, frames[K+1], ..., fl, ft, 0, 0): one call for K "
+                                    "pinned host frames, per-frame x|y|val snapshots into a KLT_FeatureTable; the "
+                                    "upload of frame k+1 overlaps the kernels of frame k (PCIe-bound), one "
+                                    "synchronisation at the end; wall clock around the call"},
             "gpu_launches": launches, "kernels": kernels, "roofline": roofline, "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -492,7 +521,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="4k", choices=sorted(WORKLOADS))

@@ -49,6 +49,27 @@ void KLTB200ResidentStep(KLT_TrackingContext tc, const KLT_PixelType *img2, int 
                          size_t pitch, int ncols, int nrows);
 void KLTB200ResidentEnd(KLT_TrackingContext tc, KLT_FeatureList fl);
 
+/* Batched driver API: track fl through a whole sequence of HOST frames in one call.
+ * Equivalent, result for result, to the reference's driver loop (src/V3/example3.c:54-76)
+ *
+ *     for (k = 1; k < nframes; k++) {
+ *       KLTTrackFeatures(tc, frames[k-1], frames[k], ncols, nrows, fl);
+ *       if (replace) KLTReplaceLostFeatures(tc, frames[k], ncols, nrows, fl);
+ *       if (ft) KLTStoreFeatureList(fl, ft, first_frame + k);
+ *     }
+ *
+ * with tc->sequentialMode = TRUE, but nothing waits for a frame's result before the next frame is
+ * queued: frame k+1 crosses PCIe (two device staging buffers) while frame k's pyramids are built
+ * and its features tracked, the features stay in HBM, every frame's x | y | val snapshot is copied
+ * into pinned memory behind the tracker, and the host synchronises once at the end.  frames[0] is
+ * only read when tc holds no previous pyramid (as img1 in KLTTrackFeatures) and may then not be
+ * NULL.  ft may be NULL; column first_frame + k receives frame k (column first_frame is not
+ * written: the caller stores the selection itself, as example3 does).  On return fl holds the
+ * state after the last frame and tc is in sequential mode with the last frame's pyramids held. */
+void KLTTrackFeaturesSequence(KLT_TrackingContext tc, KLT_PixelType *const *frames, int nframes,
+                              int ncols, int nrows, KLT_FeatureList fl, KLT_FeatureTable ft,
+                              int first_frame, int replace);
+
 #ifdef __cplusplus
 }
 #endif

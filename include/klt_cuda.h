@@ -119,6 +119,15 @@ int klt_dev_features_upload(klt_dev *d, int n, const float *x, const float *y, c
 int klt_dev_track_resident(klt_dev *d, int slot_prev, int slot_cur,
                            const klt_dev_track_params *p);
 int klt_dev_features_download(klt_dev *d, int n, float *x, float *y, int *val);   /* synchronises */
+/* Ring of pinned snapshots of the resident features for pipelined drivers
+ * (KLTTrackFeaturesSequence): klt_dev_snapshot_ring sizes it (depth <= 64 slots),
+ * klt_dev_snapshot_push queues a copy of the current x | y | val into a slot behind the work
+ * queued so far (no synchronisation), klt_dev_snapshot_wait blocks until that copy has landed and
+ * returns pointers into the slot (valid until the slot is pushed again). */
+int klt_dev_features_capacity(const klt_dev *d);
+int klt_dev_snapshot_ring(klt_dev *d, int depth);
+int klt_dev_snapshot_push(klt_dev *d, int slot);
+int klt_dev_snapshot_wait(klt_dev *d, int slot, const float **x, const float **y, const int **val);
 /* Arm an early tracker pass for the next klt_dev_build of a HOST frame (features already
  * committed, slot_prev valid): if the frame goes up in bands and the 7x7 fma tracker applies, its
  * first pass is launched right behind the first band's pyramid rows -- while the rest of the frame
@@ -156,6 +165,9 @@ void klt_dev_host_free(void *p);
  * order (== the reference built with -DKLT_USE_QSORT on glibc).  Synchronous. */
 int klt_dev_select(klt_dev *d, int slot, const klt_dev_select_params *p,
                    int n, float *x, float *y, int *val);
+/* the same on the device-resident feature arrays (klt_dev_features_upload ...): no copies, no
+ * synchronisation; with p->overwrite_all == 0 this is KLTReplaceLostFeatures */
+int klt_dev_select_resident(klt_dev *d, int slot, const klt_dev_select_params *p);
 
 /* ---- introspection (parity tests, debugging) --------------------------- */
 /* which: 0 image, 1 gradx, 2 grady.  out: dense ncols*nrows floats of that level. */

@@ -900,6 +900,7 @@ static constexpr int PROF_POOL = 2048;     // event pairs in flight before foldi
 static constexpr int TRACE_CAP = 8192;     // timeline records kept per profiling session
 static constexpr int KLT_BAND_EVENTS = 64; // events cycled by the banded frame upload
 
+static constexpr int KLT_SNAP_MAX = 64;
 struct Level {
   int w, h, pitch;           // pitch in floats
   float *img, *gx, *gy;
@@ -927,12 +928,13 @@ struct klt_dev {
   PyrSet set[KLT_DEV_SLOTS];
   float* arena;
   float* tmp;                // generic path: horizontal-pass result, W*H floats
-  unsigned char* frame;      // u8 staging of the frame being built, row pitch frame_pitch
+  unsigned char* frame;      // u8 staging of the frame being built (== frame_buf[frame_idx]), row pitch frame_pitch
+  unsigned char* frame_buf[2]; int frame_idx;   // two buffers: frame k+1 goes up while level 0 of frame k is still reading
   size_t frame_cap; int frame_pitch;
   // banded upload of host frames: copy stream, one event per band, "staging consumed" event
   cudaStream_t cstream;
   cudaEvent_t ev_band[KLT_BAND_EVENTS]; int band_ev_next;
-  cudaEvent_t ev_frame_free; int frame_busy;
+  cudaEvent_t ev_frame_free[2]; int frame_busy[2];   // per staging buffer
   int band_rows, last_bands, building_slot;
   // pageable host frames: parallel memcpy into pinned staging, chunk by chunk ahead of the DMA
   unsigned char* h_frame; size_t h_frame_cap; cudaEvent_t ev_stage_free; int stage_busy, stage_threads, last_staged;
@@ -957,6 +959,8 @@ struct klt_dev {
   int feat_out_host;            // 1: the next tracker writes its results into h_x/h_y/h_val (sync API); 2: record mode
   unsigned char* d_rec; size_t d_rec_cap; void* h_rec; int rec_stride;   // record mode (klt_dev_features_commit_records)
   cudaEvent_t ev_feat; int feat_pending;   // feature upload queued on the copy stream
+  // ring of pinned feature snapshots (klt_dev_snapshot_*)
+  unsigned char* snap_ring; size_t snap_bytes; int snap_depth, snap_events; cudaEvent_t ev_snap[KLT_SNAP_MAX];
   // selection
   int *c_val[2]; unsigned* c_idx[2]; size_t cand_cap;
   void* cub_tmp; size_t cub_bytes;
@@ -1121,7 +1125,7 @@ extern "C" int klt_dev_create(int device, klt_dev** out) {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->cstream, cudaStreamNonBlocking);
   for (int i = 0; i < KLT_BAND_EVENTS && e == cudaSuccess; ++i)
     e = cudaEventCreateWithFlags(&c->ev_band[i], cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_frame_free, cudaEventDisableTiming);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ev_frame_free[i], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_feat, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_stage_free, cudaEventDisableTiming);
   // default: up to 4 threads, but never more than the process was told to use (torchrun exports
@@ -1178,7 +1182,7 @@ extern "C" void klt_dev_destroy(klt_dev* d) {
   cudaSetDevice(d->device);
   sync_all(d);
   free_geometry(d);
-  cudaFree(d->frame);
+  cudaFree(d->frame_buf[0]); cudaFree(d->frame_buf[1]);
   cudaFree(d->d_x);
   cudaFreeHost(d->h_x);
   for (int i = 0; i < 2; ++i) { cudaFree(d->c_val[i]); cudaFree(d->c_idx[i]); }
@@ -1194,10 +1198,12 @@ extern "C" void klt_dev_destroy(klt_dev* d) {
   for (int i = 0; i < KLT_DEV_SLOTS; ++i) { cudaEventDestroy(d->ev_built[i]); cudaEventDestroy(d->ev_read[i]); }
   cudaEventDestroy(d->ev_join);
   for (int i = 0; i < KLT_BAND_EVENTS; ++i) cudaEventDestroy(d->ev_band[i]);
-  cudaEventDestroy(d->ev_frame_free);
+  cudaEventDestroy(d->ev_frame_free[0]); cudaEventDestroy(d->ev_frame_free[1]);
   cudaEventDestroy(d->ev_feat);
   cudaEventDestroy(d->ev_stage_free);
   cudaFreeHost(d->h_frame);
+  cudaFreeHost(d->snap_ring);
+  for (int i = 0; i < d->snap_events; ++i) cudaEventDestroy(d->ev_snap[i]);
   cudaStreamDestroy(d->cstream);
   cudaStreamDestroy(d->stream);
   cudaStreamDestroy(d->stream2);
@@ -1864,9 +1870,9 @@ static int feed_enqueue_band(klt_dev* d, BandFeed* f, int b) {
   return 0;
 }
 static int feed_enqueue_copies(klt_dev* d, BandFeed* f) {
-  if (d->frame_busy) {          // the previous build's level-0 kernels may still read d->frame
-    CU(cudaStreamWaitEvent(d->cstream, d->ev_frame_free, 0));
-    d->frame_busy = 0;
+  if (d->frame_busy[d->frame_idx]) {          // the previous build's level-0 kernels may still read d->frame
+    CU(cudaStreamWaitEvent(d->cstream, d->ev_frame_free[d->frame_idx], 0));
+    d->frame_busy[d->frame_idx] = 0;
   }
   f->next = 0; f->enqueued = 0;
   const size_t bytes = (size_t)f->W * f->H;
@@ -1934,9 +1940,9 @@ static int mega_build(klt_dev* d, PyrSet& S, const FusedPlan& P, int nb, const T
     d->feed_epoch += 1;
     MP.u8_base = d->feed_epoch * 8192u;
     bool flags_ok = wv != nullptr && feed->H < 8192;
-    if (d->frame_busy) {          // the previous build's level-0 tiles may still read d->frame
-      CU(cudaStreamWaitEvent(d->cstream, d->ev_frame_free, 0));
-      d->frame_busy = 0;
+    if (d->frame_busy[d->frame_idx]) {          // the previous build's level-0 tiles may still read d->frame
+      CU(cudaStreamWaitEvent(d->cstream, d->ev_frame_free[d->frame_idx], 0));
+      d->frame_busy[d->frame_idx] = 0;
     }
     int r0 = 0;
     for (int b = 0; b < feed->nbands; ++b) {
@@ -1971,8 +1977,8 @@ static int mega_build(klt_dev* d, PyrSet& S, const FusedPlan& P, int nb, const T
   }
   if (rc) return rc;
   if (feed) {
-    CU(cudaEventRecord(d->ev_frame_free, d->stream));
-    d->frame_busy = 1;
+    CU(cudaEventRecord(d->ev_frame_free[d->frame_idx], d->stream));
+    d->frame_busy[d->frame_idx] = 1;
   }
   return 0;
 }
@@ -2087,8 +2093,8 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
     }
     if (feed) {
       d->last_bands = feed->nbands;
-      CU(cudaEventRecord(d->ev_frame_free, d->stream));
-      d->frame_busy = 1;
+      CU(cudaEventRecord(d->ev_frame_free[d->frame_idx], d->stream));
+      d->frame_busy[d->frame_idx] = 1;
     }
     for (int l = 0; l < nb; ++l)
       if (rows_done[l] != (l == 0 || l >= nl ? P.tiles_y[l] : PL.tiles_y[l])) return fail(d, "banded build left level %d incomplete", l);
@@ -2129,8 +2135,8 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
     u8_to_f32_kernel<<<g, b, 0, d->stream>>>(src, spitch, W, H, S.lv[0].img, S.lv[0].pitch);
   }
   if (feed) {                        // d->frame has been consumed by the level-0 kernel(s) above
-    CU(cudaEventRecord(d->ev_frame_free, d->stream));
-    d->frame_busy = 1;
+    CU(cudaEventRecord(d->ev_frame_free[d->frame_idx], d->stream));
+    d->frame_busy[d->frame_idx] = 1;
   }
   // coarser levels
   bool grads_done[KLT_DEV_MAX_LEVELS] = {false};
@@ -2197,11 +2203,13 @@ extern "C" int klt_dev_build(klt_dev* d, int slot, const unsigned char* img, int
     const size_t bytes = (size_t)fp * H;
     if (d->frame_cap < bytes) {
       if (sync_all(d)) return fail(d, "stream synchronisation failed");
-      cudaFree(d->frame); d->frame = nullptr; d->frame_cap = 0;
-      CU(cudaMalloc(&d->frame, bytes));
+      for (int i = 0; i < 2; ++i) { cudaFree(d->frame_buf[i]); d->frame_buf[i] = nullptr; d->frame_busy[i] = 0; }
+      d->frame = nullptr; d->frame_cap = 0;
+      for (int i = 0; i < 2; ++i) CU(cudaMalloc(&d->frame_buf[i], bytes));
       d->frame_cap = bytes;
-      d->frame_busy = 0;
     }
+    d->frame_idx ^= 1;                          // the other buffer may still be read by the previous build
+    d->frame = d->frame_buf[d->frame_idx];
     // uploaded inside build_impl: band by band on the copy stream when every level runs fused
     feed.host = img; feed.W = W; feed.H = H; feed.fp = fp;
     feed_schedule(&feed, d->band_rows);
@@ -2349,6 +2357,46 @@ extern "C" int klt_dev_features_fetch(klt_dev* d, int n) {       // D2H into the
   if (d->feat_pending) { CU(cudaStreamSynchronize(d->cstream)); d->feat_pending = 0; }
   if (d->overlap) CU(cudaStreamSynchronize(d->stream));
   d->staging_busy = 0;
+  return 0;
+}
+
+// pipelined drivers: a ring of pinned snapshots of the resident features (x | y | val, `capacity`
+// entries each).  push queues the copy of the current state into a ring slot behind the work queued
+// so far and records the slot's event; wait blocks until that copy has landed.  The host thread
+// consumes frame k - depth while frames k - depth + 1 .. k are still queued or running.
+extern "C" int klt_dev_features_capacity(const klt_dev* d) { return d->feat_cap; }
+extern "C" int klt_dev_snapshot_ring(klt_dev* d, int depth) {
+  CU(cudaSetDevice(d->device));
+  if (depth < 1 || depth > KLT_SNAP_MAX) return fail(d, "snapshot ring depth %d (1..%d)", depth, KLT_SNAP_MAX);
+  if (d->feat_cap <= 0) return fail(d, "snapshot ring: no device-resident features");
+  const size_t bytes = (size_t)depth * d->feat_cap * 12;
+  if (d->snap_bytes < bytes) {
+    if (sync_all(d)) return fail(d, "stream synchronisation failed");
+    cudaFreeHost(d->snap_ring); d->snap_ring = nullptr; d->snap_bytes = 0;
+    CU(cudaHostAlloc(&d->snap_ring, bytes, cudaHostAllocDefault));
+    d->snap_bytes = bytes;
+  }
+  for (int i = d->snap_events; i < depth; ++i) {
+    CU(cudaEventCreateWithFlags(&d->ev_snap[i], cudaEventDisableTiming));
+    d->snap_events = i + 1;
+  }
+  d->snap_depth = depth;
+  return 0;
+}
+extern "C" int klt_dev_snapshot_push(klt_dev* d, int slot) {
+  CU(cudaSetDevice(d->device));
+  if (slot < 0 || slot >= d->snap_depth || d->feat_out_host != 0) return fail(d, "snapshot_push: slot %d of %d", slot, d->snap_depth);
+  { Launch l(d, KID_COPY_D2H, d->tstream);
+    CU(cudaMemcpyAsync(d->snap_ring + (size_t)slot * d->feat_cap * 12, d->d_x, (size_t)d->feat_cap * 12,
+                       cudaMemcpyDeviceToHost, d->tstream)); }
+  CU(cudaEventRecord(d->ev_snap[slot], d->tstream));
+  return 0;
+}
+extern "C" int klt_dev_snapshot_wait(klt_dev* d, int slot, const float** x, const float** y, const int** val) {
+  if (slot < 0 || slot >= d->snap_depth) return fail(d, "snapshot_wait: slot %d of %d", slot, d->snap_depth);
+  CU(cudaEventSynchronize(d->ev_snap[slot]));
+  const float* base = reinterpret_cast<const float*>(d->snap_ring + (size_t)slot * d->feat_cap * 12);
+  *x = base; *y = base + d->feat_cap; *val = reinterpret_cast<const int*>(base + 2 * (size_t)d->feat_cap);
   return 0;
 }
 
@@ -2629,8 +2677,10 @@ extern "C" int klt_dev_eigen_map(klt_dev* d, int slot, const klt_dev_select_para
   return 0;
 }
 
-extern "C" int klt_dev_select(klt_dev* d, int slot, const klt_dev_select_params* p, int n,
-                              float* x, float* y, int* val) {
+// selection over the features resident on the device (d_x | d_y | d_val): eigenvalue map, ranking,
+// minimum-distance pass; host == nullptr leaves the result on the device (no synchronisation)
+static int select_core(klt_dev* d, int slot, const klt_dev_select_params* p, int n,
+                       float* x, float* y, int* val, bool host) {
   CU(cudaSetDevice(d->device));
   if (!d->arena || slot < 0 || slot >= KLT_DEV_SLOTS || d->set[slot].built_levels < 1) return fail(d, "select: slot %d has no level 0", slot);
   if (n <= 0) return 0;
@@ -2641,7 +2691,8 @@ extern "C" int klt_dev_select(klt_dev* d, int slot, const klt_dev_select_params*
   int mindist = p->mindist < 0 ? 0 : p->mindist;
   const int dist = mindist - 1;                    // the reference works with mindist-1 (:157)
   const int min_eig = p->min_eigenvalue < 1 ? 1 : p->min_eigenvalue;   // (:148)
-  if (klt_dev_features_upload(d, n, x, y, val)) return 1;
+  if (host && klt_dev_features_upload(d, n, x, y, val)) return 1;
+  if (!host && (n != d->feat_n || d->feat_out_host != 0)) return fail(d, "select_resident: %d features are not resident on the device", n);
   const size_t npx = (size_t)d->W * d->H;
   if (d->fmap_cap < npx) {
     CU(cudaStreamSynchronize(d->stream));
@@ -2675,7 +2726,16 @@ extern "C" int klt_dev_select(klt_dev* d, int slot, const klt_dev_select_params*
                                                    g.step, d->W, d->H, d->fmap, dist, min_eig,
                                                    p->overwrite_all, n, d->d_x, d->d_y, d->d_val, d->open_slots); }
   CU(cudaGetLastError());
-  return klt_dev_features_download(d, n, x, y, val);
+  return host ? klt_dev_features_download(d, n, x, y, val) : 0;
+}
+extern "C" int klt_dev_select(klt_dev* d, int slot, const klt_dev_select_params* p, int n,
+                              float* x, float* y, int* val) {
+  return select_core(d, slot, p, n, x, y, val, true);
+}
+// KLTReplaceLostFeatures / KLTSelectGoodFeatures on the device-resident feature arrays (pipelined
+// drivers, klt_dev_features_upload ... klt_dev_features_download); nothing is synchronised
+extern "C" int klt_dev_select_resident(klt_dev* d, int slot, const klt_dev_select_params* p) {
+  return select_core(d, slot, p, d->feat_n, nullptr, nullptr, nullptr, false);
 }
 
 // ---- device timing on the context stream (benches) ------------------------------

@@ -38,6 +38,9 @@ void klt_fill_build_desc(KLT_TrackingContext tc, int ncols, int nrows,
 /* 1 if fl is a pinned block made by KLTCreateFeatureList (record mode of the tracker) */
 int klt_list_is_pinned(const void *p);
 
+/* device selection parameters from a tracking context (csrc/klt_select.c) */
+void klt_fill_select_params(KLT_TrackingContext tc, int replacing, klt_dev_select_params *sp);
+
 /* list <-> SoA staging */
 void klt_list_to_arrays(KLT_FeatureList fl, float *x, float *y, int *v);
 

@@ -21,6 +21,25 @@
     if ((call) != 0) KLTError("(KLT/B200) %s", klt_dev_error((s)->dev));      \
   } while (0)
 
+/* parameters of the device selection, with the reference's repair of a negative mindist
+ * (selectGoodFeatures.c:430-434) */
+void klt_fill_select_params(KLT_TrackingContext tc, int replacing, klt_dev_select_params *sp)
+{
+  if (tc->mindist < 0) {
+    KLTWarning("(_KLTSelectGoodFeatures) Tracking context field tc->mindist "
+               "is negative (%d); setting to zero", tc->mindist);
+    tc->mindist = 0;
+  }
+  sp->window_width = tc->window_width;
+  sp->window_height = tc->window_height;
+  sp->borderx = tc->borderx;
+  sp->bordery = tc->bordery;
+  sp->nSkippedPixels = tc->nSkippedPixels;
+  sp->mindist = tc->mindist;
+  sp->min_eigenvalue = tc->min_eigenvalue;
+  sp->overwrite_all = replacing ? 0 : 1;
+}
+
 static void select_common(KLT_TrackingContext tc, const KLT_PixelType *img, int ncols, int nrows,
                           KLT_FeatureList fl, int replacing)
 {
@@ -52,19 +71,7 @@ static void select_common(KLT_TrackingContext tc, const KLT_PixelType *img, int 
     DEVCALL(s, klt_dev_build(dev, slot, img, 0, (size_t)ncols, &q));
   }
 
-  if (tc->mindist < 0) {
-    KLTWarning("(_KLTSelectGoodFeatures) Tracking context field tc->mindist "
-               "is negative (%d); setting to zero", tc->mindist);
-    tc->mindist = 0;
-  }
-  sp.window_width = tc->window_width;
-  sp.window_height = tc->window_height;
-  sp.borderx = tc->borderx;
-  sp.bordery = tc->bordery;
-  sp.nSkippedPixels = tc->nSkippedPixels;
-  sp.mindist = tc->mindist;
-  sp.min_eigenvalue = tc->min_eigenvalue;
-  sp.overwrite_all = replacing ? 0 : 1;
+  klt_fill_select_params(tc, replacing, &sp);
 
   x = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
   y = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));

@@ -11,6 +11,7 @@
  */
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <time.h>
 
 #include "klt_internal.h"
@@ -255,4 +256,96 @@ void KLTB200ResidentEnd(KLT_TrackingContext tc, KLT_FeatureList fl)
     fl->feature[i]->val = v[i];
   }
   free(x); free(y); free(v);
+}
+
+/* ---- batched driver API: a whole sequence of host frames in one call ------------ */
+/* Replaces the reference's serial driver loop (src/V3/example3.c:54-76: KLTTrackFeatures,
+ * optional KLTReplaceLostFeatures, KLTStoreFeatureList per frame) with one pipelined call; the
+ * per-frame work is the resident pipeline above, so every frame's result is bit-identical to
+ * the per-call API's. */
+#define SEQ_DEPTH 16          /* frames queued ahead of the one the host is storing */
+
+/* frame k's snapshot -> table column and the affine fields of slots refilled at that frame */
+static void seq_consume(klt_tc_state *s, int slot, KLT_FeatureList fl, KLT_FeatureTable ft,
+                        int column, int replace)
+{
+  const float *x, *y;
+  const int *v;
+  const int n = fl->nFeatures;
+  int i;
+  DEVCALL(s, klt_dev_snapshot_wait(s->dev, slot, &x, &y, &v));
+  if (ft != NULL && n > 0) {
+    /* a table made by KLTCreateFeatureTable keeps its records in one [feature][frame] block
+     * (klt.c:210-236): address them directly and prefetch ahead -- every cell of a column sits
+     * on a different page, so chasing the two pointer levels per cell would be three cache
+     * misses per feature */
+    KLT_Feature base = ft->feature[0][0];
+    const size_t stride = (size_t)ft->nFrames;
+    const int regular = ft->feature[n - 1][column] == base + (size_t)(n - 1) * stride + column;
+    for (i = 0; i < n; i++) {
+      KLT_Feature f = regular ? base + (size_t)i * stride + column : ft->feature[i][column];
+      if (regular && i + 16 < n) __builtin_prefetch(base + (size_t)(i + 16) * stride + column, 1);
+      f->x = x[i]; f->y = y[i]; f->val = v[i];
+    }
+  }
+  if (replace)                  /* a slot refilled at this frame starts a new feature (:514-541) */
+    for (i = 0; i < n; i++)
+      if (v[i] > 0) {
+        KLT_Feature f = fl->feature[i];
+        free(f->aff_img); free(f->aff_img_gradx); free(f->aff_img_grady);
+        f->aff_img = f->aff_img_gradx = f->aff_img_grady = NULL;
+        f->aff_x = f->aff_y = -1.0f;
+        f->aff_Axx = f->aff_Ayy = 1.0f;
+        f->aff_Ayx = f->aff_Axy = 0.0f;
+      }
+}
+
+void KLTTrackFeaturesSequence(KLT_TrackingContext tc, KLT_PixelType *const *frames, int nframes,
+                              int ncols, int nrows, KLT_FeatureList fl, KLT_FeatureTable ft,
+                              int first_frame, int replace)
+{
+  klt_tc_state *s = klt_state_get(tc);
+  const int n = fl->nFeatures;
+  const int snaps = n > 0 && (ft != NULL || replace);
+  klt_dev_select_params sp;
+  int k, stored = 1;            /* next frame whose snapshot is to be consumed */
+
+  if (frames == NULL || nframes < 1)
+    KLTError("(KLTTrackFeaturesSequence) needs at least one frame");
+  if (ft != NULL) {
+    if (fl->nFeatures != ft->nFeatures)
+      KLTError("(KLTTrackFeaturesSequence) FeatureList and FeatureTable must have the same number of features");
+    if (first_frame < 0 || first_frame + nframes - 1 >= ft->nFrames)
+      KLTError("(KLTTrackFeaturesSequence) frames %d .. %d do not fit a table of %d frames",
+               first_frame, first_frame + nframes - 1, ft->nFrames);
+  }
+  for (k = 1; k < nframes; k++)
+    if (frames[k] == NULL) KLTError("(KLTTrackFeaturesSequence) frame %d is NULL", k);
+  if (KLT_verbose >= 1) {
+    fprintf(stderr, "(KLT) Tracking %d features through %d frames of %d by %d...  ",
+            KLTCountRemainingFeatures(fl), nframes - 1, ncols, nrows);
+    fflush(stderr);
+  }
+  tc->sequentialMode = TRUE;
+  if (replace) klt_fix_window(tc, "KLTSelectGoodFeatures", 1);
+  KLTB200ResidentBegin(tc, frames[0], 0, (size_t)ncols, ncols, nrows, fl);
+  if (replace) klt_fill_select_params(tc, 1, &sp);
+  if (snaps && nframes > 1) DEVCALL(s, klt_dev_snapshot_ring(s->dev, SEQ_DEPTH));
+  for (k = 1; k < nframes; k++) {
+    if (snaps && k - stored >= SEQ_DEPTH) {      /* ring full: store the oldest frame while the */
+      seq_consume(s, (stored - 1) % SEQ_DEPTH, fl, ft, first_frame + stored, replace);   /* GPU runs */
+      stored++;
+    }
+    KLTB200ResidentStep(tc, frames[k], 0, (size_t)ncols, ncols, nrows);
+    if (replace && n > 0)       /* REPLACING_SOME on the level-0 gradients just built (:342-348) */
+      DEVCALL(s, klt_dev_select_resident(s->dev, s->last_slot, &sp));
+    if (snaps) DEVCALL(s, klt_dev_snapshot_push(s->dev, (k - 1) % SEQ_DEPTH));
+  }
+  for (; snaps && stored < nframes; stored++)
+    seq_consume(s, (stored - 1) % SEQ_DEPTH, fl, ft, first_frame + stored, replace);
+  KLTB200ResidentEnd(tc, fl);
+  if (KLT_verbose >= 1) {
+    fprintf(stderr, "\n\t%d features alive after the last frame.\n", KLTCountRemainingFeatures(fl));
+    fflush(stderr);
+  }
 }

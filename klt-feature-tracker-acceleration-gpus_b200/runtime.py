@@ -119,6 +119,14 @@ DEV_API = {
     "KLTB200ResidentBegin": (None, [_TC, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_int, _FL]),
     "KLTB200ResidentStep": (None, [_TC, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_int]),
     "KLTB200ResidentEnd": (None, [_TC, _FL]),
+    "KLTTrackFeaturesSequence": (None, [_TC, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, _FL,
+                                        capi.KLT_FeatureTable, C.c_int, C.c_int]),
+    "klt_dev_features_capacity": (C.c_int, [C.c_void_p]),
+    "klt_dev_snapshot_ring": (C.c_int, [C.c_void_p, C.c_int]),
+    "klt_dev_snapshot_push": (C.c_int, [C.c_void_p, C.c_int]),
+    "klt_dev_snapshot_wait": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_void_p)]),
+    "klt_dev_select_resident": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(SelectParams)]),
     # host helpers shared with the tests
     "klt_fill_build_desc": (None, [_TC, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(BuildDesc)]),
     "_KLTGetKernelWidths": (None, [C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -151,6 +159,22 @@ class B200Library(capi.KLTLibrary):
         if self.device_count() < 1:
             raise RuntimeError("no CUDA device visible: the KLT hot path runs only on the GPU "
                                "(no CPU fallback)")
+
+    def track_sequence(self, tc, frames, fl, ft=None, first_frame=0, replace=False):
+        """KLTTrackFeaturesSequence over a list of uint8 arrays / raw host addresses of one size
+        (include/klt_b200.h): the batched form of the reference's driver loop."""
+        keep, ptrs = [], (C.c_void_p * len(frames))()
+        nrows = ncols = None
+        for i, f in enumerate(frames):
+            if isinstance(f, tuple):                       # (address, nrows, ncols)
+                ptrs[i], nrows, ncols = f[0], f[1], f[2]
+                continue
+            a = np.ascontiguousarray(f, np.uint8)
+            keep.append(a)
+            ptrs[i] = a.ctypes.data
+            nrows, ncols = a.shape
+        self.lib.KLTTrackFeaturesSequence(tc, ptrs, len(frames), ncols, nrows, fl, ft, first_frame,
+                                          1 if replace else 0)
 
     # -- device-level helpers used by stage parity tests --------------------
     def dev_check(self, dev, rc):
