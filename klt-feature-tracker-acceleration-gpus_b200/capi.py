@@ -223,6 +223,18 @@ def featurelist_to_arrays(fl):
     return x, y, v
 
 
+def featurelist_affine(fl):
+    """the affine-consistency members of every feature (klt.h:97-105): has = aff_img != NULL"""
+    n = fl.contents.nFeatures
+    out = np.zeros(n, dtype=[("has", "i4"), ("aff_x", "f4"), ("aff_y", "f4"), ("Axx", "f4"), ("Ayx", "f4"),
+                             ("Axy", "f4"), ("Ayy", "f4")])
+    f = fl.contents.feature
+    for i in range(n):
+        r = f[i].contents
+        out[i] = (1 if r.aff_img else 0, r.aff_x, r.aff_y, r.aff_Axx, r.aff_Ayx, r.aff_Axy, r.aff_Ayy)
+    return out
+
+
 def arrays_to_featurelist(fl, x, y, v):
     n = fl.contents.nFeatures
     f = fl.contents.feature

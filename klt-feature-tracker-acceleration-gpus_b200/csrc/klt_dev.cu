@@ -535,6 +535,7 @@ struct TrackArgs {
   int   ncols, nrows;
   int   lighting;            // tc->lighting_insensitive: gain / bias normalised windows (track_kernel only)
   int   prefetch;            // track7: L2 prefetch of the finer levels' footprints at kernel start
+  int   l2_keep;             // track7w: the new frame's footprints are loaded with an L2 evict_last policy
   // track7 behind a banded frame upload: pass 1 runs when only the first band's pyramid rows exist
   // (row_limit[l] = complete rows of level l of the NEW frame) and gives up on -- "defers" -- any
   // feature whose footprint would touch a later row; pass 2, after the last band, tracks exactly
@@ -2494,6 +2495,7 @@ static void fill_track_args(const klt_dev* d, const klt_dev_track_params* p, Tra
   a->ncols = d->W; a->nrows = d->H;
   a->lighting = p->lighting_insensitive ? 1 : 0;
   { static int pf = getenv("KLT_TRACK_PREFETCH") ? atoi(getenv("KLT_TRACK_PREFETCH")) : 0; a->prefetch = pf; }
+  { static int keep = getenv("KLT_TRACK_L2_KEEP") ? atoi(getenv("KLT_TRACK_L2_KEEP")) : 0; a->l2_keep = keep; }
 }
 // can this call be served by track7_kernel (the only tracker with the two-pass mode)?
 static bool track7_applies(const klt_dev* d, const klt_dev_track_params* p) {

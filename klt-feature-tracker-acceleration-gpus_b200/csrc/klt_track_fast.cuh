@@ -503,6 +503,29 @@ __device__ __forceinline__ Pix3 pix3_load(const float* __restrict__ img, int off
   r.a = __ldg(p); r.b = __ldg(p + 1); r.c = __ldg(p + 2);
   return r;
 }
+// L2 eviction policies for the gathers.  The footprints read from the NEW frame's pyramids are
+// (up to the integer cell the feature ends in) the footprints the next frame's call reads from its
+// PREVIOUS pyramids; marked evict_last they survive the ~140 MB the next pyramid build streams
+// through the 126 MB L2, so half of the next call's gathers hit L2 instead of DRAM.  The previous
+// frame's footprints are dead after this call: evict_first.
+__device__ __forceinline__ unsigned long long l2_policy(int kind) {   // 0 normal, 1 evict_last, 2 evict_first
+  unsigned long long p;
+  if (kind == 1) asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  else if (kind == 2) asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float ldg_policy(const float* p, unsigned long long pol) {
+  float v;
+  asm("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ Pix3 pix3_load(const float* __restrict__ img, int off, unsigned long long pol) {
+  const float* p = img + off;
+  Pix3 r;
+  r.a = ldg_policy(p, pol); r.b = ldg_policy(p + 1, pol); r.c = ldg_policy(p + 2, pol);
+  return r;
+}
 // bilinear samples of this lane's two window columns in its window row; the row below comes from
 // lane + 4 (lanes 28..31 hold footprint row 7 and only feed the shuffle)
 __device__ __forceinline__ void pix3_interp(const Pix3& p, float ax, float ay, float& o0, float& o1) {
@@ -525,6 +548,7 @@ track7w_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
   const int r = lane >> 2, c = lane & 3;                     // footprint row, column pair
   const bool v0 = r < 7, v1 = r < 7 && c < 3;                // window samples (2c, r) and (2c + 1, r)
   const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long pol1 = l2_policy(a.l2_keep ? 2 : 0), pol2 = l2_policy(a.l2_keep ? 1 : 0);
   pdl_wait();                                                 // pyramids and features come from earlier kernels
   if (f >= n) return;
   if (io.val[(size_t)f * io.istride] < 0) return;             // only features that are not lost (:1346)
@@ -554,8 +578,8 @@ track7w_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
       // all 18 loads of the level are issued before the first use
       const int xt1 = (int)x1, yt1 = (int)y1, xt2 = (int)x2, yt2 = (int)y2;
       const int o1 = (yt1 - 3 + r) * pitch + (xt1 - 3 + 2 * c), o2 = (yt2 - 3 + r) * pitch + (xt2 - 3 + 2 * c);
-      const Pix3 r_i = pix3_load(p1.img[l], o1), r_gx = pix3_load(p1.gx[l], o1), r_gy = pix3_load(p1.gy[l], o1);
-      c_i = pix3_load(i2, o2); c_gx = pix3_load(gx2, o2); c_gy = pix3_load(gy2, o2);
+      const Pix3 r_i = pix3_load(p1.img[l], o1, pol1), r_gx = pix3_load(p1.gx[l], o1, pol1), r_gy = pix3_load(p1.gy[l], o1, pol1);
+      c_i = pix3_load(i2, o2, pol2); c_gx = pix3_load(gx2, o2, pol2); c_gy = pix3_load(gy2, o2, pol2);
       c_xt = xt2; c_yt = yt2;
       const float ax = x1 - (float)xt1, ay = y1 - (float)yt1;
       pix3_interp(r_i, ax, ay, t_i0, t_i1);
@@ -568,7 +592,7 @@ track7w_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
       const int xt = (int)x2, yt = (int)y2;
       if (xt != c_xt || yt != c_yt) {                         // the integer footprint moved: re-read it
         const int o2 = (yt - 3 + r) * pitch + (xt - 3 + 2 * c);
-        c_i = pix3_load(i2, o2); c_gx = pix3_load(gx2, o2); c_gy = pix3_load(gy2, o2);
+        c_i = pix3_load(i2, o2, pol2); c_gx = pix3_load(gx2, o2, pol2); c_gy = pix3_load(gy2, o2, pol2);
         c_xt = xt; c_yt = yt;
       }
       const float ax = x2 - (float)xt, ay = y2 - (float)yt;
@@ -606,7 +630,7 @@ track7w_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
     if (lvl_status == KLT_TRACKED && window_oob(x2, y2, hw, hh, nc, nr)) lvl_status = KLT_OOB;
     if (lvl_status == KLT_TRACKED) {
       const int xt = (int)x2, yt = (int)y2;
-      if (xt != c_xt || yt != c_yt) c_i = pix3_load(i2, (yt - 3 + r) * pitch + (xt - 3 + 2 * c));
+      if (xt != c_xt || yt != c_yt) c_i = pix3_load(i2, (yt - 3 + r) * pitch + (xt - 3 + 2 * c), pol2);
       float s_i0, s_i1;
       pix3_interp(c_i, x2 - (float)xt, y2 - (float)yt, s_i0, s_i1);
       float sum = (v0 ? fabsf(t_i0 - s_i0) : 0.0f) + (v1 ? fabsf(t_i1 - s_i1) : 0.0f);

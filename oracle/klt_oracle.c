@@ -568,6 +568,289 @@ void klto_track(const klto_pyramids *p1, const klto_pyramids *p2,
 }
 
 /* ------------------------------------------------------------------------ */
+/* affine consistency check -- reference trackFeatures.c:506-1224, :1438-1497 */
+/* ------------------------------------------------------------------------ */
+
+/* reference trackFeatures.c:546-604 (_am_gauss_jordan_elimination, n x n system, one right-hand
+ * side): full pivoting, the pivot search compares |a| in double as fabs() does */
+static int gauss_jordan(float a[6][6], int n, float b[6])
+{
+  int indxc[6], indxr[6], ipiv[6];
+  int i, j, k, l, ll, col = 0, row = 0;
+  float big, dum, pivinv, temp;
+  for (j = 0; j < n; j++) ipiv[j] = 0;
+  for (i = 0; i < n; i++) {
+    big = 0.0f;
+    for (j = 0; j < n; j++)
+      if (ipiv[j] != 1)
+        for (k = 0; k < n; k++) {
+          if (ipiv[k] == 0) {
+            if (fabs(a[j][k]) >= big) { big = (float)fabs(a[j][k]); row = j; col = k; }
+          } else if (ipiv[k] > 1) return KLTO_SMALL_DET;
+        }
+    ++(ipiv[col]);
+    if (row != col) {
+      for (l = 0; l < n; l++) { temp = a[row][l]; a[row][l] = a[col][l]; a[col][l] = temp; }
+      temp = b[row]; b[row] = b[col]; b[col] = temp;
+    }
+    indxr[i] = row; indxc[i] = col;
+    if (a[col][col] == 0.0) return KLTO_SMALL_DET;
+    pivinv = 1.0f / a[col][col];
+    a[col][col] = 1.0f;
+    for (l = 0; l < n; l++) a[col][l] *= pivinv;
+    b[col] *= pivinv;
+    for (ll = 0; ll < n; ll++)
+      if (ll != col) {
+        dum = a[ll][col];
+        a[ll][col] = 0.0f;
+        for (l = 0; l < n; l++) a[ll][l] -= a[col][l] * dum;
+        b[ll] -= b[col] * dum;
+      }
+  }
+  (void)indxr; (void)indxc;        /* the column unscramble (:595-599) only touches the inverse */
+  return KLTO_TRACKED;
+}
+
+/* reference trackFeatures.c:952-1224 (_am_trackFeatureAffine).  img1/gx1/gy1: the feature's saved
+ * (aw+2) x (ah+2) template; img2/gx2/gy2: level 0 of the new frame.  The result position is not
+ * written back by the caller (:1490-1491), only the status and the mapping A. */
+int klto_track_affine_feature(float x1, float y1, float *x2, float *y2,
+                              const float *img1, const float *gx1, const float *gy1, int nc1, int nr1,
+                              const float *img2, const float *gx2, const float *gy2, int nc2, int nr2,
+                              int width, int height, float step_factor, int max_iterations,
+                              float small, float th, float th_aff, float max_residue,
+                              int affine_map, float mdd,
+                              float *Axx, float *Ayx, float *Axy, float *Ayy)
+{
+  const int hw = width / 2, hh = height / 2, npix = width * height;
+  float *diff = (float *)malloc(sizeof(float) * npix);
+  float *wx = (float *)malloc(sizeof(float) * npix);
+  float *wy = (float *)malloc(sizeof(float) * npix);
+  float gxx, gxy, gyy, ex, ey, dx = 0.0f, dy = 0.0f;
+  const float one_plus_eps = 1.001f;
+  const float old_x2 = *x2, old_y2 = *y2;
+  int iteration = 0, status = 0, convergence = 0, i, j, k;
+  float T[6][6], a[6];
+
+  do {
+    if (!affine_map) {
+      /* :1010-1059 pure translation against the template (lighting-insensitive variant not restated) */
+      if (x1 - hw < 0.0f || nc1 - (x1 + hw) < one_plus_eps ||
+          *x2 - hw < 0.0f || nc2 - (*x2 + hw) < one_plus_eps ||
+          y1 - hh < 0.0f || nr1 - (y1 + hh) < one_plus_eps ||
+          *y2 - hh < 0.0f || nr2 - (*y2 + hh) < one_plus_eps) { status = KLTO_OOB; break; }
+      k = 0;
+      for (j = -hh; j <= hh; j++)
+        for (i = -hw; i <= hw; i++, k++) {
+          diff[k] = bilinear(x1 + i, y1 + j, img1, nc1) - bilinear(*x2 + i, *y2 + j, img2, nc2);
+          wx[k] = bilinear(x1 + i, y1 + j, gx1, nc1) + bilinear(*x2 + i, *y2 + j, gx2, nc2);
+          wy[k] = bilinear(x1 + i, y1 + j, gy1, nc1) + bilinear(*x2 + i, *y2 + j, gy2, nc2);
+        }
+      gxx = 0.0f; gxy = 0.0f; gyy = 0.0f;
+      for (k = 0; k < npix; k++) { gxx += wx[k] * wx[k]; gxy += wx[k] * wy[k]; gyy += wy[k] * wy[k]; }
+      ex = 0.0f; ey = 0.0f;
+      for (k = 0; k < npix; k++) { ex += diff[k] * wx[k]; ey += diff[k] * wy[k]; }
+      ex *= step_factor; ey *= step_factor;
+      {
+        const float det = gxx * gyy - gxy * gxy;
+        if (det < small) status = KLTO_SMALL_DET;
+        else { dx = (gyy * ex - gxy * ey) / det; dy = (gxx * ey - gxy * ex) / det; status = KLTO_TRACKED; }
+      }
+      convergence = (fabs(dx) < th && fabs(dy) < th);
+      *x2 += dx; *y2 += dy;
+    } else {
+      /* :1061-1186 affine tracker */
+      float ul_x = *Axx * (-hw) + *Axy * hh + *x2, ul_y = *Ayx * (-hw) + *Ayy * hh + *y2;
+      float ll_x = *Axx * (-hw) + *Axy * (-hh) + *x2, ll_y = *Ayx * (-hw) + *Ayy * (-hh) + *y2;
+      float ur_x = *Axx * hw + *Axy * hh + *x2, ur_y = *Ayx * hw + *Ayy * hh + *y2;
+      float lr_x = *Axx * hw + *Axy * (-hh) + *x2, lr_y = *Ayx * hw + *Ayy * (-hh) + *y2;
+      if (x1 - hw < 0.0f || nc1 - (x1 + hw) < one_plus_eps ||
+          y1 - hh < 0.0f || nr1 - (y1 + hh) < one_plus_eps ||
+          ul_x < 0.0f || nc2 - ul_x < one_plus_eps || ll_x < 0.0f || nc2 - ll_x < one_plus_eps ||
+          ur_x < 0.0f || nc2 - ur_x < one_plus_eps || lr_x < 0.0f || nc2 - lr_x < one_plus_eps ||
+          ul_y < 0.0f || nr2 - ul_y < one_plus_eps || ll_y < 0.0f || nr2 - ll_y < one_plus_eps ||
+          ur_y < 0.0f || nr2 - ur_y < one_plus_eps || lr_y < 0.0f || nr2 - lr_y < one_plus_eps) {
+        status = KLTO_OOB; break;
+      }
+      /* :700-722 and :610-632: difference against the mapped window, gradients of frame 2 only */
+      k = 0;
+      for (j = -hh; j <= hh; j++)
+        for (i = -hw; i <= hw; i++, k++) {
+          const float g1 = bilinear(x1 + i, y1 + j, img1, nc1);
+          const float mi = *Axx * i + *Axy * j, mj = *Ayx * i + *Ayy * j;
+          diff[k] = g1 - bilinear(*x2 + mi, *y2 + mj, img2, nc2);
+          wx[k] = bilinear(*x2 + mi, *y2 + mj, gx2, nc2);
+          wy[k] = bilinear(*x2 + mi, *y2 + mj, gy2, nc2);
+        }
+      if (affine_map == 1) {
+        /* :900-928 and :846-892 */
+        for (i = 0; i < 4; i++) { a[i] = 0.0f; for (j = 0; j < 4; j++) T[i][j] = 0.0f; }
+        k = 0;
+        for (j = -hh; j <= hh; j++)
+          for (i = -hw; i <= hw; i++, k++) {
+            const float d = diff[k], dgx = d * wx[k], dgy = d * wy[k];
+            a[0] += dgx * i + dgy * j;
+            a[1] += dgy * i - dgx * j;
+            a[2] += dgx;
+            a[3] += dgy;
+          }
+        for (i = 0; i < 4; i++) a[i] *= 0.5;
+        k = 0;
+        for (j = -hh; j <= hh; j++)
+          for (i = -hw; i <= hw; i++, k++) {
+            const float gx = wx[k], gy = wy[k], x = (float)i, y = (float)j;
+            T[0][0] += (x * gx + y * gy) * (x * gx + y * gy);
+            T[0][1] += (x * gx + y * gy) * (x * gy - y * gx);
+            T[0][2] += (x * gx + y * gy) * gx;
+            T[0][3] += (x * gx + y * gy) * gy;
+            T[1][1] += (x * gy - y * gx) * (x * gy - y * gx);
+            T[1][2] += (x * gy - y * gx) * gx;
+            T[1][3] += (x * gy - y * gx) * gy;
+            T[2][2] += gx * gx;
+            T[2][3] += gx * gy;
+            T[3][3] += gy * gy;
+          }
+        for (j = 0; j < 3; j++) for (i = j + 1; i < 4; i++) T[i][j] = T[j][i];
+        status = gauss_jordan(T, 4, a);
+        *Axx += a[0]; *Ayx += a[1]; *Ayy = *Axx; *Axy = -(*Ayx);
+        dx = a[2]; dy = a[3];
+      } else {
+        /* :806-838 and :730-798 */
+        for (i = 0; i < 6; i++) { a[i] = 0.0f; for (j = 0; j < 6; j++) T[i][j] = 0.0f; }
+        k = 0;
+        for (j = -hh; j <= hh; j++)
+          for (i = -hw; i <= hw; i++, k++) {
+            const float d = diff[k], dgx = d * wx[k], dgy = d * wy[k];
+            a[0] += dgx * i; a[1] += dgy * i; a[2] += dgx * j; a[3] += dgy * j; a[4] += dgx; a[5] += dgy;
+          }
+        for (i = 0; i < 6; i++) a[i] *= 0.5;
+        k = 0;
+        for (j = -hh; j <= hh; j++)
+          for (i = -hw; i <= hw; i++, k++) {
+            const float gx = wx[k], gy = wy[k];
+            const float Gxx = gx * gx, Gxy = gx * gy, Gyy = gy * gy;
+            const float x = (float)i, y = (float)j, xx = x * x, xy = x * y, yy = y * y;
+            T[0][0] += xx * Gxx; T[0][1] += xx * Gxy; T[0][2] += xy * Gxx; T[0][3] += xy * Gxy;
+            T[0][4] += x * Gxx;  T[0][5] += x * Gxy;
+            T[1][1] += xx * Gyy; T[1][2] += xy * Gxy; T[1][3] += xy * Gyy; T[1][4] += x * Gxy; T[1][5] += x * Gyy;
+            T[2][2] += yy * Gxx; T[2][3] += yy * Gxy; T[2][4] += y * Gxx;  T[2][5] += y * Gxy;
+            T[3][3] += yy * Gyy; T[3][4] += y * Gxy;  T[3][5] += y * Gyy;
+            T[4][4] += Gxx; T[4][5] += Gxy; T[5][5] += Gyy;
+          }
+        for (j = 0; j < 5; j++) for (i = j + 1; i < 6; i++) T[i][j] = T[j][i];
+        status = gauss_jordan(T, 6, a);
+        *Axx += a[0]; *Ayx += a[1]; *Axy += a[2]; *Ayy += a[3];
+        dx = a[4]; dy = a[5];
+      }
+      *x2 += dx; *y2 += dy;
+      /* :1162-1173 corner motion */
+      ul_x -= *Axx * (-hw) + *Axy * hh + *x2;    ul_y -= *Ayx * (-hw) + *Ayy * hh + *y2;
+      ll_x -= *Axx * (-hw) + *Axy * (-hh) + *x2; ll_y -= *Ayx * (-hw) + *Ayy * (-hh) + *y2;
+      ur_x -= *Axx * hw + *Axy * hh + *x2;       ur_y -= *Ayx * hw + *Ayy * hh + *y2;
+      lr_x -= *Axx * hw + *Axy * (-hh) + *x2;    lr_y -= *Ayx * hw + *Ayy * (-hh) + *y2;
+      convergence = (fabs(dx) < th && fabs(dy) < th &&
+                     fabs(ul_x) < th_aff && fabs(ul_y) < th_aff && fabs(ll_x) < th_aff && fabs(ll_y) < th_aff &&
+                     fabs(ur_x) < th_aff && fabs(ur_y) < th_aff && fabs(lr_x) < th_aff && fabs(lr_y) < th_aff);
+    }
+    if (status == KLTO_SMALL_DET) break;
+    iteration++;
+  } while (!convergence && iteration < max_iterations);
+
+  /* :1193-1200 */
+  if (*x2 - hw < 0.0f || nc2 - (*x2 + hw) < one_plus_eps ||
+      *y2 - hh < 0.0f || nr2 - (*y2 + hh) < one_plus_eps) status = KLTO_OOB;
+  if ((*x2 - old_x2) > mdd || (*y2 - old_y2) > mdd) status = KLTO_OOB;
+  /* :1203-1214 residue */
+  if (status == KLTO_TRACKED) {
+    float sum = 0.0f;
+    k = 0;
+    for (j = -hh; j <= hh; j++)
+      for (i = -hw; i <= hw; i++, k++) {
+        const float g1 = bilinear(x1 + i, y1 + j, img1, nc1);
+        if (!affine_map) diff[k] = g1 - bilinear(*x2 + i, *y2 + j, img2, nc2);
+        else {
+          const float mi = *Axx * i + *Axy * j, mj = *Ayx * i + *Ayy * j;
+          diff[k] = g1 - bilinear(*x2 + mi, *y2 + mj, img2, nc2);
+        }
+      }
+    for (k = 0; k < npix; k++) sum += (float)fabs(diff[k]);
+    if (sum / (width * height) > max_residue) status = KLTO_LARGE_RESIDUE;
+  }
+  free(diff); free(wx); free(wy);
+  return status;
+}
+
+/* reference trackFeatures.c:1343-1497: the feature loop of KLTTrackFeatures with
+ * tc->affineConsistencyCheck >= 0.  st[f] and tmpl (n x 3 x (aw+2)(ah+2) floats: image, gradx,
+ * grady of the saved template) carry the per-feature fields aff_img*, aff_x .. aff_Ayy. */
+void klto_track_affine(const klto_pyramids *p1, const klto_pyramids *p2, const klto_params *p,
+                       const klto_affine_params *ap, int n, float *x, float *y, int *val,
+                       klto_affine_state *st, float *tmpl)
+{
+  const float ss = (float)p->subsampling;
+  const int L = p->nPyramidLevels;
+  const int ncols = p1->ncols[0], nrows = p1->nrows[0];
+  const int tw = ap->window_width + 2, th = ap->window_height + 2, tsz = tw * th;
+  int f, r, i, j;
+
+  for (f = 0; f < n; f++) {
+    float xloc, yloc, xout, yout;
+    int v = KLTO_TRACKED;
+    float *t_img = tmpl + (size_t)f * 3 * tsz, *t_gx = t_img + tsz, *t_gy = t_gx + tsz;
+    if (val[f] < 0) continue;
+    xloc = x[f]; yloc = y[f];
+    for (r = L - 1; r >= 0; r--) { xloc /= ss; yloc /= ss; }
+    xout = xloc; yout = yloc;
+    for (r = L - 1; r >= 0; r--) {
+      xloc *= ss; yloc *= ss; xout *= ss; yout *= ss;
+      v = klto_track_level_li(xloc, yloc, &xout, &yout, p1->img[r], p1->gx[r], p1->gy[r],
+                              p2->img[r], p2->gx[r], p2->gy[r], p1->ncols[r], p1->nrows[r],
+                              p->window_width, p->window_height, p->step_factor, p->max_iterations,
+                              p->min_determinant, p->min_displacement, p->max_residue,
+                              p->lighting_insensitive);
+      if (v == KLTO_SMALL_DET || v == KLTO_OOB) break;
+    }
+    if (v == KLTO_OOB ||
+        xout < p->borderx || xout > ncols - 1 - p->borderx ||
+        yout < p->bordery || yout > nrows - 1 - p->bordery) {
+      x[f] = -1.0f; y[f] = -1.0f; val[f] = KLTO_OOB; st[f].has = 0;
+    } else if (v == KLTO_SMALL_DET || v == KLTO_LARGE_RESIDUE || v == KLTO_MAX_ITERATIONS) {
+      x[f] = -1.0f; y[f] = -1.0f; val[f] = v; st[f].has = 0;
+    } else {
+      x[f] = xout; y[f] = yout; val[f] = KLTO_TRACKED;
+      if (ap->check < 0) continue;
+      if (!st[f].has) {
+        /* :1446-1457 save the template at the finest level after the first successful track */
+        const int hw = tw / 2, hh = th / 2, x0 = (int)xloc, y0 = (int)yloc;
+        int k = 0;
+        for (j = -hh; j <= hh; j++)
+          for (i = -hw; i <= hw; i++, k++) {
+            const long off = (long)(j + y0) * ncols + (i + x0);
+            t_img[k] = p1->img[0][off]; t_gx[k] = p1->gx[0][off]; t_gy[k] = p1->gy[0][off];
+          }
+        st[f].aff_x = xloc - (int)xloc + (ap->window_width + 2) / 2;
+        st[f].aff_y = yloc - (int)yloc + (ap->window_height + 2) / 2;
+        st[f].has = 1;
+      } else {
+        /* :1458-1493 */
+        float xo = xout, yo = yout;
+        v = klto_track_affine_feature(st[f].aff_x, st[f].aff_y, &xo, &yo, t_img, t_gx, t_gy, tw, th,
+                                      p2->img[0], p2->gx[0], p2->gy[0], ncols, nrows,
+                                      ap->window_width, ap->window_height, p->step_factor,
+                                      ap->max_iterations, p->min_determinant, p->min_displacement,
+                                      ap->min_displacement, ap->max_residue, ap->check,
+                                      ap->max_displacement_differ,
+                                      &st[f].Axx, &st[f].Ayx, &st[f].Axy, &st[f].Ayy);
+        val[f] = v;
+        if (v != KLTO_TRACKED) {
+          x[f] = -1.0f; y[f] = -1.0f; st[f].aff_x = -1.0f; st[f].aff_y = -1.0f; st[f].has = 0;
+        }
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------ */
 /* selection -- reference selectGoodFeatures.c                              */
 /* ------------------------------------------------------------------------ */
 

@@ -98,6 +98,30 @@ const float *klto_pyr_data(const klto_pyramids *q, int which, int level);
 void klto_track(const klto_pyramids *p1, const klto_pyramids *p2,
                 const klto_params *p, int n, float *x, float *y, int *val);
 
+/* affine consistency check (trackFeatures.c:506-1224, :1438-1497; klt.c:33-39 defaults) */
+typedef struct {
+  int   check;                  /* tc->affineConsistencyCheck: -1 off, 0 translation, 1 similarity, 2 affine */
+  int   window_width, window_height;     /* affine_window_* (15) */
+  int   max_iterations;         /* affine_max_iterations (10) */
+  float max_residue;            /* affine_max_residue (10) */
+  float min_displacement;       /* affine_min_displacement (0.02) */
+  float max_displacement_differ;/* affine_max_displacement_differ (1.5) */
+} klto_affine_params;
+typedef struct {                /* the aff_* members of KLT_FeatureRec (klt.h:97-105) */
+  int   has;                    /* aff_img != NULL */
+  float aff_x, aff_y, Axx, Ayx, Axy, Ayy;
+} klto_affine_state;
+void klto_track_affine(const klto_pyramids *p1, const klto_pyramids *p2, const klto_params *p,
+                       const klto_affine_params *ap, int n, float *x, float *y, int *val,
+                       klto_affine_state *st, float *tmpl);
+int klto_track_affine_feature(float x1, float y1, float *x2, float *y2,
+                              const float *img1, const float *gx1, const float *gy1, int nc1, int nr1,
+                              const float *img2, const float *gx2, const float *gy2, int nc2, int nr2,
+                              int width, int height, float step_factor, int max_iterations,
+                              float small, float th, float th_aff, float max_residue,
+                              int affine_map, float mdd,
+                              float *Axx, float *Ayx, float *Axy, float *Ayy);
+
 /* single level solver, exposed for edge-case tests (trackFeatures.c:381-486) */
 int klto_track_level(float x1, float y1, float *x2, float *y2,
                      const float *img1, const float *gx1, const float *gy1,

@@ -33,6 +33,31 @@ class Params(C.Structure):
     ]
 
 
+class AffineParams(C.Structure):
+    """klto_affine_params: the affine* members of KLT_TrackingContextRec (defaults klt.c:33-39)."""
+    _fields_ = [("check", C.c_int), ("window_width", C.c_int), ("window_height", C.c_int),
+                ("max_iterations", C.c_int), ("max_residue", C.c_float),
+                ("min_displacement", C.c_float), ("max_displacement_differ", C.c_float)]
+
+
+AFFINE_STATE = np.dtype([("has", "i4"), ("aff_x", "f4"), ("aff_y", "f4"), ("Axx", "f4"), ("Ayx", "f4"),
+                         ("Axy", "f4"), ("Ayy", "f4")])
+
+
+def affine_params(check=2, window=15, max_iterations=10, max_residue=10.0, min_displacement=0.02,
+                  max_displacement_differ=1.5) -> AffineParams:
+    return AffineParams(check, window, window, max_iterations, max_residue, min_displacement,
+                        max_displacement_differ)
+
+
+def affine_state(n, window=15):
+    """fresh per-feature affine fields (KLTCreateFeatureList / selection: klt.c:160-176) + templates"""
+    st = np.zeros(n, AFFINE_STATE)
+    st["aff_x"] = st["aff_y"] = -1.0
+    st["Axx"] = st["Ayy"] = 1.0
+    return st, np.zeros((n, 3, (window + 2) * (window + 2)), np.float32)
+
+
 def build(force: bool = False) -> None:
     """Compile liboracle.so (and oracle/_ref when /root/reference is present)."""
     if force or not os.path.exists(LIB_PATH) or \
@@ -82,6 +107,8 @@ class Oracle:
                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                        C.c_int, C.c_float, C.c_float, C.c_float]
         L.klto_track_level.restype = C.c_int
+        L.klto_track_affine.argtypes = [C.c_void_p, C.c_void_p, P, C.POINTER(AffineParams), C.c_int,
+                                        _f32p, _f32p, _i32p, C.c_void_p, _f32p]
         L.klto_select.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, P, C.c_int, C.c_int,
                                   C.c_int, _f32p, _f32p, _i32p]
         L.klto_sort_points.argtypes = [_i32p, C.c_int, C.c_int]
@@ -149,6 +176,14 @@ class Oracle:
     def track(self, pyr1, pyr2, p: Params, x, y, val):
         x = np.array(x, np.float32); y = np.array(y, np.float32); val = np.array(val, np.int32)
         self.lib.klto_track(pyr1.handle, pyr2.handle, C.byref(p), len(x), x, y, val)
+        return x, y, val
+
+    def track_affine(self, pyr1, pyr2, p: Params, ap: AffineParams, x, y, val, state, tmpl):
+        """KLTTrackFeatures with tc->affineConsistencyCheck >= 0; state / tmpl are updated in place."""
+        x = np.array(x, np.float32); y = np.array(y, np.float32); val = np.array(val, np.int32)
+        assert state.dtype == AFFINE_STATE and state.flags.c_contiguous and tmpl.flags.c_contiguous
+        self.lib.klto_track_affine(pyr1.handle, pyr2.handle, C.byref(p), C.byref(ap), len(x), x, y, val,
+                                   state.ctypes.data, tmpl.reshape(-1))
         return x, y, val
 
     def select(self, img, p: Params, n, sort_kind=SORT_STABLE, replace=False, last=None,

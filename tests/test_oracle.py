@@ -220,3 +220,57 @@ def test_lighting_insensitive_tracking_bit_exact_vs_reference(oracle, oracle_mod
         assert y.tobytes() == want[i][1].tobytes()
         assert np.array_equal(v, want[i][2])
         prev = cur
+
+
+def _warped(img, k):
+    """frame k of a slowly rotating / zooming / shifting copy of img (bilinear, numpy)"""
+    h, w = img.shape
+    a, sc = np.deg2rad(0.6 * k), 1.0 + 0.004 * k
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    cx, cy = w / 2.0, h / 2.0
+    xs = (np.cos(a) * (xx - cx) - np.sin(a) * (yy - cy)) / sc + cx + 0.9 * k
+    ys = (np.sin(a) * (xx - cx) + np.cos(a) * (yy - cy)) / sc + cy - 0.6 * k
+    x0 = np.clip(np.floor(xs).astype(int), 0, w - 2); y0 = np.clip(np.floor(ys).astype(int), 0, h - 2)
+    ax = np.clip(xs - x0, 0, 1); ay = np.clip(ys - y0, 0, 1)
+    f = img.astype(np.float64)
+    v = (f[y0, x0] * (1 - ax) * (1 - ay) + f[y0, x0 + 1] * ax * (1 - ay)
+         + f[y0 + 1, x0] * (1 - ax) * ay + f[y0 + 1, x0 + 1] * ax * ay)
+    return np.clip(np.rint(v), 0, 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("check", [0, 1, 2])
+@pytest.mark.parametrize("seq", ["provided", "warped"])
+def test_affine_consistency_check_bit_exact_vs_reference(oracle, oracle_mod, capi, ref_qsort, provided, check, seq):
+    """tc->affineConsistencyCheck = 0 / 1 / 2 (trackFeatures.c:506-1224, :1438-1497): template
+    creation after the first successful track, translation / similarity / affine refinement against
+    the template, status changes, and the persistent aff_* members of every feature."""
+    imgs = provided[:7] if seq == "provided" else [_warped(provided[0], k) for k in range(7)]
+    n = 120
+    R = ref_qsort
+    tc = R.make_tc(sequentialMode=1, affineConsistencyCheck=check)
+    fl = R.new_list(n)
+    R.api.select(tc, imgs[0], fl)
+    p = oracle.default_params()
+    ap = oracle_mod.affine_params(check=check)
+    x, y, v = oracle.select(imgs[0], p, n, sort_kind=oracle_mod.SORT_STABLE)
+    st, tmpl = oracle_mod.affine_state(n)
+    prev = oracle.build_pyramids(imgs[0], p)
+    changed = 0
+    for i in range(1, len(imgs)):
+        R.api.track(tc, imgs[i - 1], imgs[i], fl)
+        cur = oracle.build_pyramids(imgs[i], p)
+        plain = oracle.track(prev, cur, p, x, y, v)
+        x, y, v = oracle.track_affine(prev, cur, p, ap, x, y, v, st, tmpl)
+        changed += int((plain[2] != v).sum())
+        rx, ry, rv = R.get(fl)
+        ra = capi.featurelist_affine(fl)
+        assert np.array_equal(v, rv), "frame %d" % i
+        assert x.tobytes() == rx.tobytes() and y.tobytes() == ry.tobytes()
+        assert np.array_equal(st["has"], ra["has"])
+        live = st["has"] == 1
+        for k in ("aff_x", "aff_y", "Axx", "Ayx", "Axy", "Ayy"):
+            assert st[k][live].tobytes() == ra[k][live].tobytes(), (i, k)
+        prev = cur
+    print("affine check %d on %s: %d status changes" % (check, seq, changed))
+    R.api.KLTFreeFeatureList(fl)
+    R.api.KLTFreeTrackingContext(tc)
