@@ -158,6 +158,33 @@ int klt_dev_features_commit_records(klt_dev *d, int n, void *first_record, size_
 void *klt_dev_host_alloc(size_t bytes);     /* portable pinned host memory; NULL without a device */
 void klt_dev_host_free(void *p);
 
+/* ---- affine consistency check ------------------------------------------ */
+/* replaces the tc->affineConsistencyCheck >= 0 branch of KLTTrackFeatures and its _am_* helpers
+ * (reference src/V1/trackFeatures.c:506-1224, :1438-1497).  Exact reference arithmetic always. */
+typedef struct {
+  int   check;                    /* tc->affineConsistencyCheck: 0 translation, 1 similarity, 2 affine */
+  int   window_width, window_height;       /* tc->affine_window_* */
+  int   max_iterations;           /* tc->affine_max_iterations */
+  float max_residue;              /* tc->affine_max_residue */
+  float min_displacement;         /* tc->affine_min_displacement */
+  float max_displacement_differ;  /* tc->affine_max_displacement_differ */
+} klt_dev_affine_params;
+typedef struct {                  /* the aff_* members of KLT_FeatureRec (klt.h:97-105) */
+  int   has;                      /* aff_img != NULL: the device holds this feature's template */
+  float aff_x, aff_y, Axx, Ayx, Axy, Ayy;
+  int   flags;                    /* out: 1 = template created by this call, 2 = template released */
+} klt_dev_affine_state;
+/* One call: features committed through the staging area -> klt_dev_affine_begin (hands out the pinned
+ * state array of n records for the host to fill) -> klt_dev_affine_put_template for every feature
+ * whose template the device does not hold yet -> klt_dev_track_resident -> klt_dev_affine_check
+ * -> klt_dev_features_fetch (synchronises) -> read the state array, fetch created templates. */
+int klt_dev_affine_begin(klt_dev *d, int n, const klt_dev_affine_params *ap, klt_dev_affine_state **staging);
+int klt_dev_affine_put_template(klt_dev *d, int i, const float *img, const float *gx, const float *gy);
+int klt_dev_affine_check(klt_dev *d, int slot_prev, int slot_cur, const klt_dev_track_params *tp,
+                         const klt_dev_affine_params *ap);
+int klt_dev_affine_get_template(klt_dev *d, int i, float *img, float *gx, float *gy);
+int klt_dev_affine_get_templates(klt_dev *d, int n, float *all);
+
 /* ---- selection --------------------------------------------------------- */
 /* replaces the eigenvalue loop, _sortPointList and _enforceMinimumDistance of
  * _KLTSelectGoodFeatures (reference src/V1/selectGoodFeatures.c:373-446) on

@@ -62,6 +62,7 @@ void klt_state_drop(KLT_TrackingContext tc)
   pthread_mutex_unlock(&g_lock);
   if (s) {
     if (s->dev) klt_dev_destroy(s->dev);
+    free(s->aff_shadow);
     free(s);
   }
 }
@@ -346,11 +347,14 @@ void KLTFreeTrackingContext(KLT_TrackingContext tc)
   free(tc);
 }
 
+unsigned klt_aff_epoch = 1;
+
 void KLTFreeFeatureList(KLT_FeatureList fl)
 {
   int i;
+  klt_aff_epoch++;               /* device mirrors keyed by these template addresses are stale now */
   for (i = 0; i < fl->nFeatures; i++) {
-    /* never allocated by this library, but a caller may have attached images */
+    /* the affine consistency check's templates (klt.c:453-469) */
     free(fl->feature[i]->aff_img);
     free(fl->feature[i]->aff_img_gradx);
     free(fl->feature[i]->aff_img_grady);

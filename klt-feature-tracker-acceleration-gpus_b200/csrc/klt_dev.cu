@@ -883,18 +883,20 @@ track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
 
 #include "klt_track_fast.cuh"
 
+#include "klt_affine.cuh"
+
 // ---------------------------------------------------------------------------
 // host side of the C-ABI
 // ---------------------------------------------------------------------------
 // kernel classes, for launch accounting and per-kernel event timing
 enum KernelId {
   KID_SMOOTH_U8 = 0, KID_GRAD, KID_PYRDOWN, KID_TRACK, KID_MINEIG, KID_SORT, KID_STAMP,
-  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_L0_FUSED, KID_LEVEL_FUSED, KID_TRACK_FAST, KID_TRACK7, KID_TRACK7W, KID_LEVELS_CHAIN, KID_MEGA, KID_L0_STREAM, KID_COPY_H2D, KID_COPY_D2H, KID_COUNT
+  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_L0_FUSED, KID_LEVEL_FUSED, KID_TRACK_FAST, KID_TRACK7, KID_TRACK7W, KID_AFFINE, KID_LEVELS_CHAIN, KID_MEGA, KID_L0_STREAM, KID_COPY_H2D, KID_COPY_D2H, KID_COUNT
 };
 static const char* const kKernelNames[KID_COUNT] = {
   "smooth_u8_tile", "grad_tile", "pyrdown_tile", "track_kernel", "mineig_kernel",
   "cub_radix_sort", "stamp_existing_kernel", "enforce_mindist_kernel",
-  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel", "l0_fused_kernel", "level_fused_kernel", "track_fast_kernel", "track7_kernel", "track7w_kernel", "levels_chain_kernel", "pyramid_mega_kernel", "l0_stream_kernel",
+  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel", "l0_fused_kernel", "level_fused_kernel", "track_fast_kernel", "track7_kernel", "track7w_kernel", "affine_check_kernel", "levels_chain_kernel", "pyramid_mega_kernel", "l0_stream_kernel",
   "copy_h2d", "copy_d2h"          // not kernels: timed in profiling mode, never counted as launches
 };
 static constexpr int PROF_POOL = 2048;     // event pairs in flight before folding
@@ -960,6 +962,8 @@ struct klt_dev {
   int feat_out_host;            // 1: the next tracker writes its results into h_x/h_y/h_val (sync API); 2: record mode
   unsigned char* d_rec; size_t d_rec_cap; void* h_rec; int rec_stride;   // record mode (klt_dev_features_commit_records)
   cudaEvent_t ev_feat; int feat_pending;   // feature upload queued on the copy stream
+  // affine consistency check (klt_dev_affine_*): per-feature state + templates, positions before tracking
+  AffState* d_aff_st; AffState* h_aff_st; float* d_aff_tmpl; float* d_x0; int aff_cap, aff_tsz, aff_x0_cap;
   // ring of pinned feature snapshots (klt_dev_snapshot_*)
   unsigned char* snap_ring; size_t snap_bytes; int snap_depth, snap_events; cudaEvent_t ev_snap[KLT_SNAP_MAX];
   // selection
@@ -1204,6 +1208,7 @@ extern "C" void klt_dev_destroy(klt_dev* d) {
   cudaEventDestroy(d->ev_stage_free);
   cudaFreeHost(d->h_frame);
   cudaFreeHost(d->snap_ring);
+  cudaFree(d->d_aff_st); cudaFreeHost(d->h_aff_st); cudaFree(d->d_aff_tmpl); cudaFree(d->d_x0);
   for (int i = 0; i < d->snap_events; ++i) cudaEventDestroy(d->ev_snap[i]);
   cudaStreamDestroy(d->cstream);
   cudaStreamDestroy(d->stream);
@@ -2620,6 +2625,114 @@ extern "C" int klt_dev_track(klt_dev* d, int slot_prev, int slot_cur, const klt_
   if (klt_dev_features_upload(d, n, x, y, val)) return 1;
   if (klt_dev_track_resident(d, slot_prev, slot_cur, p)) return 1;
   return klt_dev_features_download(d, n, x, y, val);
+}
+
+// ---- affine consistency check (reference trackFeatures.c:1438-1497) ---------------------------
+// Protocol of one KLTTrackFeatures call with tc->affineConsistencyCheck >= 0:
+//   features committed (staging mode) -> klt_dev_affine_begin (returns the pinned per-feature state
+//   array for the host to fill; keeps the tracker's output on the device and saves the positions
+//   before tracking) -> [klt_dev_affine_put_template for templates the device does not mirror]
+//   -> klt_dev_track_resident -> klt_dev_affine_check -> klt_dev_features_fetch (synchronises)
+//   -> the host reads the state array (flags: 1 template created, 2 released) and fetches created
+//   templates with klt_dev_affine_get_template(s).
+static_assert(sizeof(AffState) == sizeof(klt_dev_affine_state), "affine state layout");
+extern "C" int klt_dev_affine_begin(klt_dev* d, int n, const klt_dev_affine_params* ap, klt_dev_affine_state** staging) {
+  CU(cudaSetDevice(d->device));
+  if (!ap || n <= 0 || n != d->feat_n) return fail(d, "affine_begin: %d features but %d committed", n, d->feat_n);
+  if (ap->window_width < 3 || ap->window_height < 3 || !(ap->window_width & 1) || !(ap->window_height & 1) ||
+      ap->window_width * ap->window_height > 2048)
+    return fail(d, "affine window %d x %d must be odd, >= 3 and at most 2048 pixels", ap->window_width, ap->window_height);
+  const int tsz = (ap->window_width + 2) * (ap->window_height + 2);
+  if (d->aff_cap < n || d->aff_tsz != tsz) {
+    if (sync_all(d)) return fail(d, "stream synchronisation failed");
+    cudaFree(d->d_aff_st); cudaFreeHost(d->h_aff_st); cudaFree(d->d_aff_tmpl);
+    d->d_aff_st = nullptr; d->h_aff_st = nullptr; d->d_aff_tmpl = nullptr; d->aff_cap = 0;
+    const int cap = (n + 1023) / 1024 * 1024;
+    CU(cudaMalloc(&d->d_aff_st, (size_t)cap * sizeof(AffState)));
+    CU(cudaMallocHost(&d->h_aff_st, (size_t)cap * sizeof(AffState)));
+    CU(cudaMalloc(&d->d_aff_tmpl, (size_t)cap * 3 * tsz * sizeof(float)));
+    d->aff_cap = cap; d->aff_tsz = tsz;
+  }
+  if (d->aff_x0_cap < d->feat_cap) {
+    if (sync_all(d)) return fail(d, "stream synchronisation failed");
+    cudaFree(d->d_x0); d->d_x0 = nullptr; d->aff_x0_cap = 0;
+    CU(cudaMalloc(&d->d_x0, (size_t)d->feat_cap * 12));
+    d->aff_x0_cap = d->feat_cap;
+  }
+  if (d->feat_out_host == 2) return fail(d, "affine_begin: record-mode features (use the staging area)");
+  d->feat_out_host = 0;                              // the check needs the tracker's answers on the device
+  d->early_armed = 0;
+  if (d->feat_pending) {
+    CU(cudaStreamWaitEvent(d->tstream, d->ev_feat, 0));
+    d->feat_pending = 0;
+  }
+  CU(cudaMemcpyAsync(d->d_x0, d->d_x, (size_t)d->feat_cap * 12, cudaMemcpyDeviceToDevice, d->tstream));
+  *staging = reinterpret_cast<klt_dev_affine_state*>(d->h_aff_st);
+  return 0;
+}
+extern "C" int klt_dev_affine_put_template(klt_dev* d, int i, const float* img, const float* gx, const float* gy) {
+  CU(cudaSetDevice(d->device));
+  if (i < 0 || i >= d->aff_cap || !img || !gx || !gy) return fail(d, "affine_put_template: feature %d", i);
+  const size_t tb = (size_t)d->aff_tsz * sizeof(float);
+  float* dst = d->d_aff_tmpl + (size_t)i * 3 * d->aff_tsz;
+  CU(cudaMemcpyAsync(dst, img, tb, cudaMemcpyHostToDevice, d->tstream));
+  CU(cudaMemcpyAsync(dst + d->aff_tsz, gx, tb, cudaMemcpyHostToDevice, d->tstream));
+  CU(cudaMemcpyAsync(dst + 2 * d->aff_tsz, gy, tb, cudaMemcpyHostToDevice, d->tstream));
+  return 0;
+}
+extern "C" int klt_dev_affine_check(klt_dev* d, int slot_prev, int slot_cur, const klt_dev_track_params* tp,
+                                    const klt_dev_affine_params* ap) {
+  CU(cudaSetDevice(d->device));
+  if (!klt_dev_slot_valid(d, slot_prev) || !klt_dev_slot_valid(d, slot_cur))
+    return fail(d, "affine_check: pyramid slot %d or %d not built", slot_prev, slot_cur);
+  const int n = d->feat_n;
+  if (n <= 0 || d->aff_cap < n || !d->d_x0) return fail(d, "affine_check without affine_begin");
+  AffArgs a;
+  memset(&a, 0, sizeof(a));
+  a.check = ap->check; a.aw = ap->window_width; a.ah = ap->window_height; a.max_iterations = ap->max_iterations;
+  a.max_residue = ap->max_residue; a.th_aff = ap->min_displacement; a.mdd = ap->max_displacement_differ;
+  a.step_factor = tp->step_factor; a.small = tp->min_determinant; a.th = tp->min_displacement;
+  a.nlevels = d->L; a.ss = (float)d->ss;
+  const Level& l1 = d->set[slot_prev].lv[0];
+  const Level& l2 = d->set[slot_cur].lv[0];
+  a.ncols = l2.w; a.nrows = l2.h; a.pitch = l2.pitch;
+  if (l1.pitch != l2.pitch) return fail(d, "affine_check: level-0 pitches differ");
+  a.i1 = l1.img; a.gx1 = l1.gx; a.gy1 = l1.gy;
+  a.i2 = l2.img; a.gx2 = l2.gx; a.gy2 = l2.gy;
+  const int warps = 4;
+  const size_t smem = (size_t)warps * (3 * a.aw * a.ah + 48) * sizeof(float);
+  if (set_smem(d, affine_check_kernel, smem)) return 1;
+  { Launch l(d, KID_COPY_H2D, d->tstream);
+    CU(cudaMemcpyAsync(d->d_aff_st, d->h_aff_st, (size_t)n * sizeof(AffState), cudaMemcpyHostToDevice, d->tstream)); }
+  { Launch l(d, KID_AFFINE, d->tstream);
+    const float* x0 = d->d_x0;
+    affine_check_kernel<<<(n + warps - 1) / warps, warps * 32, smem, d->tstream>>>(
+        a, n, x0, x0 + d->feat_cap, reinterpret_cast<const int*>(x0 + 2 * (size_t)d->feat_cap),
+        d->d_x, d->d_y, d->d_val, d->d_aff_st, d->d_aff_tmpl); }
+  CU(cudaGetLastError());
+  { Launch l(d, KID_COPY_D2H, d->tstream);
+    CU(cudaMemcpyAsync(d->h_aff_st, d->d_aff_st, (size_t)n * sizeof(AffState), cudaMemcpyDeviceToHost, d->tstream)); }
+  return 0;
+}
+// after the call's synchronisation: template i (image, gradx, grady: (w+2)(h+2) floats each)
+extern "C" int klt_dev_affine_get_template(klt_dev* d, int i, float* img, float* gx, float* gy) {
+  CU(cudaSetDevice(d->device));
+  if (i < 0 || i >= d->aff_cap) return fail(d, "affine_get_template: feature %d", i);
+  const size_t tb = (size_t)d->aff_tsz * sizeof(float);
+  const float* src = d->d_aff_tmpl + (size_t)i * 3 * d->aff_tsz;
+  CU(cudaMemcpyAsync(img, src, tb, cudaMemcpyDeviceToHost, d->tstream));
+  CU(cudaMemcpyAsync(gx, src + d->aff_tsz, tb, cudaMemcpyDeviceToHost, d->tstream));
+  CU(cudaMemcpyAsync(gy, src + 2 * d->aff_tsz, tb, cudaMemcpyDeviceToHost, d->tstream));
+  CU(cudaStreamSynchronize(d->tstream));
+  return 0;
+}
+// all templates of features [0, n) in one copy: n x 3 x (w+2)(h+2) floats
+extern "C" int klt_dev_affine_get_templates(klt_dev* d, int n, float* all) {
+  CU(cudaSetDevice(d->device));
+  if (n < 0 || n > d->aff_cap || !all) return fail(d, "affine_get_templates: %d features", n);
+  CU(cudaMemcpyAsync(all, d->d_aff_tmpl, (size_t)n * 3 * d->aff_tsz * sizeof(float), cudaMemcpyDeviceToHost, d->tstream));
+  CU(cudaStreamSynchronize(d->tstream));
+  return 0;
 }
 
 // ---- selection --------------------------------------------------------------------

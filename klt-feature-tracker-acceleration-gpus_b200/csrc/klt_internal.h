@@ -15,6 +15,12 @@ typedef struct klt_tc_state {
   int device;            /* CUDA device ordinal, -1 = KLT_B200_DEVICE / current */
   int exact;             /* arithmetic mode for tracking pyramids            */
   int last_slot;         /* slot holding the previous frame's pyramids       */
+  /* affine consistency check: which host template (aff_img pointer) the device's template
+   * slot i mirrors; valid for list aff_list while klt_aff_epoch == aff_epoch */
+  void **aff_shadow;
+  int aff_shadow_n;
+  const void *aff_list;
+  unsigned aff_epoch;
   struct klt_tc_state *next;
 } klt_tc_state;
 
@@ -40,6 +46,9 @@ int klt_list_is_pinned(const void *p);
 
 /* device selection parameters from a tracking context (csrc/klt_select.c) */
 void klt_fill_select_params(KLT_TrackingContext tc, int replacing, klt_dev_select_params *sp);
+
+/* bumped by KLTFreeFeatureList: template addresses may be reused afterwards */
+extern unsigned klt_aff_epoch;
 
 /* list <-> SoA staging */
 void klt_list_to_arrays(KLT_FeatureList fl, float *x, float *y, int *v);

@@ -6,8 +6,9 @@
  * (:1295-1308), building the pyramids of img2 (:1311-1321), the feature loop
  * (:1343-1437, one warp per feature in csrc/klt_dev.cu), and the pyramid
  * hand-over (:1503-1519).  tc->lighting_insensitive (:125-220) runs on the generic
- * warp-per-feature kernel.  The affine-consistency check (:506-1224) is not on the
- * accelerated path: asking for it is a KLTError rather than a silent CPU fallback.
+ * warp-per-feature kernel.  The affine-consistency check (:506-1224, :1438-1497) runs on the
+ * device too (csrc/klt_affine.cuh); this file keeps the per-feature templates the reference
+ * attaches to the feature list (aff_img*) in step with the device's copies.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -50,11 +51,113 @@ static void fill_track_params(KLT_TrackingContext tc, int exact, klt_dev_track_p
   p->lighting_insensitive = tc->lighting_insensitive ? 1 : 0;
 }
 
-static void check_supported(KLT_TrackingContext tc)
+static void check_supported(KLT_TrackingContext tc, int pipelined)
 {
-  if (tc->affineConsistencyCheck >= 0)
-    KLTError("(KLTTrackFeatures) affineConsistencyCheck >= 0 is not implemented "
-             "on the GPU path (and there is no CPU path)");
+  if (tc->affineConsistencyCheck > 2)
+    KLTError("(KLTTrackFeatures) affineConsistencyCheck = %d (must be -1, 0, 1 or 2)",
+             tc->affineConsistencyCheck);
+  if (tc->affineConsistencyCheck >= 0 && pipelined)
+    KLTError("(KLT/B200) the affine consistency check keeps per-feature templates in the caller's "
+             "feature list: use KLTTrackFeatures, not the resident / sequence pipeline");
+  if (tc->affineConsistencyCheck == 0 && tc->lighting_insensitive)
+    KLTError("(KLTTrackFeatures) affineConsistencyCheck = 0 together with lighting_insensitive is "
+             "not implemented on the GPU path (and there is no CPU path)");
+}
+
+/* ---- affine consistency check: host side (reference trackFeatures.c:1438-1497) ---------- */
+/* _KLTCreateFloatImage (klt_util.c:34-54): header and pixels in one block, freed with free() */
+static _KLT_FloatImage new_float_image(int ncols, int nrows)
+{
+  _KLT_FloatImage im = (_KLT_FloatImage)malloc(sizeof(_KLT_FloatImageRec) +
+                                               (size_t)ncols * nrows * sizeof(float));
+  if (im == NULL) KLTError("(_KLTCreateFloatImage) Out of memory");
+  im->ncols = ncols;
+  im->nrows = nrows;
+  im->data = (float *)(im + 1);
+  return im;
+}
+
+static void fill_affine_params(KLT_TrackingContext tc, klt_dev_affine_params *ap)
+{
+  ap->check = tc->affineConsistencyCheck;
+  ap->window_width = tc->affine_window_width;
+  ap->window_height = tc->affine_window_height;
+  ap->max_iterations = tc->affine_max_iterations;
+  ap->max_residue = tc->affine_max_residue;
+  ap->min_displacement = tc->affine_min_displacement;
+  ap->max_displacement_differ = tc->affine_max_displacement_differ;
+}
+
+/* fill the device's per-feature state from the list; upload templates the device does not mirror */
+static void affine_stage(KLT_TrackingContext tc, klt_tc_state *s, KLT_FeatureList fl,
+                         klt_dev_affine_state *st)
+{
+  const int n = fl->nFeatures, tw = tc->affine_window_width + 2, th = tc->affine_window_height + 2;
+  int i;
+  if (s->aff_list != (const void *)fl || s->aff_epoch != klt_aff_epoch || s->aff_shadow_n != n) {
+    free(s->aff_shadow);
+    s->aff_shadow = (void **)calloc((size_t)n, sizeof(void *));
+    if (s->aff_shadow == NULL) KLTError("(KLTTrackFeatures) Out of memory");
+    s->aff_shadow_n = n;
+    s->aff_list = fl;
+    s->aff_epoch = klt_aff_epoch;
+  }
+  for (i = 0; i < n; i++) {
+    KLT_Feature f = fl->feature[i];
+    st[i].has = f->aff_img != NULL;
+    st[i].aff_x = f->aff_x; st[i].aff_y = f->aff_y;
+    st[i].Axx = f->aff_Axx; st[i].Ayx = f->aff_Ayx; st[i].Axy = f->aff_Axy; st[i].Ayy = f->aff_Ayy;
+    st[i].flags = 0;
+    if (f->aff_img != NULL && s->aff_shadow[i] != (void *)f->aff_img) {
+      if (f->aff_img_gradx == NULL || f->aff_img_grady == NULL ||
+          f->aff_img->ncols != tw || f->aff_img->nrows != th)
+        KLTError("(KLTTrackFeatures) feature %d carries a %d by %d affine template, expected %d by %d",
+                 i, f->aff_img->ncols, f->aff_img->nrows, tw, th);
+      DEVCALL(s, klt_dev_affine_put_template(s->dev, i, f->aff_img->data, f->aff_img_gradx->data,
+                                             f->aff_img_grady->data));
+      s->aff_shadow[i] = (void *)f->aff_img;
+    }
+    if (f->aff_img == NULL) s->aff_shadow[i] = NULL;
+  }
+}
+
+/* after the call: the aff_* members of every feature that was tracked, new templates fetched */
+static void affine_collect(KLT_TrackingContext tc, klt_tc_state *s, KLT_FeatureList fl,
+                           const klt_dev_affine_state *st, const unsigned char *was_live)
+{
+  const int n = fl->nFeatures, tw = tc->affine_window_width + 2, th = tc->affine_window_height + 2;
+  const size_t tsz = (size_t)tw * th;
+  float *all = NULL;
+  int i, created = 0;
+  for (i = 0; i < n; i++) created += was_live[i] && st[i].flags == 1;
+  if (created > 8) {              /* one bulk copy instead of three small ones per feature */
+    all = (float *)malloc((size_t)n * 3 * tsz * sizeof(float));
+    if (all == NULL) KLTError("(KLTTrackFeatures) Out of memory");
+    DEVCALL(s, klt_dev_affine_get_templates(s->dev, n, all));
+  }
+  for (i = 0; i < n; i++) {
+    KLT_Feature f = fl->feature[i];
+    if (!was_live[i]) continue;
+    f->aff_x = st[i].aff_x; f->aff_y = st[i].aff_y;
+    f->aff_Axx = st[i].Axx; f->aff_Ayx = st[i].Ayx; f->aff_Axy = st[i].Axy; f->aff_Ayy = st[i].Ayy;
+    if (st[i].flags == 1) {       /* :1446-1457 template saved after the first successful track */
+      f->aff_img = new_float_image(tw, th);
+      f->aff_img_gradx = new_float_image(tw, th);
+      f->aff_img_grady = new_float_image(tw, th);
+      if (all != NULL) {
+        memcpy(f->aff_img->data, all + (size_t)i * 3 * tsz, tsz * sizeof(float));
+        memcpy(f->aff_img_gradx->data, all + (size_t)i * 3 * tsz + tsz, tsz * sizeof(float));
+        memcpy(f->aff_img_grady->data, all + (size_t)i * 3 * tsz + 2 * tsz, tsz * sizeof(float));
+      } else {
+        DEVCALL(s, klt_dev_affine_get_template(s->dev, i, f->aff_img->data, f->aff_img_gradx->data,
+                                               f->aff_img_grady->data));
+      }
+      s->aff_shadow[i] = (void *)f->aff_img;
+    } else if (f->aff_img == NULL) {
+      s->aff_shadow[i] = NULL;    /* released: freed by the caller's loop when val went negative */
+    }
+  }
+  free(all);
 }
 
 /* Returns the slot holding frame 1's pyramids, building them if necessary. */
@@ -106,6 +209,10 @@ static void track_common(KLT_TrackingContext tc, const KLT_PixelType *img1,
   klt_dev_build_desc q;
   klt_dev_track_params tp;
   int slot_prev, slot_cur, n = fl->nFeatures, i, records;
+  const int affine = tc->affineConsistencyCheck >= 0 && n > 0;
+  klt_dev_affine_params ap;
+  klt_dev_affine_state *ast = NULL;
+  unsigned char *was_live = NULL;
   float *x = NULL, *y = NULL;
   int *v = NULL;
 
@@ -115,7 +222,7 @@ static void track_common(KLT_TrackingContext tc, const KLT_PixelType *img1,
     fflush(stderr);
   }
   klt_fix_window(tc, "KLTTrackFeatures", 1);
-  check_supported(tc);
+  check_supported(tc, 0);
   dev = klt_state_device(s);
 
   /* Everything below is queued on the context stream without waiting: feature upload,
@@ -129,7 +236,7 @@ static void track_common(KLT_TrackingContext tc, const KLT_PixelType *img1,
    * packed into the staging area first (a few microseconds) for the same order on the copy stream. */
   slot_prev = prepare_previous(tc, s, img1, on_device, pitch, ncols, nrows);
   slot_cur = (slot_prev + 1) % KLT_DEV_SLOTS;
-  records = n > 0 && klt_list_is_pinned(fl) && fl->feature[n - 1] == fl->feature[0] + (n - 1);
+  records = n > 0 && !affine && klt_list_is_pinned(fl) && fl->feature[n - 1] == fl->feature[0] + (n - 1);
   if (records) {
     DEVCALL(s, klt_dev_features_commit_records(dev, n, fl->feature[0], sizeof(KLT_FeatureRec)));
   } else {
@@ -138,19 +245,28 @@ static void track_common(KLT_TrackingContext tc, const KLT_PixelType *img1,
     DEVCALL(s, klt_dev_features_commit(dev, n));
   }
   fill_track_params(tc, s->exact, &tp);
-  if (!on_device) DEVCALL(s, klt_dev_arm_early_track(dev, slot_prev, &tp));
+  if (affine) {
+    fill_affine_params(tc, &ap);
+    DEVCALL(s, klt_dev_affine_begin(dev, n, &ap, &ast));
+    affine_stage(tc, s, fl, ast);
+    was_live = (unsigned char *)malloc((size_t)n);
+    if (was_live == NULL) KLTError("(KLTTrackFeatures) Out of memory");
+    for (i = 0; i < n; i++) was_live[i] = fl->feature[i]->val >= 0;
+  } else if (!on_device) {
+    DEVCALL(s, klt_dev_arm_early_track(dev, slot_prev, &tp));
+  }
   klt_fill_build_desc(tc, ncols, nrows, tc->nPyramidLevels, 1, s->exact, &q);
   DEVCALL(s, klt_dev_build(dev, slot_cur, img2, on_device, pitch, &q));
   if (timing) t1 = now_us();
 
   fill_track_params(tc, s->exact, &tp);
   DEVCALL(s, klt_dev_track_resident(dev, slot_prev, slot_cur, &tp));
+  if (affine) DEVCALL(s, klt_dev_affine_check(dev, slot_prev, slot_cur, &tp, &ap));
   if (timing) t2 = now_us();
   DEVCALL(s, klt_dev_features_fetch(dev, n));
   if (timing) t3 = now_us();
-  /* (record mode: nothing to unpack.  The reference frees a lost feature's affine images here,
-   * trackFeatures.c:1387-1392; this library never allocates them -- the affine check is a
-   * KLTError -- and KLTFreeFeatureList releases whatever a caller attached.) */
+  /* (record mode: nothing to unpack.  A lost feature's affine templates are freed here as in the
+   * reference, trackFeatures.c:1387-1392 and :1480-1489.) */
   for (i = 0; !records && i < n; i++) {
     KLT_Feature f = fl->feature[i];
     if (f->val < 0) continue;                 /* lost features are not touched (:1346) */
@@ -163,6 +279,10 @@ static void track_common(KLT_TrackingContext tc, const KLT_PixelType *img1,
     }
   }
 
+  if (affine) {
+    affine_collect(tc, s, fl, ast, was_live);
+    free(was_live);
+  }
   hand_over(tc, s, slot_cur);
   if (timing) {
     const double t4 = now_us();
@@ -205,7 +325,7 @@ void KLTB200ResidentBegin(KLT_TrackingContext tc, const KLT_PixelType *img1, int
   int slot;
   if (!x || !y || !v) KLTError("(KLTB200ResidentBegin) Out of memory");
   klt_fix_window(tc, "KLTTrackFeatures", 1);
-  check_supported(tc);
+  check_supported(tc, 1);
   if (!tc->sequentialMode)
     KLTError("(KLTB200ResidentBegin) the resident pipeline needs tc->sequentialMode = TRUE");
   {
