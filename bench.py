@@ -72,7 +72,10 @@ def algorithmic_bytes(ncols, nrows, nlevels, ss):
         "pyrdown_tile": sum(4 * px[l - 1] + 4 * px[l] for l in range(1, nlevels)),
         "l0_fused_kernel": 13 * px[0],                                 # read u8, write L0, gx0, gy0
         "pyramid_mega_kernel": ncols * nrows + 12 * sum(px),           # whole pyramid in one launch (opt-in)
-        "level_fused_kernel": sum(4 * px[l - 1] + 12 * px[l] for l in range(1, nlevels)),
+        # one pyramid step + that level's gradients: read L_{l-1}, write L_l, gx_l, gy_l
+        "level_fused_kernel[level 1]": (4 * px[0] + 12 * px[1]) if nlevels > 1 else 0,
+        "level_fused_kernel[level 2]": (4 * px[1] + 12 * px[2]) if nlevels > 2 else 0,
+        "level_fused_kernel[level 3+]": sum(4 * px[l - 1] + 12 * px[l] for l in range(3, nlevels)),
         "frame_pipeline": ncols * nrows + 12 * sum(px),                # fully fused floor
     }
     # when level 0 is fused, the stand-alone gradient kernel only sees the coarser levels
@@ -322,8 +325,8 @@ def run_b200(args, rank, local_rank, world):
                 ent["algorithmic_bytes_per_step"] = bytes_tab[key]
                 ent["gbs"] = round(bytes_tab[key] / (per_step * 1e-3) / 1e9, 1)
             kernels[name] = ent
-        pipe = ["smooth_u8_tile", "grad_tile", "pyrdown_tile", "l0_fused_kernel", "level_fused_kernel",
-                "pyramid_mega_kernel"]
+        pipe = ["smooth_u8_tile", "grad_tile", "pyrdown_tile", "l0_fused_kernel", "level_fused_kernel[level 1]",
+                "level_fused_kernel[level 2]", "level_fused_kernel[level 3+]", "pyramid_mega_kernel"]
         hbm_kernels = {k: v for k, v in kernels.items() if "gbs" in v}
         dom = max(hbm_kernels, key=lambda k: hbm_kernels[k]["ms_per_step"]) if hbm_kernels else None
         traffic = None
