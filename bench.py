@@ -143,6 +143,8 @@ def setup_tc(L, nlevels, ss, window, device=None):
     t.sequentialMode = 1
     t.window_width = t.window_height = window
     t.nPyramidLevels, t.subsampling = nlevels, ss
+    if os.environ.get("KLT_BENCH_MAXIT"):          # diagnostic: how much of the tracker is its slowest features
+        t.max_iterations = int(os.environ["KLT_BENCH_MAXIT"])
     L.KLTUpdateTCBorder(tc)
     if device is not None:
         L.KLTB200SetDevice(tc, device)

@@ -141,6 +141,9 @@ void klt_dev_disable_early_track(klt_dev *d, int on);
 /* 7x7 fma tracking runs on track7w_kernel (one warp per feature; default) or, with
  * klt_dev_disable_track7w(d, 1) / env KLT_B200_TRACK7W=0, on track7_kernel (8 lanes per feature) */
 void klt_dev_disable_track7w(klt_dev *d, int on);
+/* the default 7x7 fma tracker is track7v_kernel (track7w's lane map with one aligned 128-bit load
+ * per lane and image); klt_dev_disable_track7v(d, 1) / env KLT_B200_TRACK7V=0 selects track7w_kernel */
+void klt_dev_disable_track7v(klt_dev *d, int on);
 int klt_dev_last_track_passes(const klt_dev *d);     /* 2 if the last tracking ran in two passes */
 /* zero-copy variant for the C host layer: pack the feature list straight into the
  * context's pinned staging area, commit it (async H2D), and after the work fetch the

@@ -891,12 +891,12 @@ track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
 // kernel classes, for launch accounting and per-kernel event timing
 enum KernelId {
   KID_SMOOTH_U8 = 0, KID_GRAD, KID_PYRDOWN, KID_TRACK, KID_MINEIG, KID_SORT, KID_STAMP,
-  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_L0_FUSED, KID_LEVEL_FUSED, KID_LEVEL_FUSED_L2, KID_LEVEL_FUSED_L3, KID_TRACK_FAST, KID_TRACK7, KID_TRACK7W, KID_AFFINE, KID_LEVELS_CHAIN, KID_MEGA, KID_L0_STREAM, KID_COPY_H2D, KID_COPY_D2H, KID_COUNT
+  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_L0_FUSED, KID_LEVEL_FUSED, KID_LEVEL_FUSED_L2, KID_LEVEL_FUSED_L3, KID_TRACK_FAST, KID_TRACK7, KID_TRACK7W, KID_TRACK7V, KID_AFFINE, KID_LEVELS_CHAIN, KID_MEGA, KID_L0_STREAM, KID_COPY_H2D, KID_COPY_D2H, KID_COUNT
 };
 static const char* const kKernelNames[KID_COUNT] = {
   "smooth_u8_tile", "grad_tile", "pyrdown_tile", "track_kernel", "mineig_kernel",
   "cub_radix_sort", "stamp_existing_kernel", "enforce_mindist_kernel",
-  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel", "l0_fused_kernel", "level_fused_kernel[level 1]", "level_fused_kernel[level 2]", "level_fused_kernel[level 3+]", "track_fast_kernel", "track7_kernel", "track7w_kernel", "affine_check_kernel", "levels_chain_kernel", "pyramid_mega_kernel", "l0_stream_kernel",
+  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel", "l0_fused_kernel", "level_fused_kernel[level 1]", "level_fused_kernel[level 2]", "level_fused_kernel[level 3+]", "track_fast_kernel", "track7_kernel", "track7w_kernel", "track7v_kernel", "affine_check_kernel", "levels_chain_kernel", "pyramid_mega_kernel", "l0_stream_kernel",
   "copy_h2d", "copy_d2h"          // not kernels: timed in profiling mode, never counted as launches
 };
 static constexpr int PROF_POOL = 2048;     // event pairs in flight before folding
@@ -955,7 +955,7 @@ struct klt_dev {
   float *h_x, *h_y; int* h_val;   // pinned staging
   int staging_busy;
   // early tracker pass behind the first uploaded band (klt_dev_arm_early_track)
-  int no_track7w;
+  int no_track7w, no_track7v;
   int early_armed, early_done, early_slot_prev, early_slot_cur, no_early, last_passes;
   klt_dev_track_params early_p;
   unsigned char* d_fdone; int fdone_cap;
@@ -1155,6 +1155,15 @@ extern "C" int klt_dev_create(int device, klt_dev** out) {
   // build 62.2 us vs 58.7 us)
   c->no_chain = getenv("KLT_B200_CHAIN") && atoi(getenv("KLT_B200_CHAIN")) ? 0 : 1;
   c->no_track7w = getenv("KLT_B200_TRACK7W") ? !atoi(getenv("KLT_B200_TRACK7W")) : 0;
+  c->no_track7v = getenv("KLT_B200_TRACK7V") ? !atoi(getenv("KLT_B200_TRACK7V")) : 1;   // opt-in until verified on the GPU
+  if (getenv("KLT_B200_L2_PERSIST_MB")) {       // experiment: L2 set-aside for evict_last lines (KLT_TRACK_L2_KEEP)
+    int maxb = 0;
+    cudaDeviceGetAttribute(&maxb, cudaDevAttrMaxPersistingL2CacheSize, c->device);
+    size_t want = (size_t)atoi(getenv("KLT_B200_L2_PERSIST_MB")) << 20;
+    if (want > (size_t)maxb) want = (size_t)maxb;
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+    fprintf(stderr, "(KLT/B200) persisting L2: %zu MB of max %d MB\n", want >> 20, maxb >> 20);
+  }
   // opt-in: measured no gain (the tracker is a latency chain: a pass over half the features takes
   // as long as a pass over all of them)
   c->no_early = getenv("KLT_B200_EARLY_TRACK") && atoi(getenv("KLT_B200_EARLY_TRACK")) ? 0 : 1;
@@ -2466,7 +2475,13 @@ static bool launch_track_fast(klt_dev* d, const PyrView& v1, const PyrView& v2, 
     case 5: launch_track_fast_t<5, 1>(d, v1, v2, a, n); return true;
     case 7:
       if (d->track7_off) { launch_track_fast_t<7, 1>(d, v1, v2, a, n); return true; }
-      if (!d->no_track7w) {                                  // one warp per feature: shortest latency chain
+      if (!d->no_track7w && !d->no_track7v) {                // one warp per feature, one 128-bit load per lane and image
+        Launch l(d, KID_TRACK7V, d->tstream);
+        launch_k(track7v_kernel, dim3((n + 3) / 4), dim3(128), 0, d->tstream, d->pdl != 0 && !d->overlap, v1, v2, a, n,
+                 feat_io(d), d->d_live);
+        return true;
+      }
+      if (!d->no_track7w) {                                  // one warp per feature, scalar loads
         Launch l(d, KID_TRACK7W, d->tstream);
         launch_k(track7w_kernel, dim3((n + 3) / 4), dim3(128), 0, d->tstream, d->pdl != 0 && !d->overlap, v1, v2, a, n,
                  feat_io(d), d->d_live);
@@ -2501,7 +2516,7 @@ static void fill_track_args(const klt_dev* d, const klt_dev_track_params* p, Tra
   a->ncols = d->W; a->nrows = d->H;
   a->lighting = p->lighting_insensitive ? 1 : 0;
   { static int pf = getenv("KLT_TRACK_PREFETCH") ? atoi(getenv("KLT_TRACK_PREFETCH")) : 0; a->prefetch = pf; }
-  { static int keep = getenv("KLT_TRACK_L2_KEEP") ? atoi(getenv("KLT_TRACK_L2_KEEP")) : 0; a->l2_keep = keep; }
+  { static int keep = getenv("KLT_TRACK_L2_KEEP") ? atoi(getenv("KLT_TRACK_L2_KEEP")) : 1; a->l2_keep = keep; }
 }
 // can this call be served by track7_kernel (the only tracker with the two-pass mode)?
 static bool track7_applies(const klt_dev* d, const klt_dev_track_params* p) {
@@ -2522,6 +2537,7 @@ static int launch_track7(klt_dev* d, const PyrView& v1, const PyrView& v2, const
 // later klt_dev_track_resident only finishes the features that pass had to defer.
 extern "C" void klt_dev_disable_early_track(klt_dev* d, int on) { d->no_early = on; }
 extern "C" void klt_dev_disable_track7w(klt_dev* d, int on) { d->no_track7w = on; }
+extern "C" void klt_dev_disable_track7v(klt_dev* d, int on) { d->no_track7v = on; }
 extern "C" int klt_dev_last_track_passes(const klt_dev* d) { return d->last_passes; }
 extern "C" int klt_dev_arm_early_track(klt_dev* d, int slot_prev, const klt_dev_track_params* p) {
   d->early_armed = 0; d->early_done = 0;

@@ -520,10 +520,15 @@ __device__ __forceinline__ float ldg_policy(const float* p, unsigned long long p
   asm("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
   return v;
 }
+// two loads per lane; the third pixel (column 2c + 2) is the first pixel of the lane to the right.
+// Lane c = 3 receives the next row's first pixel instead, which it never uses (its second window
+// column does not exist).  A third of the load instructions (and of their L1 wavefronts: every load
+// instruction of the warp touches 8 rows = 8+ cache lines) for one shuffle.  Warp-uniform callers only.
 __device__ __forceinline__ Pix3 pix3_load(const float* __restrict__ img, int off, unsigned long long pol) {
   const float* p = img + off;
   Pix3 r;
-  r.a = ldg_policy(p, pol); r.b = ldg_policy(p + 1, pol); r.c = ldg_policy(p + 2, pol);
+  r.a = ldg_policy(p, pol); r.b = ldg_policy(p + 1, pol);
+  r.c = __shfl_down_sync(0xffffffffu, r.a, 1);
   return r;
 }
 // bilinear samples of this lane's two window columns in its window row; the row below comes from
@@ -634,6 +639,196 @@ track7w_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
       float s_i0, s_i1;
       pix3_interp(c_i, x2 - (float)xt, y2 - (float)yt, s_i0, s_i1);
       float sum = (v0 ? fabsf(t_i0 - s_i0) : 0.0f) + (v1 ? fabsf(t_i1 - s_i1) : 0.0f);
+      sum = warp_sum32(sum);
+      if (sum * (1.0f / 49.0f) > a.max_residue) lvl_status = KLT_LARGE_RESIDUE;
+    }
+    int v;                                                   // return value of _trackFeature (:479-484)
+    if (lvl_status == KLT_SMALL_DET) v = KLT_SMALL_DET;
+    else if (lvl_status == KLT_OOB) v = KLT_OOB;
+    else if (lvl_status == KLT_LARGE_RESIDUE) v = KLT_LARGE_RESIDUE;
+    else if (iteration >= a.max_iterations) v = KLT_MAX_ITERATIONS;
+    else v = KLT_TRACKED;
+    status = v;
+    xout = x2; yout = y2;
+    if (v == KLT_SMALL_DET || v == KLT_OOB) break;           // :1378
+  }
+
+  if (lane == 0) {                                           // record (:1383-1437)
+    const bool outside = (xout < (float)a.borderx || xout > (float)(a.ncols - 1 - a.borderx) ||
+                          yout < (float)a.bordery || yout > (float)(a.nrows - 1 - a.bordery));
+    const size_t o = (size_t)f * io.ostride;
+    if (status == KLT_OOB || outside) { io.ox[o] = -1.0f; io.oy[o] = -1.0f; io.oval[o] = KLT_OOB; }
+    else if (status != KLT_TRACKED) { io.ox[o] = -1.0f; io.oy[o] = -1.0f; io.oval[o] = status; }
+    else { io.ox[o] = xout; io.oy[o] = yout; io.oval[o] = KLT_TRACKED; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 7x7 window, one warp per feature, ONE 128-bit load per lane and image (track7v_kernel).
+//
+// ncu on track7w_kernel: every scalar load instruction of the warp touches the 8 footprint rows,
+// i.e. 8+ cache lines = 8+ L1 wavefronts, and a level start issues 18 of them; dropping one load in
+// three (the third pixel by shuffle) took the kernel from 27.1 to 24.7 us -- it is bound by the
+// L1 wavefronts of its gathers, not by DRAM bytes (an L2 set-aside for the footprints changed the
+// DRAM traffic but not the time) and not by its iteration count.  Here lane = 4 * row + q and lanes
+// q = 0..2 load the three ALIGNED float4 chunks that cover the row's footprint (floats B .. B+11,
+// B = (xt - 3) & ~3; the footprint starts at float m = (xt - 3) & 3 of them): one load instruction
+// per image instead of two.  A lane then works on the window columns that start in its chunk,
+// w = 4q + t - m for t = 0..3 (those in 0..6 are real), with the first float of the chunk to its
+// right by shuffle.  The previous frame's samples are aligned to ITS m; they are shifted to the new
+// frame's alignment by shuffles whenever that changes.  Per-sample arithmetic as in track7w_kernel;
+// the sums run over up to four samples per lane before the xor-shuffle tree.
+// ---------------------------------------------------------------------------------------------
+struct Row5 { float x, y, z, w, n; };
+__device__ __forceinline__ Row5 row5_load(const float* __restrict__ img, int off, bool active, unsigned long long pol) {
+  Row5 r;
+  r.x = r.y = r.z = r.w = 0.0f;
+  if (active)
+    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(img + off), "l"(pol));
+  r.n = __shfl_down_sync(0xffffffffu, r.x, 1);
+  return r;
+}
+__device__ __forceinline__ void row5_interp(const Row5& p, float ax, float ay, float (&o)[4]) {
+  const float h0 = fmaf(ax, p.y - p.x, p.x), h1 = fmaf(ax, p.z - p.y, p.y);
+  const float h2 = fmaf(ax, p.w - p.z, p.z), h3 = fmaf(ax, p.n - p.w, p.w);
+  const float b0 = __shfl_down_sync(0xffffffffu, h0, 4), b1 = __shfl_down_sync(0xffffffffu, h1, 4);
+  const float b2 = __shfl_down_sync(0xffffffffu, h2, 4), b3 = __shfl_down_sync(0xffffffffu, h3, 4);
+  o[0] = fmaf(ay, b0 - h0, h0); o[1] = fmaf(ay, b1 - h1, h1);
+  o[2] = fmaf(ay, b2 - h2, h2); o[3] = fmaf(ay, b3 - h3, h3);
+}
+// out[t] = the sample that sits `delta` slots to the left in the row (slot = 4 * q + t); delta is
+// warp uniform, -3 .. 3
+__device__ __forceinline__ void row_shift(const float (&in)[4], int delta, int lane, float (&out)[4]) {
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int s = t - delta;                       // -3 .. 6
+    const int t1 = s & 3, dq = (s - t1) >> 2;      // source slot within its lane, lane offset -1 / 0 / 1
+    const float v = t1 == 0 ? in[0] : t1 == 1 ? in[1] : t1 == 2 ? in[2] : in[3];
+    out[t] = __shfl_sync(0xffffffffu, v, (lane + dq) & 31);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+track7v_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
+               unsigned long long* __restrict__ live_total) {
+  constexpr int hw = 3, hh = 3;
+  const int lane = threadIdx.x & 31;
+  const int r = lane >> 2, q = lane & 3;                     // footprint row, aligned chunk of the row
+  const bool ld = q < 3;
+  const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long pol1 = l2_policy(a.l2_keep ? 2 : 0), pol2 = l2_policy(a.l2_keep ? 1 : 0);
+  pdl_wait();                                                 // pyramids and features come from earlier kernels
+  if (f >= n) return;
+  if (io.val[(size_t)f * io.istride] < 0) return;             // only features that are not lost (:1346)
+  if (lane == 0) atomicAdd(live_total, 1ULL);
+  float xloc = io.x[(size_t)f * io.istride], yloc = io.y[(size_t)f * io.istride];
+  for (int l = a.nlevels - 1; l >= 0; --l) { xloc = xloc / a.ss; yloc = yloc / a.ss; }
+  float xout = xloc, yout = yloc;
+  int status = KLT_TRACKED;
+
+  for (int l = a.nlevels - 1; l >= 0; --l) {
+    xloc *= a.ss; yloc *= a.ss; xout *= a.ss; yout *= a.ss;
+    const int nc = p1.ncols[l], nr = p1.nrows[l], pitch = p1.pitch[l];
+    const float* __restrict__ i2 = p2.img[l];
+    const float* __restrict__ gx2 = p2.gx[l];
+    const float* __restrict__ gy2 = p2.gy[l];
+    const float x1 = xloc, y1 = yloc;
+    float x2 = xout, y2 = yout;
+    int iteration = 0, lvl_status = KLT_TRACKED;
+    bool iterating = true;
+    if (window_oob(x1, y1, hw, hh, nc, nr) || window_oob(x2, y2, hw, hh, nc, nr)) { lvl_status = KLT_OOB; iterating = false; }
+
+    float t_i[4], t_gx[4], t_gy[4];                            // previous frame, in ITS slot alignment m1
+    float u_i[4], u_gx[4], u_gy[4];                            // the same, shifted to the new frame's alignment
+    Row5 c_i, c_gx, c_gy;
+    c_i.x = c_i.y = c_i.z = c_i.w = c_i.n = 0.f; c_gx = c_i; c_gy = c_i;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { t_i[t] = t_gx[t] = t_gy[t] = 0.f; u_i[t] = u_gx[t] = u_gy[t] = 0.f; }
+    int c_xt = -1000000, c_yt = -1000000, m1 = 0, m2 = 0;
+    bool vs[4] = {false, false, false, false};                // slot t holds a window sample
+    if (iterating) {
+      // all 6 loads of the level are issued before the first use
+      const int xt1 = (int)x1, yt1 = (int)y1, xt2 = (int)x2, yt2 = (int)y2;
+      m1 = (xt1 - 3) & 3; m2 = (xt2 - 3) & 3;
+      const int o1 = (yt1 - 3 + r) * pitch + ((xt1 - 3) & ~3) + 4 * q;
+      const int o2 = (yt2 - 3 + r) * pitch + ((xt2 - 3) & ~3) + 4 * q;
+      const Row5 r_i = row5_load(p1.img[l], o1, ld, pol1), r_gx = row5_load(p1.gx[l], o1, ld, pol1),
+                 r_gy = row5_load(p1.gy[l], o1, ld, pol1);
+      c_i = row5_load(i2, o2, ld, pol2); c_gx = row5_load(gx2, o2, ld, pol2); c_gy = row5_load(gy2, o2, ld, pol2);
+      c_xt = xt2; c_yt = yt2;
+      const float ax = x1 - (float)xt1, ay = y1 - (float)yt1;
+      row5_interp(r_i, ax, ay, t_i);
+      row5_interp(r_gx, ax, ay, t_gx);
+      row5_interp(r_gy, ax, ay, t_gy);
+      row_shift(t_i, m2 - m1, lane, u_i); row_shift(t_gx, m2 - m1, lane, u_gx); row_shift(t_gy, m2 - m1, lane, u_gy);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { const int w = 4 * q + t - m2; vs[t] = r < 7 && ld && w >= 0 && w <= 6; }
+    }
+
+    float dx = 0.0f, dy = 0.0f;
+    while (iterating) {                                       // warp uniform
+      const int xt = (int)x2, yt = (int)y2;
+      if (xt != c_xt || yt != c_yt) {                         // the integer footprint moved: re-read it
+        const int o2 = (yt - 3 + r) * pitch + ((xt - 3) & ~3) + 4 * q;
+        c_i = row5_load(i2, o2, ld, pol2); c_gx = row5_load(gx2, o2, ld, pol2); c_gy = row5_load(gy2, o2, ld, pol2);
+        c_xt = xt; c_yt = yt;
+        const int m = (xt - 3) & 3;
+        if (m != m2) {
+          m2 = m;
+          row_shift(t_i, m2 - m1, lane, u_i); row_shift(t_gx, m2 - m1, lane, u_gx); row_shift(t_gy, m2 - m1, lane, u_gy);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) { const int w = 4 * q + t - m2; vs[t] = r < 7 && ld && w >= 0 && w <= 6; }
+        }
+      }
+      const float ax = x2 - (float)xt, ay = y2 - (float)yt;
+      float s_i[4], s_gx[4], s_gy[4];
+      row5_interp(c_i, ax, ay, s_i);
+      row5_interp(c_gx, ax, ay, s_gx);
+      row5_interp(c_gy, ax, ay, s_gy);
+      float gxx = 0.0f, gxy = 0.0f, gyy = 0.0f, ex = 0.0f, ey = 0.0f;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float df = vs[t] ? u_i[t] - s_i[t] : 0.0f, sx = vs[t] ? u_gx[t] + s_gx[t] : 0.0f,
+                    sy = vs[t] ? u_gy[t] + s_gy[t] : 0.0f;
+        gxx = fmaf(sx, sx, gxx); gxy = fmaf(sx, sy, gxy); gyy = fmaf(sy, sy, gyy);
+        ex = fmaf(df, sx, ex); ey = fmaf(df, sy, ey);
+      }
+      gxx = warp_sum32(gxx); gxy = warp_sum32(gxy); gyy = warp_sum32(gyy);
+      ex = warp_sum32(ex); ey = warp_sum32(ey);
+      ex *= a.step_factor; ey *= a.step_factor;
+      const float det = gxx * gyy - gxy * gxy;
+      if (det < a.min_determinant) { lvl_status = KLT_SMALL_DET; break; }
+      const float inv = __frcp_rn(det);
+      dx = (gyy * ex - gxy * ey) * inv;
+      dy = (gxx * ey - gxy * ex) * inv;
+      x2 += dx; y2 += dy;
+      ++iteration;
+      const bool again = (fabsf(dx) >= a.min_displacement || fabsf(dy) >= a.min_displacement) &&
+                         iteration < a.max_iterations;
+      if (!again) break;
+      if (window_oob(x2, y2, hw, hh, nc, nr)) { lvl_status = KLT_OOB; break; }
+    }
+
+    // after the loop (:459-474): bounds of the final position, then the residue
+    if (lvl_status == KLT_TRACKED && window_oob(x2, y2, hw, hh, nc, nr)) lvl_status = KLT_OOB;
+    if (lvl_status == KLT_TRACKED) {
+      const int xt = (int)x2, yt = (int)y2;
+      if (xt != c_xt || yt != c_yt) {
+        c_i = row5_load(i2, (yt - 3 + r) * pitch + ((xt - 3) & ~3) + 4 * q, ld, pol2);
+        const int m = (xt - 3) & 3;
+        if (m != m2) {
+          m2 = m;
+          row_shift(t_i, m2 - m1, lane, u_i);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) { const int w = 4 * q + t - m2; vs[t] = r < 7 && ld && w >= 0 && w <= 6; }
+        }
+      }
+      float s_i[4];
+      row5_interp(c_i, x2 - (float)xt, y2 - (float)yt, s_i);
+      float sum = 0.0f;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) sum += vs[t] ? fabsf(u_i[t] - s_i[t]) : 0.0f;
       sum = warp_sum32(sum);
       if (sum * (1.0f / 49.0f) > a.max_residue) lvl_status = KLT_LARGE_RESIDUE;
     }

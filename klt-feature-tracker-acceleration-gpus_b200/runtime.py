@@ -95,6 +95,7 @@ DEV_API = {
     "klt_dev_last_build_staged": (C.c_int, [C.c_void_p]),
     "klt_dev_last_build_mega": (C.c_int, [C.c_void_p]),
     "klt_dev_disable_mega": (None, [C.c_void_p, C.c_int]),
+    "klt_dev_disable_track7v": (None, [C.c_void_p, C.c_int]),
     "klt_dev_set_mega_tail": (None, [C.c_void_p, C.c_int]),
     "klt_dev_disable_stream": (None, [C.c_void_p, C.c_int]),
     "klt_dev_disable_chain": (None, [C.c_void_p, C.c_int]),

@@ -228,6 +228,24 @@ def test_track_7x7_generic_fast_kernel(L, capi, oracle, oracle_mod, provided):
     assert rep[-1][3] > 80
 
 
+@pytest.mark.parametrize("kernel", ["track7v", "track7w", "track7"])
+def test_track_7x7_kernel_generations(L, capi, oracle, oracle_mod, kernel):
+    """the three 7x7 fma trackers (one 128-bit load per lane and image: default; scalar loads;
+    8 lanes per feature) against the oracle, teacher-forced, 4 levels, on frames whose footprints
+    take every alignment"""
+    imgs = [synth_image(640, 480, seed=5, shift=(1.9 * t, -1.3 * t)) for t in range(5)]
+
+    def setup(tc):
+        tc.contents.nPyramidLevels, tc.contents.subsampling = 4, 2
+        L.KLTUpdateTCBorder(tc)
+        dev = L.KLTB200Device(tc)
+        L.klt_dev_disable_track7v(dev, 0 if kernel == "track7v" else 1)
+        L.klt_dev_disable_track7w(dev, 1 if kernel == "track7" else 0)
+
+    rep = _teacher_forced(L, capi, oracle, oracle_mod, imgs, 400, 0, tc_setup=setup)
+    assert rep[-1][3] > 250
+
+
 def test_record_mode_equals_staging_mode(L, capi, provided, monkeypatch):
     """KLTCreateFeatureList pins its block when a device is present; KLTTrackFeatures then mirrors the
     records in one copy and the tracker writes x | y | val straight back into them.  A list in
