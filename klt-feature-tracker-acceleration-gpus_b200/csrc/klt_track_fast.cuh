@@ -527,7 +527,11 @@ __device__ __forceinline__ float ldg_policy(const float* p, unsigned long long p
 __device__ __forceinline__ Pix3 pix3_load(const float* __restrict__ img, int off, unsigned long long pol) {
   const float* p = img + off;
   Pix3 r;
-  r.a = ldg_policy(p, pol); r.b = ldg_policy(p + 1, pol);
+  if ((off & 1) == 0) {        // footprint starts at an even column (warp uniform: row pitches are even): one 64-bit load
+    asm("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(r.a), "=f"(r.b) : "l"(p), "l"(pol));
+  } else {
+    r.a = ldg_policy(p, pol); r.b = ldg_policy(p + 1, pol);
+  }
   r.c = __shfl_down_sync(0xffffffffu, r.a, 1);
   return r;
 }
