@@ -54,3 +54,23 @@ def test_reference_example3_default_mode_within_tolerance(tmp_path, golden_ft):
     both = (t["val"] >= 0) & (g["val"] >= 0)
     assert np.abs(t["x"][both] - g["x"][both]).max() <= 0.05
     assert np.abs(t["y"][both] - g["y"][both]).max() <= 0.05
+
+
+@pytest.mark.parametrize("replace", [0, 1])
+def test_example3_on_the_batched_call_writes_the_same_files(tmp_path, replace):
+    """examples/example3.c (per-frame loop) and examples/example3_sequence.c (one
+    KLTTrackFeaturesSequence call) write byte-identical feature tables, binary and text."""
+    loop = os.path.join(ROOT, "examples", "example3")
+    seq = os.path.join(ROOT, "examples", "example3_sequence")
+    if not (os.path.exists(loop) and os.path.exists(seq)):
+        pytest.skip("examples not built (make -C examples)")
+    data = os.path.join(ROOT, "tests", "golden", "images_provided")
+    outs = []
+    for exe, tag in ((loop, "loop"), (seq, "seq")):
+        prefix = str(tmp_path / tag)
+        r = subprocess.run([exe, data, "0", "10", "150", prefix, str(replace)], capture_output=True, text=True,
+                           timeout=120)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append((open(prefix + ".ft", "rb").read(), open(prefix + ".txt", "rb").read()))
+    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
+    assert outs[0][0][:6] == b"KLTFT1"
