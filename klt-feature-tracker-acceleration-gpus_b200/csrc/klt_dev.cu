@@ -20,6 +20,9 @@
 // in-range inputs, so tiles may zero-fill reads outside the image.
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <climits>
 
 #include <cstdarg>
 #include <cstdio>
@@ -394,120 +397,282 @@ __global__ void stamp_existing_kernel(const float* __restrict__ x, const float* 
 
 // Greedy minimum-distance pass (selectGoodFeatures.c:168-235) on the sorted
 // candidate list, made deterministic AND parallel: one CTA walks the list in
-// batches of 1024 consecutive ranks.  Threads test the featuremap in parallel,
-// survivors are compacted in rank order, and warp 0 resolves them sequentially
-// in rank order against the candidates already accepted in this batch (the
-// only ones not yet stamped).  This reproduces the sequential result exactly
-// for any batch size.
+// batches of GBATCH = 4096 consecutive ranks (4 per thread, the next batch's
+// keys are fetched while the current one is resolved).  Threads test the
+// featuremap in parallel, survivors are compacted in rank order, and warp 0
+// resolves them in rank order, 32 at a time, against the candidates already
+// accepted in this batch (the only ones not yet stamped):
+//  * those live in a shared-memory hash table keyed by the (d+1) x (d+1) cell they fall in --
+//    two accepted candidates can never share a cell, and a conflict can only sit in the 3 x 3
+//    cells around a survivor, so the test is 9 probes whatever the number accepted;
+//  * conflicts inside the group of 32 are found with shuffles and settled by a fixed-point
+//    iteration on ballots (the lowest undecided lane is decided in every round; a lane is
+//    accepted once no earlier lane that conflicts with it is accepted or undecided).
+// Accepted candidates are compacted in place at the front of the survivor arrays; records and
+// stamps are then written by the whole CTA.  This reproduces the sequential result exactly
+// for any batch size.  (Measured on B200 before this form: the per-accepted global load of
+// open_slots[] inside the sequential loop, then the O(survivors x accepted) list test, made a
+// 4K selection spend 2.4 of its 3.1 ms here.)
 static constexpr int GB = 1024;
+static constexpr int GK = 4;
+static constexpr int GBATCH = GB * GK;
 
-// exclusive block-wide position of each thread's flag among the set flags, in
-// thread order; returns the total through *total_out (valid for all threads).
-// Contains two __syncthreads; s_wcount is scratch of GB/32 ints.
-__device__ __forceinline__ int block_rank(bool flag, int* s_wcount, int* s_total_tmp, int* total_out) {
+// exclusive block-wide prefix of each thread's count, in thread order; returns
+// the total through *total_out (valid for all threads).  Contains two
+// __syncthreads; s_wcount is scratch of GB/32 ints.
+__device__ __forceinline__ int block_prefix(int cnt, int* s_wcount, int* s_total_tmp, int* total_out) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const unsigned bal = __ballot_sync(0xffffffffu, flag);
-  if (lane == 0) s_wcount[wid] = __popc(bal);
+  int inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_wcount[wid] = inc;
   __syncthreads();
   if (wid == 0) {
     const int c = s_wcount[lane];
-    int inc = c;
+    int winc = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
+      const int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
     }
-    s_wcount[lane] = inc - c;                    // exclusive prefix over warps
-    if (lane == 31) *s_total_tmp = inc;
+    s_wcount[lane] = winc - c;                   // exclusive prefix over warps
+    if (lane == 31) *s_total_tmp = winc;
   }
   __syncthreads();
   *total_out = *s_total_tmp;
-  return s_wcount[wid] + __popc(bal & ((1u << lane) - 1u));
+  return s_wcount[wid] + inc - cnt;
 }
 
+static constexpr int GTBL = 2 * GBATCH;                  // hash slots: load <= 50 % even if a whole batch is accepted
+static constexpr unsigned GEMPTY = 0xffffffffu;
+static constexpr size_t ENFORCE_SMEM = (size_t)GBATCH * 4 + (size_t)GTBL * 4 + (size_t)GBATCH * 4 + (size_t)GBATCH * 2;
+
+__device__ __forceinline__ unsigned cell_hash(int cxc, int cyc) {
+  return ((unsigned)cxc * 73856093u ^ (unsigned)cyc * 19349663u) & (unsigned)(GTBL - 1);
+}
+
+// The walk can be split over several launches (state[] = accepted so far, done flag, number of open
+// slots; `first` starts it, `last` pads the slots that stay open), and a launch reads its candidates
+// either straight from the sorted list (INDIRECT = false: ranks 0 .. npoints-1) or through a list of
+// ranks (INDIRECT = true: ranks[0 .. *d_nranks-1], ascending) -- the candidates that the whole GPU
+// found still uncovered on the featuremap (UncoveredOp below).  That is how the sparse part of the
+// walk is kept short: with the features that survive a KLTReplaceLostFeatures call pre-stamped,
+// nearly every candidate is covered from the start, and in KLTSelectGoodFeatures after the first
+// ENFORCE_HEAD_BATCHES batches.
+static constexpr int ENFORCE_HEAD_BATCHES = 8;
+
+struct UncoveredOp {                              // for cub::DeviceSelect::If over ranks
+  const int* sval; const unsigned* sidx; const unsigned char* fmap;
+  int nxc, bx, by, step, W, min_eig;
+  __device__ __forceinline__ bool operator()(const int& r) const {
+    if (sval[r] < min_eig) return false;
+    const unsigned id = sidx[r];
+    const int cx = bx + (int)(id % (unsigned)nxc) * step, cy = by + (int)(id / (unsigned)nxc) * step;
+    return fmap[(size_t)cy * W + cx] == 0;
+  }
+};
+
+template <bool INDIRECT>
 __global__ void __launch_bounds__(GB)
-enforce_mindist_kernel(const int* __restrict__ sval, const unsigned* __restrict__ sidx, int npoints,
+enforce_mindist_kernel(const int* __restrict__ sval, const unsigned* __restrict__ sidx,
+                       const int* __restrict__ ranks, const int* __restrict__ d_nranks, int npoints,
                        int nxc, int bx, int by, int step, int W, int H,
                        unsigned char* fmap, int d, int min_eig, int overwrite_all,
-                       int n, float* x, float* y, int* val, int* open_slots) {
-  __shared__ int s_x[GB], s_y[GB], s_v[GB];      // survivors of the batch, rank order
-  __shared__ int s_ax[GB], s_ay[GB];             // accepted in this batch
+                       int n, float* x, float* y, int* val, int* open_slots,
+                       int* state, int first, int last, int max_batches) {
+  extern __shared__ __align__(16) unsigned char enf_smem[];
+  unsigned* s_xy = reinterpret_cast<unsigned*>(enf_smem);            // survivors of the batch in rank order (x | y << 16);
+  unsigned* s_tbl = s_xy + GBATCH;                                   //   the accepted ones are compacted in place at the front
+  unsigned* s_conf = s_tbl + GTBL;                                   // per survivor: which earlier ones of its group of 32 are within d
+  unsigned short* s_r = reinterpret_cast<unsigned short*>(s_conf + GBATCH);   // rank - base of the survivors
   __shared__ int s_wcount[GB / 32];
   __shared__ int s_tmp, s_nacc, s_total, s_done;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const bool spaced = d >= 1;                    // d == 0 only excludes the pixel itself, and candidates are distinct
+  const int cs = spaced ? d + 1 : 1;             // cell size of the hash grid
 
-  // open slots in ascending index (selectGoodFeatures.c:207-210)
+  if (INDIRECT) npoints = *d_nranks;
   int nopen = 0;
-  for (int b0 = 0; b0 < n; b0 += GB) {
-    const int i = b0 + tid;
-    const bool open = (i < n) && (overwrite_all || val[i] < 0);
-    int cnt;
-    const int pos = block_rank(open, s_wcount, &s_tmp, &cnt);
-    if (open) open_slots[nopen + pos] = i;
-    nopen += cnt;
-    __syncthreads();                             // s_wcount / s_tmp reuse
+  bool done;
+  if (first) {
+    // open slots in ascending index (selectGoodFeatures.c:207-210)
+    for (int b0 = 0; b0 < n; b0 += GB) {
+      const int i = b0 + tid;
+      const bool open = (i < n) && (overwrite_all || val[i] < 0);
+      int cnt;
+      const int pos = block_prefix(open ? 1 : 0, s_wcount, &s_tmp, &cnt);
+      if (open) open_slots[nopen + pos] = i;
+      nopen += cnt;
+      __syncthreads();                           // s_wcount / s_tmp reuse
+    }
+    done = (nopen == 0);
+    if (tid == 0) { s_total = 0; s_done = done; s_nacc = 0; }
+  } else {
+    nopen = state[2];
+    done = (state[1] != 0);
+    if (tid == 0) { s_total = state[0]; s_done = done; s_nacc = 0; }
   }
-  if (tid == 0) { s_total = 0; s_done = (nopen == 0); s_nacc = 0; }
   __syncthreads();
   volatile unsigned char* vmap = fmap;
-  bool done = (nopen == 0);
 
-  for (int base = 0; base < npoints && !done; base += GB) {
-    const int i = base + tid;
-    int cx = 0, cy = 0, cv = 0;
-    bool alive = false;
-    if (i < npoints) {
-      cv = sval[i];
-      const unsigned id = sidx[i];
-      cx = bx + (int)(id % (unsigned)nxc) * step;
-      cy = by + (int)(id / (unsigned)nxc) * step;
-      alive = (cv >= min_eig) && (vmap[(size_t)cy * W + cx] == 0);
+  // keys of the first batch; thread t owns the list entries base + GK*t .. base + GK*t + GK-1
+  int nv[GK]; unsigned nid[GK];
+#pragma unroll
+  for (int j = 0; j < GK; ++j) {
+    const int i = GK * tid + j;
+    nv[j] = 0; nid[j] = 0;
+    if (!done && i < npoints) { const int r = INDIRECT ? ranks[i] : i; nv[j] = sval[r]; nid[j] = sidx[r]; }
+  }
+
+  for (int base = 0, nb = 0; base < npoints && !done && nb < max_batches; base += GBATCH, ++nb) {
+    const int total0 = s_total;                  // accepted before this batch (written two barriers ago,
+                                                 // rewritten only after the next two)
+    int cv[GK], cx[GK], cy[GK];
+    bool alive[GK];
+    size_t cell[GK];
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < GK; ++j) {
+      cv[j] = nv[j];
+      cx[j] = bx + (int)(nid[j] % (unsigned)nxc) * step;
+      cy[j] = by + (int)(nid[j] / (unsigned)nxc) * step;
+      cell[j] = (size_t)cy[j] * W + cx[j];
+      alive[j] = (base + GK * tid + j < npoints) && (cv[j] >= min_eig);
     }
+    unsigned char m[GK];
+#pragma unroll
+    for (int j = 0; j < GK; ++j) m[j] = alive[j] ? vmap[cell[j]] : (unsigned char)1;
+    // the next batch's keys do not depend on the map: fetch them behind the map reads
+#pragma unroll
+    for (int j = 0; j < GK; ++j) {
+      const int i = base + GBATCH + GK * tid + j;
+      nv[j] = 0; nid[j] = 0;
+      if (i < npoints) { const int r = INDIRECT ? ranks[i] : i; nv[j] = sval[r]; nid[j] = sidx[r]; }
+    }
+    if (spaced) {
+#pragma unroll
+      for (int k = 0; k < GTBL / GB; ++k) s_tbl[tid + k * GB] = GEMPTY;
+    }
+#pragma unroll
+    for (int j = 0; j < GK; ++j) { alive[j] = alive[j] && (m[j] == 0); cnt += alive[j] ? 1 : 0; }
     int nsurv;
-    const int pos = block_rank(alive, s_wcount, &s_tmp, &nsurv);     // 2 barriers
-    if (alive) { s_x[pos] = cx; s_y[pos] = cy; s_v[pos] = cv; }
+    int pos = block_prefix(cnt, s_wcount, &s_tmp, &nsurv);           // 2 barriers
+#pragma unroll
+    for (int j = 0; j < GK; ++j)
+      if (alive[j]) { s_xy[pos] = (unsigned)cx[j] | ((unsigned)cy[j] << 16); s_r[pos] = (unsigned short)(GK * tid + j); ++pos; }
     // the list is sorted descending: once the first candidate of a batch is
     // below the threshold nothing at or after it can be accepted
-    if (tid == 0 && cv < min_eig) s_done = 1;
+    if (tid == 0 && cv[0] < min_eig) s_done = 1;
     __syncthreads();
-    if (wid == 0) {
-      int nacc = 0, total = s_total;
-      for (int s = 0; s < nsurv && total < nopen; ++s) {
-        const int px = s_x[s], py = s_y[s];
-        bool hit = false;
-        for (int a = lane; a < nacc; a += 32) {
-          const int dx = px - s_ax[a], dy = py - s_ay[a];
-          if (dx <= d && dx >= -d && dy <= d && dy >= -d) hit = true;
+    // conflicts inside each group of 32 consecutive survivors: independent of what gets accepted,
+    // so every warp prepares the groups g = wid, wid + 32, ... for the sequential walk of warp 0
+    if (spaced) {
+      for (int g0 = wid * 32; g0 < nsurv; g0 += GB) {
+        const int s = g0 + lane;
+        const unsigned pxy = s < nsurv ? s_xy[s] : 0u;
+        const int px = (int)(pxy & 0xffffu), py = (int)(pxy >> 16);
+        unsigned conf = 0;
+#pragma unroll
+        for (int i = 0; i < 31; ++i) {
+          const unsigned q = __shfl_sync(0xffffffffu, pxy, i);
+          const int dx = px - (int)(q & 0xffffu), dy = py - (int)(q >> 16);
+          if (i < lane && dx <= d && dx >= -d && dy <= d && dy >= -d) conf |= 1u << i;
         }
-        if (!__any_sync(0xffffffffu, hit)) {
-          if (lane == 0) {
-            s_ax[nacc] = px; s_ay[nacc] = py;
-            const int slot = open_slots[total];
-            x[slot] = (float)px; y[slot] = (float)py; val[slot] = s_v[s];
-          }
-          ++nacc; ++total;
-          __syncwarp();
-        }
+        s_conf[s] = conf;
       }
-      if (lane == 0) { s_nacc = nacc; s_total = total; if (total >= nopen) s_done = 1; }
+      __syncthreads();
+    }
+    if (wid == 0) {
+      const int budget = nopen - total0;
+      int nacc = 0;
+      for (int g0 = 0; g0 < nsurv && nacc < budget; g0 += 32) {
+        const int s = g0 + lane;
+        const bool valid = s < nsurv;
+        const unsigned pxy = valid ? s_xy[s] : 0u;
+        const unsigned short pr = valid ? s_r[s] : (unsigned short)0;
+        const int px = (int)(pxy & 0xffffu), py = (int)(pxy >> 16);
+        bool hit = !valid;
+        unsigned conf = 0;                       // bit i: within d of lane i's survivor (i < lane)
+        const int pcx = px / cs, pcy = py / cs;
+        if (spaced) {
+          if (nacc > 0) {
+            // the accepted of this batch: 3 x 3 cells around the survivor, linear probing
+            unsigned h[9], e[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { h[k] = cell_hash(pcx + k % 3 - 1, pcy + k / 3 - 1); e[k] = s_tbl[h[k]]; }
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+              while (e[k] != GEMPTY) {
+                const int dx = px - (int)(e[k] & 0xffffu), dy = py - (int)(e[k] >> 16);
+                if (dx <= d && dx >= -d && dy <= d && dy >= -d) hit = true;
+                h[k] = (h[k] + 1u) & (unsigned)(GTBL - 1);
+                e[k] = s_tbl[h[k]];
+              }
+            }
+          }
+          conf = s_conf[s < GBATCH ? s : GBATCH - 1];
+        }
+        const unsigned cand = __ballot_sync(0xffffffffu, !hit);
+        conf &= cand;
+        unsigned acc = 0, und = cand;
+        while (und != 0) {                       // the lowest undecided lane is decided in every round
+          const bool mine = (und >> lane) & 1u;
+          const bool rej = mine && (conf & acc) != 0;
+          const bool ok = mine && !rej && (conf & und) == 0;
+          const unsigned okm = __ballot_sync(0xffffffffu, ok), rejm = __ballot_sync(0xffffffffu, rej);
+          acc |= okm;
+          und &= ~(okm | rejm);
+        }
+        while (__popc(acc) > budget - nacc) acc &= ~(0x80000000u >> __clz(acc));   // list full: first ones in rank order
+        if ((acc >> lane) & 1u) {
+          const int p2 = nacc + __popc(acc & ((1u << lane) - 1u));   // p2 <= s: in-place compaction
+          s_xy[p2] = pxy; s_r[p2] = pr;
+          if (spaced) {
+            unsigned hh = cell_hash(pcx, pcy);
+            while (atomicCAS(&s_tbl[hh], GEMPTY, pxy) != GEMPTY) hh = (hh + 1u) & (unsigned)(GTBL - 1);
+          }
+        }
+        nacc += __popc(acc);
+        __syncwarp();
+      }
+      if (lane == 0) { s_nacc = nacc; s_total = total0 + nacc; if (total0 + nacc >= nopen) s_done = 1; }
     }
     __syncthreads();
     {
       const int nacc = s_nacc, side = 2 * d + 1;
-      if (d >= 0) {
-        const int cells = side * side;
-        for (int w = tid; w < nacc * cells; w += GB) {
-          const int a = w / cells, cidx = w - a * cells;
-          const int ix = s_ax[a] - d + cidx % side, iy = s_ay[a] - d + cidx / side;
-          if (ix >= 0 && ix < W && iy >= 0 && iy < H) fmap[(size_t)iy * W + ix] = 1;
+      for (int a = tid; a < nacc; a += GB) {     // the records of the accepted (:207-222)
+        const int slot = open_slots[total0 + a];
+        const unsigned q = s_xy[a];
+        const int li = base + s_r[a];
+        x[slot] = (float)(q & 0xffffu); y[slot] = (float)(q >> 16); val[slot] = sval[INDIRECT ? ranks[li] : li];
+      }
+      // stamps (:102-115): one warp per accepted candidate, lanes along the row (no index
+      // divisions: with them this loop was the most expensive part of a dense batch)
+      for (int a = wid; a < nacc; a += GB / 32) {
+        const unsigned q = s_xy[a];
+        const int ax = (int)(q & 0xffffu) - d, ay = (int)(q >> 16) - d;
+        for (int r = 0; r < side; ++r) {
+          const int iy = ay + r;
+          if (iy < 0 || iy >= H) continue;
+          for (int c = lane; c < side; c += 32) {
+            const int ix = ax + c;
+            if (ix >= 0 && ix < W) fmap[(size_t)iy * W + ix] = 1;
+          }
         }
       }
       done = (s_done != 0);
     }
-    __syncthreads();      // stamps visible to the next batch; s_done stable while read
+    __syncthreads();      // stamps visible to the next batch; s_done / s_total stable while read
+  }
+  const int total = s_total;
+  if (!last) {
+    if (tid == 0) { state[0] = total; state[1] = done ? 1 : 0; state[2] = nopen; }
+    return;
   }
   // out of candidates: the still-open slots become NOT_FOUND (:175-195)
-  const int total = s_total;
   for (int k = total + tid; k < nopen; k += GB) {
     const int slot = open_slots[k];
     x[slot] = -1.0f; y[slot] = -1.0f; val[slot] = KLT_NOT_FOUND;
@@ -891,12 +1056,12 @@ track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
 // kernel classes, for launch accounting and per-kernel event timing
 enum KernelId {
   KID_SMOOTH_U8 = 0, KID_GRAD, KID_PYRDOWN, KID_TRACK, KID_MINEIG, KID_SORT, KID_STAMP,
-  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_L0_FUSED, KID_LEVEL_FUSED, KID_LEVEL_FUSED_L2, KID_LEVEL_FUSED_L3, KID_TRACK_FAST, KID_TRACK7, KID_TRACK7W, KID_TRACK7V, KID_AFFINE, KID_LEVELS_CHAIN, KID_MEGA, KID_L0_STREAM, KID_COPY_H2D, KID_COPY_D2H, KID_COUNT
+  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_L0_FUSED, KID_LEVEL_FUSED, KID_LEVEL_FUSED_L2, KID_LEVEL_FUSED_L3, KID_TRACK_FAST, KID_TRACK7, KID_TRACK7W, KID_TRACK7V, KID_AFFINE, KID_LEVELS_CHAIN, KID_MEGA, KID_L0_STREAM, KID_FILTER, KID_COPY_H2D, KID_COPY_D2H, KID_COUNT
 };
 static const char* const kKernelNames[KID_COUNT] = {
   "smooth_u8_tile", "grad_tile", "pyrdown_tile", "track_kernel", "mineig_kernel",
   "cub_radix_sort", "stamp_existing_kernel", "enforce_mindist_kernel",
-  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel", "l0_fused_kernel", "level_fused_kernel[level 1]", "level_fused_kernel[level 2]", "level_fused_kernel[level 3+]", "track_fast_kernel", "track7_kernel", "track7w_kernel", "track7v_kernel", "affine_check_kernel", "levels_chain_kernel", "pyramid_mega_kernel", "l0_stream_kernel",
+  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel", "l0_fused_kernel", "level_fused_kernel[level 1]", "level_fused_kernel[level 2]", "level_fused_kernel[level 3+]", "track_fast_kernel", "track7_kernel", "track7w_kernel", "track7v_kernel", "affine_check_kernel", "levels_chain_kernel", "pyramid_mega_kernel", "l0_stream_kernel", "cub_select_uncovered",
   "copy_h2d", "copy_d2h"          // not kernels: timed in profiling mode, never counted as launches
 };
 static constexpr int PROF_POOL = 2048;     // event pairs in flight before folding
@@ -971,6 +1136,9 @@ struct klt_dev {
   void* cub_tmp; size_t cub_bytes;
   unsigned char* fmap; size_t fmap_cap;
   int* open_slots; int open_cap;
+  int* rank_list; int* sel_state;      // candidates still uncovered (ranks, ascending) / [0..2] walk state, [4] their number
+  int no_filter;
+  int enforce_attr;            // enforce_mindist_kernel's shared-memory attribute set on this device
   // dynamic tile scheduler of the persistent kernels: one counter per launch site
   unsigned* d_tile_ctr; unsigned tile_base[16];
   // timing
@@ -1200,7 +1368,7 @@ extern "C" void klt_dev_destroy(klt_dev* d) {
   cudaFree(d->d_x);
   cudaFreeHost(d->h_x);
   for (int i = 0; i < 2; ++i) { cudaFree(d->c_val[i]); cudaFree(d->c_idx[i]); }
-  cudaFree(d->cub_tmp); cudaFree(d->fmap); cudaFree(d->open_slots);
+  cudaFree(d->cub_tmp); cudaFree(d->fmap); cudaFree(d->open_slots); cudaFree(d->rank_list); cudaFree(d->sel_state);
   if (d->ev_made) { cudaEventDestroy(d->ev_a); cudaEventDestroy(d->ev_b); }
   if (d->prof_ev) { for (int i = 0; i < 2 * PROF_POOL; ++i) cudaEventDestroy(d->prof_ev[i]); free(d->prof_ev); free(d->prof_kid);
     cudaEventDestroy(d->ev_origin); free(d->trace_kid); free(d->trace_t0); free(d->trace_t1); }
@@ -2777,9 +2945,15 @@ static int ensure_candidates(klt_dev* d, size_t n) {
     CU(cudaMalloc(&d->c_val[i], n * sizeof(int)));
     CU(cudaMalloc(&d->c_idx[i], n * sizeof(unsigned)));
   }
-  size_t bytes = 0;
+  cudaFree(d->rank_list); cudaFree(d->sel_state); d->rank_list = nullptr; d->sel_state = nullptr;
+  CU(cudaMalloc(&d->rank_list, n * sizeof(int)));
+  CU(cudaMalloc(&d->sel_state, 8 * sizeof(int)));
+  size_t bytes = 0, bytes2 = 0;
   CU(cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, d->c_val[0], d->c_val[1], d->c_idx[0],
                                                d->c_idx[1], (int)n, 0, 32, d->stream));
+  CU(cub::DeviceSelect::If(nullptr, bytes2, thrust::counting_iterator<int>(0), d->rank_list, d->sel_state + 4,
+                           (int)n, UncoveredOp{}, d->stream));
+  if (bytes2 > bytes) bytes = bytes2;
   CU(cudaMalloc(&d->cub_tmp, bytes ? bytes : 16));
   d->cub_bytes = bytes;
   d->cand_cap = n;
@@ -2816,6 +2990,14 @@ static int select_core(klt_dev* d, int slot, const klt_dev_select_params* p, int
   CU(cudaSetDevice(d->device));
   if (!d->arena || slot < 0 || slot >= KLT_DEV_SLOTS || d->set[slot].built_levels < 1) return fail(d, "select: slot %d has no level 0", slot);
   if (n <= 0) return 0;
+  if (d->W > 65535 || d->H > 65535) return fail(d, "select: images larger than 65535 pixels a side are not supported");
+  if (!d->enforce_attr) {
+    CU(cudaFuncSetAttribute(enforce_mindist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENFORCE_SMEM));
+    CU(cudaFuncSetAttribute(enforce_mindist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENFORCE_SMEM));
+    const char* nf = getenv("KLT_B200_NO_FILTER");   // A/B: walk the whole sorted list in one launch
+    d->no_filter = (nf && nf[0] == '1') ? 1 : 0;
+    d->enforce_attr = 1;
+  }
   cudaStream_t saved_t = d->tstream;
   if (d->overlap) { if (sync_all(d)) return fail(d, "stream synchronisation failed"); d->tstream = d->stream; }
   struct Restore { klt_dev* d; cudaStream_t t; ~Restore() { d->tstream = t; } } restore{d, saved_t};
@@ -2853,10 +3035,42 @@ static int select_core(klt_dev* d, int slot, const klt_dev_select_params* p, int
     Launch l(d, KID_STAMP);
     stamp_existing_kernel<<<n, 128, 0, d->stream>>>(d->d_x, d->d_y, d->d_val, d->fmap, dist, d->W, d->H);
   }
-  { Launch l(d, KID_ENFORCE);
-    enforce_mindist_kernel<<<1, GB, 0, d->stream>>>(sval, sidx, (int)g.npoints, g.nxc > 0 ? g.nxc : 1, g.bx, g.by,
-                                                   g.step, d->W, d->H, d->fmap, dist, min_eig,
-                                                   p->overwrite_all, n, d->d_x, d->d_y, d->d_val, d->open_slots); }
+  {
+    const int np = (int)g.npoints, nxc = g.nxc > 0 ? g.nxc : 1;
+    // the candidates the featuremap does not cover yet, from list position `from` on, as ranks
+    auto uncovered = [&](int from) -> int {
+      Launch l(d, KID_FILTER);
+      size_t bytes = d->cub_bytes;
+      CU(cub::DeviceSelect::If(d->cub_tmp, bytes, thrust::counting_iterator<int>(from), d->rank_list, d->sel_state + 4,
+                               np - from, UncoveredOp{sval, sidx, d->fmap, nxc, g.bx, g.by, g.step, d->W, min_eig},
+                               d->stream));
+      return 0;
+    };
+    auto walk = [&](bool indirect, int first, int last, int max_batches) {
+      Launch l(d, KID_ENFORCE);
+      if (indirect)
+        enforce_mindist_kernel<true><<<1, GB, ENFORCE_SMEM, d->stream>>>(
+            sval, sidx, d->rank_list, d->sel_state + 4, 0, nxc, g.bx, g.by, g.step, d->W, d->H, d->fmap, dist, min_eig,
+            p->overwrite_all, n, d->d_x, d->d_y, d->d_val, d->open_slots, d->sel_state, first, last, max_batches);
+      else
+        enforce_mindist_kernel<false><<<1, GB, ENFORCE_SMEM, d->stream>>>(
+            sval, sidx, nullptr, nullptr, np, nxc, g.bx, g.by, g.step, d->W, d->H, d->fmap, dist, min_eig,
+            p->overwrite_all, n, d->d_x, d->d_y, d->d_val, d->open_slots, d->sel_state, first, last, max_batches);
+    };
+    const int head = ENFORCE_HEAD_BATCHES * GBATCH;
+    if (np > 0 && !p->overwrite_all && !d->no_filter) {
+      // replacement: the surviving features are stamped, most candidates are covered from the start
+      if (uncovered(0)) return 1;
+      walk(true, 1, 1, INT_MAX);
+    } else if (np > 2 * head && !d->no_filter) {
+      // selection: dense head of the list straight from the sorted arrays, the rest through the filter
+      walk(false, 1, 0, ENFORCE_HEAD_BATCHES);
+      if (uncovered(head)) return 1;
+      walk(true, 0, 1, INT_MAX);
+    } else {
+      walk(false, 1, 1, INT_MAX);
+    }
+  }
   CU(cudaGetLastError());
   return host ? klt_dev_features_download(d, n, x, y, val) : 0;
 }

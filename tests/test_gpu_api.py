@@ -42,7 +42,8 @@ def test_select_matches_oracle_stable_order(L, capi, oracle, oracle_mod, provide
 
 
 @pytest.mark.parametrize("n,mindist,min_eig", [(1, 10, 1), (2000, 10, 1), (5000, 25, 1),
-                                               (300, 0, 1), (300, 1, 500), (40000, 3, 1)])
+                                               (300, 0, 1), (300, 1, 500), (40000, 3, 1),
+                                               (40000, 2, 1), (70000, 1, 1), (3000, 5, 1), (60, 60, 1)])
 def test_select_edge_cases(L, capi, oracle, oracle_mod, provided, n, mindist, min_eig):
     """more features asked than exist (NOT_FOUND padding), mindist 0/1, thresholds"""
     tc = L.KLTCreateTrackingContext()

@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Device time of the selection kernels (mineig_kernel, cub radix sort, stamp_existing_kernel,
+enforce_mindist_kernel) per KLTSelectGoodFeatures / KLTReplaceLostFeatures call, per workload.
+   python tools/select_bench.py [4k|1080p|vga ...]
+Each line: wall time per call and the per-class CUDA-event times (klt_dev_profile_*)."""
+import ctypes as C, importlib, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa
+import numpy as np
+import torch
+pkg = importlib.import_module(bench.PKG)
+rt = importlib.import_module(bench.PKG + ".runtime")
+synth = importlib.import_module(bench.PKG + ".synth")
+capi = pkg.capi
+L = rt.load(); L.require_gpu(); L.KLTSetVerbosity(0)
+
+CASES = {  # name: (ncols, nrows, nfeat, nlevels, ss)
+    "4k": (3840, 2160, 4096, 4, 2),
+    "1080p": (1920, 1080, 1024, 2, 4),
+    "vga": (640, 480, 2000, 2, 4),
+}
+
+
+def run(name, reps=10):
+    ncols, nrows, nfeat, nlevels, ss = CASES[name]
+    tc = bench.setup_tc(L, nlevels, ss, 7, device=0)
+    dev = L.KLTB200Device(tc)
+    frames = torch.empty((3, nrows, ncols), dtype=torch.uint8, pin_memory=True)
+    bench.make_frames(synth, ncols, nrows, 3, 4321, frames.numpy())
+    p = lambda i: C.c_void_p(frames.data_ptr() + i * ncols * nrows)
+    fl = L.KLTCreateFeatureList(nfeat)
+    out = {"case": name, "size": [ncols, nrows], "features": nfeat}
+    for mode in ("select", "replace"):
+        L.KLTSelectGoodFeatures(tc, p(0), ncols, nrows, fl)
+        if mode == "replace":
+            L.KLTTrackFeatures(tc, p(0), p(1), ncols, nrows, fl)
+            x, y, v = capi.featurelist_to_arrays(fl)
+            v = v.copy(); x = x.copy(); y = y.copy()
+            lost = np.arange(nfeat) % 40 == 0            # 2.5 % of the slots open, as config 3 sees per frame
+            v[lost] = -1; x[lost] = -1; y[lost] = -1
+        call = (lambda: L.KLTSelectGoodFeatures(tc, p(0), ncols, nrows, fl)) if mode == "select" else \
+               (lambda: (capi.arrays_to_featurelist(fl, x, y, v), L.KLTReplaceLostFeatures(tc, p(1), ncols, nrows, fl)))
+        call(); call()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            call()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) / reps
+        L.klt_dev_profile_begin(dev)
+        for _ in range(reps):
+            call()
+        L.klt_dev_profile_end(dev)
+        prof = {k: round(ms / reps * 1e3, 1) for k, (n, ms) in L.profile(dev).items() if n}
+        out[mode] = {"wall_us": round(wall * 1e6, 1), "found": int((capi.featurelist_to_arrays(fl)[2] >= 0).sum()),
+                     "kernels_us": prof}
+    L.KLTFreeFeatureList(fl)
+    L.KLTFreeTrackingContext(tc)
+    return out
+
+
+if __name__ == "__main__":
+    for name in (sys.argv[1:] or list(CASES)):
+        print(json.dumps(run(name)))
