@@ -448,7 +448,7 @@ __device__ __forceinline__ int block_prefix(int cnt, int* s_wcount, int* s_total
 
 static constexpr int GTBL = 2 * GBATCH;                  // hash slots: load <= 50 % even if a whole batch is accepted
 static constexpr unsigned GEMPTY = 0xffffffffu;
-static constexpr size_t ENFORCE_SMEM = (size_t)GBATCH * 4 + (size_t)GTBL * 4 + (size_t)GBATCH * 4 + (size_t)GBATCH * 2;
+static constexpr size_t ENFORCE_SMEM = (size_t)GBATCH * 4 + (size_t)GTBL * 4 + (size_t)GBATCH * 4 * 2 + (size_t)GBATCH * 2;
 
 __device__ __forceinline__ unsigned cell_hash(int cxc, int cyc) {
   return ((unsigned)cxc * 73856093u ^ (unsigned)cyc * 19349663u) & (unsigned)(GTBL - 1);
@@ -461,8 +461,8 @@ __device__ __forceinline__ unsigned cell_hash(int cxc, int cyc) {
 // found still uncovered on the featuremap (UncoveredOp below).  That is how the sparse part of the
 // walk is kept short: with the features that survive a KLTReplaceLostFeatures call pre-stamped,
 // nearly every candidate is covered from the start, and in KLTSelectGoodFeatures after the first
-// ENFORCE_HEAD_BATCHES batches.
-static constexpr int ENFORCE_HEAD_BATCHES = 8;
+// ENFORCE_HEAD candidates.
+static constexpr int ENFORCE_HEAD = 32768;
 
 struct UncoveredOp {                              // for cub::DeviceSelect::If over ranks
   const int* sval; const unsigned* sidx; const unsigned char* fmap;
@@ -487,7 +487,8 @@ enforce_mindist_kernel(const int* __restrict__ sval, const unsigned* __restrict_
   unsigned* s_xy = reinterpret_cast<unsigned*>(enf_smem);            // survivors of the batch in rank order (x | y << 16);
   unsigned* s_tbl = s_xy + GBATCH;                                   //   the accepted ones are compacted in place at the front
   unsigned* s_conf = s_tbl + GTBL;                                   // per survivor: which earlier ones of its group of 32 are within d
-  unsigned short* s_r = reinterpret_cast<unsigned short*>(s_conf + GBATCH);   // rank - base of the survivors
+  unsigned* s_cell = s_conf + GBATCH;                                // per survivor: its cell of the hash grid (x | y << 16)
+  unsigned short* s_r = reinterpret_cast<unsigned short*>(s_cell + GBATCH);   // rank - base of the survivors
   __shared__ int s_wcount[GB / 32];
   __shared__ int s_tmp, s_nacc, s_total, s_done;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -518,16 +519,23 @@ enforce_mindist_kernel(const int* __restrict__ sval, const unsigned* __restrict_
   __syncthreads();
   volatile unsigned char* vmap = fmap;
 
-  // keys of the first batch; thread t owns the list entries base + GK*t .. base + GK*t + GK-1
+  // Batch size: gk = 1 (1024 candidates) while the map is still so empty that most candidates
+  // survive it -- every survivor costs a turn of the sequential walk, and a stamp made after a small
+  // batch saves the walk most of the neighbours ranked just behind the accepted one -- and gk = GK
+  // (4096) once fewer than a quarter of a batch survive (then the per-batch latency dominates).
+  // The size of a batch is fixed when its keys are fetched, one batch ahead.
+  // keys of the first batch; thread t owns the list entries base + gk*t .. base + gk*t + gk-1
+  int gk = (first && overwrite_all && !INDIRECT) ? 1 : GK;
   int nv[GK]; unsigned nid[GK];
 #pragma unroll
   for (int j = 0; j < GK; ++j) {
-    const int i = GK * tid + j;
+    const int i = gk * tid + j;
     nv[j] = 0; nid[j] = 0;
-    if (!done && i < npoints) { const int r = INDIRECT ? ranks[i] : i; nv[j] = sval[r]; nid[j] = sidx[r]; }
+    if (!done && j < gk && i < npoints) { const int r = INDIRECT ? ranks[i] : i; nv[j] = sval[r]; nid[j] = sidx[r]; }
   }
+  int gk_next = gk, gk_want = gk;                // layout of the prefetched keys / size wanted for the batch after them
 
-  for (int base = 0, nb = 0; base < npoints && !done && nb < max_batches; base += GBATCH, ++nb) {
+  for (int base = 0, nb = 0; base < npoints && !done && nb < max_batches; base += GB * gk, gk = gk_next, ++nb) {
     const int total0 = s_total;                  // accepted before this batch (written two barriers ago,
                                                  // rewritten only after the next two)
     int cv[GK], cx[GK], cy[GK];
@@ -540,17 +548,18 @@ enforce_mindist_kernel(const int* __restrict__ sval, const unsigned* __restrict_
       cx[j] = bx + (int)(nid[j] % (unsigned)nxc) * step;
       cy[j] = by + (int)(nid[j] / (unsigned)nxc) * step;
       cell[j] = (size_t)cy[j] * W + cx[j];
-      alive[j] = (base + GK * tid + j < npoints) && (cv[j] >= min_eig);
+      alive[j] = (j < gk) && (base + gk * tid + j < npoints) && (cv[j] >= min_eig);
     }
     unsigned char m[GK];
 #pragma unroll
     for (int j = 0; j < GK; ++j) m[j] = alive[j] ? vmap[cell[j]] : (unsigned char)1;
     // the next batch's keys do not depend on the map: fetch them behind the map reads
+    gk_next = gk_want;
 #pragma unroll
     for (int j = 0; j < GK; ++j) {
-      const int i = base + GBATCH + GK * tid + j;
+      const int i = base + GB * gk + gk_next * tid + j;
       nv[j] = 0; nid[j] = 0;
-      if (i < npoints) { const int r = INDIRECT ? ranks[i] : i; nv[j] = sval[r]; nid[j] = sidx[r]; }
+      if (j < gk_next && i < npoints) { const int r = INDIRECT ? ranks[i] : i; nv[j] = sval[r]; nid[j] = sidx[r]; }
     }
     if (spaced) {
 #pragma unroll
@@ -562,7 +571,8 @@ enforce_mindist_kernel(const int* __restrict__ sval, const unsigned* __restrict_
     int pos = block_prefix(cnt, s_wcount, &s_tmp, &nsurv);           // 2 barriers
 #pragma unroll
     for (int j = 0; j < GK; ++j)
-      if (alive[j]) { s_xy[pos] = (unsigned)cx[j] | ((unsigned)cy[j] << 16); s_r[pos] = (unsigned short)(GK * tid + j); ++pos; }
+      if (alive[j]) { s_xy[pos] = (unsigned)cx[j] | ((unsigned)cy[j] << 16); s_r[pos] = (unsigned short)(gk * tid + j); ++pos; }
+    gk_want = (nsurv * 4 > GB * gk) ? 1 : GK;     // (uniform: every thread sees the same nsurv)
     // the list is sorted descending: once the first candidate of a batch is
     // below the threshold nothing at or after it can be accepted
     if (tid == 0 && cv[0] < min_eig) s_done = 1;
@@ -582,6 +592,7 @@ enforce_mindist_kernel(const int* __restrict__ sval, const unsigned* __restrict_
           if (i < lane && dx <= d && dx >= -d && dy <= d && dy >= -d) conf |= 1u << i;
         }
         s_conf[s] = conf;
+        s_cell[s] = (unsigned)(px / cs) | ((unsigned)(py / cs) << 16);
       }
       __syncthreads();
     }
@@ -596,8 +607,10 @@ enforce_mindist_kernel(const int* __restrict__ sval, const unsigned* __restrict_
         const int px = (int)(pxy & 0xffffu), py = (int)(pxy >> 16);
         bool hit = !valid;
         unsigned conf = 0;                       // bit i: within d of lane i's survivor (i < lane)
-        const int pcx = px / cs, pcy = py / cs;
+        int pcx = 0, pcy = 0;
         if (spaced) {
+          const unsigned pc = s_cell[s];
+          pcx = (int)(pc & 0xffffu); pcy = (int)(pc >> 16);
           if (nacc > 0) {
             // the accepted of this batch: 3 x 3 cells around the survivor, linear probing
             unsigned h[9], e[9];
@@ -642,24 +655,38 @@ enforce_mindist_kernel(const int* __restrict__ sval, const unsigned* __restrict_
     }
     __syncthreads();
     {
-      const int nacc = s_nacc, side = 2 * d + 1;
+      const int nacc = s_nacc;
       for (int a = tid; a < nacc; a += GB) {     // the records of the accepted (:207-222)
         const int slot = open_slots[total0 + a];
         const unsigned q = s_xy[a];
         const int li = base + s_r[a];
         x[slot] = (float)(q & 0xffffu); y[slot] = (float)(q >> 16); val[slot] = sval[INDIRECT ? ranks[li] : li];
       }
-      // stamps (:102-115): one warp per accepted candidate, lanes along the row (no index
-      // divisions: with them this loop was the most expensive part of a dense batch)
-      for (int a = wid; a < nacc; a += GB / 32) {
-        const unsigned q = s_xy[a];
-        const int ax = (int)(q & 0xffffu) - d, ay = (int)(q >> 16) - d;
-        for (int r = 0; r < side; ++r) {
-          const int iy = ay + r;
-          if (iy < 0 || iy >= H) continue;
-          for (int c = lane; c < side; c += 32) {
-            const int ix = ax + c;
-            if (ix >= 0 && ix < W) fmap[(size_t)iy * W + ix] = 1;
+      // stamps (:102-115).  One warp per accepted candidate; the (2d+1)^2 square is written as
+      // 32-bit words -- lane = (row, word of the row), byte mask by position, red.or so that squares
+      // which share a word cannot lose each other's bytes.  (Byte stores, one row per instruction,
+      // made this loop ~1 M warp instructions for 1024 accepted candidates: more than half of the
+      // kernel on its single SM.)
+      if (d >= 0) {
+        unsigned* fmap32 = reinterpret_cast<unsigned*>(fmap);
+        for (int a = wid; a < nacc; a += GB / 32) {
+          const unsigned q = s_xy[a];
+          const int cx0 = (int)(q & 0xffffu), cy0 = (int)(q >> 16);
+          const int xa = max(cx0 - d, 0), xb = min(cx0 + d, W - 1);          // clipped column range, inclusive
+          const int ya = max(cy0 - d, 0), yb = min(cy0 + d, H - 1);
+          const int nw = (xb - xa + 1 + 3) / 4 + 1;                            // words a row can touch, whatever its alignment
+          const int items = (yb - ya + 1) * nw;
+          const float inv = 1.0f / (float)nw;
+          for (int it = lane; it < items; it += 32) {
+            int r = (int)(((float)it + 0.5f) * inv);                           // it / nw (exact for these sizes, checked below)
+            int k = it - r * nw;
+            if (k < 0) { --r; k += nw; } else if (k >= nw) { ++r; k -= nw; }
+            const size_t b0 = (size_t)(ya + r) * W + xa, b1 = b0 + (size_t)(xb - xa);   // first / last byte of the row
+            const size_t w = (b0 >> 2) + k;
+            if (w > (b1 >> 2)) continue;
+            const int lo = (w == (b0 >> 2)) ? (int)(b0 & 3) : 0, hi = (w == (b1 >> 2)) ? (int)(b1 & 3) : 3;
+            const unsigned mask = (0x01010101u >> (8 * (3 - (hi - lo)))) << (8 * lo);
+            atomicOr(fmap32 + w, mask);
           }
         }
       }
@@ -3011,7 +3038,7 @@ static int select_core(klt_dev* d, int slot, const klt_dev_select_params* p, int
   if (d->fmap_cap < npx) {
     CU(cudaStreamSynchronize(d->stream));
     cudaFree(d->fmap); d->fmap = nullptr; d->fmap_cap = 0;
-    CU(cudaMalloc(&d->fmap, npx));
+    CU(cudaMalloc(&d->fmap, npx + 4));        // (+4: the stamps are written as 32-bit words)
     d->fmap_cap = npx;
   }
   if (d->open_cap < n) {
@@ -3046,29 +3073,29 @@ static int select_core(klt_dev* d, int slot, const klt_dev_select_params* p, int
                                d->stream));
       return 0;
     };
-    auto walk = [&](bool indirect, int first, int last, int max_batches) {
+    auto walk = [&](bool indirect, int first, int last, int npts) {
       Launch l(d, KID_ENFORCE);
       if (indirect)
         enforce_mindist_kernel<true><<<1, GB, ENFORCE_SMEM, d->stream>>>(
             sval, sidx, d->rank_list, d->sel_state + 4, 0, nxc, g.bx, g.by, g.step, d->W, d->H, d->fmap, dist, min_eig,
-            p->overwrite_all, n, d->d_x, d->d_y, d->d_val, d->open_slots, d->sel_state, first, last, max_batches);
+            p->overwrite_all, n, d->d_x, d->d_y, d->d_val, d->open_slots, d->sel_state, first, last, INT_MAX);
       else
         enforce_mindist_kernel<false><<<1, GB, ENFORCE_SMEM, d->stream>>>(
-            sval, sidx, nullptr, nullptr, np, nxc, g.bx, g.by, g.step, d->W, d->H, d->fmap, dist, min_eig,
-            p->overwrite_all, n, d->d_x, d->d_y, d->d_val, d->open_slots, d->sel_state, first, last, max_batches);
+            sval, sidx, nullptr, nullptr, npts, nxc, g.bx, g.by, g.step, d->W, d->H, d->fmap, dist, min_eig,
+            p->overwrite_all, n, d->d_x, d->d_y, d->d_val, d->open_slots, d->sel_state, first, last, INT_MAX);
     };
-    const int head = ENFORCE_HEAD_BATCHES * GBATCH;
+    const int head = ENFORCE_HEAD;
     if (np > 0 && !p->overwrite_all && !d->no_filter) {
       // replacement: the surviving features are stamped, most candidates are covered from the start
       if (uncovered(0)) return 1;
-      walk(true, 1, 1, INT_MAX);
+      walk(true, 1, 1, 0);
     } else if (np > 2 * head && !d->no_filter) {
       // selection: dense head of the list straight from the sorted arrays, the rest through the filter
-      walk(false, 1, 0, ENFORCE_HEAD_BATCHES);
+      walk(false, 1, 0, head);
       if (uncovered(head)) return 1;
-      walk(true, 0, 1, INT_MAX);
+      walk(true, 0, 1, 0);
     } else {
-      walk(false, 1, 1, INT_MAX);
+      walk(false, 1, 1, np);
     }
   }
   CU(cudaGetLastError());
