@@ -1697,7 +1697,8 @@ static int l0_fused_launch(klt_dev* d, const FusedPlan& P, int W, int H, const T
                 lv.pitch));
     return 0;
   }
-  static bool attr_set[2] = {false, false};
+  static bool attr_dev[64][2] = {};              // function attributes are per device
+  bool* attr_set = attr_dev[d->device & 63];
   if (!attr_set[EXACT]) {
     CU(cudaFuncSetAttribute(l0_fused_kernel<EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L0Geo::SMEM));
     attr_set[EXACT] = true;
@@ -1719,7 +1720,8 @@ template <int SS, int R, int TX, int TY, bool EXACT>
 static int level_fused_launch_t(klt_dev* d, const FusedPlan& P, int level, const Level& a, const Level& b,
                                 const TapsR& tp, const TapsR& tg, const TapsR& td, int jr0, int jr1) {
   using G = LvGeo<SS, R, TX, TY>;
-  static bool attr_set = false;
+  static bool attr_dev[64] = {};                 // function attributes are per device
+  bool& attr_set = attr_dev[d->device & 63];
   static int cps = 0;                                                       // resident CTAs per SM
   if (!attr_set) {
     CU(cudaFuncSetAttribute(level_fused_kernel<SS, R, TX, TY, EXACT>,
@@ -1758,7 +1760,8 @@ template <int SS, int R, int TX, int TY, bool EXACT>
 static int levels_chain_launch_t(klt_dev* d, const FusedPlan& P, const PyrSet& S, int first, int nb, const TapsR& tp,
                                  const TapsR& tg, const TapsR& td, const int* jr0, const int* jr1) {
   using G = LvGeo<SS, R, TX, TY>;
-  static bool attr_set = false;
+  static bool attr_dev[64] = {};                 // function attributes are per device
+  bool& attr_set = attr_dev[d->device & 63];
   static int cps = 0;
   if (!attr_set) {
     CU(cudaFuncSetAttribute(levels_chain_kernel<SS, R, TX, TY, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
@@ -1947,7 +1950,8 @@ static int mega_schedule(klt_dev* d, const FusedPlan& P, const PyrSet& S, int nb
 template <int SS, int R, int TX, int TY, bool EXACT>
 static int mega_launch_t(klt_dev* d, const MegaParams& MP) {
   using MG = MegaGeo<SS, R, TX, TY>;
-  static bool attr_set = false;
+  static bool attr_dev[64] = {};                 // function attributes are per device
+  bool& attr_set = attr_dev[d->device & 63];
   static int cps = 0;
   if (!attr_set) {
     CU(cudaFuncSetAttribute(pyramid_mega_kernel<SS, R, TX, TY, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG::SMEM));

@@ -411,3 +411,27 @@ def test_device_frames_with_odd_pitch_and_offset(L, capi):
         L.KLTFreeFeatureList(fl)
         L.KLTFreeTrackingContext(tc)
     assert res[0] == res[1]
+
+
+def test_two_devices_in_one_process(L, capi, provided):
+    """one process, tracking contexts on two GPUs (function attributes such as the dynamic
+    shared-memory limit are per device): both give the same lists.  Needs >= 2 GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    got = []
+    for dev in (0, 1, 0):
+        tc = L.KLTCreateTrackingContext()
+        tc.contents.sequentialMode = 1
+        L.KLTB200SetDevice(tc, dev)
+        fl = L.KLTCreateFeatureList(150)
+        L.select(tc, provided[0], fl)
+        for i in (1, 2):
+            L.track(tc, provided[i - 1], provided[i], fl)
+        L.replace(tc, provided[2], fl)
+        got.append(_get(capi, fl))
+        L.KLTFreeFeatureList(fl)
+        L.KLTFreeTrackingContext(tc)
+    for a in got[1:]:
+        for u, v in zip(got[0], a):
+            assert u.tobytes() == v.tobytes()
