@@ -353,9 +353,17 @@ pyrdown_tile(const float* __restrict__ src, int spitch, int W, int H, TapsR taps
 // rounded multiply/add, the eigenvalue formula in double exactly as the
 // reference, then truncation to int.  Always exact: the result is an integer
 // ranking key, so 1-ulp differences would reorder candidates.
+// range[0] / range[1]: running maximum / minimum of the integers (both start at 0): the host
+// sorts only the bits the keys actually use.  A look at the current value first keeps all but a
+// handful of threads off the atomic.
+__device__ __forceinline__ void note_range(int* range, int vmax, int vmin) {
+  if (vmax > __ldcg(range)) atomicMax(range, vmax);
+  if (vmin < 0 && vmin < __ldcg(range + 1)) atomicMin(range + 1, vmin);
+}
+
 __global__ void mineig_kernel(const float* __restrict__ gx, const float* __restrict__ gy, int pitch,
                               int bx, int by, int step, int nxc, int nyc, int hw, int hh,
-                              int* __restrict__ vals, unsigned* __restrict__ idx) {
+                              int* __restrict__ vals, unsigned* __restrict__ idx, int* range) {
   const int ix = blockIdx.x * blockDim.x + threadIdx.x;
   const int iy = blockIdx.y * blockDim.y + threadIdx.y;
   if (ix >= nxc || iy >= nyc) return;
@@ -378,6 +386,7 @@ __global__ void mineig_kernel(const float* __restrict__ gx, const float* __restr
   const int n = iy * nxc + ix;
   vals[n] = (int)v;          // truncation toward zero, as the C cast
   idx[n] = (unsigned)n;
+  note_range(range, (int)v, (int)v);
 }
 
 // The same for the default 7x7 window and step 1, 8 consecutive candidates per thread: the 14
@@ -395,7 +404,7 @@ __device__ __forceinline__ int mineig_value(float gxx, float gxy, float gyy) {
 
 __global__ void __launch_bounds__(128)
 mineig7_kernel(const float* __restrict__ gx, const float* __restrict__ gy, int pitch,
-               int bx, int by, int nxc, int nyc, int* __restrict__ vals, unsigned* __restrict__ idx) {
+               int bx, int by, int nxc, int nyc, int* __restrict__ vals, unsigned* __restrict__ idx, int* range) {
   const int X0 = (bx & ~7) + 8 * (blockIdx.x * blockDim.x + threadIdx.x);    // absolute x of this thread's first candidate
   const int iy = blockIdx.y * blockDim.y + threadIdx.y;
   if (X0 >= bx + nxc || iy >= nyc) return;
@@ -426,15 +435,19 @@ mineig7_kernel(const float* __restrict__ gx, const float* __restrict__ gy, int p
       }
     }
   }
+  int vmax = 0, vmin = 0;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const int x = X0 + c;
     if (x >= bx && x < bx + nxc) {
       const int n = iy * nxc + (x - bx);
-      vals[n] = mineig_value(sxx[c], sxy[c], syy[c]);
+      const int v = mineig_value(sxx[c], sxy[c], syy[c]);
+      vals[n] = v;
       idx[n] = (unsigned)n;
+      vmax = max(vmax, v); vmin = min(vmin, v);
     }
   }
+  note_range(range, vmax, vmin);
 }
 
 // featuremap pre-stamp of the surviving features in REPLACING_SOME mode
@@ -3050,18 +3063,21 @@ static int ensure_candidates(klt_dev* d, size_t n) {
 
 static int run_mineig(klt_dev* d, int slot, const klt_dev_select_params* p, const CandGeo& g) {
   const Level& lv = d->set[slot].lv[0];
+  CU(cudaMemsetAsync(d->sel_state + 5, 0, 2 * sizeof(int), d->stream));        // key range: max, min
   dim3 b(32, 8), grid((g.nxc + 31) / 32, (g.nyc + 7) / 8);
   if (p->window_width / 2 == 3 && p->window_height / 2 == 3 && g.step == 1 && g.bx >= 8 && g.by >= 3 &&
       (lv.pitch & 31) == 0 && !getenv("KLT_B200_MINEIG_SCALAR")) {
     const int span = g.bx + g.nxc - (g.bx & ~7);                               // columns from the first 8-aligned block on
     dim3 b7(32, 4), g7((span + 255) / 256, (g.nyc + 3) / 4);
     Launch l(d, KID_MINEIG);
-    mineig7_kernel<<<g7, b7, 0, d->stream>>>(lv.gx, lv.gy, lv.pitch, g.bx, g.by, g.nxc, g.nyc, d->c_val[0], d->c_idx[0]);
+    mineig7_kernel<<<g7, b7, 0, d->stream>>>(lv.gx, lv.gy, lv.pitch, g.bx, g.by, g.nxc, g.nyc, d->c_val[0], d->c_idx[0],
+                                             d->sel_state + 5);
     return 0;
   }
   { Launch l(d, KID_MINEIG);
     mineig_kernel<<<grid, b, 0, d->stream>>>(lv.gx, lv.gy, lv.pitch, g.bx, g.by, g.step, g.nxc, g.nyc,
-                                             p->window_width / 2, p->window_height / 2, d->c_val[0], d->c_idx[0]); }
+                                             p->window_width / 2, p->window_height / 2, d->c_val[0], d->c_idx[0],
+                                             d->sel_state + 5); }
   return 0;
 }
 
@@ -3122,9 +3138,18 @@ static int select_core(klt_dev* d, int slot, const klt_dev_select_params* p, int
     if (ensure_candidates(d, (size_t)g.npoints)) return 1;
     if (run_mineig(d, slot, p, g)) return 1;
     size_t bytes = d->cub_bytes;
+    int end_bit = 32;
+    if (host) {
+      // the synchronous API can afford one look at the key range: eigenvalues of 8-bit frames use
+      // 15-21 bits, i.e. 2-3 radix passes instead of 4
+      int range[2] = {0, 0};
+      CU(cudaMemcpyAsync(range, d->sel_state + 5, sizeof(range), cudaMemcpyDeviceToHost, d->stream));
+      CU(cudaStreamSynchronize(d->stream));
+      if (range[1] >= 0) { end_bit = 1; while (end_bit < 31 && (range[0] >> end_bit) != 0) ++end_bit; }
+    }
     { Launch l(d, KID_SORT);   // several cub kernels, timed and counted as one
       CU(cub::DeviceRadixSort::SortPairsDescending(d->cub_tmp, bytes, d->c_val[0], d->c_val[1], d->c_idx[0],
-                                                   d->c_idx[1], (int)g.npoints, 0, 32, d->stream)); }
+                                                   d->c_idx[1], (int)g.npoints, 0, end_bit, d->stream)); }
     sval = d->c_val[1]; sidx = d->c_idx[1];
   }
   if (!p->overwrite_all) {
