@@ -300,6 +300,21 @@ def run_b200(args, rank, local_rank, world):
     prof = L.profile(dev)
     L.KLTB200ResidentEnd(tc, fl)
 
+    # ---- (4) the level-0 kernel alone, launched back to back (no event pair per launch: the
+    # brackets of pass (3) add the launch latency that the frame chain hides) ----------------
+    l0_b2b_ms = None
+    if "l0_fused_kernel" in prof:
+        q0 = L.build_desc(tc, ncols, nrows, nlevels_built=1, exact=0)
+        nb2b = max(10, min(K, 200))
+        for i in range(5):
+            L.klt_dev_build(dev, i % 3, C.c_void_p(d_ptr(idx(i))), 1, ncols, C.byref(q0))
+        L.klt_dev_timer_start(dev)
+        for i in range(nb2b):
+            L.klt_dev_build(dev, i % 3, C.c_void_p(d_ptr(idx(i))), 1, ncols, C.byref(q0))
+        ms0 = C.c_float(0)
+        L.klt_dev_timer_stop(dev, C.byref(ms0))
+        l0_b2b_ms = float(ms0.value) / nb2b
+
     # ---- reduce over ranks: sum of features, max of time -------------------------------
     if world > 1:
         t = torch.tensor([dev_ms, e2e_s, seq_s], dtype=torch.float64, device="cuda")
@@ -342,6 +357,13 @@ def run_b200(args, rank, local_rank, world):
                         "frac": round(d["gbs"] / peak, 4), "traffic": traffic, "peak_source": peak_src,
                         "bytes_per_step": d["algorithmic_bytes_per_step"],
                         "launches_per_step": d["launches_per_step"], "ms_per_step": d["ms_per_step"]}
+            if dom == "l0_fused_kernel" and l0_b2b_ms:
+                g = d["algorithmic_bytes_per_step"] / (l0_b2b_ms * 1e-3) / 1e9
+                roofline["back_to_back"] = {
+                    "ms_per_launch": round(l0_b2b_ms, 5), "gbs": round(g, 1), "frac": round(g / peak, 4),
+                    "how": "the same kernel launched back to back on distinct frames between ONE pair of "
+                           "events (level-0-only builds): its steady-state rate without the per-launch "
+                           "event brackets of `kernels`"}
             pipe_ms = sum(v["ms_per_step"] for k, v in kernels.items() if k in pipe)
             if pipe_ms > 0:
                 roofline["frame_pipeline"] = {
