@@ -435,3 +435,33 @@ def test_two_devices_in_one_process(L, capi, provided):
     for a in got[1:]:
         for u, v in zip(got[0], a):
             assert u.tobytes() == v.tobytes()
+
+
+@pytest.mark.parametrize("switch", ["KLT_B200_NO_FILTER", "KLT_B200_MINEIG_SCALAR"])
+def test_selection_alternatives_are_bit_identical(L, capi, switch, monkeypatch):
+    """the A/B switches of the selection path (whole-list walk in one launch; one thread per
+    eigenvalue candidate) give the lists of the default path: select on an empty list (the walk's
+    head / filter / tail hand-over at 640x480: 255 744 candidates), then replacement after losses."""
+    w, h, n = 640, 480, 1200
+    img0, img1 = synth_image(w, h, 31), synth_image(w, h, 31, shift=(1.5, -0.75))
+    got = []
+    for on in (0, 1):
+        if on:
+            monkeypatch.setenv(switch, "1")      # read when the context first selects
+        tc = L.KLTCreateTrackingContext()
+        tc.contents.sequentialMode = 1
+        fl = L.KLTCreateFeatureList(n)
+        L.select(tc, img0, fl)
+        a = [u.copy() for u in _get(capi, fl)]
+        L.track(tc, img0, img1, fl)
+        x, y, v = [u.copy() for u in _get(capi, fl)]
+        lost = np.arange(n) % 7 == 0
+        x[lost], y[lost], v[lost] = -1.0, -1.0, -1
+        capi.arrays_to_featurelist(fl, x, y, v)
+        L.replace(tc, img1, fl)
+        got.append(a + [u.copy() for u in _get(capi, fl)])
+        L.KLTFreeFeatureList(fl)
+        L.KLTFreeTrackingContext(tc)
+    assert (got[0][2] > 0).sum() > 500
+    for u, v in zip(got[0], got[1]):
+        assert u.tobytes() == v.tobytes()
