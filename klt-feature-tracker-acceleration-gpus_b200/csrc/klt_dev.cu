@@ -363,7 +363,7 @@ __device__ __forceinline__ void note_range(int* range, int vmax, int vmin) {
 
 __global__ void mineig_kernel(const float* __restrict__ gx, const float* __restrict__ gy, int pitch,
                               int bx, int by, int step, int nxc, int nyc, int hw, int hh,
-                              int* __restrict__ vals, unsigned* __restrict__ idx, int* range) {
+                              int* __restrict__ vals, unsigned* __restrict__ idx, int* range, int clamp_neg) {
   const int ix = blockIdx.x * blockDim.x + threadIdx.x;
   const int iy = blockIdx.y * blockDim.y + threadIdx.y;
   if (ix >= nxc || iy >= nyc) return;
@@ -384,9 +384,13 @@ __global__ void mineig_kernel(const float* __restrict__ gx, const float* __restr
   const double ev = __ddiv_rn(__dsub_rn((double)__fadd_rn(gxx, gyy), sqrt((double)rad)), 2.0);
   const float v = (float)ev;
   const int n = iy * nxc + ix;
-  vals[n] = (int)v;          // truncation toward zero, as the C cast
+  int vi = (int)v;           // truncation toward zero, as the C cast
+  // (rounding can leave a rank-deficient window a few units below zero; for the selection such a
+  // key is as dead as 0 -- the threshold is >= 1 -- and non-negative keys let the sort skip bits)
+  if (clamp_neg && vi < 0) vi = 0;
+  vals[n] = vi;
   idx[n] = (unsigned)n;
-  note_range(range, (int)v, (int)v);
+  note_range(range, vi, vi);
 }
 
 // The same for the default 7x7 window and step 1, 8 consecutive candidates per thread: the 14
@@ -404,7 +408,8 @@ __device__ __forceinline__ int mineig_value(float gxx, float gxy, float gyy) {
 
 __global__ void __launch_bounds__(128)
 mineig7_kernel(const float* __restrict__ gx, const float* __restrict__ gy, int pitch,
-               int bx, int by, int nxc, int nyc, int* __restrict__ vals, unsigned* __restrict__ idx, int* range) {
+               int bx, int by, int nxc, int nyc, int* __restrict__ vals, unsigned* __restrict__ idx, int* range,
+               int clamp_neg) {
   const int X0 = (bx & ~7) + 8 * (blockIdx.x * blockDim.x + threadIdx.x);    // absolute x of this thread's first candidate
   const int iy = blockIdx.y * blockDim.y + threadIdx.y;
   if (X0 >= bx + nxc || iy >= nyc) return;
@@ -441,7 +446,8 @@ mineig7_kernel(const float* __restrict__ gx, const float* __restrict__ gy, int p
     const int x = X0 + c;
     if (x >= bx && x < bx + nxc) {
       const int n = iy * nxc + (x - bx);
-      const int v = mineig_value(sxx[c], sxy[c], syy[c]);
+      int v = mineig_value(sxx[c], sxy[c], syy[c]);
+      if (clamp_neg && v < 0) v = 0;
       vals[n] = v;
       idx[n] = (unsigned)n;
       vmax = max(vmax, v); vmin = min(vmin, v);
@@ -1173,6 +1179,7 @@ struct Level {
 struct PyrSet {
   Level lv[KLT_DEV_MAX_LEVELS];
   int built_levels;          // 0 = nothing valid
+  double grad_bound;         // upper bound of |gx|, |gy| at level 0 (from the taps, 8-bit input); 0 = unknown
 };
 
 struct klt_dev {
@@ -2520,6 +2527,15 @@ extern "C" int klt_dev_build(klt_dev* d, int slot, const unsigned char* img, int
     d->built_pending[slot] = 1;
   }
   S.built_levels = q->nlevels_built;
+  {
+    // |gradient| <= 255 * sum|smoothing taps|^2 * sum|derivative taps| * sum|Gaussian taps|: bounds the
+    // eigenvalue keys of a selection on this slot (how many radix passes the sort needs)
+    double sg = 0.0, sd = 0.0, ss = 1.0;
+    for (int i = 0; i < q->grad_taps.gauss_width; ++i) sg += fabs((double)q->grad_taps.gauss[i]);
+    for (int i = 0; i < q->grad_taps.deriv_width; ++i) sd += fabs((double)q->grad_taps.deriv[i]);
+    if (q->smooth) { ss = 0.0; for (int i = 0; i < q->smooth_taps.gauss_width; ++i) ss += fabs((double)q->smooth_taps.gauss[i]); }
+    S.grad_bound = 255.0 * ss * ss * sd * sg;
+  }
   return 0;
 }
 
@@ -3061,7 +3077,7 @@ static int ensure_candidates(klt_dev* d, size_t n) {
   return 0;
 }
 
-static int run_mineig(klt_dev* d, int slot, const klt_dev_select_params* p, const CandGeo& g) {
+static int run_mineig(klt_dev* d, int slot, const klt_dev_select_params* p, const CandGeo& g, int clamp_neg) {
   const Level& lv = d->set[slot].lv[0];
   CU(cudaMemsetAsync(d->sel_state + 5, 0, 2 * sizeof(int), d->stream));        // key range: max, min
   dim3 b(32, 8), grid((g.nxc + 31) / 32, (g.nyc + 7) / 8);
@@ -3071,13 +3087,13 @@ static int run_mineig(klt_dev* d, int slot, const klt_dev_select_params* p, cons
     dim3 b7(32, 4), g7((span + 255) / 256, (g.nyc + 3) / 4);
     Launch l(d, KID_MINEIG);
     mineig7_kernel<<<g7, b7, 0, d->stream>>>(lv.gx, lv.gy, lv.pitch, g.bx, g.by, g.nxc, g.nyc, d->c_val[0], d->c_idx[0],
-                                             d->sel_state + 5);
+                                             d->sel_state + 5, clamp_neg);
     return 0;
   }
   { Launch l(d, KID_MINEIG);
     mineig_kernel<<<grid, b, 0, d->stream>>>(lv.gx, lv.gy, lv.pitch, g.bx, g.by, g.step, g.nxc, g.nyc,
                                              p->window_width / 2, p->window_height / 2, d->c_val[0], d->c_idx[0],
-                                             d->sel_state + 5); }
+                                             d->sel_state + 5, clamp_neg); }
   return 0;
 }
 
@@ -3088,7 +3104,7 @@ extern "C" int klt_dev_eigen_map(klt_dev* d, int slot, const klt_dev_select_para
   if (npoints) *npoints = (int)g.npoints;
   if (!out || g.npoints == 0) return 0;
   if (ensure_candidates(d, (size_t)g.npoints)) return 1;
-  if (run_mineig(d, slot, p, g)) return 1;
+  if (run_mineig(d, slot, p, g, 0)) return 1;
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(out, d->c_val[0], g.npoints * sizeof(int), cudaMemcpyDeviceToHost, d->stream));
   CU(cudaStreamSynchronize(d->stream));
@@ -3136,9 +3152,15 @@ static int select_core(klt_dev* d, int slot, const klt_dev_select_params* p, int
   const int* sval = nullptr; const unsigned* sidx = nullptr;
   if (g.npoints > 0) {
     if (ensure_candidates(d, (size_t)g.npoints)) return 1;
-    if (run_mineig(d, slot, p, g)) return 1;
+    if (run_mineig(d, slot, p, g, 1)) return 1;
     size_t bytes = d->cub_bytes;
     int end_bit = 32;
+    {
+      // keys <= (gxx + gyy) / 2 <= window pixels * bound^2 (with 1 % slack for the float roundings)
+      const double gb = d->set[slot].grad_bound;
+      const double kb = 1.01 * (double)p->window_width * (double)p->window_height * gb * gb + 2.0;
+      if (gb > 0.0 && kb < 2147483647.0) { end_bit = 1; while (end_bit < 31 && ((long long)kb >> end_bit) != 0) ++end_bit; }
+    }
     if (host) {
       // the synchronous API can afford one look at the key range: eigenvalues of 8-bit frames use
       // 15-21 bits, i.e. 2-3 radix passes instead of 4
@@ -3146,6 +3168,7 @@ static int select_core(klt_dev* d, int slot, const klt_dev_select_params* p, int
       CU(cudaMemcpyAsync(range, d->sel_state + 5, sizeof(range), cudaMemcpyDeviceToHost, d->stream));
       CU(cudaStreamSynchronize(d->stream));
       if (range[1] >= 0) { end_bit = 1; while (end_bit < 31 && (range[0] >> end_bit) != 0) ++end_bit; }
+      else end_bit = 32;
     }
     { Launch l(d, KID_SORT);   // several cub kernels, timed and counted as one
       CU(cub::DeviceRadixSort::SortPairsDescending(d->cub_tmp, bytes, d->c_val[0], d->c_val[1], d->c_idx[0],
