@@ -1699,12 +1699,18 @@ struct FusedPlan {
   int SS, R;                                    // pyramid step geometry of the fused level kernels
 };
 
-static int level_shape_for(int ss, int r, long px) {
+static int level_shape_for(int ss, int r, int w, int h, int num_sms) {
   if (ss == 2 && r == 5) {
     // tile shape by level size: big levels amortise the halo with 64x32 tiles, small levels
-    // need many small tiles to fill 148 SMs and to keep the per-CTA latency short
+    // need many small tiles to fill 148 SMs and to keep the per-CTA latency short.  In between
+    // (4K level 2: 960x540) the wave count decides: 64x32 tiles when they all fit into ONE wave of
+    // 2 CTAs per SM (255 tiles: 10.6 us), else 64x16 tiles at 3 CTAs per SM (510 tiles = 1.15
+    // waves: 12.7 us; measured on the 4K step: 74.1 -> 72.8 us).
     static int force = getenv("KLT_B200_LEVEL_TILE") ? atoi(getenv("KLT_B200_LEVEL_TILE")) : 0;
-    const int shape = force ? force : (px >= 1500000 ? 1 : (px >= 300000 ? 2 : 3));
+    const long px = (long)w * h;
+    const long tiles_64x32 = (long)((w + 63) / 64) * ((h + 31) / 32);
+    const int mid = tiles_64x32 <= 2L * num_sms ? 1 : 2;
+    const int shape = force ? force : (px >= 1500000 ? 1 : (px >= 300000 ? mid : 3));
     return shape == 1 ? SHAPE_2_5_64_32 : (shape == 2 ? SHAPE_2_5_64_16 : (shape == 4 ? SHAPE_2_5_64_24 : SHAPE_2_5_32_16));
   }
   if (ss == 4 && r == 10) return SHAPE_4_10_32_16;
@@ -1742,7 +1748,7 @@ static void fused_plan(klt_dev* d, const PyrSet& S, const unsigned char* src, in
   for (int l = 1; l < q->nlevels_built; ++l) {
     const Level& a = S.lv[l - 1];
     const Level& b = S.lv[l];
-    int shape = force_shape != SHAPE_NONE ? force_shape : level_shape_for(q->subsampling, tp.w / 2, (long)b.w * b.h);
+    int shape = force_shape != SHAPE_NONE ? force_shape : level_shape_for(q->subsampling, tp.w / 2, b.w, b.h, d->num_sms);
     bool ok = false;
     switch (shape) {
       case SHAPE_2_5_64_32: ok = level_map<2, 5, 64, 32>(&P->map[l], a); P->TX[l] = 64; P->TY[l] = 32; break;
