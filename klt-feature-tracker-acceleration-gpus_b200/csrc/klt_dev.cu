@@ -473,8 +473,8 @@ __global__ void stamp_existing_kernel(const float* __restrict__ x, const float* 
 
 // Greedy minimum-distance pass (selectGoodFeatures.c:168-235) on the sorted
 // candidate list, made deterministic AND parallel: one CTA walks the list in
-// batches of GBATCH = 4096 consecutive ranks (4 per thread, the next batch's
-// keys are fetched while the current one is resolved).  Threads test the
+// batches of 1024 or GBATCH = 4096 consecutive ranks (1 or 4 per thread, see gk
+// below; the next batch's keys are fetched while the current one is resolved).  Threads test the
 // featuremap in parallel, survivors are compacted in rank order, and warp 0
 // resolves them in rank order, 32 at a time, against the candidates already
 // accepted in this batch (the only ones not yet stamped):
@@ -558,7 +558,7 @@ enforce_mindist_kernel(const int* __restrict__ sval, const unsigned* __restrict_
                        int nxc, int bx, int by, int step, int W, int H,
                        unsigned char* fmap, int d, int min_eig, int overwrite_all,
                        int n, float* x, float* y, int* val, int* open_slots,
-                       int* state, int first, int last, int max_batches) {
+                       int* state, int first, int last) {
   extern __shared__ __align__(16) unsigned char enf_smem[];
   unsigned* s_xy = reinterpret_cast<unsigned*>(enf_smem);            // survivors of the batch in rank order (x | y << 16);
   unsigned* s_tbl = s_xy + GBATCH;                                   //   the accepted ones are compacted in place at the front
@@ -611,7 +611,7 @@ enforce_mindist_kernel(const int* __restrict__ sval, const unsigned* __restrict_
   }
   int gk_next = gk, gk_want = gk;                // layout of the prefetched keys / size wanted for the batch after them
 
-  for (int base = 0, nb = 0; base < npoints && !done && nb < max_batches; base += GB * gk, gk = gk_next, ++nb) {
+  for (int base = 0; base < npoints && !done; base += GB * gk, gk = gk_next) {
     const int total0 = s_total;                  // accepted before this batch (written two barriers ago,
                                                  // rewritten only after the next two)
     int cv[GK], cx[GK], cy[GK];
@@ -3201,11 +3201,11 @@ static int select_core(klt_dev* d, int slot, const klt_dev_select_params* p, int
       if (indirect)
         enforce_mindist_kernel<true><<<1, GB, ENFORCE_SMEM, d->stream>>>(
             sval, sidx, d->rank_list, d->sel_state + 4, 0, nxc, g.bx, g.by, g.step, d->W, d->H, d->fmap, dist, min_eig,
-            p->overwrite_all, n, d->d_x, d->d_y, d->d_val, d->open_slots, d->sel_state, first, last, INT_MAX);
+            p->overwrite_all, n, d->d_x, d->d_y, d->d_val, d->open_slots, d->sel_state, first, last);
       else
         enforce_mindist_kernel<false><<<1, GB, ENFORCE_SMEM, d->stream>>>(
             sval, sidx, nullptr, nullptr, npts, nxc, g.bx, g.by, g.step, d->W, d->H, d->fmap, dist, min_eig,
-            p->overwrite_all, n, d->d_x, d->d_y, d->d_val, d->open_slots, d->sel_state, first, last, INT_MAX);
+            p->overwrite_all, n, d->d_x, d->d_y, d->d_val, d->open_slots, d->sel_state, first, last);
     };
     const int head = ENFORCE_HEAD;
     if (np > 0 && !p->overwrite_all && !d->no_filter) {
