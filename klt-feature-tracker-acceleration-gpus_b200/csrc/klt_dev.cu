@@ -741,7 +741,7 @@ enforce_mindist_kernel(const int* __restrict__ sval, const unsigned* __restrict_
       // stamps (:102-115).  One warp per accepted candidate; the (2d+1)^2 square is written as
       // 32-bit words -- lane = (row, word of the row), byte mask by position, red.or so that squares
       // which share a word cannot lose each other's bytes.  (Byte stores, one row per instruction,
-      // made this loop ~1 M warp instructions for 1024 accepted candidates: more than half of the
+      // made this loop 0.8 M warp instructions for 1024 accepted candidates: more than half of the
       // kernel on its single SM.)
       if (d >= 0) {
         unsigned* fmap32 = reinterpret_cast<unsigned*>(fmap);
