@@ -128,23 +128,9 @@ int klt_dev_features_capacity(const klt_dev *d);
 int klt_dev_snapshot_ring(klt_dev *d, int depth);
 int klt_dev_snapshot_push(klt_dev *d, int slot);
 int klt_dev_snapshot_wait(klt_dev *d, int slot, const float **x, const float **y, const int **val);
-/* Arm an early tracker pass for the next klt_dev_build of a HOST frame (features already
- * committed, slot_prev valid): if the frame goes up in bands and the 7x7 fma tracker applies, its
- * first pass is launched right behind the first band's pyramid rows -- while the rest of the frame
- * is still on the bus -- and defers every feature whose footprint would touch a row that does not
- * exist yet; the following klt_dev_track_resident then only tracks the deferred features.
- * Results are identical to one pass.  Opt-in (env KLT_B200_EARLY_TRACK=1 or
- * klt_dev_disable_early_track(d, 0)): measured no gain, the tracker's time is a latency chain and
- * does not shrink with the number of features. */
-int klt_dev_arm_early_track(klt_dev *d, int slot_prev, const klt_dev_track_params *p);
-void klt_dev_disable_early_track(klt_dev *d, int on);
 /* 7x7 fma tracking runs on track7w_kernel (one warp per feature; default) or, with
- * klt_dev_disable_track7w(d, 1) / env KLT_B200_TRACK7W=0, on track7_kernel (8 lanes per feature) */
+ * klt_dev_disable_track7w(d, 1) / env KLT_B200_TRACK7W=0, on track_fast_kernel<7> (8 lanes per feature) */
 void klt_dev_disable_track7w(klt_dev *d, int on);
-/* the default 7x7 fma tracker is track7v_kernel (track7w's lane map with one aligned 128-bit load
- * per lane and image); klt_dev_disable_track7v(d, 1) / env KLT_B200_TRACK7V=0 selects track7w_kernel */
-void klt_dev_disable_track7v(klt_dev *d, int on);
-int klt_dev_last_track_passes(const klt_dev *d);     /* 2 if the last tracking ran in two passes */
 /* zero-copy variant for the C host layer: pack the feature list straight into the
  * context's pinned staging area, commit it (async H2D), and after the work fetch the
  * results back into the same area (D2H + synchronise). */
@@ -233,28 +219,6 @@ int klt_dev_last_build_fused(const klt_dev *d);
  * one copy.  klt_dev_last_build_bands: copies the last klt_dev_build issued (0 for a
  * device-resident frame). */
 void klt_dev_set_band_rows(klt_dev *d, int rows);
-/* 1 if the last klt_dev_build ran the whole pyramid in one pyramid_mega_kernel launch (tile-level
- * dataflow across levels, level-0 tiles gated on the uploaded bands).  Opt-in: klt_dev_disable_mega(d, 0)
- * or env KLT_B200_MEGA=1; the default is the per-level fused kernels, which measure faster. */
-int klt_dev_last_build_mega(const klt_dev *d);
-void klt_dev_disable_mega(klt_dev *d, int on);
-/* level 0 on the TMA tile kernel l0_fused_kernel (default) or, with klt_dev_disable_stream(d, 0) /
- * env KLT_B200_L0_STREAM=1, on l0_stream_kernel (warp-synchronous column streaming: no shared
- * memory, no CTA barrier).  Same bits either way; the tile kernel measures faster.
- * klt_dev_last_build_stream: which one the last build used. */
-void klt_dev_disable_stream(klt_dev *d, int on);
-/* klt_dev_disable_chain(d, 0) / env KLT_B200_CHAIN=1: levels >= 1 of a pyramid with more than two
- * levels are built by ONE levels_chain_kernel launch (one tile shape, grid barrier between levels)
- * instead of one level_fused_kernel launch per level (default: the per-level launches overlap
- * through programmatic dependent launch and measure faster).  Same bits either way. */
-void klt_dev_disable_chain(klt_dev *d, int on);
-int klt_dev_last_build_chain(const klt_dev *d);
-int klt_dev_last_build_stream(const klt_dev *d);
-/* first_level > 0 (env KLT_B200_MEGA_TAIL; default 0 = off, it measures slower): levels >=
- * first_level of a pyramid with more than first_level + 1 levels are built by ONE
- * pyramid_mega_kernel launch in tail mode instead of one launch each
- * (klt_dev_last_build_mega then returns 2). */
-void klt_dev_set_mega_tail(klt_dev *d, int first_level);
 int klt_dev_last_build_bands(const klt_dev *d);
 /* Pageable host frames of >= 1 MB are copied into a pinned staging buffer by n host threads
  * (OpenMP; default 4, env KLT_B200_STAGE_THREADS; 0 = leave the staging to cudaMemcpyAsync), ~1 MB

@@ -72,8 +72,6 @@ struct TapsF {
 static constexpr int NT = 256;   // threads per CTA of every tile kernel
 
 #include "klt_fused.cuh"
-#include "klt_mega.cuh"
-#include "klt_stream.cuh"
 
 // ---------------------------------------------------------------------------
 // generic kernels: any radius, any subsampling.  One thread per output sample.
@@ -802,15 +800,7 @@ struct TrackArgs {
   int   borderx, bordery;
   int   ncols, nrows;
   int   lighting;            // tc->lighting_insensitive: gain / bias normalised windows (track_kernel only)
-  int   prefetch;            // track7: L2 prefetch of the finer levels' footprints at kernel start
   int   l2_keep;             // track7w: the new frame's footprints are loaded with an L2 evict_last policy
-  // track7 behind a banded frame upload: pass 1 runs when only the first band's pyramid rows exist
-  // (row_limit[l] = complete rows of level l of the NEW frame) and gives up on -- "defers" -- any
-  // feature whose footprint would touch a later row; pass 2, after the last band, tracks exactly
-  // the deferred ones from scratch.  done[f]: 1 once feature f has its final answer.  pass 0: one pass.
-  int   pass;
-  int   row_limit[KLT_DEV_MAX_LEVELS];
-  unsigned char* done;
 };
 
 // Where a tracker kernel reads the features and where it records the results (element strides in
@@ -1159,12 +1149,12 @@ track_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
 // kernel classes, for launch accounting and per-kernel event timing
 enum KernelId {
   KID_SMOOTH_U8 = 0, KID_GRAD, KID_PYRDOWN, KID_TRACK, KID_MINEIG, KID_SORT, KID_STAMP,
-  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_L0_FUSED, KID_LEVEL_FUSED, KID_LEVEL_FUSED_L2, KID_LEVEL_FUSED_L3, KID_TRACK_FAST, KID_TRACK7, KID_TRACK7W, KID_TRACK7V, KID_AFFINE, KID_LEVELS_CHAIN, KID_MEGA, KID_L0_STREAM, KID_FILTER, KID_COPY_H2D, KID_COPY_D2H, KID_COUNT
+  KID_ENFORCE, KID_GENERIC_H, KID_GENERIC_V, KID_U8_TO_F32, KID_L0_FUSED, KID_LEVEL_FUSED, KID_LEVEL_FUSED_L2, KID_LEVEL_FUSED_L3, KID_TRACK_FAST, KID_TRACK7W, KID_AFFINE, KID_FILTER, KID_COPY_H2D, KID_COPY_D2H, KID_COUNT
 };
 static const char* const kKernelNames[KID_COUNT] = {
   "smooth_u8_tile", "grad_tile", "pyrdown_tile", "track_kernel", "mineig_kernel",
   "cub_radix_sort", "stamp_existing_kernel", "enforce_mindist_kernel",
-  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel", "l0_fused_kernel", "level_fused_kernel[level 1]", "level_fused_kernel[level 2]", "level_fused_kernel[level 3+]", "track_fast_kernel", "track7_kernel", "track7w_kernel", "track7v_kernel", "affine_check_kernel", "levels_chain_kernel", "pyramid_mega_kernel", "l0_stream_kernel", "cub_select_uncovered",
+  "conv_h_generic", "conv_v_generic", "u8_to_f32_kernel", "l0_fused_kernel", "level_fused_kernel[level 1]", "level_fused_kernel[level 2]", "level_fused_kernel[level 3+]", "track_fast_kernel", "track7w_kernel", "affine_check_kernel", "cub_select_uncovered",
   "copy_h2d", "copy_d2h"          // not kernels: timed in profiling mode, never counted as launches
 };
 static constexpr int PROF_POOL = 2048;     // event pairs in flight before folding
@@ -1210,24 +1200,12 @@ struct klt_dev {
   int band_rows, last_bands, building_slot;
   // pageable host frames: parallel memcpy into pinned staging, chunk by chunk ahead of the DMA
   unsigned char* h_frame; size_t h_frame_cap; cudaEvent_t ev_stage_free; int stage_busy, stage_threads, last_staged;
-  // pyramid_mega_kernel: cached schedule + dependency counters (klt_mega.cuh)
-  int no_mega, last_mega, mega_tail_from;
-  int no_chain, last_chain; unsigned chain_barrier_base;   // levels >= 1 in one launch (levels_chain_kernel)
   int pdl;                     // programmatic dependent launch along the per-frame kernel chain
-  int no_stream, stream_hs, last_stream;    // l0_stream_kernel off / output rows per segment
-  MegaSeg* d_segs; int mega_nseg, mega_nitems, mega_key[8];
-  unsigned* d_done; int mega_done_off[MEGA_MAX_LEVELS + 1];
-  unsigned mega_epoch[MEGA_MAX_LEVELS];
-  unsigned* d_u8_flag; unsigned feed_epoch;
   // features
   float *d_x, *d_y; int* d_val; int feat_cap; int feat_n;
   float *h_x, *h_y; int* h_val;   // pinned staging
   int staging_busy;
-  // early tracker pass behind the first uploaded band (klt_dev_arm_early_track)
-  int no_track7w, no_track7v;
-  int early_armed, early_done, early_slot_prev, early_slot_cur, no_early, last_passes;
-  klt_dev_track_params early_p;
-  unsigned char* d_fdone; int fdone_cap;
+  int no_track7w;
   int feat_out_host;            // 1: the next tracker writes its results into h_x/h_y/h_val (sync API); 2: record mode
   unsigned char* d_rec; size_t d_rec_cap; void* h_rec; int rec_stride;   // record mode (klt_dev_features_commit_records)
   cudaEvent_t ev_feat; int feat_pending;   // feature upload queued on the copy stream
@@ -1367,13 +1345,6 @@ extern "C" int klt_dev_last_build_fused(const klt_dev* d) { return d->last_fused
 extern "C" int klt_dev_last_build_bands(const klt_dev* d) { return d->last_bands; }
 extern "C" int klt_dev_last_build_staged(const klt_dev* d) { return d->last_staged; }
 extern "C" void klt_dev_set_stage_threads(klt_dev* d, int n) { d->stage_threads = n; }
-extern "C" int klt_dev_last_build_mega(const klt_dev* d) { return d->last_mega; }
-extern "C" void klt_dev_disable_mega(klt_dev* d, int on) { d->no_mega = on; }
-extern "C" void klt_dev_disable_stream(klt_dev* d, int on) { d->no_stream = on; }
-extern "C" void klt_dev_disable_chain(klt_dev* d, int on) { d->no_chain = on; }
-extern "C" int klt_dev_last_build_chain(const klt_dev* d) { return d->last_chain; }
-extern "C" int klt_dev_last_build_stream(const klt_dev* d) { return d->last_stream; }
-extern "C" void klt_dev_set_mega_tail(klt_dev* d, int first_level) { d->mega_tail_from = first_level; }
 extern "C" void klt_dev_set_band_rows(klt_dev* d, int rows) { d->band_rows = rows; }
 
 extern "C" int klt_dev_create(int device, klt_dev** out) {
@@ -1416,18 +1387,8 @@ extern "C" int klt_dev_create(int device, klt_dev** out) {
   c->overlap_l0_ctas = getenv("KLT_B200_OVERLAP_L0_CTAS") ? atoi(getenv("KLT_B200_OVERLAP_L0_CTAS")) : 0;
   e = cudaMalloc(&c->d_live, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemsetAsync(c->d_live, 0, sizeof(unsigned long long), c->stream);
-  if (e == cudaSuccess) e = cudaMalloc(&c->d_u8_flag, sizeof(unsigned));
-  if (e == cudaSuccess) e = cudaMemsetAsync(c->d_u8_flag, 0, sizeof(unsigned), c->stream);
-  // the single-launch pyramid (klt_mega.cuh) is opt-in: correct in both arithmetic modes, but measured
-  // slower than the per-level kernels on B200 (4K: 87 us vs 69 us resident)
-  c->no_mega = getenv("KLT_B200_MEGA") && atoi(getenv("KLT_B200_MEGA")) ? 0 : 1;
   c->pdl = getenv("KLT_B200_PDL") ? atoi(getenv("KLT_B200_PDL")) : 1;
-  // opt-in: 39 us against 46 us for the three launches when timed alone, but in the real chain the
-  // per-level launches overlap each other's tails through PDL and the grid barriers do not (4K
-  // build 62.2 us vs 58.7 us)
-  c->no_chain = getenv("KLT_B200_CHAIN") && atoi(getenv("KLT_B200_CHAIN")) ? 0 : 1;
   c->no_track7w = getenv("KLT_B200_TRACK7W") ? !atoi(getenv("KLT_B200_TRACK7W")) : 0;
-  c->no_track7v = getenv("KLT_B200_TRACK7V") ? !atoi(getenv("KLT_B200_TRACK7V")) : 1;   // opt-in until verified on the GPU
   if (getenv("KLT_B200_L2_PERSIST_MB")) {       // experiment: L2 set-aside for evict_last lines (KLT_TRACK_L2_KEEP)
     int maxb = 0;
     cudaDeviceGetAttribute(&maxb, cudaDevAttrMaxPersistingL2CacheSize, c->device);
@@ -1436,15 +1397,6 @@ extern "C" int klt_dev_create(int device, klt_dev** out) {
     cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
     fprintf(stderr, "(KLT/B200) persisting L2: %zu MB of max %d MB\n", want >> 20, maxb >> 20);
   }
-  // opt-in: measured no gain (the tracker is a latency chain: a pass over half the features takes
-  // as long as a pass over all of them)
-  c->no_early = getenv("KLT_B200_EARLY_TRACK") && atoi(getenv("KLT_B200_EARLY_TRACK")) ? 0 : 1;
-  // the streaming level-0 kernel (klt_stream.cuh) is opt-in: bit-identical, but 31.5 us vs 28.5 us for
-  // the tile kernel on a 4K frame
-  c->no_stream = getenv("KLT_B200_L0_STREAM") && atoi(getenv("KLT_B200_L0_STREAM")) ? 0 : 1;
-  c->stream_hs = getenv("KLT_B200_STREAM_HS") ? atoi(getenv("KLT_B200_STREAM_HS")) : 46;
-  if (c->stream_hs < 4) c->stream_hs = 4;
-  c->mega_tail_from = getenv("KLT_B200_MEGA_TAIL") ? atoi(getenv("KLT_B200_MEGA_TAIL")) : 0;   // opt-in too (4K: 30 us vs 21 us for levels 2+3)
   if (e == cudaSuccess) e = cudaMalloc(&c->d_tile_ctr, 16 * sizeof(unsigned));
   if (e == cudaSuccess) e = cudaMemsetAsync(c->d_tile_ctr, 0, 16 * sizeof(unsigned), c->stream);
   if (e != cudaSuccess) { cudaStreamDestroy(c->stream); free(c); return fail(nullptr, "cudaMalloc: %s", cudaGetErrorString(e)); }
@@ -1453,10 +1405,6 @@ extern "C" int klt_dev_create(int device, klt_dev** out) {
 }
 
 static void free_geometry(klt_dev* d) {
-  cudaFree(d->d_segs); d->d_segs = nullptr; d->mega_nseg = 0;
-  cudaFree(d->d_done); d->d_done = nullptr;
-  memset(d->mega_key, 0, sizeof(d->mega_key));
-  memset(d->mega_epoch, 0, sizeof(d->mega_epoch));
   cudaFree(d->arena); d->arena = nullptr;
   cudaFree(d->tmp); d->tmp = nullptr;
   memset(d->set, 0, sizeof(d->set));
@@ -1478,9 +1426,7 @@ extern "C" void klt_dev_destroy(klt_dev* d) {
     cudaEventDestroy(d->ev_origin); free(d->trace_kid); free(d->trace_t0); free(d->trace_t1); }
   cudaFree(d->d_live);
   cudaFree(d->d_tile_ctr);
-  cudaFree(d->d_u8_flag);
   cudaFree(d->d_rec);
-  cudaFree(d->d_fdone);
   for (int i = 0; i < KLT_DEV_SLOTS; ++i) { cudaEventDestroy(d->ev_built[i]); cudaEventDestroy(d->ev_read[i]); }
   cudaEventDestroy(d->ev_join);
   for (int i = 0; i < KLT_BAND_EVENTS; ++i) cudaEventDestroy(d->ev_band[i]);
@@ -1690,7 +1636,6 @@ static bool fused_grad_taps_ok(const TapsR& tg, const TapsR& td) {
 // behind its upload (klt_dev_build with a host frame) or in one go (jr0 = 0, jr1 = tiles_y).
 enum LevelShape { SHAPE_NONE = 0, SHAPE_2_5_64_32, SHAPE_2_5_64_16, SHAPE_2_5_32_16, SHAPE_4_10_32_16, SHAPE_2_5_64_24 };
 struct FusedPlan {
-  bool l0_stream;                               // level 0 runs on l0_stream_kernel (no tensor map; TY[0] = rows per segment)
   const unsigned char* src; int spitch;
   bool l0_ok;                                   // level 0 runs on l0_fused_kernel
   int shape[KLT_DEV_MAX_LEVELS];                // LevelShape of level l >= 1 (SHAPE_NONE: not fused)
@@ -1725,18 +1670,11 @@ static bool level_map(CUtensorMap* m, const Level& a) {
 // which levels of this build can run on the fused kernels, and their tensor maps
 static void fused_plan(klt_dev* d, const PyrSet& S, const unsigned char* src, int spitch,
                        const klt_dev_build_desc* q, const TapsR& ts, const TapsR& tp, const TapsR& tg,
-                       const TapsR& td, FusedPlan* P, int force_shape, bool allow_stream = true) {
+                       const TapsR& td, FusedPlan* P, int force_shape) {
   memset(P, 0, sizeof(*P));
   if (d->force_generic || d->no_fused || !fused_grad_taps_ok(tg, td)) return;
   const int W = q->ncols, H = q->nrows;
   P->src = src; P->spitch = spitch;
-  if (allow_stream && !d->no_stream && q->smooth && ts.w == 2 * StreamGeo::RS + 1 && ((uintptr_t)src & 3) == 0 &&
-      (spitch & 3) == 0 && W >= 16 && H >= 8) {
-    P->l0_stream = true; P->l0_ok = true;
-    P->TX[0] = StreamGeo::OWN; P->TY[0] = d->stream_hs;
-    P->tiles_x[0] = (W + StreamGeo::OWN - 1) / StreamGeo::OWN;
-    P->tiles_y[0] = (H + d->stream_hs - 1) / d->stream_hs;
-  } else
   if (q->smooth && ts.w == 2 * L0Geo::RS + 1 &&
       make_tensor_map(&P->map[0], src, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, W, H, (size_t)spitch, L0Geo::U8_W,
                       L0Geo::U8_H)) {
@@ -1770,16 +1708,6 @@ template <bool EXACT>
 static int l0_fused_launch(klt_dev* d, const FusedPlan& P, int W, int H, const TapsR& ts, const TapsR& tg,
                            const TapsR& td, const Level& lv, int jr0, int jr1) {
   if (jr1 <= jr0) return 0;
-  if (P.l0_stream) {                             // one warp per (strip, segment), 4 warps per CTA
-    const int nstrips = P.tiles_x[0];
-    const int task0 = jr0 * nstrips, task1 = jr1 * nstrips;
-    const int grid = (task1 - task0 + 3) / 4;
-    Launch l(d, KID_L0_STREAM);
-    CU(launch_k(l0_stream_kernel<EXACT>, dim3(grid), dim3(128), 0, d->stream, d->pdl != 0, P.src, P.spitch, W, H,
-                nstrips, P.TY[0], task0, task1, to_fused(ts), to_fused(tg), to_fused(td), lv.img, lv.gx, lv.gy,
-                lv.pitch));
-    return 0;
-  }
   static bool attr_dev[64][2] = {};              // function attributes are per device
   bool* attr_set = attr_dev[d->device & 63];
   if (!attr_set[EXACT]) {
@@ -1838,60 +1766,6 @@ static int level_fused_launch(klt_dev* d, const FusedPlan& P, int level, const L
   }
 }
 
-// levels first .. nb-1 in one launch (levels_chain_kernel); jr0 / jr1: tile-row range per level
-template <int SS, int R, int TX, int TY, bool EXACT>
-static int levels_chain_launch_t(klt_dev* d, const FusedPlan& P, const PyrSet& S, int first, int nb, const TapsR& tp,
-                                 const TapsR& tg, const TapsR& td, const int* jr0, const int* jr1) {
-  using G = LvGeo<SS, R, TX, TY>;
-  static bool attr_dev[64] = {};                 // function attributes are per device
-  bool& attr_set = attr_dev[d->device & 63];
-  static int cps = 0;
-  if (!attr_set) {
-    CU(cudaFuncSetAttribute(levels_chain_kernel<SS, R, TX, TY, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, levels_chain_kernel<SS, R, TX, TY, EXACT>, 256, G::SMEM));
-    if (cps < 1) return fail(d, "levels_chain_kernel does not fit on an SM");
-    attr_set = true;
-  }
-  ChainParams CP;
-  memset(&CP, 0, sizeof(CP));
-  int maxtiles = 0;
-  CP.nlev = nb - first;
-  for (int l = first; l < nb; ++l) {
-    const int k = l - first;
-    const Level& a = S.lv[l - 1];
-    const Level& b = S.lv[l];
-    CP.map[k] = P.map[l];
-    ChainLevel& L = CP.lv[k];
-    L.Wsrc = a.w; L.Hsrc = a.h; L.W = b.w; L.H = b.h; L.tiles_x = P.tiles_x[l];
-    L.tile0 = jr0[l] * P.tiles_x[l]; L.ntiles = jr1[l] * P.tiles_x[l];
-    L.base = d->tile_base[l & 15];
-    L.img = b.img; L.gx = b.gx; L.gy = b.gy; L.pitch = b.pitch;
-    if (L.ntiles - L.tile0 > maxtiles) maxtiles = L.ntiles - L.tile0;
-  }
-  if (maxtiles == 0) return 0;
-  const int cap = cps * d->num_sms;                        // the grid barrier needs every CTA resident
-  const int grid = maxtiles < cap ? maxtiles : cap;
-  CP.counters = d->d_tile_ctr + first;                     // the per-level counters, consecutive
-  CP.barrier = d->d_tile_ctr + 15;                        // (0..11: per-level queues, 12..14: mega kernel)
-  CP.barrier_base = d->chain_barrier_base;
-  CP.tp = to_fused(tp); CP.tg = to_fused(tg); CP.td = to_fused(td);
-  { Launch l(d, KID_LEVELS_CHAIN);
-    CU(launch_k(levels_chain_kernel<SS, R, TX, TY, EXACT>, dim3(grid), dim3(256), G::SMEM, d->stream, d->pdl != 0, CP)); }
-  for (int l = first; l < nb; ++l)
-    d->tile_base[l & 15] += (unsigned)((jr1[l] - jr0[l]) * P.tiles_x[l] + grid);
-  d->chain_barrier_base += (unsigned)(CP.nlev - 1) * (unsigned)grid;
-  return 0;
-}
-template <bool EXACT>
-static int levels_chain_launch(klt_dev* d, const FusedPlan& P, const PyrSet& S, int first, int nb, const TapsR& tp,
-                               const TapsR& tg, const TapsR& td, const int* jr0, const int* jr1) {
-  switch (P.shape[first]) {
-    case SHAPE_2_5_64_16: return levels_chain_launch_t<2, 5, 64, 16, EXACT>(d, P, S, first, nb, tp, tg, td, jr0, jr1);
-    case SHAPE_4_10_32_16: return levels_chain_launch_t<4, 10, 32, 16, EXACT>(d, P, S, first, nb, tp, tg, td, jr0, jr1);
-    default: return fail(d, "no chained kernel for this pyramid geometry");
-  }
-}
-
 // generic two-kernel separable pass through d->tmp
 template <typename SrcT, bool EXACT>
 static int generic_separable(klt_dev* d, const SrcT* src, int spitch, int W, int H, const TapsR& kh,
@@ -1905,149 +1779,6 @@ static int generic_separable(klt_dev* d, const SrcT* src, int spitch, int W, int
   dim3 g2((Wout + 31) / 32, (Hout + 7) / 8);
   { Launch l(d, KID_GENERIC_V);
     conv_v_generic<EXACT><<<g2, b, 0, d->stream>>>(d->tmp, tp, Wout, H, kv, stride, off, out, opitch, Hout); }
-  return 0;
-}
-
-// ---- pyramid_mega_kernel: schedule, dependency state, launch ------------------------------------
-typedef CUresult (*WriteValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
-static WriteValue32Fn stream_write_value32() {
-  static WriteValue32Fn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (WriteValue32Fn)p;
-    cudaGetLastError();
-  }
-  return fn;
-}
-
-// tile shape of the coarse levels inside the mega kernel: one shape per subsampling (all tile types
-// of a launch share one shared-memory footprint; 64x16 / 32x16 match level 0's 55 KB / fit 2 per SM)
-static int mega_shape_for(int ss, int r) {
-  if (ss == 2 && r == 5) return SHAPE_2_5_64_16;
-  if (ss == 4 && r == 10) return SHAPE_4_10_32_16;
-  return SHAPE_NONE;
-}
-
-// Coarse work list in topological order: walking the level-0 tile rows top to bottom, the tile
-// rows of the coarser levels each one completes (the same rule the per-level band loop uses).
-// Cached per geometry; the device checks the real dependencies, the order only has to be valid.
-// first > 0 ("tail mode"): levels < first are built by the per-level kernels before the launch; only
-// the levels >= first are listed.
-static int mega_schedule(klt_dev* d, const FusedPlan& P, const PyrSet& S, int nb, int first) {
-  const int key[8] = {d->W, d->H, d->L, d->ss, nb, P.shape[nb > 1 ? nb - 1 : 1], P.R, 1 + first};
-  if (d->d_segs && memcmp(key, d->mega_key, sizeof(key)) == 0) return 0;
-  MegaSeg segs[MEGA_MAX_SEGS];
-  memset(segs, 0, sizeof(segs));
-  int nseg = 0, nitems = 0;
-  int rows_done[KLT_DEV_MAX_LEVELS] = {0}, valid[KLT_DEV_MAX_LEVELS] = {0};
-  const int SS = P.SS, R = P.R, RG = FUSED_RG, H = S.lv[0].h;
-  auto emit = [&](int level, int j0, int j1) -> bool {
-    if (j1 <= j0) return true;
-    if (nseg > 0 && segs[nseg - 1].level == level && segs[nseg - 1].jr0 + segs[nseg - 1].n / P.tiles_x[level] == j0) {
-      segs[nseg - 1].n += (j1 - j0) * P.tiles_x[level];          // extend the previous segment
-    } else {
-      if (nseg == MEGA_MAX_SEGS) return false;
-      segs[nseg].level = level; segs[nseg].jr0 = j0; segs[nseg].w0 = nitems; segs[nseg].n = (j1 - j0) * P.tiles_x[level];
-      ++nseg;
-    }
-    nitems += (j1 - j0) * P.tiles_x[level];
-    return true;
-  };
-  // A tile row is listed only once the rows it reads have been listed at least `lag` items
-  // earlier (about one wave of the CTAs serving this queue), so that in steady state its producers
-  // have finished by the time it is claimed and nobody waits; everything is flushed at the end.
-  static int lag_env = getenv("KLT_B200_MEGA_LAG") ? atoi(getenv("KLT_B200_MEGA_LAG")) : 160;
-  struct Pend { int j0, j1, ready_pos; };
-  static const int PQ = 4096;
-  Pend* pend[KLT_DEV_MAX_LEVELS] = {nullptr};
-  int ph[KLT_DEV_MAX_LEVELS] = {0}, pt[KLT_DEV_MAX_LEVELS] = {0};      // queue head / tail
-  int queued[KLT_DEV_MAX_LEVELS] = {0}, last_emit_pos[KLT_DEV_MAX_LEVELS] = {0};
-  for (int l = 1; l < nb; ++l) pend[l] = (Pend*)malloc(sizeof(Pend) * PQ);
-  bool overflow = false;
-  for (int l = 0; l < first; ++l) {                          // complete before the launch
-    rows_done[l] = queued[l] = P.tiles_y[l];
-    valid[l] = S.lv[l].h;
-  }
-  for (int step = first > 0 ? P.tiles_y[0] : 0; step <= P.tiles_y[0] && !overflow; ++step) {
-    const bool flush = step == P.tiles_y[0];
-    const int lag = flush ? 0 : lag_env;
-    if (!flush) {
-      rows_done[0] = step + 1;
-      valid[0] = P.TY[0] * (step + 1) < H ? P.TY[0] * (step + 1) : H;
-    }
-    bool progress = true;
-    while (progress && !overflow) {
-      progress = false;
-      for (int l = first > 1 ? first : 1; l < nb && !overflow; ++l) {
-        const Level& a = S.lv[l - 1];
-        const Level& b = S.lv[l];
-        int j = queued[l];
-        while (j < P.tiles_y[l]) {
-          int need = SS * (P.TY[l] * (j + 1) - 1 + RG) + SS / 2 + R + 1;
-          if (need > a.h) need = a.h;
-          if (need > valid[l - 1]) break;
-          ++j;
-        }
-        if (j > queued[l]) {
-          if (pt[l] == PQ) { overflow = true; break; }
-          pend[l][pt[l]++] = Pend{queued[l], j, l <= first || l == 1 ? 0 : last_emit_pos[l - 1] + lag_env};
-          queued[l] = j;
-        }
-        while (ph[l] < pt[l] && (flush || pend[l][ph[l]].ready_pos <= nitems)) {
-          const Pend q = pend[l][ph[l]++];
-          if (!emit(l, q.j0, q.j1)) { overflow = true; break; }
-          rows_done[l] = q.j1;
-          valid[l] = P.TY[l] * q.j1 < b.h ? P.TY[l] * q.j1 : b.h;
-          last_emit_pos[l] = nitems;
-          progress = true;
-        }
-      }
-    }
-    (void)lag;
-  }
-  for (int l = 1; l < nb; ++l) free(pend[l]);
-  if (overflow) return 2;                                    // caller falls back to the per-level kernels
-  for (int l = 0; l < nb; ++l)
-    if (rows_done[l] != P.tiles_y[l]) return fail(d, "mega schedule left level %d incomplete", l);
-  if (sync_all(d)) return fail(d, "stream synchronisation failed");
-  cudaFree(d->d_segs); d->d_segs = nullptr;
-  cudaFree(d->d_done); d->d_done = nullptr;
-  CU(cudaMalloc(&d->d_segs, sizeof(MegaSeg) * (nseg > 0 ? nseg : 1)));
-  if (nseg > 0) CU(cudaMemcpy(d->d_segs, segs, sizeof(MegaSeg) * nseg, cudaMemcpyHostToDevice));
-  int off = 0;
-  for (int l = 0; l < nb; ++l) { d->mega_done_off[l] = off; off += P.tiles_y[l]; }
-  d->mega_done_off[nb] = off;
-  CU(cudaMalloc(&d->d_done, sizeof(unsigned) * off));
-  CU(cudaMemset(d->d_done, 0, sizeof(unsigned) * off));
-  memset(d->mega_epoch, 0, sizeof(d->mega_epoch));
-  d->mega_nseg = nseg; d->mega_nitems = nitems;
-  memcpy(d->mega_key, key, sizeof(key));
-  return 0;
-}
-
-template <int SS, int R, int TX, int TY, bool EXACT>
-static int mega_launch_t(klt_dev* d, const MegaParams& MP) {
-  using MG = MegaGeo<SS, R, TX, TY>;
-  static bool attr_dev[64] = {};                 // function attributes are per device
-  bool& attr_set = attr_dev[d->device & 63];
-  static int cps = 0;
-  if (!attr_set) {
-    CU(cudaFuncSetAttribute(pyramid_mega_kernel<SS, R, TX, TY, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG::SMEM));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, pyramid_mega_kernel<SS, R, TX, TY, EXACT>, 288, MG::SMEM));
-    if (cps < 1) return fail(d, "pyramid_mega_kernel does not fit on an SM");
-    attr_set = true;
-  }
-  // the grid must be fully resident: CTAs wait on each other's tiles
-  const int cap = cps * d->num_sms;
-  const int items = MP.nitems0 + MP.nitems1;
-  const int grid = items < cap ? items : cap;
-  { Launch l(d, KID_MEGA);
-    pyramid_mega_kernel<SS, R, TX, TY, EXACT><<<grid, 288, MG::SMEM, d->stream>>>(MP); }
   return 0;
 }
 
@@ -2202,87 +1933,6 @@ static int feed_wait(klt_dev* d, BandFeed* f, bool all, int* rows) {
   return 0;
 }
 
-// all levels of one frame in one launch.  feed != nullptr: the frame is still on the host; its
-// bands are queued on the copy stream, each followed by a write of the device word the level-0
-// tiles wait on.  Returns 2 (nothing queued) if the frame has no schedule: the caller falls back.
-template <bool EXACT>
-static int mega_build(klt_dev* d, PyrSet& S, const FusedPlan& P, int nb, const TapsR& ts, const TapsR& tp,
-                      const TapsR& tg, const TapsR& td, BandFeed* feed, int first = 0) {
-  { const int rc = mega_schedule(d, P, S, nb, first); if (rc) return rc; }
-  MegaParams MP;
-  memset(&MP, 0, sizeof(MP));
-  for (int l = 0; l < nb; ++l) {
-    MP.map[l] = P.map[l];
-    MegaLevel& L = MP.lv[l];
-    L.W = S.lv[l].w; L.H = S.lv[l].h; L.pitch = S.lv[l].pitch;
-    L.img = S.lv[l].img; L.gx = S.lv[l].gx; L.gy = S.lv[l].gy;
-    L.tiles_x = P.tiles_x[l]; L.tiles_y = P.tiles_y[l];
-    L.done_off = d->mega_done_off[l];
-    if (l >= first) d->mega_epoch[l] += 1;
-    L.target = d->mega_epoch[l] * (unsigned)P.tiles_x[l];
-  }
-  MP.ready_below = first;
-  MP.nlev = nb; MP.nseg = d->mega_nseg;
-  MP.nitems0 = first == 0 ? P.tiles_x[0] * P.tiles_y[0] : 0; MP.nitems1 = d->mega_nitems;
-  MP.segs = d->d_segs;
-  MP.ctr = d->d_tile_ctr + 12;                   // three words, reset by the kernel itself
-  { static int every = getenv("KLT_B200_MEGA_COARSE_EVERY") ? atoi(getenv("KLT_B200_MEGA_COARSE_EVERY")) : 3;
-    MP.coarse_every = every < 1 ? 1 : every;
-    static int serial = getenv("KLT_B200_MEGA_SERIAL") ? atoi(getenv("KLT_B200_MEGA_SERIAL")) : 0;
-    MP.serial = serial; }
-  MP.done = d->d_done;
-  MP.u8_flag = d->d_u8_flag;
-  MP.ts = to_fused(ts); MP.tp = to_fused(tp); MP.tg = to_fused(tg); MP.td = to_fused(td);
-  if (feed) {
-    WriteValue32Fn wv = stream_write_value32();
-    d->feed_epoch += 1;
-    MP.u8_base = d->feed_epoch * 8192u;
-    bool flags_ok = wv != nullptr && feed->H < 8192;
-    if (d->frame_busy[d->frame_idx]) {          // the previous build's level-0 tiles may still read d->frame
-      CU(cudaStreamWaitEvent(d->cstream, d->ev_frame_free[d->frame_idx], 0));
-      d->frame_busy[d->frame_idx] = 0;
-    }
-    int r0 = 0;
-    for (int b = 0; b < feed->nbands; ++b) {
-      const int rows = feed->end_row[b] - r0;
-      unsigned char* dst = d->frame + (size_t)r0 * feed->fp;
-      const unsigned char* src = feed->host + (size_t)r0 * feed->W;
-      { Launch l(d, KID_COPY_H2D, d->cstream);
-        if (feed->fp == feed->W)
-          CU(cudaMemcpyAsync(dst, src, (size_t)rows * feed->W, cudaMemcpyHostToDevice, d->cstream));
-        else
-          CU(cudaMemcpy2DAsync(dst, feed->fp, src, feed->W, feed->W, rows, cudaMemcpyHostToDevice, d->cstream)); }
-      r0 = feed->end_row[b];
-      if (flags_ok && wv((CUstream)d->cstream, (CUdeviceptr)(uintptr_t)d->d_u8_flag, MP.u8_base + (unsigned)r0, 0) != CUDA_SUCCESS)
-        flags_ok = false;
-    }
-    if (flags_ok) {
-      MP.has_feed = 1;
-    } else {                      // no in-kernel flag: gate the whole launch on the end of the upload
-      cudaEvent_t ev = d->ev_band[d->band_ev_next];
-      d->band_ev_next = (d->band_ev_next + 1) % KLT_BAND_EVENTS;
-      CU(cudaEventRecord(ev, d->cstream));
-      CU(cudaStreamWaitEvent(d->stream, ev, 0));
-      MP.has_feed = 0;
-    }
-    d->last_bands = feed->nbands;
-  }
-  int rc;
-  switch (nb > 1 ? P.shape[nb - 1] : (int)SHAPE_2_5_64_16) {   // nb == 1: only level-0 tiles exist
-    case SHAPE_2_5_64_16: rc = mega_launch_t<2, 5, 64, 16, EXACT>(d, MP); break;
-    case SHAPE_4_10_32_16: rc = mega_launch_t<4, 10, 32, 16, EXACT>(d, MP); break;
-    default: return fail(d, "no mega kernel for this pyramid geometry");
-  }
-  if (rc) return rc;
-  if (feed) {
-    CU(cudaEventRecord(d->ev_frame_free[d->frame_idx], d->stream));
-    d->frame_busy[d->frame_idx] = 1;
-  }
-  return 0;
-}
-
-static int early_track_launch(klt_dev* d, int slot_cur, const int* valid_rows, int nb);   // (tracker section)
-
 template <bool EXACT>
 static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitch,
                       const klt_dev_build_desc* q, BandFeed* feed) {
@@ -2298,20 +1948,6 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
   FusedPlan P;
   d->last_fused = 0;
   d->last_bands = 0;
-  d->last_mega = 0;
-  d->last_stream = 0;
-  d->last_chain = 0;
-  // one launch for the whole pyramid when every level qualifies (klt_mega.cuh)
-  if (!d->no_mega && nb <= MEGA_MAX_LEVELS && (nb == 1 || mega_shape_for(q->subsampling, tp.w / 2) != SHAPE_NONE)) {
-    fused_plan(d, S, src, spitch, q, ts, tp, tg, td, &P, nb > 1 ? mega_shape_for(q->subsampling, tp.w / 2) : SHAPE_NONE, false);
-    bool ok = P.l0_ok;
-    for (int l = 1; l < nb; ++l) ok = ok && P.shape[l] != SHAPE_NONE;
-    if (ok) {
-      const int rc = mega_build<EXACT>(d, S, P, nb, ts, tp, tg, td, feed);
-      if (rc == 1) return 1;
-      if (rc == 0) { d->last_fused = nb; d->last_path = 1; d->last_mega = 1; return 0; }
-    }
-  }
   fused_plan(d, S, src, spitch, q, ts, tp, tg, td, &P, SHAPE_NONE);
   bool all_fused = P.l0_ok;
   for (int l = 1; l < nb; ++l) all_fused = all_fused && P.shape[l] != SHAPE_NONE;
@@ -2321,28 +1957,6 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
     // exist -- all at once for a resident frame, band by band behind the upload of a host frame
     int rows_done[KLT_DEV_MAX_LEVELS] = {0}, valid[KLT_DEV_MAX_LEVELS] = {0};
     const int SS = P.SS, R = P.R, RG = FUSED_RG;
-    // "tail" levels (small: a launch each would be all fixed latency, ~8 us) go into one
-    // pyramid_mega_kernel launch in tail mode: tiles of level l+1 start as soon as the tile rows of
-    // level l under them are complete
-    int nl = nb;                                   // levels built by the per-level kernels
-    FusedPlan PT;
-    if (d->mega_tail_from > 0 && nb > d->mega_tail_from + 1 && nb <= MEGA_MAX_LEVELS &&
-        mega_shape_for(q->subsampling, tp.w / 2) != SHAPE_NONE) {
-      fused_plan(d, S, src, spitch, q, ts, tp, tg, td, &PT, mega_shape_for(q->subsampling, tp.w / 2), false);
-      bool ok = true;
-      for (int l = d->mega_tail_from; l < nb; ++l) ok = ok && PT.shape[l] != SHAPE_NONE;
-      if (ok) nl = d->mega_tail_from;
-    }
-    // levels >= 1: one chained launch (uniform tile shape) or one launch per level
-    FusedPlan PC;
-    bool use_chain = false;
-    if (!d->no_chain && nl > 2 && nl - 1 <= CHAIN_MAX_LEVELS && mega_shape_for(q->subsampling, tp.w / 2) != SHAPE_NONE) {
-      fused_plan(d, S, src, spitch, q, ts, tp, tg, td, &PC, mega_shape_for(q->subsampling, tp.w / 2), false);
-      use_chain = true;
-      for (int l = 1; l < nl; ++l) use_chain = use_chain && PC.shape[l] != SHAPE_NONE;
-    }
-    const FusedPlan& PL = use_chain ? PC : P;
-    d->last_chain = use_chain ? 1 : 0;
     int u8_rows = feed ? 0 : H;
     if (feed && feed_enqueue_copies(d, feed)) return 1;
     do {
@@ -2357,48 +1971,30 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
       if (l0_fused_launch<EXACT>(d, P, W, H, ts, tg, td, S.lv[0], rows_done[0], j)) return 1;
       rows_done[0] = j;
       valid[0] = P.TY[0] * j < H ? P.TY[0] * j : H;
-      int jr0[KLT_DEV_MAX_LEVELS] = {0}, jr1[KLT_DEV_MAX_LEVELS] = {0};
-      for (int l = 1; l < nl; ++l) {
+      for (int l = 1; l < nb; ++l) {
         const Level& a = S.lv[l - 1];
         const Level& b = S.lv[l];
         j = rows_done[l];
-        while (j < PL.tiles_y[l]) {
-          int need = SS * (PL.TY[l] * (j + 1) - 1 + RG) + SS / 2 + R + 1;
+        while (j < P.tiles_y[l]) {
+          int need = SS * (P.TY[l] * (j + 1) - 1 + RG) + SS / 2 + R + 1;
           if (need > a.h) need = a.h;
           if (need > valid[l - 1]) break;
           ++j;
         }
-        jr0[l] = rows_done[l]; jr1[l] = j;
-        if (!use_chain && level_fused_launch<EXACT>(d, PL, l, a, b, tp, tg, td, rows_done[l], j)) return 1;
+        if (level_fused_launch<EXACT>(d, P, l, a, b, tp, tg, td, rows_done[l], j)) return 1;
         rows_done[l] = j;
-        valid[l] = PL.TY[l] * j < b.h ? PL.TY[l] * j : b.h;
-      }
-      if (use_chain && levels_chain_launch<EXACT>(d, PL, S, 1, nl, tp, tg, td, jr0, jr1)) return 1;
-      if (feed && feed->next == 1 && feed->nbands >= 2 && nl == nb) {
-        if (early_track_launch(d, d->building_slot, valid, nb)) return 1;
+        valid[l] = P.TY[l] * j < b.h ? P.TY[l] * j : b.h;
       }
     } while (u8_rows < H);
-    if (nl < nb) {
-      const int rc = mega_build<EXACT>(d, S, PT, nb, ts, tp, tg, td, nullptr, nl);
-      if (rc == 1) return 1;
-      if (rc == 2) {                               // no schedule: per-level kernels after all
-        for (int l = nl; l < nb; ++l)
-          if (level_fused_launch<EXACT>(d, P, l, S.lv[l - 1], S.lv[l], tp, tg, td, 0, P.tiles_y[l])) return 1;
-      } else {
-        d->last_mega = 2;
-      }
-      for (int l = nl; l < nb; ++l) rows_done[l] = P.tiles_y[l];
-    }
     if (feed) {
       d->last_bands = feed->nbands;
       CU(cudaEventRecord(d->ev_frame_free[d->frame_idx], d->stream));
       d->frame_busy[d->frame_idx] = 1;
     }
     for (int l = 0; l < nb; ++l)
-      if (rows_done[l] != (l == 0 || l >= nl ? P.tiles_y[l] : PL.tiles_y[l])) return fail(d, "banded build left level %d incomplete", l);
+      if (rows_done[l] != P.tiles_y[l]) return fail(d, "banded build left level %d incomplete", l);
     d->last_fused = nb;
     d->last_path = 1;
-    d->last_stream = P.l0_stream ? 1 : 0;
     return 0;
   }
 
@@ -2413,7 +2009,6 @@ static int build_impl(klt_dev* d, PyrSet& S, const unsigned char* src, int spitc
   if (P.l0_ok) {
     if (l0_fused_launch<EXACT>(d, P, W, H, ts, tg, td, S.lv[0], 0, P.tiles_y[0])) return 1;
     grad_from = 1;
-    d->last_stream = P.l0_stream ? 1 : 0;
   }
   d->last_fused = grad_from;
   if (grad_from == 1) {
@@ -2766,29 +2361,13 @@ static bool launch_track_fast(klt_dev* d, const PyrView& v1, const PyrView& v2, 
     case 5: launch_track_fast_t<5, 1>(d, v1, v2, a, n); return true;
     case 7:
       if (d->track7_off) { launch_track_fast_t<7, 1>(d, v1, v2, a, n); return true; }
-      if (!d->no_track7w && !d->no_track7v) {                // one warp per feature, one 128-bit load per lane and image
-        Launch l(d, KID_TRACK7V, d->tstream);
-        launch_k(track7v_kernel, dim3((n + 3) / 4), dim3(128), 0, d->tstream, d->pdl != 0 && !d->overlap, v1, v2, a, n,
-                 feat_io(d), d->d_live);
-        return true;
-      }
       if (!d->no_track7w) {                                  // one warp per feature, scalar loads
         Launch l(d, KID_TRACK7W, d->tstream);
         launch_k(track7w_kernel, dim3((n + 3) / 4), dim3(128), 0, d->tstream, d->pdl != 0 && !d->overlap, v1, v2, a, n,
                  feat_io(d), d->d_live);
         return true;
       }
-      { Launch l(d, KID_TRACK7, d->tstream);
-        static int fpw = getenv("KLT_TRACK_FPW") ? atoi(getenv("KLT_TRACK_FPW")) : 4;
-        const int warps_per_block = 4;
-        if (fpw == 1)
-          track7_kernel<1><<<(n + warps_per_block - 1) / warps_per_block, 128, 0, d->tstream>>>(v1, v2, a, n, feat_io(d), d->d_live);
-        else if (fpw == 4)
-          launch_k(track7_kernel<4>, dim3((n + 4 * warps_per_block - 1) / (4 * warps_per_block)), dim3(128), 0, d->tstream,
-                   d->pdl != 0 && !d->overlap, v1, v2, a, n, feat_io(d), d->d_live);
-        else
-          track7_kernel<2><<<(n + 2 * warps_per_block - 1) / (2 * warps_per_block), 128, 0, d->tstream>>>(v1, v2, a, n, feat_io(d), d->d_live);
-      }
+      launch_track_fast_t<7, 1>(d, v1, v2, a, n);
       return true;
     case 9: launch_track_fast_t<9, 2>(d, v1, v2, a, n); return true;
     case 11: launch_track_fast_t<11, 2>(d, v1, v2, a, n); return true;
@@ -2806,62 +2385,9 @@ static void fill_track_args(const klt_dev* d, const klt_dev_track_params* p, Tra
   a->max_residue = p->max_residue; a->borderx = p->borderx; a->bordery = p->bordery;
   a->ncols = d->W; a->nrows = d->H;
   a->lighting = p->lighting_insensitive ? 1 : 0;
-  { static int pf = getenv("KLT_TRACK_PREFETCH") ? atoi(getenv("KLT_TRACK_PREFETCH")) : 0; a->prefetch = pf; }
   { static int keep = getenv("KLT_TRACK_L2_KEEP") ? atoi(getenv("KLT_TRACK_L2_KEEP")) : 1; a->l2_keep = keep; }
 }
-// can this call be served by track7_kernel (the only tracker with the two-pass mode)?
-static bool track7_applies(const klt_dev* d, const klt_dev_track_params* p) {
-  return !p->exact && !p->lighting_insensitive && !d->force_generic && !d->track7_off && !d->overlap &&
-         p->window_width == 7 && p->window_height == 7;
-}
-static int launch_track7(klt_dev* d, const PyrView& v1, const PyrView& v2, const TrackArgs& a, int n) {
-  Launch l(d, KID_TRACK7, d->tstream);
-  const int warps_per_block = 4;
-  CU(launch_k(track7_kernel<4>, dim3((n + 4 * warps_per_block - 1) / (4 * warps_per_block)), dim3(128), 0, d->tstream,
-              d->pdl != 0 && !d->overlap, v1, v2, a, n, feat_io(d), d->d_live));
-  return 0;
-}
-
-// The synchronous API arms this before klt_dev_build: if the frame then goes up in bands and
-// track7_kernel applies, the tracker's first pass is launched right behind the first band's
-// pyramid rows -- while the second band is still on the bus and the GPU would be idle -- and the
-// later klt_dev_track_resident only finishes the features that pass had to defer.
-extern "C" void klt_dev_disable_early_track(klt_dev* d, int on) { d->no_early = on; }
 extern "C" void klt_dev_disable_track7w(klt_dev* d, int on) { d->no_track7w = on; }
-extern "C" void klt_dev_disable_track7v(klt_dev* d, int on) { d->no_track7v = on; }
-extern "C" int klt_dev_last_track_passes(const klt_dev* d) { return d->last_passes; }
-extern "C" int klt_dev_arm_early_track(klt_dev* d, int slot_prev, const klt_dev_track_params* p) {
-  d->early_armed = 0; d->early_done = 0;
-  if (!p || d->no_early || !track7_applies(d, p) || !klt_dev_slot_valid(d, slot_prev) || d->feat_n <= 0) return 0;
-  d->early_armed = 1; d->early_slot_prev = slot_prev; d->early_p = *p;
-  return 0;
-}
-static int early_track_launch(klt_dev* d, int slot_cur, const int* valid_rows, int nb) {
-  if (!d->early_armed || nb != d->L) return 0;
-  d->early_armed = 0;
-  const int n = d->feat_n;
-  if (d->fdone_cap < n) {
-    CU(cudaStreamSynchronize(d->stream));
-    cudaFree(d->d_fdone); d->d_fdone = nullptr; d->fdone_cap = 0;
-    CU(cudaMalloc(&d->d_fdone, (size_t)n));
-    d->fdone_cap = n;
-  }
-  if (d->feat_pending) {
-    CU(cudaStreamWaitEvent(d->tstream, d->ev_feat, 0));
-    d->feat_pending = 0;
-  }
-  PyrView v1, v2;
-  make_view(d->set[d->early_slot_prev], d->L, &v1);
-  make_view(d->set[slot_cur], d->L, &v2);
-  TrackArgs a;
-  fill_track_args(d, &d->early_p, &a);
-  a.pass = 1; a.done = d->d_fdone;
-  for (int l = 0; l < nb; ++l) a.row_limit[l] = valid_rows[l];
-  if (launch_track7(d, v1, v2, a, n)) return 1;
-  d->early_done = 1; d->early_slot_cur = slot_cur;
-  return 0;
-}
-
 extern "C" int klt_dev_track_resident(klt_dev* d, int slot_prev, int slot_cur,
                                       const klt_dev_track_params* p) {
   CU(cudaSetDevice(d->device));
@@ -2888,18 +2414,6 @@ extern "C" int klt_dev_track_resident(klt_dev* d, int slot_prev, int slot_cur,
   make_view(d->set[slot_cur], d->L, &v2);
   TrackArgs a;
   fill_track_args(d, p, &a);
-  if (d->early_done) {                               // pass 1 ran behind the first band: finish the deferred ones
-    const bool same = d->early_slot_prev == slot_prev && d->early_slot_cur == slot_cur && track7_applies(d, p);
-    d->early_done = 0;
-    if (!same) return fail(d, "early tracker pass does not match this call");
-    a.pass = 2; a.done = d->d_fdone;
-    if (launch_track7(d, v1, v2, a, n)) return 1;
-    CU(cudaGetLastError());
-    d->last_passes = 2;
-    return 0;
-  }
-  d->early_armed = 0;
-  d->last_passes = 1;
   const int npix = a.ww * a.wh;
   const int ppl = (npix + 31) / 32;
   int rc;
@@ -2969,7 +2483,6 @@ extern "C" int klt_dev_affine_begin(klt_dev* d, int n, const klt_dev_affine_para
   }
   if (d->feat_out_host == 2) return fail(d, "affine_begin: record-mode features (use the staging area)");
   d->feat_out_host = 0;                              // the check needs the tracker's answers on the device
-  d->early_armed = 0;
   if (d->feat_pending) {
     CU(cudaStreamWaitEvent(d->tstream, d->ev_feat, 0));
     d->feat_pending = 0;

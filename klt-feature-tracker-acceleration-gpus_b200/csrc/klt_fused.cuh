@@ -616,96 +616,3 @@ level_fused_kernel(const __grid_constant__ CUtensorMap map, int Wsrc, int Hsrc, 
   pdl_launch_dependents();            // queue empty: the next kernel of the chain may move in
 }
 
-// ============================================================================================
-// levels >= 1 in ONE launch: levels_chain_kernel
-// ============================================================================================
-// The coarse levels are small: launched one kernel per level they are all fixed latency (cold
-// instruction cache, descriptor fetch, a one-tile-deep pipeline per CTA: ~8 us each at 4K for
-// 0.5 M and 0.13 M pixels).  Here one persistent grid walks the levels in order -- the same tile
-// code and tile queue per level as level_fused_kernel, one tile shape for all levels -- with a
-// grid-wide barrier between levels (all CTAs are resident: an atomic counter and a spin).
-static constexpr int CHAIN_MAX_LEVELS = 8;
-struct ChainLevel {
-  int Wsrc, Hsrc, W, H, tiles_x, tile0, ntiles;        // this launch covers tiles [tile0, ntiles)
-  unsigned base;                                       // queue base of this level's counter
-  float *img, *gx, *gy; int pitch;
-};
-struct ChainParams {
-  CUtensorMap map[CHAIN_MAX_LEVELS];                   // source (previous level) of each chained level
-  ChainLevel lv[CHAIN_MAX_LEVELS];
-  int nlev;
-  unsigned* counters;                                  // one tile counter per chained level
-  unsigned* barrier; unsigned barrier_base;            // monotonic grid-barrier counter
-  TapsF tp, tg, td;
-};
-
-template <int SS, int R, int TX, int TY, bool EXACT>
-__global__ void __launch_bounds__(256, (LvGeo<SS, R, TX, TY>::SMEM <= 58 * 1024) ? 3 : 2)
-levels_chain_kernel(const __grid_constant__ ChainParams P) {
-  using G = LvGeo<SS, R, TX, TY>;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + G::OFF_BAR);
-  volatile int* s_next = reinterpret_cast<volatile int*>(smem_raw + G::OFF_BAR + 8);
-  const int tid = threadIdx.x;
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(&P.map[0])) : "memory");
-  }
-  pdl_wait();                         // the first source level is written by the previous kernel
-  unsigned phase = 0;
-  for (int li = 0; li < P.nlev; ++li) {
-    const ChainLevel& L = P.lv[li];
-    const CUtensorMap* map = &P.map[li];
-    unsigned* counter = P.counters + li;
-    if (tid == 0) {
-      const int t = L.tile0 + (int)(atomicAdd(counter, 1u) - L.base);
-      *s_next = t;
-      if (t < L.ntiles) {
-        asm volatile("fence.proxy.async;" ::: "memory");      // other CTAs' stores (previous level) -> TMA reads
-        mbar_expect_tx(bar, G::SW * G::SH * 4);
-        tma_load_2d(smem_raw + G::OFF_SRC, map, SS * (t % L.tiles_x) * TX + G::XOFF,
-                    SS * (t / L.tiles_x) * TY + G::YOFF, bar);
-      }
-    }
-    __syncthreads();
-    int tile = *s_next;
-    while (tile < L.ntiles) {
-      const int x0 = (tile % L.tiles_x) * TX, y0 = (tile / L.tiles_x) * TY;
-      const bool border = (x0 < 8) || (y0 < 8) || (x0 + TX + 16 > L.W) || (y0 + TY + 16 > L.H);
-      mbar_wait(bar, phase);
-      phase ^= 1;
-      if (border) lv_stage_p1<EXACT, true, SS, R, TX, TY>(smem_raw, P.tp, x0, L.Wsrc);
-      else lv_stage_p1<EXACT, false, SS, R, TX, TY>(smem_raw, P.tp, x0, L.Wsrc);
-      __syncthreads();                 // source box consumed; everybody has read s_next
-      if (tid == 0) {
-        const int t = L.tile0 + (int)(atomicAdd(counter, 1u) - L.base);
-        *s_next = t;
-        if (t < L.ntiles) {
-          mbar_expect_tx(bar, G::SW * G::SH * 4);
-          tma_load_2d(smem_raw + G::OFF_SRC, map, SS * (t % L.tiles_x) * TX + G::XOFF,
-                      SS * (t / L.tiles_x) * TY + G::YOFF, bar);
-        }
-      }
-      if (border)
-        lv_stage_rest<EXACT, true, SS, R, TX, TY>(smem_raw, P.tp, P.tg, P.td, L.Hsrc, L.W, L.H, L.img, L.gx, L.gy, L.pitch, x0, y0);
-      else
-        lv_stage_rest<EXACT, false, SS, R, TX, TY>(smem_raw, P.tp, P.tg, P.td, L.Hsrc, L.W, L.H, L.img, L.gx, L.gy, L.pitch, x0, y0);
-      __syncthreads();                 // Hp / L / Hd / Hg free for the next tile
-      tile = *s_next;
-    }
-    if (li + 1 < P.nlev) {
-      // grid barrier: every tile of this level is stored before anybody loads the next level
-      __syncthreads();
-      if (tid == 0) {
-        __threadfence();
-        atomicAdd(P.barrier, 1u);
-        const unsigned target = P.barrier_base + (unsigned)(li + 1) * gridDim.x;
-        unsigned ns = 32;
-        while ((int)(ld_acquire_u32(P.barrier) - target) < 0) { __nanosleep(ns); if (ns < 256) ns <<= 1; }
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(&P.map[li + 1])) : "memory");
-      }
-      __syncthreads();
-    }
-  }
-  pdl_launch_dependents();
-}

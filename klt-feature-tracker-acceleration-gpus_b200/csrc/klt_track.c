@@ -231,8 +231,7 @@ static void track_common(KLT_TrackingContext tc, const KLT_PixelType *img1,
   static double acc[5]; static int calls;
   double t0 = timing ? now_us() : 0, t1 = 0, t2 = 0, t3 = 0;
   /* The frame upload is the long pole.  With a pinned feature list nothing has to be packed:
-   * queue the one-copy mirror of the records, arm the tracker's early pass (it runs behind the
-   * first uploaded band), then queue the frame and the pyramid kernels.  An ordinary list is
+   * queue the one-copy mirror of the records, then queue the frame and the pyramid kernels.  An ordinary list is
    * packed into the staging area first (a few microseconds) for the same order on the copy stream. */
   slot_prev = prepare_previous(tc, s, img1, on_device, pitch, ncols, nrows);
   slot_cur = (slot_prev + 1) % KLT_DEV_SLOTS;
@@ -252,8 +251,6 @@ static void track_common(KLT_TrackingContext tc, const KLT_PixelType *img1,
     was_live = (unsigned char *)malloc((size_t)n);
     if (was_live == NULL) KLTError("(KLTTrackFeatures) Out of memory");
     for (i = 0; i < n; i++) was_live[i] = fl->feature[i]->val >= 0;
-  } else if (!on_device) {
-    DEVCALL(s, klt_dev_arm_early_track(dev, slot_prev, &tp));
   }
   klt_fill_build_desc(tc, ncols, nrows, tc->nPyramidLevels, 1, s->exact, &q);
   DEVCALL(s, klt_dev_build(dev, slot_cur, img2, on_device, pitch, &q));

@@ -65,9 +65,6 @@ DEV_API = {
     "klt_dev_track": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(TrackParams), C.c_int, _f32p, _f32p, _i32p]),
     "klt_dev_features_upload": (C.c_int, [C.c_void_p, C.c_int, _f32p, _f32p, _i32p]),
     "klt_dev_track_resident": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(TrackParams)]),
-    "klt_dev_arm_early_track": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(TrackParams)]),
-    "klt_dev_disable_early_track": (None, [C.c_void_p, C.c_int]),
-    "klt_dev_last_track_passes": (C.c_int, [C.c_void_p]),
     "klt_dev_disable_track7w": (None, [C.c_void_p, C.c_int]),
     "klt_dev_features_download": (C.c_int, [C.c_void_p, C.c_int, _f32p, _f32p, _i32p]),
     "klt_dev_features_staging": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.POINTER(C.c_float)),
@@ -93,14 +90,6 @@ DEV_API = {
     "klt_dev_last_build_bands": (C.c_int, [C.c_void_p]),
     "klt_dev_set_stage_threads": (None, [C.c_void_p, C.c_int]),
     "klt_dev_last_build_staged": (C.c_int, [C.c_void_p]),
-    "klt_dev_last_build_mega": (C.c_int, [C.c_void_p]),
-    "klt_dev_disable_mega": (None, [C.c_void_p, C.c_int]),
-    "klt_dev_disable_track7v": (None, [C.c_void_p, C.c_int]),
-    "klt_dev_set_mega_tail": (None, [C.c_void_p, C.c_int]),
-    "klt_dev_disable_stream": (None, [C.c_void_p, C.c_int]),
-    "klt_dev_disable_chain": (None, [C.c_void_p, C.c_int]),
-    "klt_dev_last_build_chain": (C.c_int, [C.c_void_p]),
-    "klt_dev_last_build_stream": (C.c_int, [C.c_void_p]),
     "klt_dev_timer_start": (C.c_int, [C.c_void_p]),
     "klt_dev_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "klt_dev_profile_begin": (C.c_int, [C.c_void_p]),

@@ -229,19 +229,17 @@ def test_track_7x7_generic_fast_kernel(L, capi, oracle, oracle_mod, provided):
     assert rep[-1][3] > 80
 
 
-@pytest.mark.parametrize("kernel", ["track7v", "track7w", "track7"])
+@pytest.mark.parametrize("kernel", ["track7w", "track_fast"])
 def test_track_7x7_kernel_generations(L, capi, oracle, oracle_mod, kernel):
-    """the three 7x7 fma trackers (one 128-bit load per lane and image: default; scalar loads;
-    8 lanes per feature) against the oracle, teacher-forced, 4 levels, on frames whose footprints
-    take every alignment"""
+    """the two 7x7 fma trackers (one warp per feature: default; 8 lanes per feature) against the
+    oracle, teacher-forced, 4 levels, on frames whose footprints take every alignment"""
     imgs = [synth_image(640, 480, seed=5, shift=(1.9 * t, -1.3 * t)) for t in range(5)]
 
     def setup(tc):
         tc.contents.nPyramidLevels, tc.contents.subsampling = 4, 2
         L.KLTUpdateTCBorder(tc)
         dev = L.KLTB200Device(tc)
-        L.klt_dev_disable_track7v(dev, 0 if kernel == "track7v" else 1)
-        L.klt_dev_disable_track7w(dev, 1 if kernel == "track7" else 0)
+        L.klt_dev_disable_track7w(dev, 0 if kernel == "track7w" else 1)
 
     rep = _teacher_forced(L, capi, oracle, oracle_mod, imgs, 400, 0, tc_setup=setup)
     assert rep[-1][3] > 250
@@ -297,39 +295,6 @@ def test_lighting_insensitive_tracking(L, capi, oracle, oracle_mod, provided, ex
         tc.contents.window_width = tc.contents.window_height = window
     rep2 = _teacher_forced(L, capi, oracle, oracle_mod, imgs, 150, exact, plain)
     assert rep != rep2
-
-
-@pytest.mark.parametrize("band_rows", [64, 192, 320])
-def test_two_pass_tracking_behind_banded_upload(L, capi, band_rows):
-    """With a banded frame upload the 7x7 tracker's first pass runs behind the first band and defers
-    every feature whose footprint would touch a row that is not built yet; the second pass finishes
-    them.  The result must equal single-pass tracking bit for bit, whatever the band size."""
-    imgs = [synth_image(900, 700, seed=21, shift=(2.3 * t, -1.4 * t)) for t in range(4)]
-    res = []
-    for early in (1, 0):
-        tc = L.KLTCreateTrackingContext()
-        tc.contents.sequentialMode = 1
-        tc.contents.nPyramidLevels, tc.contents.subsampling = 4, 2
-        L.KLTUpdateTCBorder(tc)
-        dev = L.KLTB200Device(tc)
-        L.klt_dev_set_band_rows(dev, band_rows)
-        L.klt_dev_disable_early_track(dev, 1 - early)
-        L.klt_dev_disable_track7w(dev, 1)             # the two-pass mode lives in track7_kernel
-        fl = L.KLTCreateFeatureList(700)
-        L.select(tc, imgs[0], fl)
-        out = []
-        for k in range(1, 4):
-            L.track(tc, imgs[k - 1], imgs[k], fl)
-            if k > 1:                                    # (the first call also builds frame 0's pyramid)
-                assert L.klt_dev_last_track_passes(dev) == (2 if early else 1)
-            out.append(_get(capi, fl))
-        res.append(out)
-        L.KLTFreeFeatureList(fl)
-        L.KLTFreeTrackingContext(tc)
-    for a, b in zip(res[0], res[1]):
-        for u, v in zip(a, b):
-            assert u.tobytes() == v.tobytes()
-    assert (res[0][-1][2] >= 0).sum() > 300
 
 
 # ---- edge cases ---------------------------------------------------------------------------------

@@ -181,16 +181,13 @@ def test_eigenvalue_map_is_integer_exact(L, oracle, provided, shape, window, ski
 
 
 # ---- banded upload: host frames are copied in bands, kernels follow tile row by tile row -------
-@pytest.mark.parametrize("mega", [1, 0])
 @pytest.mark.parametrize("band_rows", [64, 128, 192, 0])
 @pytest.mark.parametrize("cfg", [(4, 2, (700, 900)), (2, 4, (480, 640)), (3, 2, (333, 517)), (4, 2, (64, 200)),
-                                 (1, 2, (300, 400))])
-def test_banded_build_matches_oracle(L, oracle, band_rows, cfg, mega):
-    """klt_dev_build with a host frame uploads it in bands on the copy stream.  mega = 1: one
-    pyramid_mega_kernel launch whose level-0 tiles wait for the band flag and whose coarser tiles
-    wait for the tile rows below them; mega = 0: the per-level fused kernels launched over the
-    tile rows each band completes.  Whatever the band size, the pyramids are bit-identical to
-    the oracle in exact mode (same tile code, different schedule)."""
+                                 (1, 2, (300, 400)), (5, 2, (1000, 777)), (3, 4, (600, 800))])
+def test_banded_build_matches_oracle(L, oracle, band_rows, cfg):
+    """klt_dev_build with a host frame uploads it in bands on the copy stream; the per-level fused
+    kernels are launched over the tile rows each band completes.  Whatever the band size, the
+    pyramids are bit-identical to the oracle in exact mode (same tile code, different schedule)."""
     nlev, ss, (h, w) = cfg
     img = synth_image(w, h, seed=17 * h + w)
     tc = L.KLTCreateTrackingContext()
@@ -198,10 +195,7 @@ def test_banded_build_matches_oracle(L, oracle, band_rows, cfg, mega):
     L.KLTUpdateTCBorder(tc)
     dev = L.KLTB200Device(tc)
     L.klt_dev_set_band_rows(dev, band_rows)
-    L.klt_dev_disable_mega(dev, 1 - mega)
-    L.klt_dev_set_mega_tail(dev, 0)
     _check_build(L, oracle, img, tc, exact=1, generic=0, expect_tiled=True, expect_fused=True)
-    assert L.klt_dev_last_build_mega(dev) == mega
     expect = 1 if band_rows == 0 else -(-h // band_rows)
     got = L.klt_dev_last_build_bands(dev)
     if band_rows < 0:
@@ -212,9 +206,7 @@ def test_banded_build_matches_oracle(L, oracle, band_rows, cfg, mega):
     L.dev_build(dev, 0, img, q)
     a = device_pyramids(L, dev, 0, nlev)
     L.klt_dev_set_band_rows(dev, 0)
-    L.klt_dev_disable_mega(dev, mega)              # ... and the other scheduler
     L.dev_build(dev, 1, img, q)
-    assert L.klt_dev_last_build_mega(dev) == 1 - mega
     b = device_pyramids(L, dev, 1, nlev)
     for which in range(3):
         for l in range(nlev):
@@ -222,139 +214,23 @@ def test_banded_build_matches_oracle(L, oracle, band_rows, cfg, mega):
     L.KLTFreeTrackingContext(tc)
 
 
-@pytest.mark.parametrize("tail_from", [1, 2, 3])
-@pytest.mark.parametrize("band_rows", [0, 64])
-@pytest.mark.parametrize("cfg", [(4, 2, (700, 900)), (5, 2, (1000, 777)), (3, 4, (600, 800)), (4, 2, (2160, 3840))])
-def test_tail_levels_in_one_launch(L, oracle, cfg, band_rows, tail_from):
-    """Default build path: per-level fused kernels for the big levels, ONE pyramid_mega_kernel launch
-    (tail mode) for the levels >= tail_from; bit-identical to the oracle in exact mode."""
-    nlev, ss, (h, w) = cfg
-    img = synth_image(w, h, seed=5 * h + w)
-    tc = L.KLTCreateTrackingContext()
-    tc.contents.nPyramidLevels, tc.contents.subsampling = nlev, ss
-    L.KLTUpdateTCBorder(tc)
-    dev = L.KLTB200Device(tc)
-    L.klt_dev_set_band_rows(dev, band_rows)
-    L.klt_dev_disable_mega(dev, 1)
-    L.klt_dev_set_mega_tail(dev, tail_from)
-    for rep in range(2):                              # second build: counters carry over
-        _check_build(L, oracle, img, tc, exact=1, generic=0, expect_tiled=True, expect_fused=True)
-        assert L.klt_dev_last_build_mega(dev) == (2 if nlev > tail_from + 1 else 0)
-    L.KLTFreeTrackingContext(tc)
-
-
-def test_mega_repeated_frames_and_level_counts(L, oracle):
-    """The mega kernel's completion counters are never reset (targets advance per level and per
-    frame): alternate full-pyramid builds and level-0-only builds (selection) of different frames
-    on one context and check every result against the oracle."""
+def test_repeated_frames_and_level_counts(L, oracle):
+    """The tile queues of the persistent kernels are never reset (each launch advances its queue
+    base): alternate full-pyramid builds and level-0-only builds (selection) of different frames
+    on one context, with different band schedules, and check every result against the oracle."""
     h, w = 521, 777
     tc = L.KLTCreateTrackingContext()
     tc.contents.nPyramidLevels, tc.contents.subsampling = 3, 2
     L.KLTUpdateTCBorder(tc)
     dev = L.KLTB200Device(tc)
-    L.klt_dev_disable_mega(dev, 0)
     p = params_from_tc(oracle, tc)
     for it, nb in enumerate([3, 1, 3, 3, 1, 1, 3]):
         img = synth_image(w, h, seed=100 + it)
         q = L.build_desc(tc, w, h, nlevels_built=nb, exact=1)
         L.klt_dev_set_band_rows(dev, [0, 64, 128][it % 3])
         L.dev_build(dev, it % 3, img, q)
-        assert L.klt_dev_last_build_mega(dev) == 1
         want = oracle.build_pyramids(img, p)
         for which in range(3):
             for l in range(nb):
                 assert np.array_equal(L.dev_level(dev, it % 3, which, l), want.level(which, l)), (it, which, l)
-    L.KLTFreeTrackingContext(tc)
-
-
-# ---- streaming level-0 kernel (opt-in) == tile kernel, bit for bit ---------------------------------
-@pytest.mark.parametrize("exact", [1, 0])
-@pytest.mark.parametrize("band_rows", [0, 128])
-@pytest.mark.parametrize("shape", [(240, 320), (243, 321), (37, 1000), (600, 33), (130, 257), (64, 64), (700, 900),
-                                   (1080, 1920), (67, 112), (68, 113), (8, 16)])
-def test_stream_level0_equals_tile_kernel(L, oracle, shape, band_rows, exact):
-    """l0_stream_kernel (one warp per 128-column strip marching down the rows, rings in registers)
-    applies the taps in the same order as l0_fused_kernel: identical bits in both arithmetic
-    modes, for any strip / segment / band partition; exact mode also equals the oracle."""
-    h, w = shape
-    img = synth_image(w, h, seed=3 * h + w)
-    tc = L.KLTCreateTrackingContext()
-    tc.contents.nPyramidLevels, tc.contents.subsampling = 2, 2
-    L.KLTUpdateTCBorder(tc)
-    dev = L.KLTB200Device(tc)
-    L.klt_dev_set_band_rows(dev, band_rows)
-    q = L.build_desc(tc, w, h, exact=exact)
-    got = []
-    for stream in (1, 0):
-        L.klt_dev_disable_stream(dev, 1 - stream)
-        L.dev_build(dev, stream, img, q)
-        assert L.klt_dev_last_build_stream(dev) == stream
-        got.append(device_pyramids(L, dev, stream, 2))
-    for which in range(3):
-        for l in range(2):
-            assert np.array_equal(got[0][which][l], got[1][which][l]), (which, l)
-    if exact:
-        want = oracle.build_pyramids(img, params_from_tc(oracle, tc))
-        for which in range(3):
-            assert np.array_equal(got[0][which][0], want.level(which, 0))
-    L.KLTFreeTrackingContext(tc)
-
-
-# ---- levels >= 1 in one launch (levels_chain_kernel) == one launch per level ------------------------
-@pytest.mark.parametrize("exact", [1, 0])
-@pytest.mark.parametrize("band_rows", [0, 64, 192])
-@pytest.mark.parametrize("cfg", [(4, 2, (700, 900)), (5, 2, (1000, 777)), (3, 4, (600, 800)), (3, 2, (130, 257)),
-                                 (6, 2, (1080, 1920))])
-def test_levels_chain_equals_per_level_kernels(L, oracle, cfg, band_rows, exact):
-    """levels_chain_kernel walks the coarse levels inside one persistent launch (grid barrier between
-    levels); its pyramids equal the per-level kernels' bit for bit in both arithmetic modes, for whole
-    frames and for banded uploads, and repeated builds keep the barrier / queue counters consistent."""
-    nlev, ss, (h, w) = cfg
-    tc = L.KLTCreateTrackingContext()
-    tc.contents.nPyramidLevels, tc.contents.subsampling = nlev, ss
-    L.KLTUpdateTCBorder(tc)
-    dev = L.KLTB200Device(tc)
-    L.klt_dev_set_band_rows(dev, band_rows)
-    q = L.build_desc(tc, w, h, exact=exact)
-    for rep in range(3):
-        img = synth_image(w, h, seed=7 * h + w + rep)
-        got = []
-        for chain in (1, 0):
-            L.klt_dev_disable_chain(dev, 1 - chain)
-            L.dev_build(dev, chain, img, q)
-            assert L.klt_dev_last_build_chain(dev) == chain
-            got.append(device_pyramids(L, dev, chain, nlev))
-        for which in range(3):
-            for l in range(nlev):
-                assert np.array_equal(got[0][which][l], got[1][which][l]), (rep, which, l)
-    if exact:
-        want = oracle.build_pyramids(img, params_from_tc(oracle, tc))
-        for which in range(3):
-            for l in range(nlev):
-                assert np.array_equal(got[0][which][l], want.level(which, l))
-    L.KLTFreeTrackingContext(tc)
-
-
-def test_pageable_frame_staging_matches(L, oracle):
-    """A pageable host frame of >= 1 MB is copied into pinned staging by a few host threads, chunk
-    by chunk ahead of the DMA; the pyramids are the same as with cudaMemcpyAsync's own staging."""
-    h, w = 1000, 1300
-    img = synth_image(w, h, seed=99)
-    tc = L.KLTCreateTrackingContext()
-    tc.contents.nPyramidLevels, tc.contents.subsampling = 3, 2
-    L.KLTUpdateTCBorder(tc)
-    dev = L.KLTB200Device(tc)
-    q = L.build_desc(tc, w, h, exact=1)
-    got = []
-    for threads, bands in ((4, 256), (1, 0), (0, 256)):
-        L.klt_dev_set_stage_threads(dev, threads)
-        L.klt_dev_set_band_rows(dev, bands)
-        L.dev_build(dev, 0, img, q)
-        assert L.klt_dev_last_build_staged(dev) == (1 if threads > 0 else 0)
-        got.append(device_pyramids(L, dev, 0, 3))
-    want = oracle.build_pyramids(img, params_from_tc(oracle, tc))
-    for g in got:
-        for which in range(3):
-            for l in range(3):
-                assert np.array_equal(g[which][l], want.level(which, l))
     L.KLTFreeTrackingContext(tc)
