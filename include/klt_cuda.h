@@ -101,6 +101,13 @@ void *klt_dev_stream(const klt_dev *d);                  /* the cudaStream_t all
 int klt_dev_build(klt_dev *d, int slot, const unsigned char *img,
                   int img_is_device, size_t img_pitch,
                   const klt_dev_build_desc *desc);
+/* Selection keys are truncated integers: a replacement that reuses the level-0 gradients of a
+ * slot built in fma arithmetic could rank differently from the reference
+ * (src/V1/selectGoodFeatures.c:342-348, :421).  Returns in *slot_out a slot whose level 0 is in
+ * exact arithmetic: `slot` itself when it was built that way, else level 0 is rebuilt (exact,
+ * same taps) from the u8 frame still on the device into the slot the next frame overwrites.
+ * A caller-owned device frame must still be valid. */
+int klt_dev_exact_level0(klt_dev *d, int slot, int *slot_out);
 int klt_dev_slot_valid(const klt_dev *d, int slot);      /* 1 if slot holds a full pyramid set */
 void klt_dev_invalidate(klt_dev *d, int slot);           /* slot < 0: both */
 int klt_dev_geometry(const klt_dev *d, int *ncols, int *nrows, int *nlevels, int *subsampling);

@@ -211,8 +211,29 @@ def _libc_free(p):
 
 
 # -- feature-list <-> numpy ---------------------------------------------------
+_REC_DTYPE = np.dtype({"names": ["x", "y", "val"], "formats": ["f4", "f4", "i4"], "offsets": [0, 4, 8],
+                       "itemsize": C.sizeof(KLT_FeatureRec)})
+
+
+def _records_view(fl):
+    """numpy view of the KLT_FeatureRec array when the list is the one block KLTCreateFeatureList
+    makes (header, pointer array, records back to back: reference klt.c:148-167); None otherwise"""
+    n = fl.contents.nFeatures
+    if n < 1:
+        return None
+    f = fl.contents.feature
+    a0 = C.addressof(f[0].contents)
+    if C.addressof(f[n - 1].contents) != a0 + (n - 1) * C.sizeof(KLT_FeatureRec):
+        return None
+    buf = (C.c_char * (n * C.sizeof(KLT_FeatureRec))).from_address(a0)
+    return np.frombuffer(buf, dtype=_REC_DTYPE, count=n)
+
+
 def featurelist_to_arrays(fl):
     n = fl.contents.nFeatures
+    rec = _records_view(fl)
+    if rec is not None:
+        return rec["x"].copy(), rec["y"].copy(), rec["val"].copy()
     x = np.empty(n, np.float32)
     y = np.empty(n, np.float32)
     v = np.empty(n, np.int32)
@@ -237,6 +258,12 @@ def featurelist_affine(fl):
 
 def arrays_to_featurelist(fl, x, y, v):
     n = fl.contents.nFeatures
+    rec = _records_view(fl)
+    if rec is not None:
+        rec["x"][:] = np.asarray(x, np.float32)[:n]
+        rec["y"][:] = np.asarray(y, np.float32)[:n]
+        rec["val"][:] = np.asarray(v, np.int32)[:n]
+        return
     f = fl.contents.feature
     for i in range(n):
         r = f[i].contents
@@ -247,6 +274,16 @@ def featuretable_to_array(ft):
     """-> structured array [nFeatures, nFrames] of (x, y, val)."""
     nf, nfr = ft.contents.nFeatures, ft.contents.nFrames
     out = np.zeros((nf, nfr), dtype=[("x", "f4"), ("y", "f4"), ("val", "i4")])
+    if nf > 0 and nfr > 0:
+        # a table made by KLTCreateFeatureTable keeps its records in one [feature][frame] block
+        # (reference klt.c:210-236)
+        rows = ft.contents.feature
+        a0 = C.addressof(rows[0][0].contents)
+        if C.addressof(rows[nf - 1][nfr - 1].contents) == a0 + (nf * nfr - 1) * C.sizeof(KLT_FeatureRec):
+            buf = (C.c_char * (nf * nfr * C.sizeof(KLT_FeatureRec))).from_address(a0)
+            rec = np.frombuffer(buf, dtype=_REC_DTYPE, count=nf * nfr).reshape(nf, nfr)
+            out["x"], out["y"], out["val"] = rec["x"], rec["y"], rec["val"]
+            return out
     for j in range(nf):
         row = ft.contents.feature[j]
         for i in range(nfr):

@@ -1170,6 +1170,10 @@ struct PyrSet {
   Level lv[KLT_DEV_MAX_LEVELS];
   int built_levels;          // 0 = nothing valid
   double grad_bound;         // upper bound of |gx|, |gy| at level 0 (from the taps, 8-bit input); 0 = unknown
+  // what the set was built from: the device copy of the u8 frame (ours: d->frame_buf[i], or the
+  // caller's device frame) and the build parameters -- klt_dev_exact_level0 rebuilds level 0 from them
+  const unsigned char* src; int spitch;
+  klt_dev_build_desc desc;
 };
 
 struct klt_dev {
@@ -2128,6 +2132,7 @@ extern "C" int klt_dev_build(klt_dev* d, int slot, const unsigned char* img, int
     d->built_pending[slot] = 1;
   }
   S.built_levels = q->nlevels_built;
+  S.src = src; S.spitch = spitch; S.desc = *q;
   {
     // |gradient| <= 255 * sum|smoothing taps|^2 * sum|derivative taps| * sum|Gaussian taps|: bounds the
     // eigenvalue keys of a selection on this slot (how many radix passes the sort needs)
@@ -2742,6 +2747,12 @@ static int select_core(klt_dev* d, int slot, const klt_dev_select_params* p, int
     }
   }
   CU(cudaGetLastError());
+  if (d->overlap) {
+    // the selection ran on the build stream; the feature copies that follow (snapshot, fetch) are
+    // queued on the tracker stream and must see its result
+    CU(cudaEventRecord(d->ev_join, d->stream));
+    CU(cudaStreamWaitEvent(saved_t, d->ev_join, 0));
+  }
   return host ? klt_dev_features_download(d, n, x, y, val) : 0;
 }
 extern "C" int klt_dev_select(klt_dev* d, int slot, const klt_dev_select_params* p, int n,
@@ -2752,6 +2763,34 @@ extern "C" int klt_dev_select(klt_dev* d, int slot, const klt_dev_select_params*
 // drivers, klt_dev_features_upload ... klt_dev_features_download); nothing is synchronised
 extern "C" int klt_dev_select_resident(klt_dev* d, int slot, const klt_dev_select_params* p) {
   return select_core(d, slot, p, d->feat_n, nullptr, nullptr, nullptr, false);
+}
+
+// KLTReplaceLostFeatures ranks candidates by the truncated-integer eigenvalues of the LAST TRACKED
+// frame's level-0 gradients (reference selectGoodFeatures.c:342-348).  Tracking pyramids are built
+// in fma arithmetic by default, and a 1-ulp gradient difference can move a key across an integer
+// boundary, which re-orders the greedy minimum-distance pass.  So a replacement on a slot that was
+// not built in exact arithmetic first rebuilds level 0 (image + gradients, same taps) in exact
+// arithmetic from the u8 frame, which is still on the device, into the slot the next frame will
+// overwrite anyway; *slot_out is the slot to select on.  76 us at 4K, 4 us at 640x480.
+extern "C" int klt_dev_exact_level0(klt_dev* d, int slot, int* slot_out) {
+  if (!d || !slot_out) return fail(d, "klt_dev_exact_level0: null argument");
+  if (!d->arena || slot < 0 || slot >= KLT_DEV_SLOTS || d->set[slot].built_levels < 1)
+    return fail(d, "exact_level0: slot %d has no level 0", slot);
+  const PyrSet& S = d->set[slot];
+  if (S.desc.exact) { *slot_out = slot; return 0; }
+  if (!S.src) return fail(d, "exact_level0: the frame slot %d was built from is not known", slot);
+  const int dst = (slot + 1) % KLT_DEV_SLOTS;
+  klt_dev_build_desc q = S.desc;
+  q.exact = 1; q.nlevels_built = 1;
+  const unsigned char* src = S.src;
+  if (klt_dev_build(d, dst, src, 1, (size_t)S.spitch, &q)) return 1;
+  for (int i = 0; i < 2; ++i)                  // our own staging buffer: the next upload into it must wait
+    if (src == d->frame_buf[i]) {
+      CU(cudaEventRecord(d->ev_frame_free[i], d->stream));
+      d->frame_busy[i] = 1;
+    }
+  *slot_out = dst;
+  return 0;
 }
 
 // ---- device timing on the context stream (benches) ------------------------------

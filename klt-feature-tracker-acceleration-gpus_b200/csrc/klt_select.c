@@ -60,7 +60,10 @@ static void select_common(KLT_TrackingContext tc, const KLT_PixelType *img, int 
     if (gw != ncols || gh != nrows)
       KLTError("(KLTReplaceLostFeatures) image is %d by %d but the stored pyramid is %d by %d",
                ncols, nrows, gw, gh);
-    slot = s->last_slot;                          /* reuse, img ignored (:342-348) */
+    /* reuse, img ignored (:342-348).  The ranking keys are truncated integers, so level 0 must
+     * be in exact arithmetic: a slot tracked in fma mode gets its level 0 rebuilt (exact) from the
+     * frame still on the device */
+    DEVCALL(s, klt_dev_exact_level0(dev, s->last_slot, &slot));
   } else {
     /* level 0 + its gradients only; always exact arithmetic so the integer
      * eigenvalues equal the CPU reference's.  Built in the slot that does not

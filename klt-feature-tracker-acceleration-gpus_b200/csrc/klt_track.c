@@ -454,8 +454,11 @@ void KLTTrackFeaturesSequence(KLT_TrackingContext tc, KLT_PixelType *const *fram
       stored++;
     }
     KLTB200ResidentStep(tc, frames[k], 0, (size_t)ncols, ncols, nrows);
-    if (replace && n > 0)       /* REPLACING_SOME on the level-0 gradients just built (:342-348) */
-      DEVCALL(s, klt_dev_select_resident(s->dev, s->last_slot, &sp));
+    if (replace && n > 0) {     /* REPLACING_SOME on the level-0 gradients just built (:342-348), */
+      int sel_slot = s->last_slot;               /* in exact arithmetic (integer ranking keys)         */
+      DEVCALL(s, klt_dev_exact_level0(s->dev, s->last_slot, &sel_slot));
+      DEVCALL(s, klt_dev_select_resident(s->dev, sel_slot, &sp));
+    }
     if (snaps) DEVCALL(s, klt_dev_snapshot_push(s->dev, (k - 1) % SEQ_DEPTH));
   }
   for (; snaps && stored < nframes; stored++)

@@ -60,6 +60,7 @@ DEV_API = {
     "klt_dev_stream": (C.c_void_p, [C.c_void_p]),
     "klt_dev_build": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_size_t, C.POINTER(BuildDesc)]),
     "klt_dev_slot_valid": (C.c_int, [C.c_void_p, C.c_int]),
+    "klt_dev_exact_level0": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "klt_dev_invalidate": (None, [C.c_void_p, C.c_int]),
     "klt_dev_geometry": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 4),
     "klt_dev_track": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(TrackParams), C.c_int, _f32p, _f32p, _i32p]),

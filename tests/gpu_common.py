@@ -49,22 +49,24 @@ def compare_status(gx, gy, gv, ox, oy, ov):
     return float(agree.mean()), err
 
 
-def check_fma_step(oracle, p, pyr_prev, pyr_cur, x0, y0, v0, gx, gy, gv, ox, oy, ov, where=""):
+def check_fma_step(oracle, p, pyr_prev, pyr_cur, x0, y0, v0, gx, gy, gv, ox, oy, ov, where="", fraction_gate=True):
     """north_star parity gate for one teacher-forced frame pair in fma mode:
     status codes agree on >= 99.5 % of features, coordinates within 0.01 px; every feature
     outside that must be explained by threshold proximity -- the oracle itself lands on the
     GPU's answer when its convergence / determinant / residue thresholds are nudged by 2 %
     (one Newton iteration more or less at |dx| ~ min_displacement, etc.).  Unexplained
-    deviations fail; explained ones are limited to 0.5 % of the features."""
+    deviations fail; explained ones are limited to 0.5 % of the features.
+    fraction_gate=False (populations CONSTRUCTED to sit on a threshold, tests/test_gpu_status_edges.py):
+    the two fraction limits do not apply, every deviation must still be explained."""
     import copy
     agree = (gv == ov)
-    assert agree.mean() >= STATUS_AGREE, "%s status agreement %.4f" % (where, agree.mean())
+    assert not fraction_gate or agree.mean() >= STATUS_AGREE, "%s status agreement %.4f" % (where, agree.mean())
     both = agree & (ov >= 0)
     err = np.maximum(np.abs(gx - ox), np.abs(gy - oy))
     suspects = np.nonzero((both & (err > PX_TOL)) | ~agree)[0]
     if len(suspects) == 0:
         return 0
-    assert len(suspects) <= max(1, int(0.005 * len(ov))), "%s: %d features off" % (where, len(suspects))
+    assert not fraction_gate or len(suspects) <= max(1, int(0.005 * len(ov))), "%s: %d features off" % (where, len(suspects))
     explained = np.zeros(len(suspects), bool)
     for scale_d, scale_det, scale_res in ((0.98, 1, 1), (1.02, 1, 1), (1, 0.98, 1), (1, 1.02, 1),
                                           (1, 1, 0.98), (1, 1, 1.02), (0.96, 1, 1), (1.04, 1, 1)):

@@ -160,13 +160,16 @@ def test_synthetic_translation_is_recovered(L, capi):
     L.KLTFreeTrackingContext(tc)
 
 
-def test_replace_lost_features_sequential(L, capi, oracle, oracle_mod, provided):
-    """KLTReplaceLostFeatures reuses the device-resident level-0 gradients of the
-    last tracked frame (reference selectGoodFeatures.c:342-348)."""
+@pytest.mark.parametrize("exact", [1, 0])
+def test_replace_lost_features_sequential(L, capi, oracle, oracle_mod, provided, exact):
+    """KLTReplaceLostFeatures reuses the device-resident level 0 of the last tracked frame
+    (reference selectGoodFeatures.c:342-348).  Its ranking keys are truncated integers, so in the
+    default fma mode level 0 is rebuilt in exact arithmetic for it (klt_dev_exact_level0): from the
+    oracle's tracked list the refilled list is bit-identical in BOTH modes."""
     n = 200
     tc = L.KLTCreateTrackingContext()
     tc.contents.sequentialMode = 1
-    L.KLTB200SetExact(tc, 1)
+    L.KLTB200SetExact(tc, exact)
     p = params_from_tc(oracle, tc)
     fl = L.KLTCreateFeatureList(n)
     L.select(tc, provided[0], fl)
@@ -176,6 +179,11 @@ def test_replace_lost_features_sequential(L, capi, oracle, oracle_mod, provided)
         L.track(tc, provided[i - 1], provided[i], fl)
         cur = oracle.build_pyramids(provided[i], p)
         ox, oy, ov = oracle.track(prev, cur, p, ox, oy, ov)
+        if exact:
+            x, y, v = _get(capi, fl)
+            assert np.array_equal(v, ov) and x.tobytes() == ox.tobytes() and y.tobytes() == oy.tobytes()
+        else:
+            capi.arrays_to_featurelist(fl, ox, oy, ov)          # teacher forcing
         L.replace(tc, provided[i], fl)
         ox, oy, ov = oracle.select(provided[i], p, n, sort_kind=oracle_mod.SORT_STABLE,
                                    replace=True, last=cur, x=ox, y=oy, val=ov)

@@ -190,8 +190,9 @@ def test_config2_config3_real_frames(L, capi, oracle, oracle_mod, dataset, n, re
                 assert gx.tobytes() == ox.tobytes() and gy.tobytes() == oy.tobytes() and np.array_equal(gv, ov)
             else:
                 check_fma_step(oracle, p, prev, cur, x0, y0, v0, gx, gy, gv, ox, oy, ov, "%s frame %d" % (dataset, i))
-            if replace and exact:
-                # config 3: replacement on the device-resident level-0 gradients of this frame
+            if replace:
+                # config 3: replacement on the level 0 of this frame (exact arithmetic in both modes:
+                # klt_dev_exact_level0), from the oracle's tracked list -> bit-identical in both modes
                 capi.arrays_to_featurelist(fl, ox, oy, ov)
                 L.replace(tc, imgs[i], fl)
                 ox, oy, ov = oracle.select(imgs[i], p, n, sort_kind=oracle_mod.SORT_STABLE,

@@ -138,3 +138,20 @@ def test_sequence_without_table_and_single_frame(L, capi, provided):
     _, fin = _loop(L, capi, provided[:4], 100, 0, False)
     for u, v in zip(a, fin):
         assert u.tobytes() == v.tobytes()
+
+
+@pytest.mark.parametrize("exact", [1, 0])
+def test_sequence_with_replacement_in_overlap_mode(L, capi, provided, exact, monkeypatch):
+    """KLT_B200_OVERLAP=1: the tracker and the feature copies run on a second stream, the selection
+    of a replacement on the build stream.  The snapshot / final fetch that follow on the tracker
+    stream must be ordered after the selection (an event join at the end of select_core): the
+    tables must equal the in-order pipeline's bit for bit, every time."""
+    ref = _sequence(L, capi, provided, 150, exact, True)
+    monkeypatch.setenv("KLT_B200_OVERLAP", "1")
+    for _ in range(3):
+        _same(_sequence(L, capi, provided, 150, exact, True), ref)
+    frames = [synth_image(1920, 1080, 11, shift=(1.3 * k, 0.9 * k)) for k in range(8)]
+    monkeypatch.setenv("KLT_B200_OVERLAP", "0")
+    big = _sequence(L, capi, frames, 2000, exact, True)
+    monkeypatch.setenv("KLT_B200_OVERLAP", "1")
+    _same(_sequence(L, capi, frames, 2000, exact, True), big)
