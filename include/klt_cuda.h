@@ -227,6 +227,17 @@ int klt_dev_last_build_fused(const klt_dev *d);
  * device-resident frame). */
 void klt_dev_set_band_rows(klt_dev *d, int rows);
 int klt_dev_last_build_bands(const klt_dev *d);
+/* Pageable frame buffers: a driver that reuses its malloc'ed images for the whole run (reference
+ * src/V3/example3.c:45-46,75) hands the same pageable pointers in again and again.  The second
+ * time a buffer of >= 1 MB (same address, same size) arrives it is page-locked in place
+ * (cudaHostRegister) and from then on copied by DMA directly, as a pinned frame is; up to 32
+ * buffers per context.  The registrations are dropped by klt_dev_forget_host_frames -- called by
+ * KLTStopSequentialMode and KLTFreeTrackingContext -- and by klt_dev_destroy.  A registered
+ * buffer must not be freed while the registration lives (call KLTStopSequentialMode first, or
+ * switch the cache off: env KLT_B200_REGISTER_FRAMES=0 / klt_dev_set_register_frames(d, 0)). */
+int klt_dev_forget_host_frames(klt_dev *d);
+int klt_dev_registered_host_frames(const klt_dev *d);
+void klt_dev_set_register_frames(klt_dev *d, int on);
 /* Pageable host frames of >= 1 MB are copied into a pinned staging buffer by n host threads
  * (OpenMP; default 4, env KLT_B200_STAGE_THREADS; 0 = leave the staging to cudaMemcpyAsync), ~1 MB
  * chunk by chunk ahead of the DMA.  klt_dev_last_build_staged: 1 if the last build did that. */

@@ -94,7 +94,10 @@ void KLTB200SetExact(KLT_TrackingContext tc, int exact)
   klt_tc_state *s = klt_state_get(tc);
   if (s->exact != (exact != 0)) {
     /* pyramids built in the other arithmetic mode must not be mixed in */
-    if (s->dev) klt_dev_invalidate(s->dev, -1);
+    if (s->dev) {
+      klt_dev_invalidate(s->dev, -1);
+      klt_dev_forget_host_frames(s->dev);     /* the caller may free its frame buffers now */
+    }
     tc->pyramid_last = tc->pyramid_last_gradx = tc->pyramid_last_grady = NULL;
     s->last_slot = -1;
   }
@@ -378,7 +381,10 @@ void KLTStopSequentialMode(KLT_TrackingContext tc)
   klt_tc_state *s = klt_state_find(tc);
   tc->sequentialMode = FALSE;
   if (s) {
-    if (s->dev) klt_dev_invalidate(s->dev, -1);
+    if (s->dev) {
+      klt_dev_invalidate(s->dev, -1);
+      klt_dev_forget_host_frames(s->dev);     /* the caller may free its frame buffers now */
+    }
     s->last_slot = -1;
   }
   tc->pyramid_last = tc->pyramid_last_gradx = tc->pyramid_last_grady = NULL;

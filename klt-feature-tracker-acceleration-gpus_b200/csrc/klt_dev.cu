@@ -28,7 +28,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <omp.h>
+#include <sched.h>
 
 #include "klt_cuda.h"
 
@@ -1162,6 +1162,7 @@ static constexpr int TRACE_CAP = 8192;     // timeline records kept per profilin
 static constexpr int KLT_BAND_EVENTS = 64; // events cycled by the banded frame upload
 
 static constexpr int KLT_SNAP_MAX = 64;
+static constexpr int KLT_HOST_REGS = 32; // pageable frame buffers remembered per context
 struct Level {
   int w, h, pitch;           // pitch in floats
   float *img, *gx, *gy;
@@ -1204,6 +1205,11 @@ struct klt_dev {
   int band_rows, last_bands, building_slot;
   // pageable host frames: parallel memcpy into pinned staging, chunk by chunk ahead of the DMA
   unsigned char* h_frame; size_t h_frame_cap; cudaEvent_t ev_stage_free; int stage_busy, stage_threads, last_staged;
+  // pageable frame buffers the caller keeps handing in (a driver that reuses its two malloc'ed images,
+  // reference src/V3/example3.c:45-46,75) are page-locked in place on second sight: the DMA then reads
+  // them directly and the staging copy disappears.  Released by klt_dev_forget_host_frames / destroy.
+  struct HostReg { const void* p; size_t bytes; int seen; int registered; unsigned long long stamp; } hreg[KLT_HOST_REGS];
+  int reg_frames; unsigned long long reg_clock; int last_registered;
   int pdl;                     // programmatic dependent launch along the per-frame kernel chain
   // features
   float *d_x, *d_y; int* d_val; int feat_cap; int feat_n;
@@ -1382,10 +1388,18 @@ extern "C" int klt_dev_create(int device, klt_dev** out) {
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_stage_free, cudaEventDisableTiming);
   // default: up to 4 threads, but never more than the process was told to use (torchrun exports
   // OMP_NUM_THREADS=1 per rank so that 8 ranks do not oversubscribe the host)
-  c->stage_threads = getenv("KLT_B200_STAGE_THREADS") ? atoi(getenv("KLT_B200_STAGE_THREADS"))
-                                                      : (omp_get_max_threads() < 4 ? omp_get_max_threads() : 4);
-  if (c->stage_threads > omp_get_num_procs()) c->stage_threads = omp_get_num_procs();
+  {
+    int want = 4;
+    if (getenv("OMP_NUM_THREADS") && atoi(getenv("OMP_NUM_THREADS")) > 0 && atoi(getenv("OMP_NUM_THREADS")) < want)
+      want = atoi(getenv("OMP_NUM_THREADS"));
+    if (getenv("KLT_B200_STAGE_THREADS")) want = atoi(getenv("KLT_B200_STAGE_THREADS"));
+    cpu_set_t cs;
+    CPU_ZERO(&cs);
+    const int avail = sched_getaffinity(0, sizeof(cs), &cs) == 0 ? CPU_COUNT(&cs) : 1;
+    c->stage_threads = want > avail ? avail : want;
+  }
   c->band_rows = getenv("KLT_B200_BAND_ROWS") ? atoi(getenv("KLT_B200_BAND_ROWS")) : -1;
+  c->reg_frames = getenv("KLT_B200_REGISTER_FRAMES") ? atoi(getenv("KLT_B200_REGISTER_FRAMES")) : 0;   // opt-in: see klt_cuda.h
   if (e != cudaSuccess) { free(c); return fail(nullptr, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
   c->tstream = c->stream;
   c->overlap_l0_ctas = getenv("KLT_B200_OVERLAP_L0_CTAS") ? atoi(getenv("KLT_B200_OVERLAP_L0_CTAS")) : 0;
@@ -1419,6 +1433,7 @@ extern "C" void klt_dev_destroy(klt_dev* d) {
   if (!d) return;
   cudaSetDevice(d->device);
   sync_all(d);
+  klt_dev_forget_host_frames(d);
   free_geometry(d);
   cudaFree(d->frame_buf[0]); cudaFree(d->frame_buf[1]);
   cudaFree(d->d_x);
@@ -1856,14 +1871,58 @@ static bool host_ptr_is_pageable(const void* p) {
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
   return at.type == cudaMemoryTypeUnregistered;
 }
-static void parallel_memcpy(unsigned char* dst, const unsigned char* src, size_t bytes, int nthreads) {
-  if (nthreads <= 1 || bytes < (256u << 10)) { memcpy(dst, src, bytes); return; }
-  const int parts = nthreads;
-#pragma omp parallel for num_threads(nthreads) schedule(static)
-  for (int p = 0; p < parts; ++p) {
-    const size_t a = bytes / parts * p, b = p == parts - 1 ? bytes : bytes / parts * (p + 1);
-    memcpy(dst + a, src + a, b - a);
+// A pageable frame pointer: remember it; the second time the same buffer (address and size) comes
+// in, page-lock it in place.  Returns true when the buffer is page-locked now.
+static bool host_frame_register(klt_dev* d, const void* p, size_t bytes) {
+  if (!d->reg_frames) return false;
+  klt_dev::HostReg* slot = nullptr;
+  klt_dev::HostReg* victim = &d->hreg[0];
+  for (int i = 0; i < KLT_HOST_REGS; ++i) {
+    klt_dev::HostReg& r = d->hreg[i];
+    if (r.p == p && r.bytes == bytes) { slot = &r; break; }
+    if (!r.registered && (victim->registered || r.stamp < victim->stamp)) victim = &r;
   }
+  d->reg_clock += 1;
+  if (!slot) {
+    if (victim->registered) return false;            // table full of live registrations: keep staging
+    victim->p = p; victim->bytes = bytes; victim->seen = 1; victim->stamp = d->reg_clock;
+    return false;
+  }
+  slot->stamp = d->reg_clock;
+  if (slot->seen < 0) return false;                   // registration failed before: do not retry
+  slot->seen += 1;
+  if (slot->seen < 2) return false;
+  if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) != cudaSuccess) {
+    cudaGetLastError();
+    slot->seen = -1;
+    return false;
+  }
+  slot->registered = 1;
+  d->last_registered += 1;
+  return true;
+}
+extern "C" int klt_dev_forget_host_frames(klt_dev* d) {
+  if (!d) return 0;
+  bool any = false;
+  for (int i = 0; i < KLT_HOST_REGS; ++i) any = any || d->hreg[i].registered;
+  if (any) {
+    CU(cudaSetDevice(d->device));
+    if (sync_all(d)) return fail(d, "stream synchronisation failed");
+    for (int i = 0; i < KLT_HOST_REGS; ++i)
+      if (d->hreg[i].registered && cudaHostUnregister(const_cast<void*>(d->hreg[i].p)) != cudaSuccess) cudaGetLastError();
+  }
+  memset(d->hreg, 0, sizeof(d->hreg));
+  return 0;
+}
+extern "C" int klt_dev_registered_host_frames(const klt_dev* d) {
+  int n = 0;
+  for (int i = 0; i < KLT_HOST_REGS; ++i) n += d->hreg[i].registered;
+  return n;
+}
+extern "C" void klt_dev_set_register_frames(klt_dev* d, int on) { d->reg_frames = on; }
+#include "klt_stage.h"
+static void parallel_memcpy(unsigned char* dst, const unsigned char* src, size_t bytes, int nthreads) {
+  stage_team().copy(dst, src, bytes, nthreads);
 }
 static int feed_enqueue_band(klt_dev* d, BandFeed* f, int b) {
   const int r0 = b == 0 ? 0 : f->end_row[b - 1], r1 = f->end_row[b];
@@ -1877,7 +1936,7 @@ static int feed_enqueue_band(klt_dev* d, BandFeed* f, int b) {
     else
       CU(cudaMemcpy2DAsync(dst, f->fp, src, f->W, f->W, rows, cudaMemcpyHostToDevice, d->cstream));
   } else {
-    static unsigned chunk_kb = getenv("KLT_B200_STAGE_CHUNK_KB") ? (unsigned)atoi(getenv("KLT_B200_STAGE_CHUNK_KB")) : 2048u;
+    static unsigned chunk_kb = getenv("KLT_B200_STAGE_CHUNK_KB") ? (unsigned)atoi(getenv("KLT_B200_STAGE_CHUNK_KB")) : 1024u;
     int chunk_rows = (int)((chunk_kb << 10) / (unsigned)f->W);
     if (chunk_rows < 1) chunk_rows = 1;
     for (int y = r0; y < r1; y += chunk_rows) {
@@ -1909,7 +1968,9 @@ static int feed_enqueue_copies(klt_dev* d, BandFeed* f) {
   }
   f->next = 0; f->enqueued = 0;
   const size_t bytes = (size_t)f->W * f->H;
-  f->staged = d->stage_threads > 0 && bytes >= (1u << 20) && host_ptr_is_pageable(f->host);
+  bool pageable = bytes >= (1u << 20) && host_ptr_is_pageable(f->host);
+  if (pageable && host_frame_register(d, f->host, bytes)) pageable = false;
+  f->staged = d->stage_threads > 0 && pageable;
   d->last_staged = f->staged ? 1 : 0;
   if (f->staged) {
     if (d->h_frame_cap < bytes) {
@@ -2606,7 +2667,8 @@ static int run_mineig(klt_dev* d, int slot, const klt_dev_select_params* p, cons
   CU(cudaMemsetAsync(d->sel_state + 5, 0, 2 * sizeof(int), d->stream));        // key range: max, min
   dim3 b(32, 8), grid((g.nxc + 31) / 32, (g.nyc + 7) / 8);
   if (p->window_width / 2 == 3 && p->window_height / 2 == 3 && g.step == 1 && g.bx >= 8 && g.by >= 3 &&
-      (lv.pitch & 31) == 0 && !getenv("KLT_B200_MINEIG_SCALAR")) {
+      (lv.pitch & 31) == 0 && ((g.bx + g.nxc - 1) & ~7) + 12 <= lv.pitch &&      // the 16-column row loads stay inside the pitch
+      !getenv("KLT_B200_MINEIG_SCALAR")) {
     const int span = g.bx + g.nxc - (g.bx & ~7);                               // columns from the first 8-aligned block on
     dim3 b7(32, 4), g7((span + 255) / 256, (g.nyc + 3) / 4);
     Launch l(d, KID_MINEIG);

@@ -14,16 +14,18 @@
 #include "pnmio.h"
 
 /* next header token, skipping whitespace and # comments; "" at EOF */
-static void next_token(FILE *fp, char *tok, int cap)
+/* returns 1 when the token was ended by a comment that abuts it ("255#c\n"): the comment's
+ * newline, which then is the single separator after the token, has already been consumed */
+static int next_token(FILE *fp, char *tok, int cap)
 {
-  int c, n = 0;
+  int c, n = 0, ate_separator = 0;
   tok[0] = '\0';
   for (;;) {
     c = fgetc(fp);
-    if (c == EOF) return;
+    if (c == EOF) break;
     if (c == '#') {
       while (c != '\n' && c != EOF) c = fgetc(fp);
-      if (n > 0) break;
+      if (n > 0) { ate_separator = 1; break; }
       continue;
     }
     if (c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f' || c == '\v') {
@@ -33,6 +35,7 @@ static void next_token(FILE *fp, char *tok, int cap)
     if (n < cap - 1) tok[n++] = (char)c;
   }
   tok[n] = '\0';
+  return ate_separator;
 }
 
 void pnmReadHeader(FILE *fp, int *magic, int *ncols, int *nrows, int *maxval)
@@ -48,9 +51,10 @@ void pnmReadHeader(FILE *fp, int *magic, int *ncols, int *nrows, int *maxval)
   *nrows = atoi(tok);
   if (*ncols < 0 || *nrows < 0 || *ncols > 10000 || *nrows > 10000)
     KLTError("(pnmReadHeader) The dimensions %d x %d are unacceptable", *ncols, *nrows);
-  next_token(fp, tok, sizeof tok);
+  /* the single whitespace after maxval -- unless a comment abutting maxval already took its
+   * newline (the reference, pnmio.c:66-69, reads one byte regardless and loses the first pixel) */
+  if (!next_token(fp, tok, sizeof tok)) fgetc(fp);
   *maxval = atoi(tok);
-  fgetc(fp);                               /* the single whitespace after maxval */
   if (*maxval != 255)
     KLTWarning("(pnmReadHeader) Maxval is not 255, but %d", *maxval);
 }

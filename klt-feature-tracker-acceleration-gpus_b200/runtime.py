@@ -89,6 +89,9 @@ DEV_API = {
     "klt_dev_last_build_fused": (C.c_int, [C.c_void_p]),
     "klt_dev_set_band_rows": (None, [C.c_void_p, C.c_int]),
     "klt_dev_last_build_bands": (C.c_int, [C.c_void_p]),
+    "klt_dev_forget_host_frames": (C.c_int, [C.c_void_p]),
+    "klt_dev_registered_host_frames": (C.c_int, [C.c_void_p]),
+    "klt_dev_set_register_frames": (None, [C.c_void_p, C.c_int]),
     "klt_dev_set_stage_threads": (None, [C.c_void_p, C.c_int]),
     "klt_dev_last_build_staged": (C.c_int, [C.c_void_p]),
     "klt_dev_timer_start": (C.c_int, [C.c_void_p]),

@@ -229,6 +229,19 @@ def test_pnm_io_and_overlay(L, capi, provided, tmp_path):
     L.KLTFreeFeatureList(fl)
 
 
+def test_pgm_header_comment_placements(L, tmp_path):
+    """'#' comments anywhere in the header, including one that abuts maxval ("255#c\\n": its newline
+    IS the single separator, so no further byte may be skipped -- the reference, pnmio.c:66-69,
+    loses the first pixel there)."""
+    px = (np.arange(6 * 4, dtype=np.uint8) * 9 + 7).reshape(4, 6)
+    for k, hdr in enumerate([b"P5\n6 4\n255\n", b"P5\n# made by x\n6 4\n255\n", b"P5 6 4 255\n",
+                             b"P5\n6 4 # size\n255\n", b"P5\n6 4\n255#c\n", b"P5\n6 4\n255 # c\n"[:0] or b"P5\n6#w\n4\n255\n"]):
+        f = tmp_path / ("h%d.pgm" % k)
+        f.write_bytes(hdr + px.tobytes())
+        got = L.read_pgm(str(f))
+        assert got.shape == (4, 6) and np.array_equal(got, px), hdr
+
+
 def test_hot_path_fails_loudly_without_gpu(L):
     """No CPU fallback: on a box without a CUDA device the hot path is a
     KLTError (message + exit(1)), never a silent CPU computation."""
