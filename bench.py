@@ -12,6 +12,13 @@ Metric: tracked features/s = features with val >= 0 entering the calls / time.
 At N > 1 every rank runs its own independent sequence on its own GPU (no
 collective on the data path); value is the sum over ranks / max time over ranks.
 
+The same line also carries, at every N, BASELINE.json configs[4] -- the multi-sequence workload
+north_star names for 2/4/8 GPUs -- under "config5": 64 independent synthetic 1080p sequences,
+1024 features each, sequence s on GPU s mod N, STRONG scaling (total work fixed), one
+KLTTrackFeaturesSequence pipeline per sequence over pinned host frames, results checksummed and
+gathered on the host; and "h2d_probe": what this box's host->device path delivers per GPU when
+all N GPUs copy at once (the ceiling of every end-to-end number).
+
 One JSON line on stdout (rank 0).  Keys are described in DESIGN.md section 6.
 """
 from __future__ import annotations
@@ -58,6 +65,23 @@ def emit_json(obj):
         os.write(_JSON_FD, line.encode())
 
 
+def workload_config(name):
+    """the `config` object, identical in both arms (the driver compares them)"""
+    ncols, nrows, nfeat, nlevels, ss, window, nframes = WORKLOADS[name]
+    px, w, h = 0, ncols, nrows
+    for _ in range(nlevels):
+        px += w * h
+        w //= ss
+        h //= ss
+    return {"workload": "synthetic %dx%d translated sequence (2.3,-1.4 px/frame), %d features, %d pyramid levels "
+                        "(subsampling %d), window %dx%d, one independent sequence per GPU"
+                        % (ncols, nrows, nfeat, nlevels, ss, window, window),
+            "l2": "%s: %d distinct frames (%.0f MB) cycled ping-pong; every step also writes "
+                  "%.0f MB of new pyramids" % ("inputs larger than L2" if nframes * ncols * nrows > 126e6 else
+                                               "inputs SMALLER than the 126 MB L2 (not a valid bench workload)",
+                                               nframes, nframes * ncols * nrows / 1e6, 12 * px / 1e6)}
+
+
 def algorithmic_bytes(ncols, nrows, nlevels, ss):
     """per new frame, read the u8 frame once + write the three f32
     pyramids: W*H + 12 * sum_l W_l*H_l (integer division per level)."""
@@ -71,7 +95,6 @@ def algorithmic_bytes(ncols, nrows, nlevels, ss):
         "grad_tile": 12 * sum(px),                                     # read L_l, write gx_l, gy_l
         "pyrdown_tile": sum(4 * px[l - 1] + 4 * px[l] for l in range(1, nlevels)),
         "l0_fused_kernel": 13 * px[0],                                 # read u8, write L0, gx0, gy0
-        "pyramid_mega_kernel": ncols * nrows + 12 * sum(px),           # whole pyramid in one launch (opt-in)
         # one pyramid step + that level's gradients: read L_{l-1}, write L_l, gx_l, gy_l
         "level_fused_kernel[level 1]": (4 * px[0] + 12 * px[1]) if nlevels > 1 else 0,
         "level_fused_kernel[level 2]": (4 * px[1] + 12 * px[2]) if nlevels > 2 else 0,
@@ -149,6 +172,185 @@ def setup_tc(L, nlevels, ss, window, device=None):
     if device is not None:
         L.KLTB200SetDevice(tc, device)
     return tc
+
+
+# --------------------------------------------------------------------------- config 5
+def run_config5(args, L, capi, synth, torch, dist, rank, local_rank, world, barrier):
+    """BASELINE.json configs[4] / SURVEY 8(d) config 5: 64 independent synthetic 1920x1080 sequences
+    (seed 1000 + s, velocity in [-3, 3]^2 px/frame), 1024 features each, tc defaults (2 levels,
+    subsampling 4, 7x7), sequence s -> GPU s mod N.  Strong scaling: the total work is the same at
+    every N.  Each sequence is a chain of KLTTrackFeaturesSequence calls (one per segment of frames,
+    pinned host frames, per-frame results into a KLT_FeatureTable that the host thread folds into a
+    checksum and a compact table); `inflight` sequences per GPU are driven at once from host threads
+    so that one sequence's PCIe transfer overlaps another's kernels.  No collective on the data
+    path; the per-sequence checksums are gathered on rank 0 afterwards (they must not depend on N)."""
+    import queue
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+    multiseq = importlib.import_module(PKG + ".multiseq")
+    NSEQ, W, H, NF, T = 64, 1920, 1080, 1024, 17
+    SEG, NSEG, INFLIGHT = args.c5_segment, args.c5_segments, args.c5_inflight
+    mine = multiseq.my_sequences(NSEQ, rank, world)
+    vel = np.random.default_rng(2024).uniform(-3.0, 3.0, size=(NSEQ, 2))
+    t0 = time.time()
+    frames = torch.empty((max(len(mine), 1), T, H, W), dtype=torch.uint8, pin_memory=True)
+    fh = frames.numpy()
+    for k, s in enumerate(mine):
+        for t in range(T):
+            synth.frame(W, H, seed=1000 + s, t=float(t), velocity=tuple(vel[s]), out=fh[k, t])
+    log("[rank %d] config 5: %d sequences x %d frames generated in %.1fs" % (rank, len(mine), T, time.time() - t0))
+    rec = C.sizeof(capi.KLT_FeatureRec)
+    ctx = []
+    for k, s in enumerate(mine):
+        tc = L.KLTCreateTrackingContext()
+        tc.contents.sequentialMode = 1
+        L.KLTB200SetDevice(tc, local_rank)
+        fl = L.KLTCreateFeatureList(NF)
+        L.KLTSelectGoodFeatures(tc, C.c_void_p(frames[k, 0].data_ptr()), W, H, fl)
+        sel = capi.featurelist_to_arrays(fl)
+        segs = []
+        for j in range(NSEG):                  # segment j: steps j*SEG .. (j+1)*SEG; its frame 0 = the held pyramid
+            segs.append((C.c_void_p * (SEG + 1))(*[frames[k, synth.pingpong_index(j * SEG + i, T)].data_ptr()
+                                                   for i in range(SEG + 1)]))
+        # warm-up (>= 3 steps per context: pinned rings, kernel attributes), then back to the selection
+        L.KLTTrackFeaturesSequence(tc, segs[0], 4, W, H, fl, None, 0, 0)
+        L.KLTStopSequentialMode(tc)
+        tc.contents.sequentialMode = 1
+        capi.arrays_to_featurelist(fl, *sel)
+        ctx.append((tc, fl, segs))
+    tables = queue.Queue()
+    made = []
+    for _ in range(max(1, INFLIGHT)):
+        ft = L.KLTCreateFeatureTable(SEG + 1, NF)
+        C.memset(C.cast(ft.contents.feature[0][0], C.c_void_p), 0, (SEG + 1) * NF * rec)
+        made.append(ft)
+        tables.put(ft)
+    for tc, fl, _ in ctx:
+        live = C.c_ulonglong(0)
+        L.klt_dev_live_total(L.KLTB200Device(tc), C.byref(live), 1)
+
+    def run_one(k):
+        tc, fl, segs = ctx[k]
+        ft = tables.get()
+        base = C.cast(ft.contents.feature[0][0], C.c_void_p).value
+        view = np.frombuffer((C.c_char * ((SEG + 1) * NF * rec)).from_address(base), dtype=capi._REC_DTYPE,
+                             count=(SEG + 1) * NF).reshape(NF, SEG + 1)
+        crc = 0
+        for j in range(NSEG):
+            L.KLTTrackFeaturesSequence(tc, segs[j], SEG + 1, W, H, fl, ft, 0, 0)
+            for f in ("x", "y", "val"):         # the host gather: columns 1..SEG -> compact, checksummed
+                crc = zlib.crc32(np.ascontiguousarray(view[f][:, 1:]).tobytes(), crc)
+        tables.put(ft)
+        return crc
+
+    barrier()
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=max(1, INFLIGHT)) as pool:
+        crcs = list(pool.map(run_one, range(len(ctx))))
+    torch.cuda.synchronize()
+    secs = time.perf_counter() - t0
+    barrier()
+    feats = 0
+    for tc, fl, _ in ctx:
+        live = C.c_ulonglong(0)
+        L.klt_dev_live_total(L.KLTB200Device(tc), C.byref(live), 1)
+        feats += int(live.value)
+    alive = [int(L.KLTCountRemainingFeatures(fl)) for _, fl, _ in ctx]
+    local = {int(s): int(c) for s, c in zip(mine, crcs)}
+    local_alive = {int(s): a for s, a in zip(mine, alive)}
+    if world > 1:
+        bucket = [None] * world if rank == 0 else None
+        dist.gather_object((local, local_alive), bucket, dst=0)
+        t = torch.tensor([secs], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        c = torch.tensor([float(feats)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        secs, feats = float(t[0]), int(c[0])
+        if rank == 0:
+            local, local_alive = {}, {}
+            for a, b in bucket:
+                local.update(a)
+                local_alive.update(b)
+    for ft in made:
+        L.KLTFreeFeatureTable(ft)
+    for tc, fl, _ in ctx:
+        L.KLTFreeFeatureList(fl)
+        L.KLTFreeTrackingContext(tc)
+    del frames
+    if rank != 0:
+        return None
+    assert len(local) == NSEQ
+    all_crc = 0
+    for s in sorted(local):
+        all_crc = zlib.crc32(int(local[s]).to_bytes(4, "little"), all_crc)
+    nframes_total = NSEQ * SEG * NSEG
+    h2d = (SEG * NSEG + 1) * W * H                       # per sequence: every tracked frame + the first one
+    return {"metric": METRIC, "value": round(feats / secs, 1), "unit": UNIT, "scaling": "strong",
+            "frames_per_s": round(nframes_total / secs, 1), "seconds": round(secs, 4), "n_gpus": world,
+            "e2e": {"value": round(feats / secs, 1), "unit": UNIT,
+                    "h2d_bytes_per_step": W * H, "d2h_bytes_per_step": 12 * NF,
+                    "per_gpu_h2d_gbs": round(NSEQ * h2d / world / secs / 1e9, 1)},
+            "config": {"workload": "BASELINE config 5: %d independent synthetic %dx%d sequences, %d features each, "
+                                   "%d tracked frames each (%d distinct frames per sequence cycled ping-pong), tc "
+                                   "defaults (2 levels, subsampling 4, 7x7), sequence s on GPU s mod N"
+                                   % (NSEQ, W, H, NF, SEG * NSEG, T),
+                       "api": "KLTTrackFeaturesSequence, %d calls of %d frames per sequence, pinned host frames, "
+                              "%d sequences in flight per GPU; value == e2e (there is no resident variant: "
+                              "every frame crosses PCIe inside the timed region)" % (NSEG, SEG, INFLIGHT)},
+            "tables_crc32": "%08x" % all_crc,
+            "features_alive_at_end_min_max": [min(local_alive.values()), max(local_alive.values())]}
+
+
+# --------------------------------------------------------------------------- host I/O (SURVEY 8f N4)
+def io_throughput(L, capi, fh):
+    """Feature-table / PPM writers and the PGM reader: this library vs the reference's own C code
+    (oracle/_ref), same inputs, byte-identical outputs (tests/test_host.py), wall clock per call."""
+    import tempfile
+    ref, _ = _ref_library(capi)
+    W, H, NF, NFR = 640, 480, 1000, 200
+    img = np.ascontiguousarray(fh[0][:H, :W])
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, lib in (("b200", L), ("reference", ref)):
+            if lib is None:
+                continue
+            fl = lib.KLTCreateFeatureList(NF)
+            ft = lib.KLTCreateFeatureTable(NFR, NF)
+            rng = np.random.default_rng(5)
+            x = rng.uniform(10, W - 10, NF).astype(np.float32)
+            y = rng.uniform(10, H - 10, NF).astype(np.float32)
+            v = np.zeros(NF, np.int32)
+            capi.arrays_to_featurelist(fl, x, y, v)
+            for k in range(NFR):
+                lib.KLTStoreFeatureList(fl, ft, k)
+            ppm = os.path.join(tmp, name + ".ppm").encode()
+            txt = os.path.join(tmp, name + ".txt").encode()
+            bin_ = os.path.join(tmp, name + ".ft").encode()
+            pgm = os.path.join(tmp, name + ".pgm").encode()
+            lib.pgmWriteFile(pgm, img.ctypes.data_as(C.c_void_p), W, H)
+            buf = np.empty((H, W), np.uint8)
+            nc, nr = C.c_int(0), C.c_int(0)
+
+            def timeit(fn, reps):
+                fn()
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    fn()
+                return (time.perf_counter() - t0) / reps
+            e = {}
+            e["KLTWriteFeatureListToPPM_ms"] = round(1e3 * timeit(
+                lambda: lib.KLTWriteFeatureListToPPM(fl, img.ctypes.data_as(C.c_void_p), W, H, ppm), 20), 3)
+            e["pgmReadFile_ms"] = round(1e3 * timeit(
+                lambda: lib.pgmReadFile(pgm, buf.ctypes.data_as(C.c_void_p), C.byref(nc), C.byref(nr)), 50), 3)
+            e["KLTWriteFeatureTable_text_ms"] = round(1e3 * timeit(
+                lambda: lib.KLTWriteFeatureTable(ft, txt, b"%5.1f"), 3), 2)
+            e["KLTWriteFeatureTable_binary_ms"] = round(1e3 * timeit(
+                lambda: lib.KLTWriteFeatureTable(ft, bin_, None), 5), 3)
+            lib.KLTFreeFeatureTable(ft)
+            lib.KLTFreeFeatureList(fl)
+            out[name] = e
+    out["case"] = "640x480 frame, %d features, %d-frame table; files on the box's tmpfs/disk" % (NF, NFR)
+    return out
 
 
 # --------------------------------------------------------------------------- B200 arm
@@ -241,8 +443,19 @@ def run_b200(args, rank, local_rank, world):
     barrier()
     launches = int(L.klt_dev_launch_count(dev) - launches0)
     L.klt_dev_live_total(dev, C.byref(live), 1)
-    L.KLTB200ResidentEnd(tc, fl)
     dev_ms, dev_feats = float(ms.value), int(live.value)
+    # ---- (1b) the same loop for max(K, 2000) more steps: a timed region of >= 0.1 s (K = 20 is 1.5 ms)
+    KS = max(K, 2000)
+    barrier()
+    L.klt_dev_timer_start(dev)
+    for _ in range(KS):
+        L.KLTB200ResidentStep(tc, C.c_void_p(d_ptr(idx(step))), 1, ncols, ncols, nrows)
+        step += 1
+    L.klt_dev_timer_stop(dev, C.byref(ms))
+    barrier()
+    L.klt_dev_live_total(dev, C.byref(live), 1)
+    sus_ms, sus_feats = float(ms.value), int(live.value)
+    L.KLTB200ResidentEnd(tc, fl)
     alive_end = int(L.KLTCountRemainingFeatures(fl))
 
     # ---- (2) e2e: the public KLTTrackFeatures call, pinned HOST frames ---------------
@@ -285,6 +498,62 @@ def run_b200(args, rank, local_rank, world):
     wall1 = time.time()
     clocks = sampler.stop(wall0, wall1) if sampler else None
 
+    # ---- (2c) e2e with PAGEABLE frames: what the reference's own driver passes (it mallocs its two
+    # images and refills them, src/V3/example3.c:45-46,75).  Two ordinary numpy buffers are refilled
+    # from the sequence before every call (outside the timed sum).  Default: staged through pinned
+    # memory by the staging team; "registered": the buffers are page-locked in place on second sight
+    # (opt-in, KLT_B200_REGISTER_FRAMES=1).  N = 1 only (torchrun pins every rank to one host thread).
+    pageable = None
+    if world == 1:
+        pageable = {}
+        bufs = [np.empty((nrows, ncols), np.uint8) for _ in range(2)]
+        for mode in ("staged", "registered"):
+            L.klt_dev_set_register_frames(dev, 1 if mode == "registered" else 0)
+            restart()
+            np.copyto(bufs[0], fh[idx(0)])
+            step, secs, feats_p = 1, 0.0, 0
+            KP = max(K, 50)
+            for it in range(W + KP):
+                cur, prv = bufs[step & 1], bufs[(step - 1) & 1]
+                np.copyto(cur, fh[idx(step)])                     # the driver's pgmReadFile into its buffer
+                if it == W:
+                    L.klt_dev_live_total(dev, C.byref(live), 1)
+                t0 = time.perf_counter()
+                L.KLTTrackFeatures(tc, C.c_void_p(prv.ctypes.data), C.c_void_p(cur.ctypes.data), ncols, nrows, fl)
+                if it >= W:
+                    secs += time.perf_counter() - t0
+                step += 1
+            L.klt_dev_live_total(dev, C.byref(live), 1)
+            pageable[mode] = {"value": round(int(live.value) / secs, 1), "unit": UNIT,
+                              "ms_per_step": round(secs / KP * 1e3, 4), "steps": KP,
+                              "host_buffers_page_locked_in_place": int(L.klt_dev_registered_host_frames(dev))}
+            L.KLTStopSequentialMode(tc)                            # drops the registrations
+            tc.contents.sequentialMode = 1
+        L.klt_dev_set_register_frames(dev, 0)
+
+    # ---- (2d) what the box's host->device path gives each GPU when all N copy at once ----------
+    probe_src = frames_h[:4]
+    probe_dst = torch.empty_like(frames_d[:4])
+    st = torch.cuda.Stream()
+    ncopies = 64
+    with torch.cuda.stream(st):
+        for i in range(8):
+            probe_dst[i % 4].copy_(probe_src[i % 4], non_blocking=True)
+        st.synchronize()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(st)
+        for i in range(ncopies):
+            probe_dst[i % 4].copy_(probe_src[i % 4], non_blocking=True)
+        ev1.record(st)
+        st.synchronize()
+    barrier()
+    h2d_gbs = ncopies * fbytes / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+    del probe_dst
+
+    # ---- (5) BASELINE config 5: 64 independent 1080p sequences over the N GPUs (strong scaling) ----
+    c5 = run_config5(args, L, capi, synth, torch, dist, rank, local_rank, world, barrier)
+
     # ---- (3) per-kernel device time (CUDA events on the launching stream) ------------
     restart()
     L.KLTB200ResidentBegin(tc, C.c_void_p(d_ptr(0)), 1, ncols, ncols, nrows, fl)
@@ -316,13 +585,14 @@ def run_b200(args, rank, local_rank, world):
         l0_b2b_ms = float(ms0.value) / nb2b
 
     # ---- reduce over ranks: sum of features, max of time -------------------------------
+    h2d_min = h2d_sum = h2d_gbs
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_s, seq_s], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dev_ms, e2e_s, seq_s, sus_ms, -h2d_gbs], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        c = torch.tensor([dev_feats, e2e_feats, seq_feats], dtype=torch.float64, device="cuda")
+        c = torch.tensor([dev_feats, e2e_feats, seq_feats, sus_feats, h2d_gbs], dtype=torch.float64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        dev_ms, e2e_s, seq_s = float(t[0]), float(t[1]), float(t[2])
-        dev_feats, e2e_feats, seq_feats = int(c[0]), int(c[1]), int(c[2])
+        dev_ms, e2e_s, seq_s, sus_ms, h2d_min = float(t[0]), float(t[1]), float(t[2]), float(t[3]), -float(t[4])
+        dev_feats, e2e_feats, seq_feats, sus_feats, h2d_sum = int(c[0]), int(c[1]), int(c[2]), int(c[3]), float(c[4])
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -343,7 +613,7 @@ def run_b200(args, rank, local_rank, world):
                 ent["gbs"] = round(bytes_tab[key] / (per_step * 1e-3) / 1e9, 1)
             kernels[name] = ent
         pipe = ["smooth_u8_tile", "grad_tile", "pyrdown_tile", "l0_fused_kernel", "level_fused_kernel[level 1]",
-                "level_fused_kernel[level 2]", "level_fused_kernel[level 3+]", "pyramid_mega_kernel"]
+                "level_fused_kernel[level 2]", "level_fused_kernel[level 3+]"]
         hbm_kernels = {k: v for k, v in kernels.items() if "gbs" in v}
         dom = max(hbm_kernels, key=lambda k: hbm_kernels[k]["ms_per_step"]) if hbm_kernels else None
         traffic = None
@@ -376,15 +646,13 @@ def run_b200(args, rank, local_rank, world):
             "warmup": W, "ms_per_step": round(dev_ms / K, 5), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "frames_per_s": round(K * world / (dev_ms * 1e-3), 1),
-            "config": {"workload": "synthetic %dx%d translated sequence (2.3,-1.4 px/frame), %d features, "
-                                   "%d pyramid levels (subsampling %d), window %dx%d, one independent "
-                                   "sequence per GPU" % (ncols, nrows, nfeat, nlevels, ss, window, window),
-                       "features_selected": nsel, "features_alive_at_end": alive_end,
-                       "l2": "inputs larger than L2: %d distinct frames (%.0f MB) cycled ping-pong; every step "
-                             "also writes %.0f MB of new pyramids" % (nframes, nframes * fbytes / 1e6,
-                                                                     12 * sum(px) / 1e6),
-                       "arithmetic": "fma (default mode); exact mode is the parity-test mode",
-                       "select_ms": round(t_select2 * 1e3, 2)},
+            "config": workload_config(args.workload),
+            "details": {"features_selected": nsel, "features_alive_at_end": alive_end,
+                        "arithmetic": "fma (default mode); exact mode is the parity-test mode",
+                        "select_ms": round(t_select2 * 1e3, 2)},
+            "sustained": {"steps": KS, "ms_per_step": round(sus_ms / KS, 5),
+                          "value": round(sus_feats / (sus_ms * 1e-3), 1), "unit": UNIT,
+                          "how": "the loop of `value` continued for max(K, 2000) steps between one pair of events"},
             "e2e": {"value": round(e2e_feats / e2e_s, 1), "unit": UNIT,
                     "frames_per_s": round(K * world / e2e_s, 1), "ms_per_step": round(e2e_s / K * 1e3, 4),
                     "h2d_bytes_per_step": fbytes + 64 * nfeat, "d2h_bytes_per_step": 12 * nfeat,
@@ -400,10 +668,27 @@ def run_b200(args, rank, local_rank, world):
                                     "upload of frame k+1 overlaps the kernels of frame k (PCIe-bound), one "
                                     "synchronisation at the end; wall clock around the call"},
             "gpu_launches": launches, "kernels": kernels, "roofline": roofline, "clocks": clocks,
+            "h2d_probe": {"per_gpu_gbs_min": round(h2d_min, 1), "aggregate_gbs": round(h2d_sum, 1),
+                          "e2e_per_gpu_gbs": round((fbytes + 64 * nfeat) * K / e2e_s / 1e9, 1),
+                          "e2e_sequence_per_gpu_gbs": round(fbytes * K / seq_s / 1e9, 1),
+                          "how": "every rank copies 64 pinned %.1f MB frames to its GPU back to back, all ranks "
+                                 "at once, CUDA events; e2e_*: bytes the end-to-end legs move per second per GPU"
+                                 % (fbytes / 1e6)},
+            "config5": c5,
         }
+        if pageable is not None:
+            out["e2e_pageable"] = dict(pageable["staged"], api="KLTTrackFeatures with two ordinary (pageable) frame "
+                                       "buffers refilled by the driver every frame, as the reference's example3 does; "
+                                       "staged through pinned memory by the library")
+            out["e2e_pageable_registered"] = dict(pageable["registered"], api="same buffers, page-locked in place by "
+                                                  "the library on second sight (KLT_B200_REGISTER_FRAMES=1, opt-in)")
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(capi, fh, ncols, nrows, nfeat, nlevels, ss, window,
                                                budget_s=args.cpu_budget)
+            try:
+                out["host_io"] = io_throughput(L, capi, fh)
+            except Exception as e:                      # never lose the bench line over the I/O side show
+                out["host_io"] = {"error": repr(e)}
         emit_json(out)
     barrier()
     L.KLTFreeFeatureList(fl)
@@ -477,16 +762,15 @@ def cpu_baseline(capi, frames, ncols, nrows, nfeat, nlevels, ss, window, budget_
                       "KLTTrackFeatures only, as the reference driver times it)" % (done, ncols, nrows, nfeat)}
 
 
+_REF_FRAMES = None          # the synthetic frames, generated once in the parent and inherited by the forked workers
+
+
 def _ref_worker(args):
-    (widx, workload, warmup, steps, budget_s, seed) = args
+    (widx, workload, warmup, steps, budget_s) = args
     pkg = importlib.import_module(PKG)
-    synth = importlib.import_module(PKG + ".synth")
     ncols, nrows, nfeat, nlevels, ss, window, _ = WORKLOADS[workload]
-    frames = np.empty((6, nrows, ncols), np.uint8)
-    for t in range(6):
-        synth.frame(ncols, nrows, seed=seed + widx, t=float(t), out=frames[t], threads=1)
     t_begin = [0.0]
-    feats, secs, done, kind = _cpu_sequence(pkg.capi, frames, ncols, nrows, nfeat, nlevels, ss, window,
+    feats, secs, done, kind = _cpu_sequence(pkg.capi, _REF_FRAMES, ncols, nrows, nfeat, nlevels, ss, window,
                                             warmup, steps, budget_s,
                                             start_evt=lambda: t_begin.__setitem__(0, time.time()))
     return feats, secs, done, kind, t_begin[0], time.time()
@@ -494,11 +778,18 @@ def _ref_worker(args):
 
 def run_reference(args, rank, world):
     """The reference's own CPU implementation (oracle/_ref = its unmodified sources compiled in
-    place), on all host cores: the library is single-threaded, so one independent sequence per core."""
+    place), on all host cores: the library is single-threaded, so one independent sequence per core
+    (every worker runs the same synthetic sequence; nothing is shared but the read-only frames)."""
     if rank != 0:
         return
     import multiprocessing as mp
-    ncols, nrows, nfeat, nlevels, ss, window, _ = WORKLOADS[args.workload]
+    global _REF_FRAMES
+    pkg = importlib.import_module(PKG)
+    synth = importlib.import_module(PKG + ".synth")
+    ncols, nrows, nfeat, nlevels, ss, window, nframes = WORKLOADS[args.workload]
+    # load the library in THIS process too (the forked workers inherit the mapping): the driver
+    # records the native libraries of the process it launched
+    lib, kind0 = _ref_library(pkg.capi)
     cores = os.cpu_count() or 1
     try:
         cores = len(os.sched_getaffinity(0))
@@ -510,10 +801,10 @@ def run_reference(args, rank, world):
     except Exception:
         avail_gb = 16.0
     procs = max(1, min(cores, 64, int(avail_gb * 0.6 / max(per_proc_gb, 1e-3))))
-    # a reference step at 4K costs about a second: bound the sample so the run ends in minutes
-    budget = args.ref_budget
-    warm = min(args.warmup, 1)
-    jobs = [(w, args.workload, warm, args.steps, budget, 12345) for w in range(procs)]
+    _REF_FRAMES = np.empty((nframes, nrows, ncols), np.uint8)
+    make_frames(synth, ncols, nrows, nframes, 12345, _REF_FRAMES)
+    # a reference step at 4K costs about half a second: the timed loop is bounded by --ref-budget
+    jobs = [(w, args.workload, args.warmup, args.steps, args.ref_budget) for w in range(procs)]
     t0 = time.time()
     with mp.get_context("fork").Pool(procs) as pool:
         res = pool.map(_ref_worker, jobs)
@@ -525,19 +816,16 @@ def run_reference(args, rank, world):
     kind = res[0][3]
     steps_done = min(r[2] for r in res)
     value = feats / secs
-    sample = ("%d independent sequences in parallel (one per host core, the library is single-threaded), "
+    sample = ("%d copies of the sequence in parallel (one per host core, the library is single-threaded), "
               "each: select + %d warm-up + %d timed KLTTrackFeatures calls at %dx%d / %d features; "
-              "timed-phase wall %.1fs" % (procs, warm, steps_done, ncols, nrows, nfeat, span))
+              "timed-phase wall %.1fs" % (procs, args.warmup, steps_done, ncols, nrows, nfeat, span))
     out = {
         "impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT,
-        "n_gpus": args.gpus, "steps": steps_done, "warmup": warm,
+        "n_gpus": args.gpus, "steps": steps_done, "warmup": args.warmup,
         "ms_per_step": round(secs / max(steps_done, 1) * 1e3, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "frames_per_s": round(frames_done / secs, 3),
-        "config": {"workload": "synthetic %dx%d translated sequence (2.3,-1.4 px/frame), %d features, "
-                               "%d pyramid levels (subsampling %d), window %dx%d"
-                               % (ncols, nrows, nfeat, nlevels, ss, window, window),
-                   "requested_steps": args.steps, "requested_warmup": args.warmup},
+        "config": workload_config(args.workload),
         "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
         "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "total_wall_s": round(time.time() - t0, 1),
@@ -556,11 +844,14 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--ref-budget", type=float, default=90.0,
                     help="--impl reference: stop a worker's timed loop after this many seconds")
+    ap.add_argument("--c5-segment", type=int, default=128, help="config 5: frames per KLTTrackFeaturesSequence call")
+    ap.add_argument("--c5-segments", type=int, default=8, help="config 5: calls per sequence")
+    ap.add_argument("--c5-inflight", type=int, default=4, help="config 5: sequences in flight per GPU")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.warmup < 3 and args.impl == "b200":
+    if args.warmup < 3:
         log("warmup raised to 3 (timing rules)")
         args.warmup = 3
     if args.impl == "reference":
