@@ -1686,6 +1686,11 @@ static bool level_map(CUtensorMap* m, const Level& a) {
   return make_tensor_map(m, a.img, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.w, a.h, (size_t)a.pitch * 4, G::SW, G::SH);
 }
 
+using L0GeoB = L0GeoT<48, 6, 6, 4>;      // 48-row tiles: 2 even passes in stages A / C, 54 KB of shared memory, 4 CTAs / SM
+static int l0_variant() {                // 0: 64-row tiles, 3 CTAs / SM; 1 (default): 48-row tiles, 4 CTAs / SM
+  static int v = getenv("KLT_B200_L0_TILE") ? atoi(getenv("KLT_B200_L0_TILE")) : 1;
+  return v;
+}
 // which levels of this build can run on the fused kernels, and their tensor maps
 static void fused_plan(klt_dev* d, const PyrSet& S, const unsigned char* src, int spitch,
                        const klt_dev_build_desc* q, const TapsR& ts, const TapsR& tp, const TapsR& tg,
@@ -1694,12 +1699,12 @@ static void fused_plan(klt_dev* d, const PyrSet& S, const unsigned char* src, in
   if (d->force_generic || d->no_fused || !fused_grad_taps_ok(tg, td)) return;
   const int W = q->ncols, H = q->nrows;
   P->src = src; P->spitch = spitch;
+  const int l0_ty = l0_variant() == 1 ? L0GeoB::TY : L0Geo::TY, l0_u8h = l0_variant() == 1 ? L0GeoB::U8_H : L0Geo::U8_H;
   if (q->smooth && ts.w == 2 * L0Geo::RS + 1 &&
-      make_tensor_map(&P->map[0], src, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, W, H, (size_t)spitch, L0Geo::U8_W,
-                      L0Geo::U8_H)) {
+      make_tensor_map(&P->map[0], src, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, W, H, (size_t)spitch, L0Geo::U8_W, l0_u8h)) {
     P->l0_ok = true;
-    P->TX[0] = L0Geo::TX; P->TY[0] = L0Geo::TY;
-    P->tiles_x[0] = (W + L0Geo::TX - 1) / L0Geo::TX; P->tiles_y[0] = (H + L0Geo::TY - 1) / L0Geo::TY;
+    P->TX[0] = L0Geo::TX; P->TY[0] = l0_ty;
+    P->tiles_x[0] = (W + L0Geo::TX - 1) / L0Geo::TX; P->tiles_y[0] = (H + l0_ty - 1) / l0_ty;
   }
   P->SS = q->subsampling; P->R = tp.w / 2;
   for (int l = 1; l < q->nlevels_built; ++l) {
@@ -1723,26 +1728,37 @@ static void fused_plan(klt_dev* d, const PyrSet& S, const unsigned char* src, in
 }
 
 // fused level 0 (u8 -> L0, gx0, gy0), tile rows [jr0, jr1)
-template <bool EXACT>
-static int l0_fused_launch(klt_dev* d, const FusedPlan& P, int W, int H, const TapsR& ts, const TapsR& tg,
-                           const TapsR& td, const Level& lv, int jr0, int jr1) {
-  if (jr1 <= jr0) return 0;
-  static bool attr_dev[64][2] = {};              // function attributes are per device
-  bool* attr_set = attr_dev[d->device & 63];
-  if (!attr_set[EXACT]) {
-    CU(cudaFuncSetAttribute(l0_fused_kernel<EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L0Geo::SMEM));
-    attr_set[EXACT] = true;
+template <class G, bool EXACT>
+static int l0_fused_launch_t(klt_dev* d, const FusedPlan& P, int W, int H, const TapsR& ts, const TapsR& tg,
+                             const TapsR& td, const Level& lv, int jr0, int jr1) {
+  static bool attr_dev[64] = {};                 // function attributes are per device
+  bool& attr_set = attr_dev[d->device & 63];
+  static int cps = 0;
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(l0_fused_kernel<G, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, l0_fused_kernel<G, EXACT>, 256, G::SMEM));
+    if (cps < 1) cps = 1;
+    attr_set = true;
   }
   const int tiles_x = P.tiles_x[0];
   const int tile0 = jr0 * tiles_x, tile1 = jr1 * tiles_x, n = tile1 - tile0;
-  const int cps = (d->overlap && d->overlap_l0_ctas > 0) ? d->overlap_l0_ctas : 3;
-  const int grid = n < cps * d->num_sms ? n : cps * d->num_sms;               // persistent, 3 CTAs / SM
+  const int per_sm = (d->overlap && d->overlap_l0_ctas > 0) ? d->overlap_l0_ctas : cps;
+  const int grid = n < per_sm * d->num_sms ? n : per_sm * d->num_sms;         // persistent
   { Launch l(d, KID_L0_FUSED);
-    CU(launch_k(l0_fused_kernel<EXACT>, dim3(grid), dim3(256), L0Geo::SMEM, d->stream, d->pdl != 0, P.map[0], W, H,
+    CU(launch_k(l0_fused_kernel<G, EXACT>, dim3(grid), dim3(256), G::SMEM, d->stream, d->pdl != 0, P.map[0], W, H,
                 tiles_x, tile0, tile1, d->d_tile_ctr, d->tile_base[0], to_fused(ts), to_fused(tg), to_fused(td), lv.img,
                 lv.gx, lv.gy, lv.pitch));
     d->tile_base[0] += (unsigned)(n + grid); }
   return 0;
+}
+template <bool EXACT>
+static int l0_fused_launch(klt_dev* d, const FusedPlan& P, int W, int H, const TapsR& ts, const TapsR& tg,
+                           const TapsR& td, const Level& lv, int jr0, int jr1) {
+  if (jr1 <= jr0) return 0;
+  switch (P.TY[0]) {
+    case L0GeoB::TY: return l0_fused_launch_t<L0GeoB, EXACT>(d, P, W, H, ts, tg, td, lv, jr0, jr1);
+    default: return l0_fused_launch_t<L0Geo, EXACT>(d, P, W, H, ts, tg, td, lv, jr0, jr1);
+  }
 }
 
 // fused coarser level (L_{l-1} -> L_l, gx_l, gy_l), tile rows [jr0, jr1)

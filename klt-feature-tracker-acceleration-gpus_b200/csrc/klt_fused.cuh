@@ -226,8 +226,11 @@ __device__ __forceinline__ void stage_vgrad_both(const float* sHd, const float* 
 // ============================================================================================
 // level 0
 // ============================================================================================
-struct L0Geo {
-  static constexpr int TX = 64, TY = 64;
+// TY_: tile height; PYB_ / PYD_: output rows per thread of the two vertical stages; CPS_: resident
+// CTAs per SM the kernel is compiled for (register budget).
+template <int TY_, int PYB_, int PYD_, int CPS_>
+struct L0GeoT {
+  static constexpr int TX = 64, TY = TY_, PYB = PYB_, PYD = PYD_, CPS = CPS_;
   static constexpr int RS = 2, RG = FUSED_RG;                          // smoothing / gradient radii
   static constexpr int U8_W = 96, U8_H = TY + 2 * (RS + RG);           // 96 x 74 bytes, col c <-> x0-16+c
   static constexpr int HS_P = 76, HS_H = U8_H;                         // col c <-> x0-4+c, row r <-> y0-5+r
@@ -240,13 +243,14 @@ struct L0Geo {
   static constexpr int OFF_HG = OFF_L0 + L0_H * L0_P * 4;
   static constexpr int OFF_BAR = OFF_HG + HG_H * HG_P * 4;
   static constexpr int SMEM = OFF_BAR + 16;
+  static_assert(L0_H % PYB == 0 && TY % PYD == 0 && (TX / 4) * (TY / PYD) <= 128 && (L0_H / PYB) * 18 <= 256, "stage B / D mapping");
 };
+using L0Geo = L0GeoT<64, 5, 8, 3>;       // (tile width, halo and radii are the same for every variant)
 
 // stage A item: 8 outputs (Hs cols 8g..8g+7 <-> global x0-4+8g+q) of row r from 12 u8 pixels
-template <bool EXACT, bool BORDER>
+template <class G, bool EXACT, bool BORDER>
 __device__ __forceinline__ void l0_stage_a_item(const unsigned char* sU8, float* sHs, const TapsF& ts,
                                                 int r, int g, int x0, int W) {
-  using G = L0Geo;
   constexpr int RS = G::RS;
   const uint2 wa = *reinterpret_cast<const uint2*>(sU8 + r * G::U8_W + 8 * g + 8);
   const uint2 wb = *reinterpret_cast<const uint2*>(sU8 + r * G::U8_W + 8 * g + 16);
@@ -274,9 +278,8 @@ __device__ __forceinline__ void l0_stage_a_item(const unsigned char* sU8, float*
   dst[1] = make_float4(o[4], o[5], o[6], o[7]);
 }
 
-template <bool EXACT, bool BORDER>
+template <class G, bool EXACT, bool BORDER>
 __device__ __forceinline__ void l0_fused_tile(unsigned char* smem, int W, const TapsF& ts, int x0) {
-  using G = L0Geo;
   const unsigned char* sU8 = smem + G::OFF_U8;
   float* sHs = reinterpret_cast<float*>(smem + G::OFF_HS);
   const int tid = threadIdx.x;
@@ -287,20 +290,19 @@ __device__ __forceinline__ void l0_fused_tile(unsigned char* smem, int W, const 
     const int sub = lane & 3, rpar = (lane >> 2) & 1, half = (lane >> 3) & 1, rpair = lane >> 4;
     for (int rb = warp * 4; rb < G::HS_H; rb += 32) {
       const int r = rb + 2 * rpair + rpar;
-      if (r < G::HS_H) l0_stage_a_item<EXACT, BORDER>(sU8, sHs, ts, r, 4 * half + sub, x0, W);
+      if (r < G::HS_H) l0_stage_a_item<G, EXACT, BORDER>(sU8, sHs, ts, r, 4 * half + sub, x0, W);
     }
-    if (tid < G::HS_H) l0_stage_a_item<EXACT, BORDER>(sU8, sHs, ts, tid, 8, x0, W);   // 9th group
+    if (tid < G::HS_H) l0_stage_a_item<G, EXACT, BORDER>(sU8, sHs, ts, tid, 8, x0, W);   // 9th group
   }
 }
 
-template <bool EXACT, bool BORDER>
+template <class G, bool EXACT, bool BORDER>
 __device__ __forceinline__ void l0_fused_tile_rest(unsigned char* smem, int W, int H, const TapsF& ts,
                                                    const TapsF& tg, const TapsF& td,
                                                    float* __restrict__ out_img,
                                                    float* __restrict__ out_gx,
                                                    float* __restrict__ out_gy, int opitch, int x0,
                                                    int y0) {
-  using G = L0Geo;
   constexpr int RS = G::RS, RG = G::RG;
   float* sHs = reinterpret_cast<float*>(smem + G::OFF_HS);
   float* sL0 = reinterpret_cast<float*>(smem + G::OFF_L0);
@@ -309,14 +311,15 @@ __device__ __forceinline__ void l0_fused_tile_rest(unsigned char* smem, int W, i
   const int tid = threadIdx.x;
 
   // ---- stage B: vertical Gaussian, Hs -> L0 (shared + HBM) ------------------------------------
-  // 18 column groups of 4 (col c <-> x0-4+c) x 14 row blocks of 5.  Threads 0..223 take groups
-  // 0..15 (a quarter warp = 8 consecutive groups of one row block: contiguous 128 B), threads
-  // 224..251 the two halo groups.
-  if (tid < 252) {
-    constexpr int PY = 5;
+  // 18 column groups of 4 (col c <-> x0-4+c) x NBLK row blocks of PYB (14 x 5 for the 64-row tile).
+  // The first 16 * NBLK threads take groups 0..15 (a quarter warp = 8 consecutive groups of one row
+  // block: contiguous 128 B), the next 2 * NBLK the two halo groups.
+  constexpr int NBLK = G::L0_H / G::PYB;
+  if (tid < 18 * NBLK) {
+    constexpr int PY = G::PYB;
     int blk, j;
-    if (tid < 224) { blk = tid >> 4; j = tid & 15; }
-    else { blk = (tid - 224) >> 1; j = 16 + ((tid - 224) & 1); }
+    if (tid < 16 * NBLK) { blk = tid >> 4; j = tid & 15; }
+    else { blk = (tid - 16 * NBLK) >> 1; j = 16 + ((tid - 16 * NBLK) & 1); }
     float4 acc[PY];
 #pragma unroll
     for (int q = 0; q < PY; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -349,7 +352,7 @@ __device__ __forceinline__ void l0_fused_tile_rest(unsigned char* smem, int W, i
 
   stage_hgrad<EXACT, BORDER, G::TX, G::L0_H, G::L0_P, G::HG_P>(sL0, sHd, sHg, tg, td, x0, W);
   tile_sync();
-  stage_vgrad_both<EXACT, BORDER, G::TX, G::TY, 8, G::HG_P>(sHd, sHg, tg, td, out_gx, out_gy, opitch,
+  stage_vgrad_both<EXACT, BORDER, G::TX, G::TY, G::PYD, G::HG_P>(sHd, sHg, tg, td, out_gx, out_gy, opitch,
                                                             x0, y0, W, H);
 }
 
@@ -359,13 +362,12 @@ __device__ __forceinline__ void l0_fused_tile_rest(unsigned char* smem, int W, i
 // stands at base + (ntiles - tile0) + gridDim.x, which the host uses as the next launch's base (no
 // reset needed).
 // The claim for the NEXT tile is made one tile ahead, so its TMA load can be issued early.
-template <bool EXACT>
-__global__ void __launch_bounds__(256, 3)
+template <class G, bool EXACT>
+__global__ void __launch_bounds__(256, G::CPS)
 l0_fused_kernel(const __grid_constant__ CUtensorMap map, int W, int H, int tiles_x, int tile0, int ntiles,
                 unsigned* __restrict__ counter, unsigned base,
                 TapsF ts, TapsF tg, TapsF td, float* __restrict__ out_img,
                 float* __restrict__ out_gx, float* __restrict__ out_gy, int opitch) {
-  using G = L0Geo;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + G::OFF_BAR);
   volatile int* s_next = reinterpret_cast<volatile int*>(smem_raw + G::OFF_BAR + 8);
@@ -394,8 +396,8 @@ l0_fused_kernel(const __grid_constant__ CUtensorMap map, int W, int H, int tiles
     const bool border = (x0 < 8) || (y0 < 8) || (x0 + G::TX + 8 > W) || (y0 + G::TY + 8 > H);
     mbar_wait(bar, phase);
     phase ^= 1;
-    if (border) l0_fused_tile<EXACT, true>(smem_raw, W, ts, x0);
-    else l0_fused_tile<EXACT, false>(smem_raw, W, ts, x0);
+    if (border) l0_fused_tile<G, EXACT, true>(smem_raw, W, ts, x0);
+    else l0_fused_tile<G, EXACT, false>(smem_raw, W, ts, x0);
     __syncthreads();                 // u8 tile consumed; everybody has read s_next
     if (tid == 0) {
       const int t = tile0 + (int)(atomicAdd(counter, 1u) - base);
@@ -406,8 +408,8 @@ l0_fused_kernel(const __grid_constant__ CUtensorMap map, int W, int H, int tiles
                     (t / tiles_x) * G::TY - (G::RS + G::RG), bar);
       }
     }
-    if (border) l0_fused_tile_rest<EXACT, true>(smem_raw, W, H, ts, tg, td, out_img, out_gx, out_gy, opitch, x0, y0);
-    else l0_fused_tile_rest<EXACT, false>(smem_raw, W, H, ts, tg, td, out_img, out_gx, out_gy, opitch, x0, y0);
+    if (border) l0_fused_tile_rest<G, EXACT, true>(smem_raw, W, H, ts, tg, td, out_img, out_gx, out_gy, opitch, x0, y0);
+    else l0_fused_tile_rest<G, EXACT, false>(smem_raw, W, H, ts, tg, td, out_img, out_gx, out_gy, opitch, x0, y0);
     // stage D reads Hd (aliased on Hs) and Hg: the next tile's stage A must not start before
     __syncthreads();
     tile = *s_next;
