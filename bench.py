@@ -504,7 +504,7 @@ def run_b200(args, rank, local_rank, world):
     # memory by the staging team; "registered": the buffers are page-locked in place on second sight
     # (opt-in, KLT_B200_REGISTER_FRAMES=1).  N = 1 only (torchrun pins every rank to one host thread).
     pageable = None
-    if world == 1 and not args.only_4k:
+    if world == 1:
         pageable = {}
         bufs = [np.empty((nrows, ncols), np.uint8) for _ in range(2)]
         for mode in ("staged", "registered"):
@@ -844,7 +844,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--ref-budget", type=float, default=90.0,
                     help="--impl reference: stop a worker's timed loop after this many seconds")
-    ap.add_argument("--only-4k", action="store_true", help="development: skip config 5, the pageable legs and the CPU legs")
+    ap.add_argument("--only-4k", action="store_true", help="development: skip config 5 and the CPU legs")
     ap.add_argument("--c5-segment", type=int, default=128, help="config 5: frames per KLTTrackFeaturesSequence call")
     ap.add_argument("--c5-segments", type=int, default=8, help="config 5: calls per sequence")
     ap.add_argument("--c5-inflight", type=int, default=4, help="config 5: sequences in flight per GPU")

@@ -1219,6 +1219,8 @@ struct klt_dev {
   int feat_out_host;            // 1: the next tracker writes its results into h_x/h_y/h_val (sync API); 2: record mode
   unsigned char* d_rec; size_t d_rec_cap; void* h_rec; int rec_stride;   // record mode (klt_dev_features_commit_records)
   cudaEvent_t ev_feat; int feat_pending;   // feature upload queued on the copy stream
+  // ... or not queued yet: it goes BEHIND the bands of the frame that is built next (feat_flush)
+  int feat_deferred; void* feat_def_dst; const void* feat_def_src; size_t feat_def_bytes;
   // affine consistency check (klt_dev_affine_*): per-feature state + templates, positions before tracking
   AffState* d_aff_st; AffState* h_aff_st; float* d_aff_tmpl; float* d_x0; int aff_cap, aff_tsz, aff_x0_cap;
   // ring of pinned feature snapshots (klt_dev_snapshot_*)
@@ -1940,6 +1942,7 @@ extern "C" void klt_dev_set_register_frames(klt_dev* d, int on) { d->reg_frames 
 static void parallel_memcpy(unsigned char* dst, const unsigned char* src, size_t bytes, int nthreads) {
   stage_team().copy(dst, src, bytes, nthreads);
 }
+static int feat_flush(klt_dev* d);
 static int feed_enqueue_band(klt_dev* d, BandFeed* f, int b) {
   const int r0 = b == 0 ? 0 : f->end_row[b - 1], r1 = f->end_row[b];
   if (!f->staged) {
@@ -1975,6 +1978,7 @@ static int feed_enqueue_band(klt_dev* d, BandFeed* f, int b) {
   d->band_ev_next = (d->band_ev_next + 1) % KLT_BAND_EVENTS;
   CU(cudaEventRecord(f->ev[b], d->cstream));
   f->enqueued = b + 1;
+  if (b == f->nbands - 1 && feat_flush(d)) return 1;   // the committed feature upload goes behind the frame
   return 0;
 }
 static int feed_enqueue_copies(klt_dev* d, BandFeed* f) {
@@ -2265,6 +2269,7 @@ extern "C" int klt_dev_features_upload(klt_dev* d, int n, const float* x, const 
   if (n < 0) return fail(d, "negative feature count");
   if (ensure_features(d, n > 0 ? n : 1)) return 1;
   if (staging_quiesce(d)) return 1;
+  d->feat_deferred = 0;                               // (a committed but never queued upload is superseded)
   memcpy(d->h_x, x, n * sizeof(float));
   memcpy(d->h_y, y, n * sizeof(float));
   memcpy(d->h_val, val, n * sizeof(int));
@@ -2283,15 +2288,25 @@ extern "C" int klt_dev_features_staging(klt_dev* d, int n, float** x, float** y,
   *x = d->h_x; *y = d->h_y; *val = d->h_val;
   return 0;
 }
+// queue the committed feature upload on the copy stream now (behind whatever is already there)
+static int feat_flush(klt_dev* d) {
+  if (!d->feat_deferred) return 0;
+  d->feat_deferred = 0;
+  if (d->feat_def_bytes > 0) {
+    Launch l(d, KID_COPY_H2D, d->cstream);
+    CU(cudaMemcpyAsync(d->feat_def_dst, d->feat_def_src, d->feat_def_bytes, cudaMemcpyHostToDevice, d->cstream));
+  }
+  CU(cudaEventRecord(d->ev_feat, d->cstream));
+  d->feat_pending = 1;
+  return 0;
+}
 extern "C" int klt_dev_features_commit(klt_dev* d, int n) {      // H2D of the staging area (async)
   CU(cudaSetDevice(d->device));
   if (n > d->feat_cap) return fail(d, "commit of %d features, capacity %d", n, d->feat_cap);
-  // on the copy stream, ahead of the frame bands: the tracker is gated on ev_feat, the image
-  // kernels are not (on the compute stream this small copy would sit behind the whole frame upload)
-  { Launch l(d, KID_COPY_H2D, d->cstream);
-    CU(cudaMemcpyAsync(d->d_x, d->h_x, (size_t)d->feat_cap * 12, cudaMemcpyHostToDevice, d->cstream)); }
-  CU(cudaEventRecord(d->ev_feat, d->cstream));
-  d->feat_pending = 1;
+  // on the copy stream, BEHIND the bands of the frame the next klt_dev_build uploads (feat_flush):
+  // only the tracker needs the features, and it runs after the last band's kernels anyway; ahead of
+  // the frame the copy would delay every byte of it (12 us of a 235 us call at 4K / 4096 features)
+  d->feat_deferred = 1; d->feat_def_dst = d->d_x; d->feat_def_src = d->h_x; d->feat_def_bytes = (size_t)d->feat_cap * 12;
   d->staging_busy = 1;
   d->feat_out_host = 1;
   d->feat_n = n;
@@ -2310,12 +2325,7 @@ extern "C" int klt_dev_features_commit_records(klt_dev* d, int n, void* first_re
     CU(cudaMalloc(&d->d_rec, bytes ? bytes : 16));
     d->d_rec_cap = bytes ? bytes : 16;
   }
-  if (n > 0) {
-    Launch l(d, KID_COPY_H2D, d->cstream);
-    CU(cudaMemcpyAsync(d->d_rec, first_record, bytes, cudaMemcpyHostToDevice, d->cstream));
-  }
-  CU(cudaEventRecord(d->ev_feat, d->cstream));
-  d->feat_pending = 1;
+  d->feat_deferred = 1; d->feat_def_dst = d->d_rec; d->feat_def_src = first_record; d->feat_def_bytes = bytes;
   d->feat_out_host = 2;
   d->h_rec = first_record;
   d->rec_stride = (int)(stride_bytes / 4);
@@ -2333,6 +2343,7 @@ extern "C" void klt_dev_host_free(void* p) { if (p) cudaFreeHost(p); }
 extern "C" int klt_dev_features_fetch(klt_dev* d, int n) {       // D2H into the staging area + sync
   CU(cudaSetDevice(d->device));
   if (n > d->feat_n) return fail(d, "download of %d features but %d resident", n, d->feat_n);
+  if (feat_flush(d)) return 1;
   if (d->feat_out_host == 0) {
     Launch l(d, KID_COPY_D2H, d->tstream);
     CU(cudaMemcpyAsync(d->h_x, d->d_x, (size_t)d->feat_cap * 12, cudaMemcpyDeviceToHost, d->tstream));
@@ -2479,6 +2490,7 @@ extern "C" int klt_dev_track_resident(klt_dev* d, int slot_prev, int slot_cur,
     return fail(d, "tracking window %d x %d must be odd and >= 3", p->window_width, p->window_height);
   const int n = d->feat_n;
   if (n == 0) return 0;
+  if (feat_flush(d)) return 1;
   if (d->feat_pending) {                             // features uploaded on the copy stream
     CU(cudaStreamWaitEvent(d->tstream, d->ev_feat, 0));
     d->feat_pending = 0;
@@ -2565,6 +2577,7 @@ extern "C" int klt_dev_affine_begin(klt_dev* d, int n, const klt_dev_affine_para
   }
   if (d->feat_out_host == 2) return fail(d, "affine_begin: record-mode features (use the staging area)");
   d->feat_out_host = 0;                              // the check needs the tracker's answers on the device
+  if (feat_flush(d)) return 1;
   if (d->feat_pending) {
     CU(cudaStreamWaitEvent(d->tstream, d->ev_feat, 0));
     d->feat_pending = 0;

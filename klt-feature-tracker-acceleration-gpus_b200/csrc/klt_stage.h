@@ -4,11 +4,47 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
 #include <vector>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+// The staged bytes are read next by the GPU's DMA engine, not by this CPU: streaming (non-temporal)
+// stores put them straight into DRAM -- no read-for-ownership of the destination lines, nothing
+// dirty left in this core's caches for the DMA reads to snoop out.  KLT_B200_STAGE_NT=0 keeps memcpy.
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) static inline void klt_stream_copy_avx2(unsigned char* dst, const unsigned char* src, size_t n) {
+  size_t head = (32 - ((uintptr_t)dst & 31)) & 31;
+  if (head > n) head = n;
+  if (head) { memcpy(dst, src, head); dst += head; src += head; n -= head; }
+  size_t i = 0;
+  for (; i + 128 <= n; i += 128) {
+    const __m256i a = _mm256_loadu_si256((const __m256i*)(src + i));
+    const __m256i b = _mm256_loadu_si256((const __m256i*)(src + i + 32));
+    const __m256i c = _mm256_loadu_si256((const __m256i*)(src + i + 64));
+    const __m256i e = _mm256_loadu_si256((const __m256i*)(src + i + 96));
+    _mm256_stream_si256((__m256i*)(dst + i), a);
+    _mm256_stream_si256((__m256i*)(dst + i + 32), b);
+    _mm256_stream_si256((__m256i*)(dst + i + 64), c);
+    _mm256_stream_si256((__m256i*)(dst + i + 96), e);
+  }
+  for (; i + 32 <= n; i += 32) _mm256_stream_si256((__m256i*)(dst + i), _mm256_loadu_si256((const __m256i*)(src + i)));
+  if (i < n) memcpy(dst + i, src + i, n - i);
+  _mm_sfence();
+}
+#endif
+static inline void klt_stage_copy(unsigned char* dst, const unsigned char* src, size_t n) {
+#if defined(__x86_64__)
+  static const int nt = (getenv("KLT_B200_STAGE_NT") ? atoi(getenv("KLT_B200_STAGE_NT")) : 1) && __builtin_cpu_supports("avx2");
+  if (nt && n >= 4096) { klt_stream_copy_avx2(dst, src, n); return; }
+#endif
+  memcpy(dst, src, n);
+}
 
 // Staging team: a few process-wide helper threads that copy slices of a chunk next to the calling
 // thread.  They spin on a generation counter for a short while after their last job (a frame is
@@ -32,7 +68,7 @@ struct StageTeam {
     const size_t unit = (bytes / parts + 63) & ~(size_t)63;
     const size_t a = unit * k < bytes ? unit * k : bytes;
     const size_t b = k == parts - 1 ? bytes : (unit * (k + 1) < bytes ? unit * (k + 1) : bytes);
-    if (b > a) memcpy(dst + a, src + a, b - a);
+    if (b > a) klt_stage_copy(dst + a, src + a, b - a);
   }
   void run(int id) {
     unsigned seen = 0;
@@ -60,7 +96,7 @@ struct StageTeam {
   }
   void copy(unsigned char* d, const unsigned char* s, size_t n, int nthreads) {
     if (nthreads > MAXW + 1) nthreads = MAXW + 1;
-    if (nthreads <= 1 || n < (256u << 10)) { memcpy(d, s, n); return; }
+    if (nthreads <= 1 || n < (256u << 10)) { klt_stage_copy(d, s, n); return; }
     std::lock_guard<std::mutex> job(job_mu);
     while ((int)workers.size() < nthreads - 1) { const int id = (int)workers.size(); workers.emplace_back([this, id] { run(id); }); }
     dst = d; src = s; bytes = n; parts = nthreads;
