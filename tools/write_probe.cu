@@ -28,6 +28,32 @@ __global__ void copy4(const float4* __restrict__ s, float4* d, size_t n4) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
 }
 
+// the tile kernels' store pattern: persistent CTAs claim TW x TH tiles in raster order; a warp writes
+// 32 / (TW / 4) row segments of TW * 4 bytes per instruction, plane after plane
+template <int TW, int TH>
+__global__ void fill3_tiled(float* a, float* b, float* c, int W, int H, unsigned* ctr, unsigned base, const unsigned char* u8) {
+  __shared__ int s_tile;
+  const int tiles_x = W / TW, ntiles = tiles_x * (H / TH);
+  constexpr int CG = TW / 4, RPP = 256 / CG;            // column groups, rows per pass
+  const int j = threadIdx.x % CG, r0 = threadIdx.x / CG;
+  for (;;) {
+    if (threadIdx.x == 0) s_tile = (int)(atomicAdd(ctr, 1u) - base);
+    __syncthreads();
+    const int t = s_tile;
+    __syncthreads();
+    if (t >= ntiles) break;
+    const int x0 = (t % tiles_x) * TW, y0 = (t / tiles_x) * TH;
+    float v = 1.0f;
+    if (u8) v = (float)u8[(size_t)(y0 + r0) * W + x0 + 4 * j];
+    const float4 w = make_float4(v, v + 1, v + 2, v + 3);
+    float* pl[3] = {a, b, c};
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      for (int r = r0; r < TH; r += RPP)
+        *reinterpret_cast<float4*>(pl[k] + (size_t)(y0 + r) * W + x0 + 4 * j) = w;
+  }
+}
+
 int main() {
   const size_t px = 3840ull * 2160, n4 = px / 4;
   const int SETS = 3;
@@ -60,6 +86,21 @@ int main() {
     }
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));
     printf("copy     grid %4d: %6.2f us / launch  %7.1f GB/s (read + write)\n", grid, ms / REPS * 1e3, 2.0 * n4 * 16 / (ms / REPS * 1e-3) / 1e9);
+  }
+  {
+    unsigned* ctr; CK(cudaMalloc(&ctr, 4)); CK(cudaMemset(ctr, 0, 4));
+    unsigned base = 0;
+#define TILED(TW, TH, CPS, U8)                                                                              \
+    {                                                                                                       \
+      const int grid = 148 * CPS;                                                                           \
+      for (int i = 0; i < 4; ++i) { fill3_tiled<TW, TH><<<grid, 256>>>((float*)pl[i % SETS][0], (float*)pl[i % SETS][1], (float*)pl[i % SETS][2], 3840, 2160, ctr, base, U8 ? (const unsigned char*)u8[i % SETS] : nullptr); base += (3840 / TW) * (2160 / TH) + grid; } \
+      CK(cudaEventRecord(e0));                                                                              \
+      for (int i = 0; i < REPS; ++i) { fill3_tiled<TW, TH><<<grid, 256>>>((float*)pl[i % SETS][0], (float*)pl[i % SETS][1], (float*)pl[i % SETS][2], 3840, 2160, ctr, base, U8 ? (const unsigned char*)u8[i % SETS] : nullptr); base += (3840 / TW) * (2160 / TH) + grid; } \
+      CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));         \
+      printf("tiled %3dx%-3d %d CTAs/SM%s: %6.2f us / launch  %7.1f GB/s written\n", TW, TH, CPS, U8 ? " +u8" : "    ", ms / REPS * 1e3, 12.0 * px / (ms / REPS * 1e-3) / 1e9); \
+    }
+    TILED(64, 48, 4, 0) TILED(64, 48, 4, 1) TILED(64, 16, 4, 0) TILED(128, 24, 4, 0) TILED(128, 48, 4, 0) TILED(256, 24, 4, 0) TILED(256, 48, 4, 0)
+    TILED(64, 48, 8, 0) TILED(128, 24, 8, 0) TILED(256, 24, 8, 0) TILED(256, 24, 8, 1)
   }
   CK(cudaEventRecord(e0));
   for (int i = 0; i < REPS; ++i) for (int k = 0; k < 3; ++k) CK(cudaMemsetAsync(pl[i % SETS][k], i, px * 4));
