@@ -213,6 +213,12 @@ class Pyramids:
         ptr = self.o.lib.klto_pyr_data(self.handle, which, l)
         return np.ctypeslib.as_array(ptr, shape=(nr.value, nc.value)).copy()
 
+    def view(self, which: int, l: int) -> np.ndarray:
+        """the level's data in place (writable, no copy): for sensitivity experiments in the tests"""
+        nc, nr = C.c_int(0), C.c_int(0)
+        self.o.lib.klto_pyr_dims(self.handle, l, C.byref(nc), C.byref(nr))
+        return np.ctypeslib.as_array(self.o.lib.klto_pyr_data(self.handle, which, l), shape=(nr.value, nc.value))
+
     def __del__(self):
         try:
             self.o.lib.klto_free_pyramids(self.handle)

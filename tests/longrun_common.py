@@ -140,6 +140,22 @@ def drift_table(oracle_tab, gpu_tab, checkpoints=None):
                      "frac_gt_0.01px": float((d > 0.01).mean()) if d.size else 0.0,
                      "frac_gt_0.1px": float((d > 0.1).mean()) if d.size else 0.0,
                      "frac_gt_1px": float((d > 1.0).mean()) if d.size else 0.0})
+    # With replacement the SLOTS stop corresponding as soon as one run loses a feature one frame
+    # earlier than the other (the refill lands elsewhere), although both keep following the same
+    # image points: compare the two point SETS as well (nearest oracle point of every GPU point;
+    # features are >= mindist apart, so the match is unambiguous).
+    try:
+        from scipy.spatial import cKDTree
+        for row in rows:
+            k = row["frame"]
+            ao, ag = OV[k] >= 0, GV[k] >= 0
+            if ao.any() and ag.any():
+                dist, _ = cKDTree(np.stack([OX[k][ao], OY[k][ao]], 1)).query(np.stack([GX[k][ag], GY[k][ag]], 1))
+                row["set_match_within_0.01px"] = float((dist <= 0.01).mean())
+                row["set_match_within_0.1px"] = float((dist <= 0.1).mean())
+                row["set_match_within_1px"] = float((dist <= 1.0).mean())
+    except ImportError:
+        pass
     alive_o, alive_g = OV[1:] >= 0, GV[1:] >= 0
     both = alive_o & alive_g
     d = np.maximum(np.abs(OX[1:] - GX[1:]), np.abs(OY[1:] - GY[1:]))[both]

@@ -35,6 +35,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--data", default=None)
     ap.add_argument("--frames", type=int, default=0, help="limit the number of frames (0: all)")
+    ap.add_argument("--only", default="", help="config2 or config3")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "full_sequences.json"))
     args = ap.parse_args()
     data = args.data
@@ -52,6 +53,8 @@ def main():
     report = {"data": data, "configs": {}}
     for name, dataset, last, n, replace in (("config2", "images_traffic", 551, 1000, False),
                                             ("config3", "images_laptops", 1003, 2000, True)):
+        if args.only and args.only != name:
+            continue
         if args.frames:
             last = min(last, args.frames)
         frames = [capi.read_pgm_numpy(os.path.join(data, dataset, "img%d.pgm" % i)) for i in range(1, last + 1)]
