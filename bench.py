@@ -484,7 +484,8 @@ def run_b200(args, rank, local_rank, world):
     C.memset(C.cast(ft.contents.feature[0][0], C.c_void_p), 0,          # map the table's pages now
              (K + 1) * nfeat * C.sizeof(capi.KLT_FeatureRec))
     warm = (C.c_void_p * (W + 1))(*[h_ptr(idx(s)) for s in range(W + 1)])
-    L.KLTTrackFeaturesSequence(tc, warm, W + 1, ncols, nrows, fl, None, 0, 0)
+    # (with a table, so that the pinned snapshot ring exists before the timed call)
+    L.KLTTrackFeaturesSequence(tc, warm, W + 1, ncols, nrows, fl, ft if W <= K else None, 0, 0)
     seq = (C.c_void_p * (K + 1))(*[h_ptr(idx(W + s)) for s in range(K + 1)])
     L.klt_dev_live_total(dev, C.byref(live), 1)
     barrier()
