@@ -1408,6 +1408,10 @@ extern "C" int klt_dev_create(int device, klt_dev** out) {
   e = cudaMalloc(&c->d_live, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemsetAsync(c->d_live, 0, sizeof(unsigned long long), c->stream);
   c->pdl = getenv("KLT_B200_PDL") ? atoi(getenv("KLT_B200_PDL")) : 1;
+  if (getenv("KLT_B200_L2_HINTS")) {              // (per device: the symbol lives in this device's module image)
+    const int hints = atoi(getenv("KLT_B200_L2_HINTS")) & 3;
+    cudaMemcpyToSymbol(c_l2_hints, &hints, sizeof(int));
+  }
   c->no_track7w = getenv("KLT_B200_TRACK7W") ? !atoi(getenv("KLT_B200_TRACK7W")) : 0;
   if (getenv("KLT_B200_L2_PERSIST_MB")) {       // experiment: L2 set-aside for evict_last lines (KLT_TRACK_L2_KEEP)
     int maxb = 0;
@@ -1774,7 +1778,8 @@ static int level_fused_launch_t(klt_dev* d, const FusedPlan& P, int level, const
   if (!attr_set) {
     CU(cudaFuncSetAttribute(level_fused_kernel<SS, R, TX, TY, EXACT>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, level_fused_kernel<SS, R, TX, TY, EXACT>, 256, G::SMEM));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, level_fused_kernel<SS, R, TX, TY, EXACT>,
+                                                     lv_threads<SS, R, TX, TY>(), G::SMEM));
     if (cps < 1) cps = 1;
     attr_set = true;
   }
@@ -1783,7 +1788,7 @@ static int level_fused_launch_t(klt_dev* d, const FusedPlan& P, int level, const
   const int grid = n < cps * d->num_sms ? n : cps * d->num_sms;             // persistent
   // (accounted per pyramid level: every level runs its own template instantiation / tile shape)
   { Launch l(d, level <= 1 ? KID_LEVEL_FUSED : level == 2 ? KID_LEVEL_FUSED_L2 : KID_LEVEL_FUSED_L3);
-    CU(launch_k(level_fused_kernel<SS, R, TX, TY, EXACT>, dim3(grid), dim3(256), G::SMEM, d->stream, d->pdl != 0,
+    CU(launch_k(level_fused_kernel<SS, R, TX, TY, EXACT>, dim3(grid), dim3(lv_threads<SS, R, TX, TY>()), G::SMEM, d->stream, d->pdl != 0,
                 P.map[level], a.w, a.h, b.w, b.h, tiles_x, tile0, tile1, d->d_tile_ctr + (level & 15),
                 d->tile_base[level & 15], to_fused(tp), to_fused(tg), to_fused(td), b.img, b.gx, b.gy, b.pitch));
     d->tile_base[level & 15] += (unsigned)(n + grid); }

@@ -105,6 +105,28 @@ __device__ __forceinline__ void fma4(float4& a, const float4& v, const TapsF& t,
   }
 }
 
+// L2 residency hints for the pyramid stores.  The smoothed image L_l is what the next kernel of the
+// chain reads back in full (level l+1 is made from it), the gradients are only gathered later, at a
+// few thousand footprints, by the tracker.  A 4K level 0 is 100 MB of stores through a 126 MB L2 that
+// still holds the previous frame: left alone, most of L_0 is gone again before level_fused_kernel
+// asks for it (ncu, no cache flush: 33 MB of DRAM reads for level 1 = all of L_0).  c_l2_hints (env
+// KLT_B200_L2_HINTS) bit 0: L_l is stored evict_last; bit 1: gx_l / gy_l are stored evict_first.
+// Measured on the 4K step (us): 0: 72.93, 1: 74.54 (the tracker's gradient gathers miss: 20.8 -> 22.9),
+// 2: 72.33 (level 1: 24.7 -> 22.9), 3: 73.96.  Default 2.
+__constant__ int c_l2_hints = 2;
+__device__ __forceinline__ unsigned long long store_policy(bool keep) {
+  unsigned long long p_keep, p_drop, p_norm;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p_keep));
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p_drop));
+  asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p_norm));
+  return keep ? ((c_l2_hints & 1) ? p_keep : p_norm) : ((c_l2_hints & 2) ? p_drop : p_norm);
+}
+__device__ __forceinline__ void stg128(float* p, const float4& v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w), "l"(pol)
+               : "memory");
+}
+
 static constexpr int FUSED_RG = 3;       // gradient radius the fused kernels are built for
 
 // Programmatic dependent launch: a CTA of the per-frame chain that finds its tile queue empty lets
@@ -119,14 +141,15 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 // barrier among the 256 threads that compute a tile (== __syncthreads() in the 256-thread kernels;
 // pyramid_mega_kernel carries a ninth, scheduling warp that must stay out of it)
-__device__ __forceinline__ void tile_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+template <int NTH = 256>
+__device__ __forceinline__ void tile_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTH) : "memory"); }
 
 // ---- stage C: horizontal DoG and Gaussian of a level tile ---------------------------------
 // sL [LH][LP]: tile col c <-> global x0-4+c.   sHd, sHg [LH][HP]: col c <-> global x0+c.
 // 8 outputs per thread from a 16-float window (4 x LDS.128); a warp covers 8 groups x 4 rows
 // (TX = 64) or 4 groups x 8 rows (TX = 32); a quarter warp is 4 groups x 2 rows, conflict free
 // because LP/4 and HP/4 are odd.
-template <bool EXACT, bool BORDER, int TX, int LH, int LP, int HP>
+template <bool EXACT, bool BORDER, int TX, int LH, int LP, int HP, int NTH = 256>
 __device__ __forceinline__ void stage_hgrad(const float* sL, float* sHd, float* sHg, const TapsF& tg,
                                             const TapsF& td, int x0, int W) {
   constexpr int RG = FUSED_RG;
@@ -136,7 +159,7 @@ __device__ __forceinline__ void stage_hgrad(const float* sL, float* sHd, float* 
   const int sub = lane & 3, rpar = (lane >> 2) & 1, rem = lane >> 3;
   const int g = NGC == 8 ? 4 * (rem & 1) + sub : sub;
   const int rl = NGC == 8 ? 2 * (rem >> 1) + rpar : 2 * rem + rpar;
-  for (int rb = warp * RPW; rb < LH; rb += 8 * RPW) {
+  for (int rb = warp * RPW; rb < LH; rb += (NTH / 32) * RPW) {
     const int r = rb + rl;
     if (r < LH) {
       float win[16];
@@ -179,6 +202,7 @@ __device__ __forceinline__ void stage_vgrad(const float* __restrict__ src, const
                                             float* __restrict__ out, int opitch, int xg, int yg0,
                                             int W, int H) {
   constexpr int R = FUSED_RG;
+  const unsigned long long pol = store_policy(false);
   float4 acc[PY];
 #pragma unroll
   for (int q = 0; q < PY; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -196,25 +220,26 @@ __device__ __forceinline__ void stage_vgrad(const float* __restrict__ src, const
     const int yg = yg0 + q;
     if (BORDER) {
       if (yg < R || yg >= H - R) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (xg < W && yg < H) *reinterpret_cast<float4*>(out + (size_t)yg * opitch + xg) = acc[q];
+      if (xg < W && yg < H) stg128(out + (size_t)yg * opitch + xg, acc[q], pol);
     } else {
-      *reinterpret_cast<float4*>(out + (size_t)yg * opitch + xg) = acc[q];
+      stg128(out + (size_t)yg * opitch + xg, acc[q], pol);
     }
   }
 }
 
 // gx = V_gauss(Hd), gy = V_deriv(Hg); first half of the CTA does gx, second half gy (warp uniform)
-template <bool EXACT, bool BORDER, int TX, int TY, int PY, int HP>
+template <bool EXACT, bool BORDER, int TX, int TY, int PY, int HP, int NTH = 256>
 __device__ __forceinline__ void stage_vgrad_both(const float* sHd, const float* sHg, const TapsF& tg,
                                                  const TapsF& td, float* out_gx, float* out_gy,
                                                  int opitch, int x0, int y0, int W, int H) {
   constexpr int NCG = TX / 4, NRB = TY / PY, ITEMS = NCG * NRB;       // per output image
-  static_assert(ITEMS <= 128, "stage D mapping");
+  constexpr int HALF = NTH / 2;
+  static_assert(ITEMS <= HALF, "stage D mapping");
   const int tid = threadIdx.x;
-  const int t = tid & 127;
+  const int t = tid & (HALF - 1);
   if (t < ITEMS) {
     const int blk = t / NCG, j = t - blk * NCG;
-    if (tid < 128)
+    if (tid < HALF)
       stage_vgrad<EXACT, BORDER, PY, HP, false>(sHd + (blk * PY) * HP + 4 * j, tg, out_gx, opitch,
                                                 x0 + 4 * j, y0 + blk * PY, W, H);
     else
@@ -317,6 +342,7 @@ __device__ __forceinline__ void l0_fused_tile_rest(unsigned char* smem, int W, i
   constexpr int NBLK = G::L0_H / G::PYB;
   if (tid < 18 * NBLK) {
     constexpr int PY = G::PYB;
+    const unsigned long long pol_img = store_policy(true);
     int blk, j;
     if (tid < 16 * NBLK) { blk = tid >> 4; j = tid & 15; }
     else { blk = (tid - 16 * NBLK) >> 1; j = 16 + ((tid - 16 * NBLK) & 1); }
@@ -344,7 +370,7 @@ __device__ __forceinline__ void l0_fused_tile_rest(unsigned char* smem, int W, i
       *reinterpret_cast<float4*>(sL0 + rr * G::L0_P + 4 * j) = acc[q];
       if (j >= 1 && j <= 16 && rr >= RG && rr < RG + G::TY) {
         if (!BORDER || (xg < W && yg < H))
-          *reinterpret_cast<float4*>(out_img + (size_t)yg * opitch + xg) = acc[q];
+          stg128(out_img + (size_t)yg * opitch + xg, acc[q], pol_img);
       }
     }
   }
@@ -478,7 +504,7 @@ __device__ __forceinline__ void lv_p1_item(const float* sSrc, float* sHp, const 
   *reinterpret_cast<float4*>(sHp + r * G::HPP + 4 * g) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
-template <bool EXACT, bool BORDER, int SS, int R, int TX, int TY>
+template <bool EXACT, bool BORDER, int SS, int R, int TX, int TY, int NTH = 256>
 __device__ __forceinline__ void lv_stage_p1(const unsigned char* smem, const TapsF& tp, int x0, int Wsrc) {
   using G = LvGeo<SS, R, TX, TY>;
   const float* sSrc = reinterpret_cast<const float*>(smem + G::OFF_SRC);
@@ -489,19 +515,19 @@ __device__ __forceinline__ void lv_stage_p1(const unsigned char* smem, const Tap
   if (SS == 2) { g8 = 4 * ((lane >> 3) & 1) + (lane & 3); rl = 2 * (lane >> 4) + ((lane >> 2) & 1); }
   else         { g8 = 2 * (lane >> 3) + (lane & 1);       rl = (lane >> 1) & 3; }
   constexpr int NMAIN = (G::NGL / 8) * 8, NCH = NMAIN / 8, NRB = (G::SH + 3) / 4;
-  for (int u = warp; u < NRB * NCH; u += 8) {
+  for (int u = warp; u < NRB * NCH; u += NTH / 32) {
     const int rbk = u / NCH, ch = u - rbk * NCH;
     const int r = 4 * rbk + rl;
     if (r < G::SH) lv_p1_item<EXACT, BORDER, SS, R, TX, TY>(sSrc, sHp, tp, r, 8 * ch + g8, x0, Wsrc);
   }
   constexpr int NTAIL = G::NGL - NMAIN;
-  for (int it = tid; it < G::SH * NTAIL; it += 256) {
+  for (int it = tid; it < G::SH * NTAIL; it += NTH) {
     const int r = it / NTAIL, g = NMAIN + it - r * NTAIL;
     lv_p1_item<EXACT, BORDER, SS, R, TX, TY>(sSrc, sHp, tp, r, g, x0, Wsrc);
   }
 }
 
-template <bool EXACT, bool BORDER, int SS, int R, int TX, int TY>
+template <bool EXACT, bool BORDER, int SS, int R, int TX, int TY, int NTH = 256>
 __device__ __forceinline__ void lv_stage_rest(unsigned char* smem, const TapsF& tp, const TapsF& tg,
                                               const TapsF& td, int Hsrc, int W, int H,
                                               float* __restrict__ out_img, float* __restrict__ out_gx,
@@ -520,7 +546,8 @@ __device__ __forceinline__ void lv_stage_rest(unsigned char* smem, const TapsF& 
     constexpr int NMAIN = (G::NGL / 8) * 8, NPAIR = G::LH / 2, NTAIL = G::NGL - NMAIN;
     static_assert(G::LH % 2 == 0, "level tile height must be even");
     constexpr int NR2 = SS + 2 * R + 1;
-    for (int it = tid; it < NPAIR * G::NGL; it += 256) {
+    const unsigned long long pol_img = store_policy(true);
+    for (int it = tid; it < NPAIR * G::NGL; it += NTH) {
       int pr, j;
       if (it < NPAIR * NMAIN) { pr = it / NMAIN; j = it - pr * NMAIN; }
       else { const int t2 = it - NPAIR * NMAIN; pr = t2 / NTAIL; j = NMAIN + t2 - pr * NTAIL; }
@@ -547,28 +574,34 @@ __device__ __forceinline__ void lv_stage_rest(unsigned char* smem, const TapsF& 
         *reinterpret_cast<float4*>(sL + rr * G::LP + 4 * j) = acc[q];
         if (j >= 1 && j <= G::NGL - 2 && rr >= RG && rr < RG + TY) {
           if (!BORDER || (xg < W && yg < H))
-            *reinterpret_cast<float4*>(out_img + (size_t)yg * opitch + xg) = acc[q];
+            stg128(out_img + (size_t)yg * opitch + xg, acc[q], pol_img);
         }
       }
     }
   }
-  tile_sync();
-  stage_hgrad<EXACT, BORDER, TX, G::LH, G::LP, G::HP>(sL, sHd, sHg, tg, td, x0, W);
-  tile_sync();
-  constexpr int PY = (TX / 4) * (TY / 4) <= 128 ? 4 : 8;
-  stage_vgrad_both<EXACT, BORDER, TX, TY, PY, G::HP>(sHd, sHg, tg, td, out_gx, out_gy, opitch, x0, y0, W, H);
+  tile_sync<NTH>();
+  stage_hgrad<EXACT, BORDER, TX, G::LH, G::LP, G::HP, NTH>(sL, sHd, sHg, tg, td, x0, W);
+  tile_sync<NTH>();
+  // output rows per thread of the last stage: as few as the thread count allows (fewer rows = more items)
+  constexpr int PY = (TX / 4) * (TY / 2) <= NTH / 2 ? 2 : ((TX / 4) * (TY / 4) <= NTH / 2 ? 4 : 8);
+  stage_vgrad_both<EXACT, BORDER, TX, TY, PY, G::HP, NTH>(sHd, sHg, tg, td, out_gx, out_gy, opitch, x0, y0, W, H);
 }
 
 // W,H: size of the level being produced; Wsrc,Hsrc: size of the level it is made from.
 // Dynamic tile scheduler as in l0_fused_kernel.
+// NTH threads per CTA: 256, or 512 for the big-tile shapes whose shared-memory footprint allows only two
+// CTAs per SM (16 warps per SM leave the tile's four-stage chain latency bound; 32 do not).
+template <int SS, int R, int TX, int TY>
+__host__ __device__ constexpr int lv_threads() { return (LvGeo<SS, R, TX, TY>::SMEM > 75 * 1024 && SS == 2) ? 512 : 256; }
 template <int SS, int R, int TX, int TY, bool EXACT>
-__global__ void __launch_bounds__(256, (LvGeo<SS, R, TX, TY>::SMEM <= 75 * 1024) ? 3 : 2)
+__global__ void __launch_bounds__((lv_threads<SS, R, TX, TY>()), (LvGeo<SS, R, TX, TY>::SMEM <= 75 * 1024) ? 3 : 2)
 level_fused_kernel(const __grid_constant__ CUtensorMap map, int Wsrc, int Hsrc, int W, int H,
                    int tiles_x, int tile0, int ntiles, unsigned* __restrict__ counter, unsigned base,
                    TapsF tp, TapsF tg, TapsF td,
                    float* __restrict__ out_img, float* __restrict__ out_gx,
                    float* __restrict__ out_gy, int opitch) {
   using G = LvGeo<SS, R, TX, TY>;
+  constexpr int NTH = lv_threads<SS, R, TX, TY>();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + G::OFF_BAR);
   volatile int* s_next = reinterpret_cast<volatile int*>(smem_raw + G::OFF_BAR + 8);
@@ -596,8 +629,8 @@ level_fused_kernel(const __grid_constant__ CUtensorMap map, int Wsrc, int Hsrc, 
     const bool border = (x0 < 8) || (y0 < 8) || (x0 + TX + 16 > W) || (y0 + TY + 16 > H);
     mbar_wait(bar, phase);
     phase ^= 1;
-    if (border) lv_stage_p1<EXACT, true, SS, R, TX, TY>(smem_raw, tp, x0, Wsrc);
-    else lv_stage_p1<EXACT, false, SS, R, TX, TY>(smem_raw, tp, x0, Wsrc);
+    if (border) lv_stage_p1<EXACT, true, SS, R, TX, TY, NTH>(smem_raw, tp, x0, Wsrc);
+    else lv_stage_p1<EXACT, false, SS, R, TX, TY, NTH>(smem_raw, tp, x0, Wsrc);
     __syncthreads();                 // source box consumed; everybody has read s_next
     if (tid == 0) {
       const int t = tile0 + (int)(atomicAdd(counter, 1u) - base);
@@ -609,9 +642,9 @@ level_fused_kernel(const __grid_constant__ CUtensorMap map, int Wsrc, int Hsrc, 
       }
     }
     if (border)
-      lv_stage_rest<EXACT, true, SS, R, TX, TY>(smem_raw, tp, tg, td, Hsrc, W, H, out_img, out_gx, out_gy, opitch, x0, y0);
+      lv_stage_rest<EXACT, true, SS, R, TX, TY, NTH>(smem_raw, tp, tg, td, Hsrc, W, H, out_img, out_gx, out_gy, opitch, x0, y0);
     else
-      lv_stage_rest<EXACT, false, SS, R, TX, TY>(smem_raw, tp, tg, td, Hsrc, W, H, out_img, out_gx, out_gy, opitch, x0, y0);
+      lv_stage_rest<EXACT, false, SS, R, TX, TY, NTH>(smem_raw, tp, tg, td, Hsrc, W, H, out_img, out_gx, out_gy, opitch, x0, y0);
     __syncthreads();                 // Hp / L / Hd / Hg free for the next tile
     tile = *s_next;
   }
