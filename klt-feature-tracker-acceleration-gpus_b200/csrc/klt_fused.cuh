@@ -403,7 +403,11 @@ l0_fused_kernel(const __grid_constant__ CUtensorMap map, int W, int H, int tiles
     // descriptor fetch overlaps the predecessor's tail (we may be resident before it has finished)
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(&map)) : "memory");
   }
-  pdl_wait();                         // the u8 frame / the pyramid slot we overwrite may still be in use
+  // Nothing this kernel READS comes from its predecessor in the stream (the u8 frame is resident, or
+  // its upload is ordered by an event the launch itself waited for); only the pyramid slot it WRITES
+  // may still be in use (the previous frame's tracker reads the other two slots and the feature
+  // arrays).  So the first tile's load and horizontal pass run before griddepcontrol.wait -- under
+  // the predecessor's tail -- and the wait sits in front of the first global store.
   if (tid == 0) {
     const int t = tile0 + (int)(atomicAdd(counter, 1u) - base);
     *s_next = t;
@@ -416,6 +420,7 @@ l0_fused_kernel(const __grid_constant__ CUtensorMap map, int W, int H, int tiles
   __syncthreads();
   int tile = *s_next;
   unsigned phase = 0;
+  bool waited = false;
   while (tile < ntiles) {
     const int x0 = (tile % tiles_x) * G::TX, y0 = (tile / tiles_x) * G::TY;
     // tiles whose 8-pixel margin stays inside the image never meet a zero band
@@ -434,12 +439,14 @@ l0_fused_kernel(const __grid_constant__ CUtensorMap map, int W, int H, int tiles
                     (t / tiles_x) * G::TY - (G::RS + G::RG), bar);
       }
     }
+    if (!waited) { pdl_wait(); waited = true; }
     if (border) l0_fused_tile_rest<G, EXACT, true>(smem_raw, W, H, ts, tg, td, out_img, out_gx, out_gy, opitch, x0, y0);
     else l0_fused_tile_rest<G, EXACT, false>(smem_raw, W, H, ts, tg, td, out_img, out_gx, out_gy, opitch, x0, y0);
     // stage D reads Hd (aliased on Hs) and Hg: the next tile's stage A must not start before
     __syncthreads();
     tile = *s_next;
   }
+  if (!waited) pdl_wait();            // (a CTA that got no tile)
   pdl_launch_dependents();            // queue empty: the next kernel of the chain may move in
 }
 

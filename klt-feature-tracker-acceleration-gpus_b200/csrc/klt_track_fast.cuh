@@ -313,6 +313,9 @@ track7w_kernel(PyrView p1, PyrView p2, TrackArgs a, int n, FeatIO io,
   const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned long long pol1 = l2_policy(a.l2_keep ? 2 : 0), pol2 = l2_policy(a.l2_keep ? 1 : 0);
   pdl_wait();                                                 // pyramids and features come from earlier kernels
+  // the whole grid is resident at once (a warp per feature, no shared memory): whatever follows in
+  // the stream -- the next frame's level-0 kernel -- may move into the SMs as these warps retire
+  pdl_launch_dependents();
   if (f >= n) return;
   if (io.val[(size_t)f * io.istride] < 0) return;             // only features that are not lost (:1346)
   if (lane == 0) atomicAdd(live_total, 1ULL);
