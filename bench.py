@@ -301,6 +301,86 @@ def run_config5(args, L, capi, synth, torch, dist, rank, local_rank, world, barr
             "features_alive_at_end_min_max": [min(local_alive.values()), max(local_alive.values())]}
 
 
+# --------------------------------------------------------------------------- configs 2 / 3 at their own size
+def small_frame_legs(L, capi, synth, torch):
+    """BASELINE configs 2 and 3 are 640x480 sequences (1000 features; 2000 features with
+    KLTReplaceLostFeatures after every frame).  The real frames do not travel with the repo (their
+    full-length parity report is profiles/r2_full_sequences*.json); this times the same driver loops
+    on a synthetic 640x480 sequence of 240 frames (translation + 0.2 deg/frame rotation + 0.1 % zoom)
+    through the per-call API and through KLTTrackFeaturesSequence, host frames, wall clock."""
+    W, H, NFR = 640, 480, 241
+    frames = torch.empty((NFR, H, W), dtype=torch.uint8, pin_memory=True)
+    fh = frames.numpy()
+    for t in range(NFR):
+        synth.frame(W, H, seed=2024, t=float(t), velocity=(1.7, -1.1), rot_deg=0.2, scale=1.001, out=fh[t])
+    ptr = lambda i: C.c_void_p(frames.data_ptr() + i * W * H)
+    out = {}
+    for name, n, replace in (("config2_like", 1000, False), ("config3_like", 2000, True)):
+        res = {}
+        for api in ("per_call", "sequence"):
+            tc = L.KLTCreateTrackingContext()
+            tc.contents.sequentialMode = 1
+            L.KLTB200SetDevice(tc, torch.cuda.current_device())
+            fl = L.KLTCreateFeatureList(n)
+            ft = L.KLTCreateFeatureTable(NFR, n)
+            C.memset(C.cast(ft.contents.feature[0][0], C.c_void_p), 0, NFR * n * C.sizeof(capi.KLT_FeatureRec))
+            L.KLTSelectGoodFeatures(tc, ptr(0), W, H, fl)
+            dev = L.KLTB200Device(tc)
+            for k in range(1, 9):                         # warm-up on the first frames
+                L.KLTTrackFeatures(tc, ptr(k - 1), ptr(k), W, H, fl)
+                if replace:
+                    L.KLTReplaceLostFeatures(tc, ptr(k), W, H, fl)
+            live = C.c_ulonglong(0)
+            L.klt_dev_live_total(dev, C.byref(live), 1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if api == "per_call":
+                for k in range(9, NFR):
+                    L.KLTTrackFeatures(tc, ptr(k - 1), ptr(k), W, H, fl)
+                    if replace:
+                        L.KLTReplaceLostFeatures(tc, ptr(k), W, H, fl)
+                    L.KLTStoreFeatureList(fl, ft, k)
+            else:
+                seq = (C.c_void_p * (NFR - 8))(*[ptr(k).value for k in range(8, NFR)])
+                L.KLTTrackFeaturesSequence(tc, seq, NFR - 8, W, H, fl, ft, 8, 1 if replace else 0)
+            secs = time.perf_counter() - t0
+            L.klt_dev_live_total(dev, C.byref(live), 1)
+            res[api] = {"frames_per_s": round((NFR - 9) / secs, 1), "features_per_s": round(int(live.value) / secs, 1),
+                        "us_per_frame": round(secs / (NFR - 9) * 1e6, 1),
+                        "alive_at_end": int(L.KLTCountRemainingFeatures(fl))}
+            L.KLTFreeFeatureTable(ft)
+            L.KLTFreeFeatureList(fl)
+            L.KLTFreeTrackingContext(tc)
+        out[name] = dict(res, features=n, replace=replace)
+    out["frames"] = "synthetic %dx%d, %d tracked frames, tc defaults (2 levels, subsampling 4, 7x7)" % (W, H, NFR - 9)
+    return out
+
+
+# --------------------------------------------------------------------------- what a store-heavy kernel can get
+def write_ceiling():
+    """tools/write_probe.bin (built by __graft_entry__.build): a kernel that does nothing but read the
+    u8 frame and write three float planes in the level-0 kernel's own tile pattern, back to back on
+    buffers larger than L2.  The roofline denominator (a copy: half reads, half writes) is not
+    reachable for traffic that is 92 % stores; this is."""
+    exe = os.path.join(ROOT, "tools", "write_probe.bin")
+    if not os.path.exists(exe):
+        return None
+    try:
+        txt = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
+    except Exception:
+        return None
+    out = {}
+    for line in txt.splitlines():
+        f = line.split()
+        if line.startswith("tiled  64x48  4 CTAs/SM +u8"):
+            out["tiled_fill_plus_u8_us"] = float(f[f.index("us") - 1])
+        elif line.startswith("fill     grid 2368"):
+            out["fill_only_us"] = float(f[f.index("us") - 1])
+        elif line.startswith("cudaMemcpy D2D"):
+            out["memcpy_d2d_gbs"] = float(f[f.index("GB/s") - 1])
+    return out or None
+
+
 # --------------------------------------------------------------------------- host I/O (SURVEY 8f N4)
 def io_throughput(L, capi, fh):
     """Feature-table / PPM writers and the PGM reader: this library vs the reference's own C code
@@ -635,6 +715,17 @@ def run_b200(args, rank, local_rank, world):
                     "how": "the same kernel launched back to back on distinct frames between ONE pair of "
                            "events (level-0-only builds): its steady-state rate without the per-launch "
                            "event brackets of `kernels`"}
+            wc = write_ceiling() if dom == "l0_fused_kernel" else None
+            if wc and "tiled_fill_plus_u8_us" in wc:
+                t_att = wc["tiled_fill_plus_u8_us"] * 1e-6
+                roofline["attainable"] = dict(
+                    wc, gbs=round(d["algorithmic_bytes_per_step"] / t_att / 1e9, 1),
+                    frac_of_peak=round(d["algorithmic_bytes_per_step"] / t_att / 1e9 / peak, 4),
+                    kernel_vs_attainable=round(t_att / (l0_b2b_ms * 1e-3), 4) if l0_b2b_ms else None,
+                    how="tools/write_probe.cu on the same GPU in the same run: the time of a kernel that only "
+                        "moves this kernel's bytes (1 B read + 12 B written per pixel, same 64x48 tile store "
+                        "pattern, 4 CTAs per SM, back to back); kernel_vs_attainable = that time / the "
+                        "kernel's back-to-back time")
             pipe_ms = sum(v["ms_per_step"] for k, v in kernels.items() if k in pipe)
             if pipe_ms > 0:
                 roofline["frame_pipeline"] = {
@@ -686,6 +777,10 @@ def run_b200(args, rank, local_rank, world):
         if world == 1 and not args.no_cpu_baseline and not args.only_4k:
             out["cpu_baseline"] = cpu_baseline(capi, fh, ncols, nrows, nfeat, nlevels, ss, window,
                                                budget_s=args.cpu_budget)
+            try:
+                out["small_frames"] = small_frame_legs(L, capi, synth, torch)
+            except Exception as e:
+                out["small_frames"] = {"error": repr(e)}
             try:
                 out["host_io"] = io_throughput(L, capi, fh)
             except Exception as e:                      # never lose the bench line over the I/O side show
