@@ -216,6 +216,11 @@ int klt_dev_last_build_path(const klt_dev *d);
 void klt_dev_force_generic(klt_dev *d, int on);
 /* keep the tiled kernels but not the fused TMA level-0 kernel (cross-check); default 0 */
 void klt_dev_disable_fused(klt_dev *d, int on);
+/* which level-0 kernel the fused path uses, process wide (env KLT_B200_L0_TILE at first use):
+ * 0: l0_fused_kernel with 64x64 tiles, 1 (default): 64x48 tiles, 2: l0_march_kernel (column strips
+ * marched down by three-warp teams; same results, measured slower -- kept as a cross-check) */
+void klt_dev_set_l0_kernel(int variant);
+int klt_dev_l0_kernel(void);
 /* number of pyramid levels the last klt_dev_build produced with the fused TMA kernels
  * (level 0: l0_fused_kernel, coarser levels: level_fused_kernel); 0 if none */
 int klt_dev_last_build_fused(const klt_dev *d);

@@ -72,6 +72,7 @@ struct TapsF {
 static constexpr int NT = 256;   // threads per CTA of every tile kernel
 
 #include "klt_fused.cuh"
+#include "klt_march.cuh"
 
 // ---------------------------------------------------------------------------
 // generic kernels: any radius, any subsampling.  One thread per output sample.
@@ -1667,6 +1668,7 @@ struct FusedPlan {
   CUtensorMap map[KLT_DEV_MAX_LEVELS];          // source of level l (u8 frame for l = 0, L_{l-1} else)
   int TX[KLT_DEV_MAX_LEVELS], TY[KLT_DEV_MAX_LEVELS], tiles_x[KLT_DEV_MAX_LEVELS], tiles_y[KLT_DEV_MAX_LEVELS];
   int SS, R;                                    // pyramid step geometry of the fused level kernels
+  bool l0_march;                                // level 0 on l0_march_kernel (strips x segments) instead of tiles
 };
 
 static int level_shape_for(int ss, int r, int w, int h, int num_sms) {
@@ -1693,10 +1695,15 @@ static bool level_map(CUtensorMap* m, const Level& a) {
 }
 
 using L0GeoB = L0GeoT<48, 6, 6, 4>;      // 48-row tiles: 2 even passes in stages A / C, 54 KB of shared memory, 4 CTAs / SM
-static int l0_variant() {                // 0: 64-row tiles, 3 CTAs / SM; 1 (default): 48-row tiles, 4 CTAs / SM
-  static int v = getenv("KLT_B200_L0_TILE") ? atoi(getenv("KLT_B200_L0_TILE")) : 1;
-  return v;
+// 0: 64-row tiles, 3 CTAs / SM; 1 (default): 48-row tiles, 4 CTAs / SM; 2: l0_march_kernel (klt_march.cuh: the
+// barrier-free strip formulation, bit-identical, measured slower: 32.5 vs 28.7 us per 4K frame)
+static int g_l0_variant = -1;
+static int l0_variant() {
+  if (g_l0_variant < 0) g_l0_variant = getenv("KLT_B200_L0_TILE") ? atoi(getenv("KLT_B200_L0_TILE")) : 1;
+  return g_l0_variant;
 }
+extern "C" void klt_dev_set_l0_kernel(int variant) { g_l0_variant = variant; }
+extern "C" int klt_dev_l0_kernel(void) { return l0_variant(); }
 // which levels of this build can run on the fused kernels, and their tensor maps
 static void fused_plan(klt_dev* d, const PyrSet& S, const unsigned char* src, int spitch,
                        const klt_dev_build_desc* q, const TapsR& ts, const TapsR& tp, const TapsR& tg,
@@ -1706,7 +1713,22 @@ static void fused_plan(klt_dev* d, const PyrSet& S, const unsigned char* src, in
   const int W = q->ncols, H = q->nrows;
   P->src = src; P->spitch = spitch;
   const int l0_ty = l0_variant() == 1 ? L0GeoB::TY : L0Geo::TY, l0_u8h = l0_variant() == 1 ? L0GeoB::U8_H : L0Geo::U8_H;
-  if (q->smooth && ts.w == 2 * L0Geo::RS + 1 &&
+  if (l0_variant() == 2 && q->smooth && ts.w == 2 * MarchGeo::RS + 1 &&
+      make_tensor_map(&P->map[0], src, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, W, H, (size_t)spitch, MarchGeo::IN_W, MarchGeo::PU)) {
+    // strips of 120 columns x segments of rows, one task per team of the grid when the frame is big
+    // enough (4K: 32 strips x 37 segments of 59 rows = 1184 tasks = 148 SMs x 2 CTAs x 4 teams)
+    static int force_seg = getenv("KLT_B200_L0_SEG") ? atoi(getenv("KLT_B200_L0_SEG")) : 0;
+    const int nstrips = (W + MarchGeo::SWI - 1) / MarchGeo::SWI;
+    const int teams = 2 * d->num_sms * MarchGeo::TEAMS;
+    int nseg = teams / nstrips;
+    if (nseg < 1) nseg = 1;
+    int seg_rows = (H + nseg - 1) / nseg;
+    if (seg_rows < 16) seg_rows = 16;
+    if (force_seg > 0) seg_rows = force_seg;
+    P->l0_ok = true; P->l0_march = true;
+    P->TX[0] = MarchGeo::SWI; P->TY[0] = seg_rows;
+    P->tiles_x[0] = nstrips; P->tiles_y[0] = (H + seg_rows - 1) / seg_rows;
+  } else if (q->smooth && ts.w == 2 * L0Geo::RS + 1 &&
       make_tensor_map(&P->map[0], src, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, W, H, (size_t)spitch, L0Geo::U8_W, l0_u8h)) {
     P->l0_ok = true;
     P->TX[0] = L0Geo::TX; P->TY[0] = l0_ty;
@@ -1757,10 +1779,34 @@ static int l0_fused_launch_t(klt_dev* d, const FusedPlan& P, int W, int H, const
     d->tile_base[0] += (unsigned)(n + grid); }
   return 0;
 }
+// level 0 on the marching kernel, segments [jr0, jr1)
+template <bool EXACT>
+static int l0_march_launch(klt_dev* d, const FusedPlan& P, int W, int H, const TapsR& ts, const TapsR& tg,
+                           const TapsR& td, const Level& lv, int jr0, int jr1) {
+  using G = MarchGeo;
+  static bool attr_dev[64] = {};                 // function attributes are per device
+  bool& attr_set = attr_dev[d->device & 63];
+  static int cps = 0;
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(l0_march_kernel<EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, l0_march_kernel<EXACT>, G::NTH, G::SMEM));
+    if (cps < 1) cps = 1;
+    attr_set = true;
+  }
+  const int nstrips = P.tiles_x[0];
+  const int task0 = jr0 * nstrips, task1 = jr1 * nstrips, n = task1 - task0;
+  const int ctas = (n + G::TEAMS - 1) / G::TEAMS;
+  const int grid = ctas < cps * d->num_sms ? ctas : cps * d->num_sms;
+  { Launch l(d, KID_L0_FUSED);
+    CU(launch_k(l0_march_kernel<EXACT>, dim3(grid), dim3(G::NTH), G::SMEM, d->stream, d->pdl != 0, P.map[0], W, H,
+                nstrips, P.TY[0], task0, task1, to_fused(ts), to_fused(tg), to_fused(td), lv.img, lv.gx, lv.gy, lv.pitch)); }
+  return 0;
+}
 template <bool EXACT>
 static int l0_fused_launch(klt_dev* d, const FusedPlan& P, int W, int H, const TapsR& ts, const TapsR& tg,
                            const TapsR& td, const Level& lv, int jr0, int jr1) {
   if (jr1 <= jr0) return 0;
+  if (P.l0_march) return l0_march_launch<EXACT>(d, P, W, H, ts, tg, td, lv, jr0, jr1);
   switch (P.TY[0]) {
     case L0GeoB::TY: return l0_fused_launch_t<L0GeoB, EXACT>(d, P, W, H, ts, tg, td, lv, jr0, jr1);
     default: return l0_fused_launch_t<L0Geo, EXACT>(d, P, W, H, ts, tg, td, lv, jr0, jr1);

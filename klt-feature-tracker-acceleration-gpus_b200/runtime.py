@@ -86,6 +86,8 @@ DEV_API = {
     "klt_dev_last_build_path": (C.c_int, [C.c_void_p]),
     "klt_dev_force_generic": (None, [C.c_void_p, C.c_int]),
     "klt_dev_disable_fused": (None, [C.c_void_p, C.c_int]),
+    "klt_dev_set_l0_kernel": (None, [C.c_int]),
+    "klt_dev_l0_kernel": (C.c_int, []),
     "klt_dev_last_build_fused": (C.c_int, [C.c_void_p]),
     "klt_dev_set_band_rows": (None, [C.c_void_p, C.c_int]),
     "klt_dev_last_build_bands": (C.c_int, [C.c_void_p]),

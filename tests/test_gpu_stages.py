@@ -62,6 +62,15 @@ def _check_build(L, oracle, img, tc, exact, generic, expect_tiled=None, expect_f
     L.klt_dev_disable_fused(dev, 0)
 
 
+@pytest.fixture
+def march_kernel(L):
+    """level 0 on l0_march_kernel (klt_march.cuh) for the duration of a test"""
+    before = L.klt_dev_l0_kernel()
+    L.klt_dev_set_l0_kernel(2)
+    yield
+    L.klt_dev_set_l0_kernel(before)
+
+
 SHAPES = [(240, 320), (243, 321), (48, 64), (37, 1000), (600, 33), (130, 257), (64, 64), (65, 129),
           (200, 16), (40, 44)]
 
@@ -233,4 +242,20 @@ def test_repeated_frames_and_level_counts(L, oracle):
         for which in range(3):
             for l in range(nb):
                 assert np.array_equal(L.dev_level(dev, it % 3, which, l), want.level(which, l)), (it, which, l)
+    L.KLTFreeTrackingContext(tc)
+
+
+MARCH_SHAPES = [(240, 320), (243, 321), (37, 1000), (600, 33), (130, 257), (65, 129), (200, 16), (480, 640), (1080, 1920)]
+
+
+@pytest.mark.parametrize("shape", MARCH_SHAPES)
+@pytest.mark.parametrize("exact", [1, 0])
+def test_march_level0_matches_oracle(L, oracle, march_kernel, shape, exact):
+    """l0_march_kernel (strips x segments, three-warp teams) against the oracle: bit-identical in
+    exact mode, within the image tolerance in fma mode; widths that are not a multiple of the 120-column
+    strip, frames shorter than one segment, one-strip frames."""
+    h, w = shape
+    img = synth_image(w, h, seed=11 + h + w)
+    tc = L.KLTCreateTrackingContext()
+    _check_build(L, oracle, img, tc, exact, 0, expect_fused=True)
     L.KLTFreeTrackingContext(tc)
