@@ -5,7 +5,7 @@
  * and the 29 prototypes are ABI-identical so that the reference's example3
  * drivers (src/V1/example3.c, src/V3/example3.c) compile and link unchanged.
  * Layout check: sizeof(KLT_FeatureRec) == 64, sizeof(KLT_TrackingContextRec)
- * == 136 on LP64 (tests/test_abi.py).
+ * == 136 on LP64 (tests/test_host.py::test_abi_matches_c_compiler).
  *
  * What differs is below the API: KLTSelectGoodFeatures, KLTTrackFeatures and
  * KLTReplaceLostFeatures run on the GPU (include/klt_cuda.h); there is no CPU
@@ -41,7 +41,8 @@ typedef unsigned char KLT_PixelType;
 #define KLT_LARGE_RESIDUE    -5
 
 /* dense row-major float image (reference src/V4/klt_util.h:8-12); only used by
- * the aff_img* members below, which this library keeps NULL. */
+ * the aff_img* members below: the per-feature templates of the affine consistency check, mirrored
+ * from the device store (csrc/klt_affine.cuh) when tc->affineConsistencyCheck >= 0. */
 #ifndef _KLT_UTIL_H_
 #define _KLT_UTIL_H_
 typedef struct {
@@ -58,7 +59,7 @@ typedef struct {
   KLT_BOOL sequentialMode;        /* keep the last frame's pyramids between calls */
   KLT_BOOL smoothBeforeSelecting;
   KLT_BOOL writeInternalImages;   /* accepted, ignored (debug dumps are out of scope) */
-  KLT_BOOL lighting_insensitive;  /* must stay FALSE (not on the accelerated path) */
+  KLT_BOOL lighting_insensitive;  /* TRUE: gain / bias normalised windows (reference trackFeatures.c:125-220) */
 
   int min_eigenvalue;
   float min_determinant;
@@ -75,7 +76,8 @@ typedef struct {
   int nPyramidLevels;
   int subsampling;
 
-  /* affine consistency check: fields kept for layout; check must stay -1 */
+  /* affine consistency check (reference trackFeatures.c:1438-1497): -1 off, 0 translation,
+   * 1 similarity, 2 affine -- runs on the device (csrc/klt_affine.cuh) */
   int affine_window_width, affine_window_height;
   int affineConsistencyCheck;
   int affine_max_iterations;

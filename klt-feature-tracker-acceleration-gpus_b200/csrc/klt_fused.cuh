@@ -79,8 +79,15 @@ __device__ __forceinline__ float4 lds128(const float* p) {
 }
 
 // u8 -> f32 without the conversion pipe: 0x4B0000bb is the float 2^23 + bb.
+#ifndef KLT_U8_I2F
+#define KLT_U8_I2F 0
+#endif
 __device__ __forceinline__ float u8_to_float(unsigned word, unsigned byte_sel) {
+#if KLT_U8_I2F
+  return (float)((word >> (8 * byte_sel)) & 0xffu);       // one I2F.U8 with a byte selector (conversion pipe)
+#else
   return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7440u + byte_sel)) - 8388608.0f;
+#endif
 }
 
 // packed FP32 FMA (Blackwell FFMA2): (ax, ay) += (vx, vy) * (kk.x, kk.y), each half an ordinary
