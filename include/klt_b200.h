@@ -65,7 +65,10 @@ void KLTB200ResidentEnd(KLT_TrackingContext tc, KLT_FeatureList fl);
  * only read when tc holds no previous pyramid (as img1 in KLTTrackFeatures) and may then not be
  * NULL.  ft may be NULL; column first_frame + k receives frame k (column first_frame is not
  * written: the caller stores the selection itself, as example3 does).  On return fl holds the
- * state after the last frame and tc is in sequential mode with the last frame's pyramids held. */
+ * state after the last frame and tc is in sequential mode with the last frame's pyramids held.
+ * tc->affineConsistencyCheck >= 0 is honoured (reference trackFeatures.c:1438-1497): the per-feature
+ * affine state and templates live on the device during the call and are attached to fl at its end,
+ * exactly as the loop above leaves them. */
 void KLTTrackFeaturesSequence(KLT_TrackingContext tc, KLT_PixelType *const *frames, int nframes,
                               int ncols, int nrows, KLT_FeatureList fl, KLT_FeatureTable ft,
                               int first_frame, int replace);

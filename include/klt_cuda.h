@@ -178,6 +178,17 @@ int klt_dev_affine_begin(klt_dev *d, int n, const klt_dev_affine_params *ap, klt
 int klt_dev_affine_put_template(klt_dev *d, int i, const float *img, const float *gx, const float *gy);
 int klt_dev_affine_check(klt_dev *d, int slot_prev, int slot_cur, const klt_dev_track_params *tp,
                          const klt_dev_affine_params *ap);
+/* The check inside the resident / sequence pipeline (KLTTrackFeaturesSequence): the per-feature state
+ * stays on the device between frames.  Set up with klt_dev_affine_begin + the staging array +
+ * klt_dev_affine_put_template as above, then klt_dev_affine_upload_states ONCE; per frame
+ * klt_dev_affine_keep_positions (before the tracker), klt_dev_track_resident,
+ * klt_dev_affine_check_resident; klt_dev_affine_fetch_states (synchronises) hands the states back in
+ * the staging array at the end; templates through klt_dev_affine_get_template(s). */
+int klt_dev_affine_upload_states(klt_dev *d, int n);
+int klt_dev_affine_keep_positions(klt_dev *d);
+int klt_dev_affine_check_resident(klt_dev *d, int slot_prev, int slot_cur, const klt_dev_track_params *tp,
+                                  const klt_dev_affine_params *ap);
+int klt_dev_affine_fetch_states(klt_dev *d, int n, klt_dev_affine_state **staging);
 int klt_dev_affine_get_template(klt_dev *d, int i, float *img, float *gx, float *gy);
 int klt_dev_affine_get_templates(klt_dev *d, int n, float *all);
 

@@ -33,6 +33,7 @@ struct AffArgs {
   float step_factor, small, th;
   int   nlevels; float ss;
   int   ncols, nrows, pitch;                 // level 0
+  int   resident;                            // the state array lives on the device across frames (sequence call)
   const float *i1, *gx1, *gy1;               // previous frame, level 0: template source
   const float *i2, *gx2, *gy2;               // new frame, level 0
 };
@@ -107,14 +108,19 @@ affine_check_kernel(AffArgs a, int n, const float* __restrict__ x0, const float*
   float* sy = sx + npix;
   float* sT = sy + npix;                                      // 36
   float* sa = sT + 36;                                        // 6 (+ padding)
-  const AffState s = st[f];
+  AffState s = st[f];
+  if (a.resident && val0[f] > 0) {
+    // a slot KLTReplaceLostFeatures refilled since the last frame: a new feature, its affine members
+    // start over (selectGoodFeatures.c:514-541) -- in the per-call API the host list carries the reset
+    s.has = 0; s.aff_x = -1.0f; s.aff_y = -1.0f; s.Axx = 1.0f; s.Ayx = 0.0f; s.Axy = 0.0f; s.Ayy = 1.0f;
+  }
   float* t_img = tmpl + (size_t)f * 3 * tsz;
   float* t_gx = t_img + tsz;
   float* t_gy = t_gx + tsz;
   __syncwarp();                                               // every lane has read st[f]
 
   if (val[f] != KLT_TRACKED) {       // lost by the translation tracker: the template goes (:1383-1431)
-    if (lane == 0 && s.has) { st[f].has = 0; st[f].flags = 2; }
+    if (lane == 0 && (s.has || (a.resident && val0[f] > 0))) { AffState o = s; o.has = 0; o.flags = 2; st[f] = o; }
     return;
   }
 

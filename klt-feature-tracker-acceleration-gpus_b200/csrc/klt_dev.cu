@@ -2647,8 +2647,47 @@ extern "C" int klt_dev_affine_put_template(klt_dev* d, int i, const float* img, 
   CU(cudaMemcpyAsync(dst + 2 * d->aff_tsz, gy, tb, cudaMemcpyHostToDevice, d->tstream));
   return 0;
 }
+static int affine_check_core(klt_dev* d, int slot_prev, int slot_cur, const klt_dev_track_params* tp,
+                             const klt_dev_affine_params* ap, bool resident);
 extern "C" int klt_dev_affine_check(klt_dev* d, int slot_prev, int slot_cur, const klt_dev_track_params* tp,
                                     const klt_dev_affine_params* ap) {
+  return affine_check_core(d, slot_prev, slot_cur, tp, ap, false);
+}
+// ---- the check inside the resident / sequence pipeline: the per-feature state stays on the device ----
+// klt_dev_affine_begin + the staging array + klt_dev_affine_put_template set it up as for the per-call
+// API; klt_dev_affine_upload_states sends the state up ONCE; then, per frame,
+// klt_dev_affine_keep_positions (before the tracker: the positions the templates are cut at),
+// klt_dev_track_resident, klt_dev_affine_check_resident; klt_dev_affine_fetch_states at the end.  The
+// kernel keeps `has` itself (a lost feature releases its template, a first successful track cuts one),
+// which is all the host does between the calls of the per-call API.
+extern "C" int klt_dev_affine_upload_states(klt_dev* d, int n) {
+  CU(cudaSetDevice(d->device));
+  if (n <= 0 || d->aff_cap < n) return fail(d, "affine_upload_states without affine_begin");
+  Launch l(d, KID_COPY_H2D, d->tstream);
+  CU(cudaMemcpyAsync(d->d_aff_st, d->h_aff_st, (size_t)n * sizeof(AffState), cudaMemcpyHostToDevice, d->tstream));
+  return 0;
+}
+extern "C" int klt_dev_affine_keep_positions(klt_dev* d) {
+  CU(cudaSetDevice(d->device));
+  if (!d->d_x0 || d->aff_x0_cap < d->feat_cap) return fail(d, "affine_keep_positions without affine_begin");
+  CU(cudaMemcpyAsync(d->d_x0, d->d_x, (size_t)d->feat_cap * 12, cudaMemcpyDeviceToDevice, d->tstream));
+  return 0;
+}
+extern "C" int klt_dev_affine_check_resident(klt_dev* d, int slot_prev, int slot_cur, const klt_dev_track_params* tp,
+                                             const klt_dev_affine_params* ap) {
+  return affine_check_core(d, slot_prev, slot_cur, tp, ap, true);
+}
+extern "C" int klt_dev_affine_fetch_states(klt_dev* d, int n, klt_dev_affine_state** staging) {
+  CU(cudaSetDevice(d->device));
+  if (n <= 0 || d->aff_cap < n || !staging) return fail(d, "affine_fetch_states without affine_begin");
+  { Launch l(d, KID_COPY_D2H, d->tstream);
+    CU(cudaMemcpyAsync(d->h_aff_st, d->d_aff_st, (size_t)n * sizeof(AffState), cudaMemcpyDeviceToHost, d->tstream)); }
+  CU(cudaStreamSynchronize(d->tstream));
+  *staging = reinterpret_cast<klt_dev_affine_state*>(d->h_aff_st);
+  return 0;
+}
+static int affine_check_core(klt_dev* d, int slot_prev, int slot_cur, const klt_dev_track_params* tp,
+                             const klt_dev_affine_params* ap, bool resident) {
   CU(cudaSetDevice(d->device));
   if (!klt_dev_slot_valid(d, slot_prev) || !klt_dev_slot_valid(d, slot_cur))
     return fail(d, "affine_check: pyramid slot %d or %d not built", slot_prev, slot_cur);
@@ -2660,6 +2699,7 @@ extern "C" int klt_dev_affine_check(klt_dev* d, int slot_prev, int slot_cur, con
   a.max_residue = ap->max_residue; a.th_aff = ap->min_displacement; a.mdd = ap->max_displacement_differ;
   a.step_factor = tp->step_factor; a.small = tp->min_determinant; a.th = tp->min_displacement;
   a.nlevels = d->L; a.ss = (float)d->ss;
+  a.resident = resident ? 1 : 0;
   const Level& l1 = d->set[slot_prev].lv[0];
   const Level& l2 = d->set[slot_cur].lv[0];
   a.ncols = l2.w; a.nrows = l2.h; a.pitch = l2.pitch;
@@ -2669,16 +2709,20 @@ extern "C" int klt_dev_affine_check(klt_dev* d, int slot_prev, int slot_cur, con
   const int warps = 4;
   const size_t smem = (size_t)warps * (3 * a.aw * a.ah + 48) * sizeof(float);
   if (set_smem(d, affine_check_kernel, smem)) return 1;
-  { Launch l(d, KID_COPY_H2D, d->tstream);
-    CU(cudaMemcpyAsync(d->d_aff_st, d->h_aff_st, (size_t)n * sizeof(AffState), cudaMemcpyHostToDevice, d->tstream)); }
+  if (!resident) {
+    Launch l(d, KID_COPY_H2D, d->tstream);
+    CU(cudaMemcpyAsync(d->d_aff_st, d->h_aff_st, (size_t)n * sizeof(AffState), cudaMemcpyHostToDevice, d->tstream));
+  }
   { Launch l(d, KID_AFFINE, d->tstream);
     const float* x0 = d->d_x0;
     affine_check_kernel<<<(n + warps - 1) / warps, warps * 32, smem, d->tstream>>>(
         a, n, x0, x0 + d->feat_cap, reinterpret_cast<const int*>(x0 + 2 * (size_t)d->feat_cap),
         d->d_x, d->d_y, d->d_val, d->d_aff_st, d->d_aff_tmpl); }
   CU(cudaGetLastError());
-  { Launch l(d, KID_COPY_D2H, d->tstream);
-    CU(cudaMemcpyAsync(d->h_aff_st, d->d_aff_st, (size_t)n * sizeof(AffState), cudaMemcpyDeviceToHost, d->tstream)); }
+  if (!resident) {
+    Launch l(d, KID_COPY_D2H, d->tstream);
+    CU(cudaMemcpyAsync(d->h_aff_st, d->d_aff_st, (size_t)n * sizeof(AffState), cudaMemcpyDeviceToHost, d->tstream));
+  }
   return 0;
 }
 // after the call's synchronisation: template i (image, gradx, grady: (w+2)(h+2) floats each)

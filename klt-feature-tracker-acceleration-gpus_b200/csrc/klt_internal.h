@@ -19,6 +19,7 @@ typedef struct klt_tc_state {
    * slot i mirrors; valid for list aff_list while klt_aff_epoch == aff_epoch */
   void **aff_shadow;
   int aff_shadow_n;
+  int in_sequence;            /* KLTTrackFeaturesSequence is setting the resident pipeline up (affine check allowed) */
   const void *aff_list;
   unsigned aff_epoch;
   struct klt_tc_state *next;

@@ -56,9 +56,9 @@ static void check_supported(KLT_TrackingContext tc, int pipelined)
   if (tc->affineConsistencyCheck > 2)
     KLTError("(KLTTrackFeatures) affineConsistencyCheck = %d (must be -1, 0, 1 or 2)",
              tc->affineConsistencyCheck);
-  if (tc->affineConsistencyCheck >= 0 && pipelined)
+  if (tc->affineConsistencyCheck >= 0 && pipelined == 1)
     KLTError("(KLT/B200) the affine consistency check keeps per-feature templates in the caller's "
-             "feature list: use KLTTrackFeatures, not the resident / sequence pipeline");
+             "feature list: use KLTTrackFeatures or KLTTrackFeaturesSequence, not KLTB200Resident*");
   if (tc->affineConsistencyCheck == 0 && tc->lighting_insensitive)
     KLTError("(KLTTrackFeatures) affineConsistencyCheck = 0 together with lighting_insensitive is "
              "not implemented on the GPU path (and there is no CPU path)");
@@ -155,6 +155,48 @@ static void affine_collect(KLT_TrackingContext tc, klt_tc_state *s, KLT_FeatureL
       s->aff_shadow[i] = (void *)f->aff_img;
     } else if (f->aff_img == NULL) {
       s->aff_shadow[i] = NULL;    /* released: freed by the caller's loop when val went negative */
+    }
+  }
+  free(all);
+}
+
+/* after KLTTrackFeaturesSequence: the device held the per-feature state for the whole call; what it
+ * ends with is what the per-call loop would have left in the list -- the aff_* members, a template for
+ * every feature that holds one (cut once per feature life, so the copy is the template whenever it was
+ * cut), none for the features that lost theirs */
+static void affine_collect_resident(KLT_TrackingContext tc, klt_tc_state *s, KLT_FeatureList fl)
+{
+  const int n = fl->nFeatures, tw = tc->affine_window_width + 2, th = tc->affine_window_height + 2;
+  const size_t tsz = (size_t)tw * th;
+  klt_dev_affine_state *st = NULL;
+  float *all;
+  int i;
+  DEVCALL(s, klt_dev_affine_fetch_states(s->dev, n, &st));
+  all = (float *)malloc((size_t)n * 3 * tsz * sizeof(float));
+  if (all == NULL) KLTError("(KLTTrackFeaturesSequence) Out of memory");
+  DEVCALL(s, klt_dev_affine_get_templates(s->dev, n, all));
+  for (i = 0; i < n; i++) {
+    KLT_Feature f = fl->feature[i];
+    if (f->val > 0) {           /* refilled after the last check: a new feature the device has not met yet */
+      st[i].has = 0; st[i].aff_x = st[i].aff_y = -1.0f;
+      st[i].Axx = st[i].Ayy = 1.0f; st[i].Ayx = st[i].Axy = 0.0f;
+    }
+    f->aff_x = st[i].aff_x; f->aff_y = st[i].aff_y;
+    f->aff_Axx = st[i].Axx; f->aff_Ayx = st[i].Ayx; f->aff_Axy = st[i].Axy; f->aff_Ayy = st[i].Ayy;
+    if (st[i].has) {
+      if (f->aff_img == NULL) {
+        f->aff_img = new_float_image(tw, th);
+        f->aff_img_gradx = new_float_image(tw, th);
+        f->aff_img_grady = new_float_image(tw, th);
+      }
+      memcpy(f->aff_img->data, all + (size_t)i * 3 * tsz, tsz * sizeof(float));
+      memcpy(f->aff_img_gradx->data, all + (size_t)i * 3 * tsz + tsz, tsz * sizeof(float));
+      memcpy(f->aff_img_grady->data, all + (size_t)i * 3 * tsz + 2 * tsz, tsz * sizeof(float));
+      s->aff_shadow[i] = (void *)f->aff_img;
+    } else {
+      free(f->aff_img); free(f->aff_img_gradx); free(f->aff_img_grady);
+      f->aff_img = f->aff_img_gradx = f->aff_img_grady = NULL;
+      s->aff_shadow[i] = NULL;
     }
   }
   free(all);
@@ -322,7 +364,7 @@ void KLTB200ResidentBegin(KLT_TrackingContext tc, const KLT_PixelType *img1, int
   int slot;
   if (!x || !y || !v) KLTError("(KLTB200ResidentBegin) Out of memory");
   klt_fix_window(tc, "KLTTrackFeatures", 1);
-  check_supported(tc, 1);
+  check_supported(tc, s->in_sequence ? 2 : 1);
   if (!tc->sequentialMode)
     KLTError("(KLTB200ResidentBegin) the resident pipeline needs tc->sequentialMode = TRUE");
   {
@@ -425,6 +467,10 @@ void KLTTrackFeaturesSequence(KLT_TrackingContext tc, KLT_PixelType *const *fram
   const int n = fl->nFeatures;
   const int snaps = n > 0 && (ft != NULL || replace);
   klt_dev_select_params sp;
+  const int affine = tc->affineConsistencyCheck >= 0 && n > 0;
+  klt_dev_affine_params ap;
+  klt_dev_affine_state *ast = NULL;
+  klt_dev_track_params tp;
   int k, stored = 1;            /* next frame whose snapshot is to be consumed */
 
   if (frames == NULL || nframes < 1)
@@ -445,15 +491,28 @@ void KLTTrackFeaturesSequence(KLT_TrackingContext tc, KLT_PixelType *const *fram
   }
   tc->sequentialMode = TRUE;
   if (replace) klt_fix_window(tc, "KLTSelectGoodFeatures", 1);
+  s->in_sequence = 1;
   KLTB200ResidentBegin(tc, frames[0], 0, (size_t)ncols, ncols, nrows, fl);
+  s->in_sequence = 0;
   if (replace) klt_fill_select_params(tc, 1, &sp);
+  if (affine) {                 /* the per-feature state goes up once and stays on the device */
+    fill_affine_params(tc, &ap);
+    fill_track_params(tc, s->exact, &tp);
+    DEVCALL(s, klt_dev_affine_begin(s->dev, n, &ap, &ast));
+    affine_stage(tc, s, fl, ast);
+    DEVCALL(s, klt_dev_affine_upload_states(s->dev, n));
+  }
   if (snaps && nframes > 1) DEVCALL(s, klt_dev_snapshot_ring(s->dev, SEQ_DEPTH));
   for (k = 1; k < nframes; k++) {
     if (snaps && k - stored >= SEQ_DEPTH) {      /* ring full: store the oldest frame while the */
       seq_consume(s, (stored - 1) % SEQ_DEPTH, fl, ft, first_frame + stored, replace);   /* GPU runs */
       stored++;
     }
+    if (affine) DEVCALL(s, klt_dev_affine_keep_positions(s->dev));   /* where the templates are cut (:1446-1457) */
     KLTB200ResidentStep(tc, frames[k], 0, (size_t)ncols, ncols, nrows);
+    if (affine)
+      DEVCALL(s, klt_dev_affine_check_resident(s->dev, (s->last_slot + KLT_DEV_SLOTS - 1) % KLT_DEV_SLOTS,
+                                               s->last_slot, &tp, &ap));
     if (replace && n > 0) {     /* REPLACING_SOME on the level-0 gradients just built (:342-348), */
       int sel_slot = s->last_slot;               /* in exact arithmetic (integer ranking keys)         */
       DEVCALL(s, klt_dev_exact_level0(s->dev, s->last_slot, &sel_slot));
@@ -464,6 +523,7 @@ void KLTTrackFeaturesSequence(KLT_TrackingContext tc, KLT_PixelType *const *fram
   for (; snaps && stored < nframes; stored++)
     seq_consume(s, (stored - 1) % SEQ_DEPTH, fl, ft, first_frame + stored, replace);
   KLTB200ResidentEnd(tc, fl);
+  if (affine) affine_collect_resident(tc, s, fl);
   if (KLT_verbose >= 1) {
     fprintf(stderr, "\n\t%d features alive after the last frame.\n", KLTCountRemainingFeatures(fl));
     fflush(stderr);

@@ -152,3 +152,54 @@ def test_affine_check_fma_mode_agrees_with_exact_mode(L, capi, provided):
     both = (ev >= 0) & (fv >= 0)
     assert both.sum() > 50
     assert max(np.abs(ex[both] - fx[both]).max(), np.abs(ey[both] - fy[both]).max()) <= 0.01
+
+
+@pytest.mark.parametrize("replace", [0, 1])
+@pytest.mark.parametrize("check,exact", [(2, 1), (1, 1), (0, 1), (2, 0)])
+def test_affine_check_inside_the_sequence_call(L, capi, provided, check, exact, replace):
+    """KLTTrackFeaturesSequence with tc->affineConsistencyCheck >= 0: the per-feature state (template
+    held or not, aff_x / aff_y, the map A) and the templates stay on the device for the whole call and
+    come back at its end.  Everything the call leaves behind -- the feature table, the final list, its
+    affine members and template images -- is what the per-call loop leaves (reference driver loop
+    src/V3/example3.c:54-76 around trackFeatures.c:1438-1497), bit for bit, with and without
+    KLTReplaceLostFeatures after every frame (a refilled slot starts a new feature)."""
+    n, imgs = 150, provided[:9]
+
+    def run(sequence):
+        tc = L.KLTCreateTrackingContext()
+        tc.contents.sequentialMode = 1
+        tc.contents.affineConsistencyCheck = check
+        L.KLTB200SetExact(tc, exact)
+        fl = L.KLTCreateFeatureList(n)
+        ft = L.KLTCreateFeatureTable(len(imgs), n)
+        L.select(tc, imgs[0], fl)
+        L.KLTStoreFeatureList(fl, ft, 0)
+        if sequence:
+            L.track_sequence(tc, imgs[:5], fl, ft, 0, replace)       # two calls: the state travels through
+            L.track_sequence(tc, imgs[4:], fl, ft, 4, replace)       # the list's host images in between
+        else:
+            for k in range(1, len(imgs)):
+                L.track(tc, imgs[k - 1], imgs[k], fl)
+                if replace:
+                    L.replace(tc, imgs[k], fl)
+                L.KLTStoreFeatureList(fl, ft, k)
+        out = (capi.featuretable_to_array(ft), capi.featurelist_to_arrays(fl), capi.featurelist_affine(fl),
+               [_templates(fl, i) for i in range(n)])
+        L.KLTFreeFeatureTable(ft)
+        L.KLTFreeFeatureList(fl)
+        L.KLTFreeTrackingContext(tc)
+        return out
+
+    (ta, la, aa, ma), (tb, lb, ab, mb) = run(True), run(False)
+    assert ta.tobytes() == tb.tobytes(), "feature tables differ in %d cells" % int((ta != tb).sum())
+    for u, v in zip(la, lb):
+        assert u.tobytes() == v.tobytes()
+    assert np.array_equal(aa["has"], ab["has"])
+    for k in ("aff_x", "aff_y", "Axx", "Ayx", "Axy", "Ayy"):
+        assert aa[k].tobytes() == ab[k].tobytes(), k
+    for i in range(n):
+        assert (ma[i] is None) == (mb[i] is None), i
+        if ma[i] is not None:
+            for w in range(3):
+                assert ma[i][w].tobytes() == mb[i][w].tobytes(), (i, w)
+    assert (aa["has"] == 1).sum() > 20
