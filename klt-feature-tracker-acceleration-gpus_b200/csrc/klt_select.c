@@ -6,10 +6,10 @@
  * reused and `img` is ignored), the eigenvalue map + ranking + minimum-distance
  * pass (device, csrc/klt_dev.cu) and the verbose messages (:478-494, :523-540).
  *
- * Ranking ties are broken in raster order, i.e. the result equals the
- * reference built with -DKLT_USE_QSORT (stable glibc sort); the default
- * reference build uses an unstable hand-written quicksort whose tie order a
- * parallel sort cannot reproduce.
+ * Ranking ties are broken in raster order (a stable sort of the raster-ordered
+ * candidates); the default reference build uses an unstable hand-written
+ * quicksort whose tie order a parallel sort cannot reproduce, its
+ * -DKLT_USE_QSORT build happens to sort stably with glibc.
  */
 #include <stdio.h>
 #include <stdlib.h>
