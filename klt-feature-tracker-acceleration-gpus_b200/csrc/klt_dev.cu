@@ -1719,7 +1719,7 @@ static void fused_plan(klt_dev* d, const PyrSet& S, const unsigned char* src, in
     // enough (4K: 32 strips x 37 segments of 59 rows = 1184 tasks = 148 SMs x 2 CTAs x 4 teams)
     static int force_seg = getenv("KLT_B200_L0_SEG") ? atoi(getenv("KLT_B200_L0_SEG")) : 0;
     const int nstrips = (W + MarchGeo::SWI - 1) / MarchGeo::SWI;
-    const int teams = 2 * d->num_sms * MarchGeo::TEAMS;
+    const int teams = MarchGeo::CPS * d->num_sms * MarchGeo::TEAMS;
     int nseg = teams / nstrips;
     if (nseg < 1) nseg = 1;
     int seg_rows = (H + nseg - 1) / nseg;

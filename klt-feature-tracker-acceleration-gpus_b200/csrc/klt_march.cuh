@@ -49,7 +49,12 @@ struct MarchGeo {
   static constexpr int PU = 2 * RS + 1;         // producer: 5 running sums, chunks of 5 ring rows
   static constexpr int CU = 2 * RG + 1;         // consumers: 7 running sums, groups of 7 ring rows
   static constexpr int RING_ROWS = PU * CU;     // 35: one revolution = 7 chunks = 5 groups, nothing straddles the wrap
-  static constexpr int TEAMS = 4;               // teams per CTA
+#ifndef MARCH_TEAMS
+#define MARCH_TEAMS 4
+#define MARCH_CPS 2
+#endif
+  static constexpr int TEAMS = MARCH_TEAMS;     // teams per CTA
+  static constexpr int CPS = MARCH_CPS;         // CTAs per SM the kernel is compiled for
   static constexpr int NTH = TEAMS * 96;
   static constexpr int ROW_BYTES = LW * 4;
   static constexpr int RING_BYTES = RING_ROWS * ROW_BYTES;              // per team: 17.5 KB
@@ -319,7 +324,7 @@ __device__ __forceinline__ void march_consume(unsigned ring_s, unsigned full_s, 
 // Tasks [task0, ntasks) = (segment, strip) pairs in raster order, dealt round-robin to the teams of
 // the grid (whole segments per launch when a frame is built band by band behind its upload).
 template <bool EXACT>
-__global__ void __launch_bounds__(MarchGeo::NTH, 2)
+__global__ void __launch_bounds__(MarchGeo::NTH, MarchGeo::CPS)
 l0_march_kernel(const __grid_constant__ CUtensorMap map, int W, int H, int nstrips, int seg_rows,
                 int task0, int ntasks, TapsF ts, TapsF tg, TapsF td, float* __restrict__ out_img,
                 float* __restrict__ out_gx, float* __restrict__ out_gy, int opitch) {
