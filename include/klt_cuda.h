@@ -227,6 +227,16 @@ int klt_dev_last_build_path(const klt_dev *d);
 void klt_dev_force_generic(klt_dev *d, int on);
 /* keep the tiled kernels but not the fused TMA level-0 kernel (cross-check); default 0 */
 void klt_dev_disable_fused(klt_dev *d, int on);
+/* Debug aid (compute-sanitizer's stand-in): guard mode (env KLT_B200_GUARD=1 or klt_dev_set_guard
+ * before the next build) puts a 4 KB canary band in front of every plane of the pyramid arena and
+ * behind the last one; klt_dev_check_guards synchronises and counts the canary words a kernel has
+ * damaged (0 = no store left its plane) and names the first damaged band. */
+void klt_dev_set_guard(klt_dev *d, int on);
+int klt_dev_check_guards(klt_dev *d, long long *damaged_words, int *first_band);
+/* (for the guard test) device address of a plane (which: 0 image, 1 gradx, 2 grady), NULL if not
+ * allocated; a synchronous raw host-to-device write */
+void *klt_dev_plane_address(const klt_dev *d, int slot, int which, int level);
+int klt_dev_poke(klt_dev *d, void *device_dst, const void *host_src, size_t bytes);
 /* which level-0 kernel the fused path uses, process wide (env KLT_B200_L0_TILE at first use):
  * 0: l0_fused_kernel with 64x64 tiles, 1 (default): 64x48 tiles, 2: l0_march_kernel (column strips
  * marched down by three-warp teams; same results, measured slower -- kept as a cross-check) */

@@ -1195,6 +1195,8 @@ struct klt_dev {
   int W, H, L, ss;
   PyrSet set[KLT_DEV_SLOTS];
   float* arena;
+  size_t arena_floats;
+  int guard;                 // debug: canary bands between the planes of the arena (klt_dev_set_guard)
   float* tmp;                // generic path: horizontal-pass result, W*H floats
   unsigned char* frame;      // u8 staging of the frame being built (== frame_buf[frame_idx]), row pitch frame_pitch
   unsigned char* frame_buf[2]; int frame_idx;   // two buffers: frame k+1 goes up while level 0 of frame k is still reading
@@ -1409,6 +1411,7 @@ extern "C" int klt_dev_create(int device, klt_dev** out) {
   e = cudaMalloc(&c->d_live, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemsetAsync(c->d_live, 0, sizeof(unsigned long long), c->stream);
   c->pdl = getenv("KLT_B200_PDL") ? atoi(getenv("KLT_B200_PDL")) : 1;
+  c->guard = getenv("KLT_B200_GUARD") ? (atoi(getenv("KLT_B200_GUARD")) != 0) : 0;
   if (getenv("KLT_B200_L2_HINTS")) {              // (per device: the symbol lives in this device's module image)
     const int hints = atoi(getenv("KLT_B200_L2_HINTS")) & 3;
     cudaMemcpyToSymbol(c_l2_hints, &hints, sizeof(int));
@@ -1429,6 +1432,8 @@ extern "C" int klt_dev_create(int device, klt_dev** out) {
   return 0;
 }
 
+static constexpr size_t KLT_GUARD_FLOATS = 1024;      // 4 KB: keeps every plane 128-byte aligned
+static constexpr int KLT_GUARD_BYTE = 0xA5;
 static void free_geometry(klt_dev* d) {
   cudaFree(d->arena); d->arena = nullptr;
   cudaFree(d->tmp); d->tmp = nullptr;
@@ -1488,7 +1493,13 @@ static int ensure_geometry(klt_dev* d, int W, int H, int L, int ss) {
     per_set += 3 * (size_t)ps[l] * h;
     if (L > 1) { w /= ss; h /= ss; }
   }
-  CU(cudaMalloc(&d->arena, KLT_DEV_SLOTS * per_set * sizeof(float) + 256));   // + slack for aligned over-reads
+  // guard mode (debug): a canary band in front of every plane and behind the last one; the kernels
+  // never write outside a plane's pitch x height, klt_dev_check_guards verifies it
+  const size_t gap = d->guard ? KLT_GUARD_FLOATS : 0;
+  const size_t total = KLT_DEV_SLOTS * (per_set + 3 * (size_t)L * gap) + gap;
+  CU(cudaMalloc(&d->arena, total * sizeof(float) + 256));   // + slack for aligned over-reads
+  d->arena_floats = total;
+  if (d->guard) CU(cudaMemset(d->arena, KLT_GUARD_BYTE, total * sizeof(float) + 256));
   CU(cudaMalloc(&d->tmp, (size_t)ps[0] * H * sizeof(float)));
   float* p = d->arena;
   for (int s = 0; s < KLT_DEV_SLOTS; ++s)
@@ -1496,9 +1507,65 @@ static int ensure_geometry(klt_dev* d, int W, int H, int L, int ss) {
       Level& lv = d->set[s].lv[l];
       lv.w = ws[l]; lv.h = hs[l]; lv.pitch = ps[l];
       const size_t n = (size_t)ps[l] * hs[l];
-      lv.img = p; p += n; lv.gx = p; p += n; lv.gy = p; p += n;
+      p += gap; lv.img = p; p += n; p += gap; lv.gx = p; p += n; p += gap; lv.gy = p; p += n;
     }
   d->W = W; d->H = H; d->L = L; d->ss = ss;
+  return 0;
+}
+
+// Debug aid in place of compute-sanitizer (closed on the pool): with guard mode on, every plane of
+// the pyramid arena is preceded by a 4 KB canary band (and the last one followed by one); a kernel
+// that stores outside its plane lands in a band.  Returns the number of damaged canary words and the
+// index (slot * 3 L + 3 level + plane; 3 L * slots = the band behind the last plane) of the first
+// damaged band.  Switching the mode re-allocates the arena at the next build.
+extern "C" void klt_dev_set_guard(klt_dev* d, int on) {
+  if (d->guard == (on ? 1 : 0)) return;
+  sync_all(d);
+  free_geometry(d);
+  d->guard = on ? 1 : 0;
+}
+extern "C" int klt_dev_check_guards(klt_dev* d, long long* damaged_words, int* first_band) {
+  if (damaged_words) *damaged_words = 0;
+  if (first_band) *first_band = -1;
+  if (!d->guard || !d->arena) return 0;
+  CU(cudaSetDevice(d->device));
+  if (sync_all(d)) return fail(d, "stream synchronisation failed");
+  unsigned* h = (unsigned*)malloc(KLT_GUARD_FLOATS * sizeof(unsigned));
+  if (!h) return fail(d, "out of memory");
+  const unsigned want = 0x01010101u * (unsigned)KLT_GUARD_BYTE;
+  long long bad = 0;
+  int first = -1, band = 0;
+  auto check = [&](const float* at) -> int {
+    if (cudaMemcpy(h, at, KLT_GUARD_FLOATS * sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    for (size_t i = 0; i < KLT_GUARD_FLOATS; ++i)
+      if (h[i] != want) { bad += 1; if (first < 0) first = band; }
+    band += 1;
+    return 0;
+  };
+  int rc = 0;
+  for (int s = 0; s < KLT_DEV_SLOTS && !rc; ++s)
+    for (int l = 0; l < d->L && !rc; ++l) {
+      const Level& lv = d->set[s].lv[l];
+      rc = check(lv.img - KLT_GUARD_FLOATS) || check(lv.gx - KLT_GUARD_FLOATS) || check(lv.gy - KLT_GUARD_FLOATS);
+    }
+  if (!rc) rc = check(d->arena + d->arena_floats - KLT_GUARD_FLOATS);
+  free(h);
+  if (rc) return fail(d, "guard check: copy failed");
+  if (damaged_words) *damaged_words = bad;
+  if (first_band) *first_band = first;
+  return 0;
+}
+
+// (for the guard test: where a plane lives, and a raw host-to-device write)
+extern "C" void* klt_dev_plane_address(const klt_dev* d, int slot, int which, int level) {
+  if (!d->arena || slot < 0 || slot >= KLT_DEV_SLOTS || level < 0 || level >= d->L) return nullptr;
+  const Level& lv = d->set[slot].lv[level];
+  return which == 0 ? (void*)lv.img : which == 1 ? (void*)lv.gx : which == 2 ? (void*)lv.gy : nullptr;
+}
+extern "C" int klt_dev_poke(klt_dev* d, void* device_dst, const void* host_src, size_t bytes) {
+  CU(cudaSetDevice(d->device));
+  if (sync_all(d)) return fail(d, "stream synchronisation failed");
+  CU(cudaMemcpy(device_dst, host_src, bytes, cudaMemcpyHostToDevice));
   return 0;
 }
 

@@ -87,6 +87,10 @@ DEV_API = {
     "klt_dev_force_generic": (None, [C.c_void_p, C.c_int]),
     "klt_dev_disable_fused": (None, [C.c_void_p, C.c_int]),
     "klt_dev_set_l0_kernel": (None, [C.c_int]),
+    "klt_dev_set_guard": (None, [C.c_void_p, C.c_int]),
+    "klt_dev_plane_address": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "klt_dev_poke": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "klt_dev_check_guards": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_int)]),
     "klt_dev_l0_kernel": (C.c_int, []),
     "klt_dev_last_build_fused": (C.c_int, [C.c_void_p]),
     "klt_dev_set_band_rows": (None, [C.c_void_p, C.c_int]),
