@@ -1197,6 +1197,7 @@ struct klt_dev {
   float* arena;
   size_t arena_floats;
   int guard;                 // debug: canary bands between the planes of the arena (klt_dev_set_guard)
+  struct Guarded { void* user; size_t bytes; } guarded[24]; int nguarded;   // ... and around the selection / feature buffers
   float* tmp;                // generic path: horizontal-pass result, W*H floats
   unsigned char* frame;      // u8 staging of the frame being built (== frame_buf[frame_idx]), row pitch frame_pitch
   unsigned char* frame_buf[2]; int frame_idx;   // two buffers: frame k+1 goes up while level 0 of frame k is still reading
@@ -1434,6 +1435,31 @@ extern "C" int klt_dev_create(int device, klt_dev** out) {
 
 static constexpr size_t KLT_GUARD_FLOATS = 1024;      // 4 KB: keeps every plane 128-byte aligned
 static constexpr int KLT_GUARD_BYTE = 0xA5;
+// cudaMalloc / cudaFree with a canary band on either side in guard mode (the selection and feature buffers)
+static cudaError_t guarded_malloc(klt_dev* d, void** out, size_t bytes) {
+  if (!d->guard || d->nguarded >= (int)(sizeof(d->guarded) / sizeof(d->guarded[0]))) return cudaMalloc(out, bytes);
+  const size_t gb = KLT_GUARD_FLOATS * sizeof(float), padded = (bytes + 255) / 256 * 256;
+  unsigned char* base = nullptr;
+  cudaError_t e = cudaMalloc(&base, padded + 2 * gb);
+  if (e != cudaSuccess) return e;
+  e = cudaMemset(base, KLT_GUARD_BYTE, padded + 2 * gb);
+  if (e != cudaSuccess) { cudaFree(base); return e; }
+  *out = base + gb;
+  d->guarded[d->nguarded].user = base + gb; d->guarded[d->nguarded].bytes = bytes; d->nguarded += 1;
+  return cudaSuccess;
+}
+template <typename T>
+static cudaError_t guarded_malloc(klt_dev* d, T** out, size_t bytes) { return guarded_malloc(d, reinterpret_cast<void**>(out), bytes); }
+static void guarded_free(klt_dev* d, void* p) {
+  if (!p) return;
+  for (int i = 0; i < d->nguarded; ++i)
+    if (d->guarded[i].user == p) {
+      cudaFree(static_cast<unsigned char*>(p) - KLT_GUARD_FLOATS * sizeof(float));
+      d->guarded[i] = d->guarded[--d->nguarded];
+      return;
+    }
+  cudaFree(p);
+}
 static void free_geometry(klt_dev* d) {
   cudaFree(d->arena); d->arena = nullptr;
   cudaFree(d->tmp); d->tmp = nullptr;
@@ -1448,10 +1474,10 @@ extern "C" void klt_dev_destroy(klt_dev* d) {
   klt_dev_forget_host_frames(d);
   free_geometry(d);
   cudaFree(d->frame_buf[0]); cudaFree(d->frame_buf[1]);
-  cudaFree(d->d_x);
+  guarded_free(d, d->d_x);
   cudaFreeHost(d->h_x);
-  for (int i = 0; i < 2; ++i) { cudaFree(d->c_val[i]); cudaFree(d->c_idx[i]); }
-  cudaFree(d->cub_tmp); cudaFree(d->fmap); cudaFree(d->open_slots); cudaFree(d->rank_list); cudaFree(d->sel_state);
+  for (int i = 0; i < 2; ++i) { guarded_free(d, d->c_val[i]); guarded_free(d, d->c_idx[i]); }
+  cudaFree(d->cub_tmp); guarded_free(d, d->fmap); guarded_free(d, d->open_slots); guarded_free(d, d->rank_list); guarded_free(d, d->sel_state);
   if (d->ev_made) { cudaEventDestroy(d->ev_a); cudaEventDestroy(d->ev_b); }
   if (d->prof_ev) { for (int i = 0; i < 2 * PROF_POOL; ++i) cudaEventDestroy(d->prof_ev[i]); free(d->prof_ev); free(d->prof_kid);
     cudaEventDestroy(d->ev_origin); free(d->trace_kid); free(d->trace_t0); free(d->trace_t1); }
@@ -1522,12 +1548,19 @@ extern "C" void klt_dev_set_guard(klt_dev* d, int on) {
   if (d->guard == (on ? 1 : 0)) return;
   sync_all(d);
   free_geometry(d);
+  // the selection buffers are re-created on demand (the feature arrays keep their state: they are
+  // guarded when they are allocated after this call)
+  for (int i = 0; i < 2; ++i) { guarded_free(d, d->c_val[i]); guarded_free(d, d->c_idx[i]); d->c_val[i] = nullptr; d->c_idx[i] = nullptr; }
+  guarded_free(d, d->rank_list); guarded_free(d, d->sel_state); d->rank_list = nullptr; d->sel_state = nullptr;
+  cudaFree(d->cub_tmp); d->cub_tmp = nullptr; d->cand_cap = 0;
+  guarded_free(d, d->fmap); d->fmap = nullptr; d->fmap_cap = 0;
+  guarded_free(d, d->open_slots); d->open_slots = nullptr; d->open_cap = 0;
   d->guard = on ? 1 : 0;
 }
 extern "C" int klt_dev_check_guards(klt_dev* d, long long* damaged_words, int* first_band) {
   if (damaged_words) *damaged_words = 0;
   if (first_band) *first_band = -1;
-  if (!d->guard || !d->arena) return 0;
+  if (!d->guard) return 0;
   CU(cudaSetDevice(d->device));
   if (sync_all(d)) return fail(d, "stream synchronisation failed");
   unsigned* h = (unsigned*)malloc(KLT_GUARD_FLOATS * sizeof(unsigned));
@@ -1543,12 +1576,19 @@ extern "C" int klt_dev_check_guards(klt_dev* d, long long* damaged_words, int* f
     return 0;
   };
   int rc = 0;
-  for (int s = 0; s < KLT_DEV_SLOTS && !rc; ++s)
+  for (int s = 0; d->arena && s < KLT_DEV_SLOTS && !rc; ++s)
     for (int l = 0; l < d->L && !rc; ++l) {
       const Level& lv = d->set[s].lv[l];
       rc = check(lv.img - KLT_GUARD_FLOATS) || check(lv.gx - KLT_GUARD_FLOATS) || check(lv.gy - KLT_GUARD_FLOATS);
     }
-  if (!rc) rc = check(d->arena + d->arena_floats - KLT_GUARD_FLOATS);
+  if (!rc && d->arena) rc = check(d->arena + d->arena_floats - KLT_GUARD_FLOATS);
+  // selection / feature buffers: band in front and band behind (from the first 256-byte boundary after the buffer)
+  band = 1000;
+  for (int i = 0; i < d->nguarded && !rc; ++i) {
+    const unsigned char* u = static_cast<const unsigned char*>(d->guarded[i].user);
+    rc = check(reinterpret_cast<const float*>(u - KLT_GUARD_FLOATS * sizeof(float))) ||
+         check(reinterpret_cast<const float*>(u + (d->guarded[i].bytes + 255) / 256 * 256));
+  }
   free(h);
   if (rc) return fail(d, "guard check: copy failed");
   if (damaged_words) *damaged_words = bad;
@@ -2360,12 +2400,12 @@ extern "C" int klt_dev_read_level(klt_dev* d, int slot, int which, int level, fl
 static int ensure_features(klt_dev* d, int n) {
   if (n <= d->feat_cap) return 0;
   if (sync_all(d)) return fail(d, "stream synchronisation failed");
-  cudaFree(d->d_x);
+  guarded_free(d, d->d_x);
   cudaFreeHost(d->h_x);
   d->d_x = d->d_y = nullptr; d->d_val = nullptr; d->h_x = d->h_y = nullptr; d->h_val = nullptr;
   d->feat_cap = 0;
   const int cap = (n + 1023) / 1024 * 1024;
-  CU(cudaMalloc(&d->d_x, (size_t)cap * 12));
+  CU(guarded_malloc(d, &d->d_x, (size_t)cap * 12));
   CU(cudaMallocHost(&d->h_x, (size_t)cap * 12));
   d->d_y = d->d_x + cap; d->d_val = reinterpret_cast<int*>(d->d_y + cap);
   d->h_y = d->h_x + cap; d->h_val = reinterpret_cast<int*>(d->h_y + cap);
@@ -2832,15 +2872,15 @@ static CandGeo cand_geometry(const klt_dev* d, const klt_dev_select_params* p) {
 static int ensure_candidates(klt_dev* d, size_t n) {
   if (n <= d->cand_cap) return 0;
   CU(cudaStreamSynchronize(d->stream));
-  for (int i = 0; i < 2; ++i) { cudaFree(d->c_val[i]); cudaFree(d->c_idx[i]); d->c_val[i] = nullptr; d->c_idx[i] = nullptr; }
+  for (int i = 0; i < 2; ++i) { guarded_free(d, d->c_val[i]); guarded_free(d, d->c_idx[i]); d->c_val[i] = nullptr; d->c_idx[i] = nullptr; }
   cudaFree(d->cub_tmp); d->cub_tmp = nullptr; d->cand_cap = 0;
   for (int i = 0; i < 2; ++i) {
-    CU(cudaMalloc(&d->c_val[i], n * sizeof(int)));
-    CU(cudaMalloc(&d->c_idx[i], n * sizeof(unsigned)));
+    CU(guarded_malloc(d, &d->c_val[i], n * sizeof(int)));
+    CU(guarded_malloc(d, &d->c_idx[i], n * sizeof(unsigned)));
   }
-  cudaFree(d->rank_list); cudaFree(d->sel_state); d->rank_list = nullptr; d->sel_state = nullptr;
-  CU(cudaMalloc(&d->rank_list, n * sizeof(int)));
-  CU(cudaMalloc(&d->sel_state, 8 * sizeof(int)));
+  guarded_free(d, d->rank_list); guarded_free(d, d->sel_state); d->rank_list = nullptr; d->sel_state = nullptr;
+  CU(guarded_malloc(d, &d->rank_list, n * sizeof(int)));
+  CU(guarded_malloc(d, &d->sel_state, 8 * sizeof(int)));
   size_t bytes = 0, bytes2 = 0;
   CU(cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, d->c_val[0], d->c_val[1], d->c_idx[0],
                                                d->c_idx[1], (int)n, 0, 32, d->stream));
@@ -2915,14 +2955,14 @@ static int select_core(klt_dev* d, int slot, const klt_dev_select_params* p, int
   const size_t npx = (size_t)d->W * d->H;
   if (d->fmap_cap < npx) {
     CU(cudaStreamSynchronize(d->stream));
-    cudaFree(d->fmap); d->fmap = nullptr; d->fmap_cap = 0;
-    CU(cudaMalloc(&d->fmap, npx + 4));        // (+4: the stamps are written as 32-bit words)
+    guarded_free(d, d->fmap); d->fmap = nullptr; d->fmap_cap = 0;
+    CU(guarded_malloc(d, &d->fmap, npx + 4));        // (+4: the stamps are written as 32-bit words)
     d->fmap_cap = npx;
   }
   if (d->open_cap < n) {
     CU(cudaStreamSynchronize(d->stream));
-    cudaFree(d->open_slots); d->open_slots = nullptr; d->open_cap = 0;
-    CU(cudaMalloc(&d->open_slots, (size_t)n * sizeof(int)));
+    guarded_free(d, d->open_slots); d->open_slots = nullptr; d->open_cap = 0;
+    CU(guarded_malloc(d, &d->open_slots, (size_t)n * sizeof(int)));
     d->open_cap = n;
   }
   CU(cudaMemsetAsync(d->fmap, 0, npx, d->stream));

@@ -96,6 +96,38 @@ def test_select_track_replace_sequence_on_a_guarded_arena(L, capi):
     L.KLTFreeTrackingContext(tc)
 
 
+@pytest.mark.parametrize("shape,n,mindist,window", [((243, 321), 500, 10, 7), ((97, 1217), 2000, 3, 5),
+                                                     ((480, 640), 4000, 1, 7), ((1081, 1923), 1024, 25, 9),
+                                                     ((130, 257), 50, 40, 11)])
+def test_selection_buffers_stay_inside_their_allocations(L, capi, shape, n, mindist, window):
+    """the eigenvalue map, the candidate lists of the radix sort, the rank list of the uncovered filter,
+    the minimum-distance map (stamped as 32-bit words), the open-slot list and the feature arrays, each
+    between two canary bands: selection, tracking and replacement with more features than the frame
+    holds, tiny and huge minimum distances, other windows"""
+    h, w = shape
+    frames = [synth_image(w, h, 9, shift=(1.1 * k, 0.7 * k)) for k in range(3)]
+    tc = L.KLTCreateTrackingContext()
+    tc.contents.sequentialMode = 1
+    tc.contents.mindist = mindist
+    tc.contents.window_width = tc.contents.window_height = window
+    L.KLTUpdateTCBorder(tc)
+    dev = L.KLTB200Device(tc)
+    L.klt_dev_set_guard(dev, 1)
+    fl = L.KLTCreateFeatureList(n)
+    L.select(tc, frames[0], fl)
+    _guards_intact(L, dev, "select")
+    for k in (1, 2):
+        L.track(tc, frames[k - 1], frames[k], fl)
+        x, y, v = capi.featurelist_to_arrays(fl)
+        v = v.copy(); x = x.copy(); y = y.copy()
+        v[::7] = -1; x[::7] = -1.0; y[::7] = -1.0               # open every seventh slot
+        capi.arrays_to_featurelist(fl, x, y, v)
+        L.replace(tc, frames[k], fl)
+        _guards_intact(L, dev, "track + replace %d" % k)
+    L.KLTFreeFeatureList(fl)
+    L.KLTFreeTrackingContext(tc)
+
+
 def test_a_store_outside_a_plane_is_seen(L, oracle):
     """the check itself: one float written right behind level 0's grady plane is reported"""
     img = synth_image(320, 240, seed=1)
