@@ -25,11 +25,22 @@ int KLT_verbose = 1;
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 static klt_tc_state *g_states = NULL;
 
+/* The hot calls look their context up once per call: a per-thread one-entry cache in front of the
+ * list keeps the process-wide lock off that path (a driver thread works on one tc at a time; 64
+ * contexts on 4 threads in the config-5 runner).  g_epoch moves whenever a state is dropped, which is
+ * the only event that can turn a cached pointer stale. */
+static unsigned long g_epoch = 1;
+static __thread KLT_TrackingContext t_tc;
+static __thread klt_tc_state *t_state;
+static __thread unsigned long t_epoch;
+
 klt_tc_state *klt_state_find(KLT_TrackingContext tc)
 {
   klt_tc_state *s;
+  if (t_state != NULL && t_tc == tc && t_epoch == __atomic_load_n(&g_epoch, __ATOMIC_ACQUIRE)) return t_state;
   pthread_mutex_lock(&g_lock);
   for (s = g_states; s != NULL && s->tc != tc; s = s->next) ;
+  t_tc = tc; t_state = s; t_epoch = g_epoch;
   pthread_mutex_unlock(&g_lock);
   return s;
 }
@@ -49,6 +60,7 @@ klt_tc_state *klt_state_get(KLT_TrackingContext tc)
   pthread_mutex_lock(&g_lock);
   s->next = g_states;
   g_states = s;
+  t_tc = tc; t_state = s; t_epoch = g_epoch;
   pthread_mutex_unlock(&g_lock);
   return s;
 }
@@ -59,6 +71,7 @@ void klt_state_drop(KLT_TrackingContext tc)
   pthread_mutex_lock(&g_lock);
   for (pp = &g_states; *pp; pp = &(*pp)->next)
     if ((*pp)->tc == tc) { s = *pp; *pp = s->next; break; }
+  __atomic_add_fetch(&g_epoch, 1, __ATOMIC_RELEASE);     /* every thread's cached entry is void now */
   pthread_mutex_unlock(&g_lock);
   if (s) {
     if (s->dev) klt_dev_destroy(s->dev);

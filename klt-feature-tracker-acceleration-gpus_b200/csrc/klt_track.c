@@ -270,7 +270,7 @@ static void track_common(KLT_TrackingContext tc, const KLT_PixelType *img1,
   /* Everything below is queued on the context stream without waiting: feature upload,
    * frame upload, pyramid kernels, tracker, result download; one synchronisation at the end. */
   const int timing = timing_on();
-  static double acc[5]; static int calls;
+  static __thread double acc[5]; static __thread int calls;     /* (KLT_B200_TIMING: per calling thread) */
   double t0 = timing ? now_us() : 0, t1 = 0, t2 = 0, t3 = 0;
   /* The frame upload is the long pole.  With a pinned feature list nothing has to be packed:
    * queue the one-copy mirror of the records, then queue the frame and the pyramid kernels.  An ordinary list is
