@@ -259,3 +259,31 @@ def test_march_level0_matches_oracle(L, oracle, march_kernel, shape, exact):
     tc = L.KLTCreateTrackingContext()
     _check_build(L, oracle, img, tc, exact, 0, expect_fused=True)
     L.KLTFreeTrackingContext(tc)
+
+
+@pytest.mark.parametrize("band_rows", [64, 128, -1])
+def test_march_level0_behind_a_banded_upload(L, oracle, march_kernel, band_rows):
+    """l0_march_kernel launched segment by segment behind the bands of a host frame (its producer reads
+    up to a chunk of padding rows past a segment: they may lie in a band that has not arrived, and must
+    reach no output): bit-identical to the oracle and to the single-shot build."""
+    h, w = 1080, 1923
+    img = synth_image(w, h, seed=5)
+    tc = L.KLTCreateTrackingContext()
+    tc.contents.nPyramidLevels, tc.contents.subsampling = 3, 2
+    L.KLTUpdateTCBorder(tc)
+    dev = L.KLTB200Device(tc)
+    L.klt_dev_set_band_rows(dev, band_rows)
+    _check_build(L, oracle, img, tc, exact=1, generic=0, expect_fused=True)
+    assert band_rows < 0 or L.klt_dev_last_build_bands(dev) > 1     # (automatic: one copy below 4 MB)
+    q = L.build_desc(tc, w, h, exact=0)
+    other = synth_image(w, h, seed=6)                  # what the staging buffer held before
+    L.dev_build(dev, 2, other, q)
+    L.dev_build(dev, 0, img, q)
+    a = device_pyramids(L, dev, 0, 3)
+    L.klt_dev_set_band_rows(dev, 0)
+    L.dev_build(dev, 1, img, q)
+    b = device_pyramids(L, dev, 1, 3)
+    for which in range(3):
+        for l in range(3):
+            assert np.array_equal(a[which][l], b[which][l])
+    L.KLTFreeTrackingContext(tc)
