@@ -34,6 +34,7 @@ struct AffArgs {
   int   nlevels; float ss;
   int   ncols, nrows, pitch;                 // level 0
   int   resident;                            // the state array lives on the device across frames (sequence call)
+  int   lighting;                            // tc->lighting_insensitive: check 0 refines on gain / bias normalised windows
   const float *i1, *gx1, *gy1;               // previous frame, level 0: template source
   const float *i2, *gx2, *gy2;               // new frame, level 0
 };
@@ -183,6 +184,41 @@ affine_check_kernel(AffArgs a, int n, const float* __restrict__ x0, const float*
           ul_y < 0.0f || ASUB(fr, ul_y) < eps1 || ll_y < 0.0f || ASUB(fr, ll_y) < eps1 ||
           ur_y < 0.0f || ASUB(fr, ur_y) < eps1 || lr_y < 0.0f || ASUB(fr, lr_y) < eps1) { status = KLT_OOB; break; }
     }
+    if (a.check == 0 && a.lighting) {
+      // :1024-1028 -> :125-220: gain / bias normalised windows, template against frame.  Pass 1 leaves
+      // the raw samples g1 (template) in sd and g2 (frame) in sx; four lanes sum them sequentially in
+      // raster order (sum g1, sum g2, sum g1^2, sum g2^2: the reference's order and rounding); pass 2
+      // forms  g1 - g2 * alpha - belta  and  grad1 + grad2 * alpha_g  (whose gain is the reference's
+      // sqrt(mean g1 / mean g2), :202).
+      for (int k = lane; k < npix; k += 32) {
+        const float fi = (float)(k % a.aw - hw), fj = (float)(k / a.aw - hh);
+        sd[k] = aff_bilinear(t_img, tw, AADD(x1, fi), AADD(y1, fj));
+        sx[k] = aff_bilinear(a.i2, a.pitch, AADD(x2, fi), AADD(y2, fj));
+      }
+      __syncwarp();
+      float acc = 0.0f;
+      if (lane < 4) {
+        const float* A = (lane & 1) ? sx : sd;
+        if (lane < 2) { for (int k = 0; k < npix; ++k) acc = AADD(acc, A[k]); }
+        else          { for (int k = 0; k < npix; ++k) acc = AADD(acc, AMUL(A[k], A[k])); }
+      }
+      const float s1 = __shfl_sync(0xffffffffu, acc, 0), s2 = __shfl_sync(0xffffffffu, acc, 1);
+      const float q1 = __shfl_sync(0xffffffffu, acc, 2), q2 = __shfl_sync(0xffffffffu, acc, 3);
+      const float fn = (float)npix;
+      const float alpha = (float)sqrt((double)__fdiv_rn(__fdiv_rn(q1, fn), __fdiv_rn(q2, fn)));
+      const float m1 = __fdiv_rn(s1, fn), m2 = __fdiv_rn(s2, fn);
+      const float belta = ASUB(m1, AMUL(alpha, m2));
+      const float alphag = (float)sqrt((double)__fdiv_rn(m1, m2));
+      __syncwarp();
+      for (int k = lane; k < npix; k += 32) {
+        const float fi = (float)(k % a.aw - hw), fj = (float)(k / a.aw - hh);
+        const float tx = AADD(x1, fi), ty = AADD(y1, fj), qx = AADD(x2, fi), qy = AADD(y2, fj);
+        const float g1 = sd[k], g2 = sx[k];
+        sd[k] = ASUB(ASUB(g1, AMUL(g2, alpha)), belta);
+        sx[k] = AADD(aff_bilinear(t_gx, tw, tx, ty), AMUL(aff_bilinear(a.gx2, a.pitch, qx, qy), alphag));
+        sy[k] = AADD(aff_bilinear(t_gy, tw, tx, ty), AMUL(aff_bilinear(a.gy2, a.pitch, qx, qy), alphag));
+      }
+    } else
     // window samples (:68-123 for check 0; :700-722 and :610-632 otherwise)
     for (int k = lane; k < npix; k += 32) {
       const float fi = (float)(k % a.aw - hw), fj = (float)(k / a.aw - hh);

@@ -2807,6 +2807,7 @@ static int affine_check_core(klt_dev* d, int slot_prev, int slot_cur, const klt_
   a.step_factor = tp->step_factor; a.small = tp->min_determinant; a.th = tp->min_displacement;
   a.nlevels = d->L; a.ss = (float)d->ss;
   a.resident = resident ? 1 : 0;
+  a.lighting = tp->lighting_insensitive ? 1 : 0;
   const Level& l1 = d->set[slot_prev].lv[0];
   const Level& l2 = d->set[slot_cur].lv[0];
   a.ncols = l2.w; a.nrows = l2.h; a.pitch = l2.pitch;

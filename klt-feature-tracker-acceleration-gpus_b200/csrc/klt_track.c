@@ -59,9 +59,6 @@ static void check_supported(KLT_TrackingContext tc, int pipelined)
   if (tc->affineConsistencyCheck >= 0 && pipelined == 1)
     KLTError("(KLT/B200) the affine consistency check keeps per-feature templates in the caller's "
              "feature list: use KLTTrackFeatures or KLTTrackFeaturesSequence, not KLTB200Resident*");
-  if (tc->affineConsistencyCheck == 0 && tc->lighting_insensitive)
-    KLTError("(KLTTrackFeatures) affineConsistencyCheck = 0 together with lighting_insensitive is "
-             "not implemented on the GPU path (and there is no CPU path)");
 }
 
 /* ---- affine consistency check: host side (reference trackFeatures.c:1438-1497) ---------- */

@@ -359,7 +359,7 @@ static int window_oob(float x, float y, int hw, int hh, int nc, int nr)
  * gain alpha = sqrt(mean(g1^2) / mean(g2^2)), bias belta = mean(g1) - alpha * mean(g2) over the
  * window, imgdiff = g1 - g2 * alpha - belta.  All sums are sequential float sums in raster order;
  * the sqrt is the double sqrt of a float quotient. */
-static void intensity_difference_li(const float *img1, const float *img2, int nc, float x1, float y1,
+static void intensity_difference_li(const float *img1, int nc1, const float *img2, int nc2, float x1, float y1,
                                     float x2, float y2, int ww, int wh, float *diff)
 {
   const int hw = ww / 2, hh = wh / 2;
@@ -368,8 +368,8 @@ static void intensity_difference_li(const float *img1, const float *img2, int nc
   int i, j;
   for (j = -hh; j <= hh; j++)
     for (i = -hw; i <= hw; i++) {
-      g1 = bilinear(x1 + i, y1 + j, img1, nc);
-      g2 = bilinear(x2 + i, y2 + j, img2, nc);
+      g1 = bilinear(x1 + i, y1 + j, img1, nc1);
+      g2 = bilinear(x2 + i, y2 + j, img2, nc2);
       sum1 += g1; sum2 += g2;
       sum1_squared += g1 * g1;
       sum2_squared += g2 * g2;
@@ -382,8 +382,8 @@ static void intensity_difference_li(const float *img1, const float *img2, int nc
   belta = mean1 - alpha * mean2;
   for (j = -hh; j <= hh; j++)
     for (i = -hw; i <= hw; i++) {
-      g1 = bilinear(x1 + i, y1 + j, img1, nc);
-      g2 = bilinear(x2 + i, y2 + j, img2, nc);
+      g1 = bilinear(x1 + i, y1 + j, img1, nc1);
+      g2 = bilinear(x2 + i, y2 + j, img2, nc2);
       *diff++ = g1 - g2 * alpha - belta;
     }
 }
@@ -392,7 +392,7 @@ static void intensity_difference_li(const float *img1, const float *img2, int nc
  * square root of the ratio of the window MEANS (the variables are called sum*_squared but
  * accumulate g, not g*g, :202) -- restated as it is. */
 static void gradient_sum_li(const float *gx1, const float *gy1, const float *gx2, const float *gy2,
-                            const float *img1, const float *img2, int nc, float x1, float y1,
+                            const float *img1, int nc1, const float *img2, int nc2, float x1, float y1,
                             float x2, float y2, int ww, int wh, float *wx, float *wy)
 {
   const int hw = ww / 2, hh = wh / 2;
@@ -400,8 +400,8 @@ static void gradient_sum_li(const float *gx1, const float *gy1, const float *gx2
   int i, j;
   for (j = -hh; j <= hh; j++)
     for (i = -hw; i <= hw; i++) {
-      g1 = bilinear(x1 + i, y1 + j, img1, nc);
-      g2 = bilinear(x2 + i, y2 + j, img2, nc);
+      g1 = bilinear(x1 + i, y1 + j, img1, nc1);
+      g2 = bilinear(x2 + i, y2 + j, img2, nc2);
       sum1_squared += g1; sum2_squared += g2;
     }
   mean1 = sum1_squared / (ww * wh);
@@ -409,11 +409,11 @@ static void gradient_sum_li(const float *gx1, const float *gy1, const float *gx2
   alpha = (float)sqrt(mean1 / mean2);
   for (j = -hh; j <= hh; j++)
     for (i = -hw; i <= hw; i++) {
-      g1 = bilinear(x1 + i, y1 + j, gx1, nc);
-      g2 = bilinear(x2 + i, y2 + j, gx2, nc);
+      g1 = bilinear(x1 + i, y1 + j, gx1, nc1);
+      g2 = bilinear(x2 + i, y2 + j, gx2, nc2);
       *wx++ = g1 + g2 * alpha;
-      g1 = bilinear(x1 + i, y1 + j, gy1, nc);
-      g2 = bilinear(x2 + i, y2 + j, gy2, nc);
+      g1 = bilinear(x1 + i, y1 + j, gy1, nc1);
+      g2 = bilinear(x2 + i, y2 + j, gy2, nc2);
       *wy++ = g1 + g2 * alpha;
     }
 }
@@ -458,8 +458,8 @@ int klto_track_level_li(float x1, float y1, float *x2, float *y2,
     /* :68-87 and :98-123 intensity difference and gradient sum windows */
     k = 0;
     if (lighting) {
-      intensity_difference_li(img1, img2, nc, x1, y1, *x2, *y2, ww, wh, diff);
-      gradient_sum_li(gx1, gy1, gx2, gy2, img1, img2, nc, x1, y1, *x2, *y2, ww, wh, wx, wy);
+      intensity_difference_li(img1, nc, img2, nc, x1, y1, *x2, *y2, ww, wh, diff);
+      gradient_sum_li(gx1, gy1, gx2, gy2, img1, nc, img2, nc, x1, y1, *x2, *y2, ww, wh, wx, wy);
     } else
     for (j = -hh; j <= hh; j++)
       for (i = -hw; i <= hw; i++, k++) {
@@ -509,7 +509,7 @@ int klto_track_level_li(float x1, float y1, float *x2, float *y2,
     float sum = 0.0f;
     k = 0;
     if (lighting)
-      intensity_difference_li(img1, img2, nc, x1, y1, *x2, *y2, ww, wh, diff);
+      intensity_difference_li(img1, nc, img2, nc, x1, y1, *x2, *y2, ww, wh, diff);
     else
     for (j = -hh; j <= hh; j++)
       for (i = -hw; i <= hw; i++, k++)
@@ -620,7 +620,7 @@ int klto_track_affine_feature(float x1, float y1, float *x2, float *y2,
                               int width, int height, float step_factor, int max_iterations,
                               float small, float th, float th_aff, float max_residue,
                               int affine_map, float mdd,
-                              float *Axx, float *Ayx, float *Axy, float *Ayy)
+                              float *Axx, float *Ayx, float *Axy, float *Ayy, int lighting)
 {
   const int hw = width / 2, hh = height / 2, npix = width * height;
   float *diff = (float *)malloc(sizeof(float) * npix);
@@ -634,12 +634,16 @@ int klto_track_affine_feature(float x1, float y1, float *x2, float *y2,
 
   do {
     if (!affine_map) {
-      /* :1010-1059 pure translation against the template (lighting-insensitive variant not restated) */
+      /* :1010-1059 pure translation against the template */
       if (x1 - hw < 0.0f || nc1 - (x1 + hw) < one_plus_eps ||
           *x2 - hw < 0.0f || nc2 - (*x2 + hw) < one_plus_eps ||
           y1 - hh < 0.0f || nr1 - (y1 + hh) < one_plus_eps ||
           *y2 - hh < 0.0f || nr2 - (*y2 + hh) < one_plus_eps) { status = KLTO_OOB; break; }
       k = 0;
+      if (lighting) {             /* :1024-1028 gain / bias normalised windows, template against frame */
+        intensity_difference_li(img1, nc1, img2, nc2, x1, y1, *x2, *y2, width, height, diff);
+        gradient_sum_li(gx1, gy1, gx2, gy2, img1, nc1, img2, nc2, x1, y1, *x2, *y2, width, height, wx, wy);
+      } else
       for (j = -hh; j <= hh; j++)
         for (i = -hw; i <= hw; i++, k++) {
           diff[k] = bilinear(x1 + i, y1 + j, img1, nc1) - bilinear(*x2 + i, *y2 + j, img2, nc2);
@@ -840,7 +844,8 @@ void klto_track_affine(const klto_pyramids *p1, const klto_pyramids *p2, const k
                                       ap->max_iterations, p->min_determinant, p->min_displacement,
                                       ap->min_displacement, ap->max_residue, ap->check,
                                       ap->max_displacement_differ,
-                                      &st[f].Axx, &st[f].Ayx, &st[f].Axy, &st[f].Ayy);
+                                      &st[f].Axx, &st[f].Ayx, &st[f].Axy, &st[f].Ayy,
+                                      p->lighting_insensitive);
         val[f] = v;
         if (v != KLTO_TRACKED) {
           x[f] = -1.0f; y[f] = -1.0f; st[f].aff_x = -1.0f; st[f].aff_y = -1.0f; st[f].has = 0;

@@ -120,7 +120,7 @@ int klto_track_affine_feature(float x1, float y1, float *x2, float *y2,
                               int width, int height, float step_factor, int max_iterations,
                               float small, float th, float th_aff, float max_residue,
                               int affine_map, float mdd,
-                              float *Axx, float *Ayx, float *Axy, float *Ayy);
+                              float *Axx, float *Ayx, float *Axy, float *Ayy, int lighting);
 
 /* single level solver, exposed for edge-case tests (trackFeatures.c:381-486) */
 int klto_track_level(float x1, float y1, float *x2, float *y2,

@@ -203,3 +203,41 @@ def test_affine_check_inside_the_sequence_call(L, capi, provided, check, exact, 
             for w in range(3):
                 assert ma[i][w].tobytes() == mb[i][w].tobytes(), (i, w)
     assert (aa["has"] == 1).sum() > 20
+
+
+@pytest.mark.parametrize("sequence", [False, True])
+def test_affine_check_0_with_lighting_insensitive(L, capi, oracle, oracle_mod, provided, sequence):
+    """affineConsistencyCheck = 0 together with lighting_insensitive (reference trackFeatures.c:1024-1028):
+    the translation refinement against the template runs on gain / bias normalised windows.  Exact mode,
+    frames with a growing brightness gain and offset: bit-identical to the oracle (pinned against the
+    compiled reference in tests/test_oracle.py), through the per-call API and through the sequence call."""
+    from tests.test_oracle import _ramped
+    imgs = _ramped(provided, 7)
+    n = 120
+    tc = L.KLTCreateTrackingContext()
+    tc.contents.sequentialMode = 1
+    tc.contents.affineConsistencyCheck = 0
+    tc.contents.lighting_insensitive = 1
+    L.KLTB200SetExact(tc, 1)
+    fl = L.KLTCreateFeatureList(n)
+    L.select(tc, imgs[0], fl)
+    p = params_from_tc(oracle, tc)
+    assert p.lighting_insensitive == 1
+    ap = oracle_mod.affine_params(check=0)
+    x, y, v = oracle.select(imgs[0], p, n, sort_kind=oracle_mod.SORT_STABLE)
+    st, tmpl = oracle_mod.affine_state(n)
+    prev = oracle.build_pyramids(imgs[0], p)
+    if sequence:
+        L.track_sequence(tc, imgs, fl, None, 0, False)
+    for i in range(1, len(imgs)):
+        if not sequence:
+            L.track(tc, imgs[i - 1], imgs[i], fl)
+        cur = oracle.build_pyramids(imgs[i], p)
+        x, y, v = oracle.track_affine(prev, cur, p, ap, x, y, v, st, tmpl)
+        if not sequence:
+            _check_frame(capi, fl, x, y, v, st, tmpl, "frame %d" % i)
+        prev = cur
+    _check_frame(capi, fl, x, y, v, st, tmpl, "end")
+    assert (st["has"] == 1).sum() > 20
+    L.KLTFreeFeatureList(fl)
+    L.KLTFreeTrackingContext(tc)

@@ -222,6 +222,55 @@ def test_lighting_insensitive_tracking_bit_exact_vs_reference(oracle, oracle_mod
         prev = cur
 
 
+def _ramped(provided, n):
+    """the provided frames with a brightness gain / offset growing from frame to frame"""
+    imgs = [provided[0]]
+    for k in range(1, n):
+        f = provided[k].astype(np.float32) * (1.0 + 0.01 * k) + 0.5 * k
+        imgs.append(np.clip(f, 0, 255).astype(np.uint8))
+    return imgs
+
+
+def test_affine_check_0_with_lighting_insensitive_bit_exact_vs_reference(oracle, oracle_mod, capi, ref_qsort, provided):
+    """tc->affineConsistencyCheck = 0 together with tc->lighting_insensitive (trackFeatures.c:1024-1028):
+    the translation refinement against the template runs on the gain / bias normalised windows, the
+    final residue on the plain difference (:1196-1199)."""
+    imgs = _ramped(provided, 7)
+    n = 120
+    R = ref_qsort
+    tc = R.make_tc(sequentialMode=1, affineConsistencyCheck=0, lighting_insensitive=1)
+    fl = R.new_list(n)
+    R.api.select(tc, imgs[0], fl)
+    p = oracle.default_params()
+    p.lighting_insensitive = 1
+    ap = oracle_mod.affine_params(check=0)
+    x, y, v = oracle.select(imgs[0], p, n, sort_kind=oracle_mod.SORT_STABLE)
+    st, tmpl = oracle_mod.affine_state(n)
+    prev = oracle.build_pyramids(imgs[0], p)
+    p_plain = oracle.default_params()
+    differs = 0
+    for i in range(1, len(imgs)):
+        R.api.track(tc, imgs[i - 1], imgs[i], fl)
+        cur = oracle.build_pyramids(imgs[i], p)
+        st2, tmpl2 = st.copy(), tmpl.copy()
+        plain = oracle.track_affine(prev, cur, p_plain, ap, x.copy(), y.copy(), v.copy(), st2, tmpl2)
+        x, y, v = oracle.track_affine(prev, cur, p, ap, x, y, v, st, tmpl)
+        differs += int((plain[2] != v).sum()) + int((plain[0] != x).sum())
+        rx, ry, rv = R.get(fl)
+        ra = capi.featurelist_affine(fl)
+        assert np.array_equal(v, rv), "frame %d" % i
+        assert x.tobytes() == rx.tobytes() and y.tobytes() == ry.tobytes()
+        assert np.array_equal(st["has"], ra["has"])
+        live = st["has"] == 1
+        for k in ("aff_x", "aff_y", "Axx", "Ayx", "Axy", "Ayy"):
+            assert st[k][live].tobytes() == ra[k][live].tobytes(), (i, k)
+        prev = cur
+    assert differs > 0                                  # the flag matters on these frames
+    assert (st["has"] == 1).sum() > 20
+    R.api.KLTFreeFeatureList(fl)
+    R.api.KLTFreeTrackingContext(tc)
+
+
 def _warped(img, k):
     """frame k of a slowly rotating / zooming / shifting copy of img (bilinear, numpy)"""
     h, w = img.shape
