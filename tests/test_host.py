@@ -256,3 +256,33 @@ def test_hot_path_fails_loudly_without_gpu(L):
     assert "KLT Error" in r.stderr and "SURVIVED" not in r.stdout
     with pytest.raises(RuntimeError):
         L.require_gpu()
+
+
+def test_contexts_from_many_threads(L):
+    """The side table tc -> device state behind a per-thread one-entry cache (csrc/klt_context.c): four
+    threads create, configure and free contexts in a loop -- every free voids the other threads' cached
+    entries -- and a context freed by one thread and re-created at the same address by another must not
+    find the old state (KLTB200SetExact is stored in the state: a fresh context starts with 0)."""
+    import threading
+    errors = []
+
+    def worker(seed):
+        try:
+            for it in range(300):
+                tcs = [L.KLTCreateTrackingContext() for _ in range(3)]
+                for k, tc in enumerate(tcs):
+                    assert L.KLTB200GetExact(tc) == 0, "stale state on a fresh context"
+                    L.KLTB200SetExact(tc, (seed + k + it) & 1)
+                for k, tc in enumerate(tcs):
+                    assert L.KLTB200GetExact(tc) == ((seed + k + it) & 1)
+                for tc in tcs:
+                    L.KLTFreeTrackingContext(tc)
+        except Exception as e:                       # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
