@@ -362,7 +362,8 @@ __device__ __forceinline__ void note_range(int* range, int vmax, int vmin) {
 
 __global__ void mineig_kernel(const float* __restrict__ gx, const float* __restrict__ gy, int pitch,
                               int bx, int by, int step, int nxc, int nyc, int hw, int hh,
-                              int* __restrict__ vals, unsigned* __restrict__ idx, int* range, int clamp_neg) {
+                              int* __restrict__ vals, unsigned* __restrict__ idx, int* range, int clamp_neg,
+                              const unsigned char* __restrict__ covered, int W) {
   const int ix = blockIdx.x * blockDim.x + threadIdx.x;
   const int iy = blockIdx.y * blockDim.y + threadIdx.y;
   if (ix >= nxc || iy >= nyc) return;
@@ -387,6 +388,7 @@ __global__ void mineig_kernel(const float* __restrict__ gx, const float* __restr
   // (rounding can leave a rank-deficient window a few units below zero; for the selection such a
   // key is as dead as 0 -- the threshold is >= 1 -- and non-negative keys let the sort skip bits)
   if (clamp_neg && vi < 0) vi = 0;
+  if (covered && covered[(size_t)y * W + x]) vi = 0;       // (replacement: see run_mineig)
   vals[n] = vi;
   idx[n] = (unsigned)n;
   note_range(range, vi, vi);
@@ -408,7 +410,7 @@ __device__ __forceinline__ int mineig_value(float gxx, float gxy, float gyy) {
 __global__ void __launch_bounds__(128)
 mineig7_kernel(const float* __restrict__ gx, const float* __restrict__ gy, int pitch,
                int bx, int by, int nxc, int nyc, int* __restrict__ vals, unsigned* __restrict__ idx, int* range,
-               int clamp_neg) {
+               int clamp_neg, const unsigned char* __restrict__ covered, int W) {
   const int X0 = (bx & ~7) + 8 * (blockIdx.x * blockDim.x + threadIdx.x);    // absolute x of this thread's first candidate
   const int iy = blockIdx.y * blockDim.y + threadIdx.y;
   if (X0 >= bx + nxc || iy >= nyc) return;
@@ -447,6 +449,7 @@ mineig7_kernel(const float* __restrict__ gx, const float* __restrict__ gy, int p
       const int n = iy * nxc + (x - bx);
       int v = mineig_value(sxx[c], sxy[c], syy[c]);
       if (clamp_neg && v < 0) v = 0;
+      if (covered && covered[(size_t)y * W + x]) v = 0;
       vals[n] = v;
       idx[n] = (unsigned)n;
       vmax = max(vmax, v); vmin = min(vmin, v);
@@ -1235,7 +1238,7 @@ struct klt_dev {
   unsigned char* fmap; size_t fmap_cap;
   int* open_slots; int open_cap;
   int* rank_list; int* sel_state;      // candidates still uncovered (ranks, ascending) / [0..2] walk state, [4] their number
-  int no_filter;
+  int no_filter; int replace_filter;
   int enforce_attr;            // enforce_mindist_kernel's shared-memory attribute set on this device
   // dynamic tile scheduler of the persistent kernels: one counter per launch site
   unsigned* d_tile_ctr; unsigned tile_base[16];
@@ -2894,7 +2897,13 @@ static int ensure_candidates(klt_dev* d, size_t n) {
   return 0;
 }
 
-static int run_mineig(klt_dev* d, int slot, const klt_dev_select_params* p, const CandGeo& g, int clamp_neg) {
+// covered (replacement only): the minimum-distance map with the surviving features already stamped.
+// A candidate under a stamp can never be accepted, whatever its key (selectGoodFeatures.c:176-177), so
+// its key is written as 0 -- below every threshold: the sort moves all of them behind the live
+// candidates and the walk stops in front of them, without a separate filter pass over the sorted list
+// (80 us per 4K call, 21 us at 640x480).
+static int run_mineig(klt_dev* d, int slot, const klt_dev_select_params* p, const CandGeo& g, int clamp_neg,
+                      const unsigned char* covered = nullptr) {
   const Level& lv = d->set[slot].lv[0];
   CU(cudaMemsetAsync(d->sel_state + 5, 0, 2 * sizeof(int), d->stream));        // key range: max, min
   dim3 b(32, 8), grid((g.nxc + 31) / 32, (g.nyc + 7) / 8);
@@ -2905,13 +2914,13 @@ static int run_mineig(klt_dev* d, int slot, const klt_dev_select_params* p, cons
     dim3 b7(32, 4), g7((span + 255) / 256, (g.nyc + 3) / 4);
     Launch l(d, KID_MINEIG);
     mineig7_kernel<<<g7, b7, 0, d->stream>>>(lv.gx, lv.gy, lv.pitch, g.bx, g.by, g.nxc, g.nyc, d->c_val[0], d->c_idx[0],
-                                             d->sel_state + 5, clamp_neg);
+                                             d->sel_state + 5, clamp_neg, covered, d->W);
     return 0;
   }
   { Launch l(d, KID_MINEIG);
     mineig_kernel<<<grid, b, 0, d->stream>>>(lv.gx, lv.gy, lv.pitch, g.bx, g.by, g.step, g.nxc, g.nyc,
                                              p->window_width / 2, p->window_height / 2, d->c_val[0], d->c_idx[0],
-                                             d->sel_state + 5, clamp_neg); }
+                                             d->sel_state + 5, clamp_neg, covered, d->W); }
   return 0;
 }
 
@@ -2942,6 +2951,7 @@ static int select_core(klt_dev* d, int slot, const klt_dev_select_params* p, int
     CU(cudaFuncSetAttribute(enforce_mindist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENFORCE_SMEM));
     const char* nf = getenv("KLT_B200_NO_FILTER");   // A/B: walk the whole sorted list in one launch
     d->no_filter = (nf && nf[0] == '1') ? 1 : 0;
+    { const char* rf = getenv("KLT_B200_REPLACE_FILTER"); d->replace_filter = (rf && rf[0] == '1') ? 1 : 0; }
     d->enforce_attr = 1;
   }
   cudaStream_t saved_t = d->tstream;
@@ -2967,10 +2977,15 @@ static int select_core(klt_dev* d, int slot, const klt_dev_select_params* p, int
     d->open_cap = n;
   }
   CU(cudaMemsetAsync(d->fmap, 0, npx, d->stream));
+  const bool prestamp = !p->overwrite_all && !d->no_filter && !d->replace_filter;
+  if (!p->overwrite_all && prestamp) {
+    Launch l(d, KID_STAMP);
+    stamp_existing_kernel<<<n, 128, 0, d->stream>>>(d->d_x, d->d_y, d->d_val, d->fmap, dist, d->W, d->H);
+  }
   const int* sval = nullptr; const unsigned* sidx = nullptr;
   if (g.npoints > 0) {
     if (ensure_candidates(d, (size_t)g.npoints)) return 1;
-    if (run_mineig(d, slot, p, g, 1)) return 1;
+    if (run_mineig(d, slot, p, g, 1, prestamp ? d->fmap : nullptr)) return 1;
     size_t bytes = d->cub_bytes;
     int end_bit = 32;
     {
@@ -2993,7 +3008,7 @@ static int select_core(klt_dev* d, int slot, const klt_dev_select_params* p, int
                                                    d->c_idx[1], (int)g.npoints, 0, end_bit, d->stream)); }
     sval = d->c_val[1]; sidx = d->c_idx[1];
   }
-  if (!p->overwrite_all) {
+  if (!p->overwrite_all && !prestamp) {
     Launch l(d, KID_STAMP);
     stamp_existing_kernel<<<n, 128, 0, d->stream>>>(d->d_x, d->d_y, d->d_val, d->fmap, dist, d->W, d->H);
   }
@@ -3020,8 +3035,12 @@ static int select_core(klt_dev* d, int slot, const klt_dev_select_params* p, int
             p->overwrite_all, n, d->d_x, d->d_y, d->d_val, d->open_slots, d->sel_state, first, last);
     };
     const int head = ENFORCE_HEAD;
-    if (np > 0 && !p->overwrite_all && !d->no_filter) {
-      // replacement: the surviving features are stamped, most candidates are covered from the start
+    if (np > 0 && prestamp) {
+      // replacement: the candidates under the surviving features' stamps carry key 0 (run_mineig) and
+      // sit behind the live ones; the walk reads the sorted arrays directly and ends at the first dead key
+      walk(false, 1, 1, np);
+    } else if (np > 0 && !p->overwrite_all && !d->no_filter) {
+      // (KLT_B200_REPLACE_FILTER=1, the round-1 path: filter the sorted list for uncovered candidates)
       if (uncovered(0)) return 1;
       walk(true, 1, 1, 0);
     } else if (np > 2 * head && !d->no_filter) {

@@ -410,7 +410,7 @@ def test_two_devices_in_one_process(L, capi, provided):
             assert u.tobytes() == v.tobytes()
 
 
-@pytest.mark.parametrize("switch", ["KLT_B200_NO_FILTER", "KLT_B200_MINEIG_SCALAR"])
+@pytest.mark.parametrize("switch", ["KLT_B200_NO_FILTER", "KLT_B200_MINEIG_SCALAR", "KLT_B200_REPLACE_FILTER"])
 def test_selection_alternatives_are_bit_identical(L, capi, switch, monkeypatch):
     """the A/B switches of the selection path (whole-list walk in one launch; one thread per
     eigenvalue candidate) give the lists of the default path: select on an empty list (the walk's
